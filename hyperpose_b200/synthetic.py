@@ -1,0 +1,120 @@
+"""Seeded synthetic conf / PAF tensors and frames for tests and bench.
+
+There are no weights, media or fixtures in the reference tree (scripts/downloader.py
+needs the network), so every measurement uses tensors synthesised the way the
+reference synthesises its *training targets*:
+
+* conf: per joint ``max_persons exp(-d^2 / (2*7^2))`` sampled at cell centres
+  ``8*i + 3.5`` and cut at 4.6052  (hyperpose/Model/openpose/utils.py:55-86),
+  background channel ``clip(1 - max, 0, 1)`` (utils.py:48);
+* PAF: unit limb vector within 1 cell of the segment, averaged over overlaps
+  (utils.py:174-216), channel pairs in ``CocoLimb`` order (openpose/define.py:24-25),
+  which is the order ``COCOPAIRS_NET`` (src/coco.hpp:10-30) indexes.
+
+numpy only; nothing here is on the product path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+STRIDE = 8
+N_PARTS = 18
+N_LIMBS = 19
+
+# hyperpose/Model/openpose/define.py:24-25
+COCO_LIMB = list(zip([1, 8, 9, 1, 11, 12, 1, 2, 3, 2, 1, 5, 6, 5, 1, 0, 0, 14, 15],
+                     [8, 9, 10, 11, 12, 13, 2, 3, 4, 16, 5, 6, 7, 17, 0, 14, 15, 16, 17]))
+
+# (x, y) of the 18 COCO parts in a unit person box (y down)
+_TEMPLATE = np.array([
+    (0.50, 0.08), (0.50, 0.20), (0.36, 0.20), (0.30, 0.37), (0.27, 0.52), (0.64, 0.20),
+    (0.70, 0.37), (0.73, 0.52), (0.42, 0.53), (0.41, 0.73), (0.40, 0.93), (0.58, 0.53),
+    (0.59, 0.73), (0.60, 0.93), (0.46, 0.05), (0.54, 0.05), (0.41, 0.08), (0.59, 0.08)],
+    dtype=np.float64)
+
+
+def random_skeletons(rng: np.random.Generator, n_persons: int, height: int, width: int) -> np.ndarray:
+    """[P,18,2] joint (x, y) positions in network-input pixels."""
+    out = np.zeros((n_persons, N_PARTS, 2))
+    for p in range(n_persons):
+        ph = rng.uniform(0.55, 0.9) * height            # person height in pixels
+        pw = ph * rng.uniform(0.75, 0.95)
+        x0 = rng.uniform(-0.1 * pw, width - 0.9 * pw)
+        y0 = rng.uniform(0.0, max(1.0, height - ph))
+        jit = rng.normal(0.0, 0.012, size=(N_PARTS, 2))
+        pts = (_TEMPLATE + jit) * np.array([pw, ph]) + np.array([x0, y0])
+        out[p] = pts
+    return out
+
+
+def conf_paf_from_skeletons(skel: np.ndarray, hf: int, wf: int, rng: np.random.Generator | None = None,
+                            noise: float = 0.02):
+    """conf f32[19,hf,wf], paf f32[38,hf,wf] for joints given in input pixels."""
+    conf = np.zeros((N_PARTS + 1, hf, wf), dtype=np.float64)
+    ys = np.arange(hf) * STRIDE + (STRIDE / 2 - 0.5)
+    xs = np.arange(wf) * STRIDE + (STRIDE / 2 - 0.5)
+    for person in skel:
+        for k, (cx, cy) in enumerate(person):
+            if cx < 0 or cy < 0 or cx >= wf * STRIDE or cy >= hf * STRIDE:
+                continue
+            d2 = ((ys - cy) ** 2)[:, None] + ((xs - cx) ** 2)[None, :]
+            e = d2 / (2 * 7.0 * 7.0)
+            g = np.exp(-e)
+            g[e > 4.6052] = 0
+            conf[k] = np.maximum(conf[k], g)
+    conf[-1] = np.clip(1 - conf[:-1].max(axis=0), 0.0, 1.0)
+
+    vec = np.zeros((2 * N_LIMBS, hf, wf), dtype=np.float64)
+    cnt = np.zeros((N_LIMBS, hf, wf), dtype=np.float64)
+    yy, xx = np.mgrid[0:hf, 0:wf]
+    for person in skel / STRIDE:
+        for i, (a, b) in enumerate(COCO_LIMB):
+            (x1, y1), (x2, y2) = person[a], person[b]
+            vx, vy = x2 - x1, y2 - y1
+            ln = np.hypot(vx, vy)
+            if ln == 0:
+                continue
+            nx, ny = vx / ln, vy / ln
+            x_lo, x_hi = max(0, int(round(min(x1, x2) - 1))), min(wf, int(round(max(x1, x2) + 1)))
+            y_lo, y_hi = max(0, int(round(min(y1, y2) - 1))), min(hf, int(round(max(y1, y2) + 1)))
+            if x_lo >= x_hi or y_lo >= y_hi:
+                continue
+            sub_x, sub_y = xx[y_lo:y_hi, x_lo:x_hi], yy[y_lo:y_hi, x_lo:x_hi]
+            dist = np.abs((sub_x - x1) * ny - (sub_y - y1) * nx)
+            m = (dist <= 1).astype(np.float64)
+            cnt[i, y_lo:y_hi, x_lo:x_hi] += m
+            vec[2 * i, y_lo:y_hi, x_lo:x_hi] += nx * m
+            vec[2 * i + 1, y_lo:y_hi, x_lo:x_hi] += ny * m
+    nz = cnt > 0
+    for i in range(N_LIMBS):
+        vec[2 * i][nz[i]] /= cnt[i][nz[i]]
+        vec[2 * i + 1][nz[i]] /= cnt[i][nz[i]]
+    if rng is not None and noise > 0:
+        conf = conf + rng.uniform(0, noise, size=conf.shape)
+        vec = vec + rng.uniform(-noise, noise, size=vec.shape)
+    return conf.astype(np.float32), vec.astype(np.float32)
+
+
+def make_frame_tensors(seed: int, n_persons, hf: int = 46, wf: int = 54, noise: float = 0.02):
+    """One frame: (conf[19,hf,wf], paf[38,hf,wf]).  n_persons: int or (lo, hi) inclusive."""
+    rng = np.random.default_rng(seed)
+    if isinstance(n_persons, tuple):
+        n_persons = int(rng.integers(n_persons[0], n_persons[1] + 1))
+    skel = random_skeletons(rng, n_persons, hf * STRIDE, wf * STRIDE)
+    return conf_paf_from_skeletons(skel, hf, wf, rng, noise)
+
+
+def make_batch_tensors(seed: int, n_frames: int, n_persons, hf: int = 46, wf: int = 54, noise: float = 0.02):
+    """(conf[N,19,hf,wf], paf[N,38,hf,wf]); frame i uses seed ``seed*100003 + i``."""
+    cs, ps = [], []
+    for i in range(n_frames):
+        c, p = make_frame_tensors(seed * 100003 + i, n_persons, hf, wf, noise)
+        cs.append(c)
+        ps.append(p)
+    return np.stack(cs), np.stack(ps)
+
+
+def make_frames_u8(seed: int, n_frames: int, height: int, width: int) -> np.ndarray:
+    """u8[N,height,width,3] BGR frames (cfg2 default_rng(1), cfg3 default_rng(2))."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(n_frames, height, width, 3), dtype=np.uint8)

@@ -1,0 +1,7 @@
+"""oracle/ -- CPU checker (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  hyperpose_b200/ must never import it.
+"""
+from .binding import (OrcHuman, OrcPeak, OrcConn, build, load_oracle, load_ref, oracle_process,
+                      ref_available, RefParser, resize_area_up, gaussian17, gauss_kernel, area_up_tab)

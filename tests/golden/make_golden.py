@@ -1,0 +1,81 @@
+"""Generates tests/golden/*.npz.  Run in the BUILD container only (needs Python cv2 and
+/root/reference; neither is required at test time):
+
+    python tests/golden/make_golden.py
+
+1. cv_pin.npz      -- outputs of the real OpenCV (Python cv2) for the two third-party
+                      primitives on the reference's path: cv::resize(INTER_AREA) upscale
+                      (src/post_process.hpp:50) and cv::GaussianBlur(17x17, sigma=3)
+                      (post_process.hpp:66-67), on seeded inputs; small cases stored in full,
+                      full-size cases as sha256 of the output bytes.
+2. ref_humans.npz  -- human_t lists produced by the reference's OWN src/paf.cpp (compiled
+                      verbatim into oracle/_ref by oracle/Makefile) on the seeded synthetic
+                      frames of hyperpose_b200/synthetic.py.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (name, seed, persons, hf, wf, res_w, res_h, conf_thresh, paf_thresh)
+FRAME_CASES = [
+    ("cfg1_p1", 0, 1, 46, 54, -1, -1, 0.05, 0.05),
+    ("cfg1_p3", 1, 3, 46, 54, -1, -1, 0.05, 0.05),
+    ("cfg3_p5", 2, 5, 46, 82, -1, -1, 0.05, 0.05),
+    ("cfg4_crowd", 3, (10, 20), 46, 54, -1, -1, 0.05, 0.05),
+    ("cfg3_crowd", 5, 12, 46, 82, -1, -1, 0.05, 0.05),
+    ("square", 6, 4, 46, 46, -1, -1, 0.05, 0.05),
+    ("user_res", 7, 3, 46, 54, 216, 184, 0.05, 0.05),       # untransposed 4x resolution set by the user
+    ("user_res_odd", 8, 3, 46, 54, 300, 200, 0.1, 0.08),
+    ("empty", 9, 0, 46, 54, -1, -1, 0.05, 0.05),
+    ("tiny", 10, 1, 12, 16, -1, -1, 0.05, 0.05),
+]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    import cv2
+    from hyperpose_b200 import synthetic as syn
+    import oracle
+
+    out = {"cv2_version": np.array(cv2.__version__)}
+    out["gauss_kernel"] = cv2.getGaussianKernel(17, 3.0, cv2.CV_32F).ravel()
+    rng = np.random.default_rng(1234)
+    small = [(23, 27, 108, 92), (12, 16, 64, 48), (9, 9, 36, 36), (10, 7, 31, 40), (5, 20, 80, 20)]
+    for i, (sh, sw, dh, dw) in enumerate(small):
+        img = rng.random((sh, sw), dtype=np.float32) * 2 - 0.5
+        up = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+        out[f"small{i}_in"] = img
+        out[f"small{i}_shape"] = np.array([dh, dw])
+        out[f"small{i}_up"] = up
+        out[f"small{i}_blur"] = cv2.GaussianBlur(up, (17, 17), 3.0)
+    big = [(46, 54, 216, 184), (46, 82, 328, 184), (46, 46, 184, 184), (46, 54, 184, 216)]
+    for i, (sh, sw, dh, dw) in enumerate(big):
+        img = np.random.default_rng(100 + i).random((sh, sw), dtype=np.float32)
+        up = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+        out[f"big{i}_dims"] = np.array([sh, sw, dh, dw])
+        out[f"big{i}_up_sha"] = np.array(sha(up))
+        out[f"big{i}_blur_sha"] = np.array(sha(cv2.GaussianBlur(up, (17, 17), 3.0)))
+    np.savez_compressed(os.path.join(HERE, "cv_pin.npz"), **out)
+
+    ref = {}
+    for (name, seed, P, hf, wf, rw, rh, ct, pt) in FRAME_CASES:
+        conf, paf = syn.make_frame_tensors(seed, P, hf, wf)
+        rp = oracle.RefParser(ct, pt, rw, rh)
+        ref[name + "_humans"] = rp.process(conf, paf)
+        ref[name + "_in_sha"] = np.array(sha(conf) + sha(paf))
+        rp.close()
+    np.savez_compressed(os.path.join(HERE, "ref_humans.npz"), **ref)
+    print("wrote", os.listdir(HERE))
+
+
+if __name__ == "__main__":
+    main()
