@@ -1,0 +1,1036 @@
+// paf_parser.cu -- B200 (sm_100a) PAF post-processing: conf/PAF tensors -> human_t records.
+//
+// Replaces the reference's CPU parser hyperpose::parser::paf
+//   src/paf.cpp:57-375, src/post_process.hpp:26-205, src/coco.hpp:6-52
+// with four batched CUDA kernels (grid covers every frame of the batch):
+//
+//   K1 paf_peaks_kernel    resize_area (post_process.hpp:26-52) + smooth (:54-69) + 3x3 max-pool NMS
+//                          (:71-102) + peak scan (:175-192), fused per smem tile.  The 4x up-sampled maps
+//                          are never written to HBM.  Tiles whose source values cannot reach conf_thresh
+//                          are skipped (provably peak-free, see tile_can_skip()).
+//   K2 paf_order_kernel    restores the reference's channel-major / row-major peak order and ids.
+//   K3 paf_limb_kernel     get_connection_candidates + get_connections (paf.cpp:93-144, 234-272): 10 lanes
+//                          per peak pair sample the PAF line integral (up-sampling recomputed on the fly from
+//                          the 1/8-resolution field staged in shared memory), ballot/shuffle reductions,
+//                          then score-ordered greedy matching.
+//   K4 paf_assemble_kernel get_humans (paf.cpp:146-232) + conversion (:359-372): one warp per frame.
+//
+// Arithmetic contract (bit-exactness with oracle/paf_oracle.c): every fp32 operation on the result path
+// is spelled with an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__fmaf_rn/__fdiv_rn) in
+// the order the oracle documents; the double-precision steps of the reference (paf.cpp:74,104,129) are
+// done in double.  The file is additionally compiled with -fmad=false.
+//
+// No CPU fallback exists: every entry point fails with HP_ERR_CUDA when CUDA is unavailable.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/hyperpose_b200.h"
+#include "common.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// topology (src/coco.hpp:10-52)
+// ---------------------------------------------------------------------------------------------
+__constant__ int c_pairs_net[HP_N_PAIRS][2] = {
+    {12, 13}, {20, 21}, {14, 15}, {16, 17}, {22, 23}, {24, 25}, {0, 1}, {2, 3}, {4, 5}, {6, 7},
+    {8, 9}, {10, 11}, {28, 29}, {30, 31}, {34, 35}, {32, 33}, {36, 37}, {18, 19}, {26, 27}};
+__constant__ int c_pairs[HP_N_PAIRS][2] = {
+    {1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11},
+    {11, 12}, {12, 13}, {1, 0}, {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17}};
+
+// cv::getGaussianKernel(17, 3.0, CV_32F) (post_process.hpp:58,66-67; ksize 17 from paf.cpp:330-331):
+// exp(-(i-8)^2/18) normalised in double, rounded to fp32.
+__constant__ float c_g17[17] = {
+    0x1.f41be6p-9f, 0x1.1faf48p-7f, 0x1.282c02p-6f, 0x1.10d854p-5f, 0x1.c1d86ep-5f,
+    0x1.4bd66ep-4f, 0x1.b616fp-4f, 0x1.02c558p-3f, 0x1.118dcap-3f, 0x1.02c558p-3f,
+    0x1.b616fp-4f, 0x1.4bd66ep-4f, 0x1.c1d86ep-5f, 0x1.10d854p-5f, 0x1.282c02p-6f,
+    0x1.1faf48p-7f, 0x1.f41be6p-9f};
+
+constexpr int THRESH_VECTOR_CNT1 = 8; // paf.cpp:57
+constexpr int THRESH_PART_CNT = 4;    // paf.cpp:58
+constexpr int STEP_PAF = 10;          // paf.cpp:60
+
+enum : int { FLAG_PEAK_OVERFLOW = 1, FLAG_CAND_OVERFLOW = 2, FLAG_HUMAN_OVERFLOW = 4 };
+
+// cv::borderInterpolate(BORDER_REFLECT_101)
+__host__ __device__ inline int refl101(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * len - 2 - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: fused up-sample + Gaussian + NMS + peak emission
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 256;
+constexpr int TH = 30, TW = 62;          // interior tile of the up-map handled by one CTA
+constexpr int HALO = 9;                  // 8 (17-tap blur) + 1 (3x3 NMS)
+constexpr int UT_H = TH + 2 * HALO;      // 48 rows of up-sampled values (virtual = reflected coordinates)
+constexpr int UT_W = TW + 2 * HALO;      // 80 cols
+constexpr int UT_LD = UT_W + 1;          // 81: odd stride -> row-parallel accesses are conflict-free
+constexpr int RT_W = TW + 2;             // 64 row-pass output columns (interior + 1 each side)
+constexpr int RT_LD = RT_W + 1;          // 65
+constexpr int CT_H = TH + 2;             // 32 column-pass output rows
+constexpr int SRC_MAX_H = UT_H + 1, SRC_MAX_W = UT_W + 1; // scale >= 1 => at most one source px per up px (+1)
+constexpr int RUN = 8;                   // outputs per thread per pass (sliding window of RUN+16 inputs)
+
+struct PeakParams {
+    const float* conf; // [N, c_conf, H, W]
+    int c_conf, H, W, UH, UW;
+    const int* xi; const float* xf; // [UW] area-upscale table
+    const int* yi; const float* yf; // [UH]
+    float thresh;
+    float skip_below; // tiles whose source max is <= this cannot contain a peak; -inf disables skipping
+    int tiles_x;
+    int pcap;            // capacity per (frame, part)
+    int* peak_cnt;       // [N,18]
+    int* raw_key;        // [N,18,pcap]  y*UW + x
+    float* raw_score;    // [N,18,pcap]
+    int* flags;          // [N]
+    int n8, n4;          // column classes of the separable filter (see oracle/paf_oracle.c)
+};
+
+__global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams p)
+{
+    // sSrc (dead after the up-sample) and sTmp (row-pass output) share storage.
+    __shared__ float sU[UT_H * UT_LD];
+    __shared__ float sA[(SRC_MAX_H * SRC_MAX_W > UT_H * RT_LD) ? SRC_MAX_H * SRC_MAX_W : UT_H * RT_LD];
+    __shared__ float sS[CT_H * RT_LD];
+    __shared__ int sXi[UT_W], sYi[UT_H];
+    __shared__ float sXf[UT_W], sYf[UT_H];
+    __shared__ int sBounds[4]; // src row lo/hi, col lo/hi
+    __shared__ float sMax[K1_THREADS / 32];
+    __shared__ int sSkip;
+
+    const int tid = threadIdx.x;
+    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int part = blockIdx.y, frame = blockIdx.z;
+    const int x0 = tx * TW, y0 = ty * TH;
+    const int H = p.H, W = p.W, UH = p.UH, UW = p.UW;
+    const float* src = p.conf + ((size_t)frame * p.c_conf + part) * H * W;
+
+    if (tid < 4) sBounds[tid] = (tid & 1) ? -1 : 0x7fffffff;
+    __syncthreads();
+    // stage the coefficient tables of the (reflected) rows / columns this tile needs
+    for (int i = tid; i < UT_W + UT_H; i += K1_THREADS) {
+        if (i < UT_W) {
+            const int rx = refl101(x0 - HALO + i, UW);
+            const int s = __ldg(p.xi + rx);
+            sXi[i] = s;
+            sXf[i] = __ldg(p.xf + rx);
+            atomicMin(&sBounds[2], s);
+            atomicMax(&sBounds[3], min(s + 1, W - 1));
+        } else {
+            const int j = i - UT_W;
+            const int ry = refl101(y0 - HALO + j, UH);
+            const int s = __ldg(p.yi + ry);
+            sYi[j] = s;
+            sYf[j] = __ldg(p.yf + ry);
+            atomicMin(&sBounds[0], s);
+            atomicMax(&sBounds[1], min(s + 1, H - 1));
+        }
+    }
+    __syncthreads();
+    const int sr0 = sBounds[0], sr1 = sBounds[1], sc0 = sBounds[2], sc1 = sBounds[3];
+    const int sh = sr1 - sr0 + 1, sw = sc1 - sc0 + 1; // <= SRC_MAX_H x SRC_MAX_W because UH >= H, UW >= W
+    float* sSrc = sA;
+    float lmax = -INFINITY;
+    for (int i = tid; i < sh * sw; i += K1_THREADS) {
+        const int r = i / sw, c = i - r * sw;
+        const float v = __ldg(src + (size_t)(sr0 + r) * W + sc0 + c);
+        sSrc[i] = v;
+        lmax = fmaxf(lmax, v); // fmaxf ignores NaN: a NaN never enables the skip on its own
+        if (v != v) lmax = INFINITY;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((tid & 31) == 0) sMax[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        float m = sMax[0];
+        for (int i = 1; i < K1_THREADS / 32; ++i) m = fmaxf(m, sMax[i]);
+        // tile_can_skip: every smoothed value is a (rounded) convex combination of source values:
+        //   |lerp| <= m(1+2^-22), two 17-tap passes with sum(k) <= 1+1.3e-8 and <= 34 roundings
+        //   => smoothed <= m(1+3e-6) for m >= 0;  skip_below = thresh*(1-1e-5) keeps a 3x margin.
+        sSkip = (m <= p.skip_below) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sSkip) return;
+
+    // ---- up-sample into virtual (reflected) coordinates: sU[vy][vx] = up(refl(y0-9+vy), refl(x0-9+vx))
+    //      HResizeLinear then VResizeLinear, products rounded separately (oracle orc_resize_area_up)
+    for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
+        const int vy = i / UT_W, vx = i - vy * UT_W;
+        const int sx0 = sXi[vx], sx1 = min(sx0 + 1, W - 1);
+        const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
+        const float a1 = sXf[vx], a0 = __fsub_rn(1.f, a1);
+        const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
+        const float* r0 = sSrc + (sy0 - sr0) * sw - sc0;
+        const float* r1 = sSrc + (sy1 - sr0) * sw - sc0;
+        const float h0 = __fadd_rn(__fmul_rn(r0[sx0], a0), __fmul_rn(r0[sx1], a1));
+        const float h1 = __fadd_rn(__fmul_rn(r1[sx0], a0), __fmul_rn(r1[sx1], a1));
+        sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    }
+    __syncthreads(); // sSrc is dead from here; sA becomes sTmp
+
+    // ---- row pass: sTmp[vy][c], c = 0..63 <-> real column j = x0 - 1 + c; taps left->right.
+    //      work item = (row, run of 8 columns); adjacent threads take adjacent rows (odd strides).
+    float* sTmp = sA;
+    for (int it = tid; it < UT_H * (RT_W / RUN); it += K1_THREADS) {
+        const int vy = it % UT_H, run = it / UT_H;
+        const int c0 = run * RUN;
+        const float* in = sU + vy * UT_LD + c0; // window input k for output c is in[c - c0 + k] (vx = c + k)
+        float w[RUN + 16];
+#pragma unroll
+        for (int k = 0; k < RUN + 16; ++k) w[k] = in[k];
+        const int jlast = x0 - 1 + c0 + RUN - 1;
+        float acc[RUN];
+        if (jlast < p.n4) {
+#pragma unroll
+            for (int o = 0; o < RUN; ++o) acc[o] = __fmul_rn(c_g17[0], w[o]);
+#pragma unroll
+            for (int t = 1; t < 17; ++t)
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) acc[o] = __fmaf_rn(c_g17[t], w[o + t], acc[o]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < RUN; ++o) {
+                const bool fma = (x0 - 1 + c0 + o) < p.n4;
+                float s = __fmul_rn(c_g17[0], w[o]);
+#pragma unroll
+                for (int t = 1; t < 17; ++t)
+                    s = fma ? __fmaf_rn(c_g17[t], w[o + t], s) : __fadd_rn(s, __fmul_rn(c_g17[t], w[o + t]));
+                acc[o] = s;
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < RUN; ++o) sTmp[vy * RT_LD + c0 + o] = acc[o];
+    }
+    __syncthreads();
+
+    // ---- column pass (symmetric): sS[r][c], r = 0..31 <-> real row i = y0 - 1 + r (virtual row r + 8).
+    //      one work item per thread: column c = tid % 64, run of 8 rows r0 = (tid / 64) * 8.
+    {
+        const int c = tid % RT_W, r0 = (tid / RT_W) * RUN;
+        const int j = x0 - 1 + c;
+        const bool col_ok = (j >= 0 && j < UW);
+        const bool fma = j < p.n8;
+        float w[RUN + 16];
+#pragma unroll
+        for (int k = 0; k < RUN + 16; ++k) w[k] = sTmp[(r0 + k) * RT_LD + c];
+#pragma unroll
+        for (int o = 0; o < RUN; ++o) {
+            float s = __fmul_rn(c_g17[8], w[o + 8]);
+#pragma unroll
+            for (int t = 1; t <= 8; ++t) {
+                const float a = __fadd_rn(w[o + 8 + t], w[o + 8 - t]);
+                s = fma ? __fmaf_rn(c_g17[8 + t], a, s) : __fadd_rn(s, __fmul_rn(c_g17[8 + t], a));
+            }
+            const int i = y0 - 1 + r0 + o;
+            const bool ok = col_ok && i >= 0 && i < UH;
+            sS[(r0 + o) * RT_LD + c] = ok ? s : -INFINITY; // out-of-image neighbours never win the max
+        }
+    }
+    __syncthreads();
+
+    // ---- threshold + 3x3 NMS (same_max_pool_3x3_2d skips out-of-range neighbours) + emission
+    for (int it = tid; it < TH * TW; it += K1_THREADS) {
+        const int r = it / TW, c = it - r * TW;
+        const int i = y0 + r, j = x0 + c;
+        if (i >= UH || j >= UW) continue;
+        const float* q = sS + (r + 1) * RT_LD + (c + 1);
+        const float v = q[0];
+        if (!(v > p.thresh)) continue;
+        float m = v;
+        m = fmaxf(m, q[-RT_LD - 1]); m = fmaxf(m, q[-RT_LD]); m = fmaxf(m, q[-RT_LD + 1]);
+        m = fmaxf(m, q[-1]);                                   m = fmaxf(m, q[1]);
+        m = fmaxf(m, q[RT_LD - 1]);  m = fmaxf(m, q[RT_LD]);   m = fmaxf(m, q[RT_LD + 1]);
+        if (v == m) {
+            int* cnt = p.peak_cnt + frame * HP_N_PARTS + part;
+            const int slot = atomicAdd(cnt, 1);
+            if (slot < p.pcap) {
+                const size_t o = ((size_t)frame * HP_N_PARTS + part) * p.pcap + slot;
+                p.raw_key[o] = i * UW + j;
+                p.raw_score[o] = sU[(r + HALO) * UT_LD + (c + HALO)]; // score = UNsmoothed up-map value
+            } else {
+                atomicOr(p.flags + frame, FLAG_PEAK_OVERFLOW);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: per (frame, part) rank-sort by scan position -> all_peaks in reference order, ids = index
+// ---------------------------------------------------------------------------------------------
+struct OrderParams {
+    int pcap, UW;
+    const int* peak_cnt;    // [N,18]
+    const int* raw_key;
+    const float* raw_score;
+    int* part_base;         // [N,19]
+    int* px; int* py; float* pscore; // [N, 18*pcap]
+};
+
+__global__ void __launch_bounds__(128) paf_order_kernel(const OrderParams p)
+{
+    extern __shared__ int sKey[];
+    const int part = blockIdx.x, frame = blockIdx.y;
+    const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
+    const int n = min(cnt[part], p.pcap);
+    int base = 0;
+    for (int q = 0; q < part; ++q) base += min(cnt[q], p.pcap);
+    if (part == 0 && threadIdx.x == 0) {
+        int b = 0;
+        for (int q = 0; q < HP_N_PARTS; ++q) {
+            p.part_base[frame * (HP_N_PARTS + 1) + q] = b;
+            b += min(cnt[q], p.pcap);
+        }
+        p.part_base[frame * (HP_N_PARTS + 1) + HP_N_PARTS] = b;
+    }
+    const size_t raw = ((size_t)frame * HP_N_PARTS + part) * p.pcap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sKey[i] = p.raw_key[raw + i];
+    __syncthreads();
+    const size_t out = (size_t)frame * HP_N_PARTS * p.pcap + base;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int k = sKey[i];
+        int rank = 0;
+        for (int q = 0; q < n; ++q) rank += (sKey[q] < k); // keys are unique pixel positions
+        p.px[out + rank] = k % p.UW;
+        p.py[out + rank] = k / p.UW;
+        p.pscore[out + rank] = p.raw_score[raw + i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: limb scoring + greedy matching, one CTA per (limb, frame)
+// ---------------------------------------------------------------------------------------------
+constexpr int K3_THREADS = 128;
+constexpr int MAX_PCAP = 4096; // bitmap size for the greedy pass
+
+struct LimbParams {
+    const float* paf; // [N, c_paf, H, W]
+    int c_paf, H, W, UH, UW;
+    const int* xi; const float* xf; const int* yi; const float* yf;
+    float paf_thresh;
+    int feat_height; // m_feature_size.height == W of the feature map (paf.cpp:329,354)
+    int pcap, ccap;
+    const int* part_base; const int* px; const int* py; const float* pscore;
+    unsigned long long* cand;        // [N,19,ccap]
+    unsigned long long* cand_sorted; // [N,19,ccap]
+    hp_connection* conn;             // [N,19,pcap]
+    int* conn_cnt;                   // [N,19]
+    int* flags;
+    int stage_bytes; // dynamic smem available for staging the two PAF channels (0 = never stage)
+};
+
+// up-sampled PAF value at up-map pixel (lx, ly), recomputed from the low-resolution field
+// exactly as orc_resize_area_up does (horizontal lerp on two source rows, then vertical).
+__device__ __forceinline__ float up_sample(const float* P, int W, int H, int lx, int ly,
+                                           const int* xi, const float* xf, const int* yi, const float* yf)
+{
+    const int sx0 = __ldg(xi + lx), sx1 = min(sx0 + 1, W - 1);
+    const int sy0 = __ldg(yi + ly), sy1 = min(sy0 + 1, H - 1);
+    const float a1 = __ldg(xf + lx), a0 = __fsub_rn(1.f, a1);
+    const float b1 = __ldg(yf + ly), b0 = __fsub_rn(1.f, b1);
+    const float h0 = __fadd_rn(__fmul_rn(P[sy0 * W + sx0], a0), __fmul_rn(P[sy0 * W + sx1], a1));
+    const float h1 = __fadd_rn(__fmul_rn(P[sy1 * W + sx0], a0), __fmul_rn(P[sy1 * W + sx1], a1));
+    return __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+}
+
+// candidate key: score bits (positive floats order like unsigned ints) | inverted (idx1, idx2)
+// => max key == best score, ties broken by idx1 asc then idx2 asc (frozen tie-break).
+__device__ __forceinline__ unsigned long long make_key(float score, int ia, int ib)
+{
+    return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)(0xffffffffu - (((unsigned)ia << 16) | (unsigned)ib));
+}
+
+__global__ void __launch_bounds__(K3_THREADS) paf_limb_kernel(const LimbParams p)
+{
+    extern __shared__ float sPaf[];
+    __shared__ int sNcand;
+    __shared__ unsigned sUsedA[MAX_PCAP / 32], sUsedB[MAX_PCAP / 32];
+
+    const int limb = blockIdx.x, frame = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pa = c_pairs[limb][0], pb = c_pairs[limb][1];
+    const int* pbase = p.part_base + frame * (HP_N_PARTS + 1);
+    const int base_a = pbase[pa], na = pbase[pa + 1] - base_a;
+    const int base_b = pbase[pb], nb = pbase[pb + 1] - base_b;
+    int* conn_cnt = p.conn_cnt + frame * HP_N_PAIRS + limb;
+    if (na == 0 || nb == 0) {
+        if (tid == 0) *conn_cnt = 0;
+        return;
+    }
+    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
+    const int* px = p.px + peak_off;
+    const int* py = p.py + peak_off;
+    const int H = p.H, W = p.W;
+    const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
+    const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
+    const int npairs = na * nb;
+
+    if (tid == 0) sNcand = 0;
+    // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
+    if (npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
+        for (int i = tid; i < H * W; i += K3_THREADS) {
+            sPaf[i] = __ldg(P1 + i);
+            sPaf[H * W + i] = __ldg(P2 + i);
+        }
+        P1 = sPaf;
+        P2 = sPaf + H * W;
+    }
+    __syncthreads();
+
+    unsigned long long* cand = p.cand + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+    unsigned long long* sorted = p.cand_sorted + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+
+    // ---- get_connection_candidates: 3 peak pairs per warp pass, 10 lanes (= 10 samples) per pair
+    const int grp = lane / STEP_PAF, smp = lane - grp * STEP_PAF;
+    const unsigned gmask = (grp < 3) ? (0x3ffu << (grp * STEP_PAF)) : 0u;
+    constexpr int NW = K3_THREADS / 32;
+    for (int pb0 = warp * 3; pb0 < npairs; pb0 += NW * 3) { // warp-uniform trip count
+        const int pidx = pb0 + grp;
+        const bool active = (grp < 3) && (pidx < npairs);
+        int ia = 0, ib = 0;
+        float score = 0.f, norm = 1.f;
+        bool valid = false;
+        if (active) {
+            ia = pidx / nb;
+            ib = pidx - ia * nb;
+            const int ax = px[base_a + ia], ay = py[base_a + ia];
+            const int bx = px[base_b + ib], by = py[base_b + ib];
+            const int dx = bx - ax, dy = by - ay;
+            norm = (float)sqrt((double)(dx * dx + dy * dy)); // paf.cpp:104
+            valid = !((double)norm < 1e-12);                   // paf.cpp:105
+            if (valid) {
+                const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
+                const float stepx = __fdiv_rn((float)dx, (float)STEP_PAF); // paf.cpp:77-78
+                const float stepy = __fdiv_rn((float)dy, (float)STEP_PAF);
+                const float fx = __fadd_rn((float)ax, __fmul_rn((float)smp, stepx));
+                const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
+                const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
+                const int ly = (int)((double)fy + 0.5);
+                const float vpx = up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                const float vpy = up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
+            }
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, valid && score > p.paf_thresh);
+        const int criterion1 = __popc(ball & gmask);
+        float sum = 0.f; // sequential i = 0..9 accumulation order of paf.cpp:121-127
+#pragma unroll
+        for (int i = 0; i < STEP_PAF; ++i) {
+            const int srcl = min(grp * STEP_PAF + i, 31);
+            sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, score, srcl));
+        }
+        if (valid && smp == 0) {
+            double pen = 0.5 * (double)p.feat_height / (double)norm - 1.0; // paf.cpp:129
+            if (pen > 0.0) pen = 0.0;
+            const float criterion2 = (float)((double)__fdiv_rn(sum, (float)STEP_PAF) + pen);
+            if (criterion1 > THRESH_VECTOR_CNT1 && criterion2 > 0.f) {
+                const int slot = atomicAdd(&sNcand, 1);
+                if (slot < p.ccap) cand[slot] = make_key(criterion2, ia, ib);
+            }
+        }
+    }
+    __syncthreads();
+    int ncand = sNcand;
+    if (ncand > p.ccap) {
+        if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
+        ncand = p.ccap;
+    }
+    __threadfence_block();
+
+    // ---- std::sort by score desc (paf.cpp:249-250): rank sort on unique keys
+    for (int i = tid; i < ncand; i += K3_THREADS) {
+        const unsigned long long k = cand[i];
+        int rank = 0;
+        for (int q = 0; q < ncand; ++q) rank += (cand[q] > k);
+        sorted[rank] = k;
+    }
+    for (int i = tid; i < MAX_PCAP / 32; i += K3_THREADS) { sUsedA[i] = 0u; sUsedB[i] = 0u; }
+    __syncthreads();
+    __threadfence_block();
+
+    // ---- greedy one-to-one selection in score order (paf.cpp:252-270)
+    if (tid == 0) {
+        hp_connection* conn = p.conn + ((size_t)frame * HP_N_PAIRS + limb) * p.pcap;
+        const int max_conn = min(na, nb);
+        int nconn = 0;
+        for (int i = 0; i < ncand && nconn < max_conn; ++i) {
+            const unsigned long long k = sorted[i];
+            const unsigned inv = 0xffffffffu - (unsigned)(k & 0xffffffffu);
+            const int ia = (int)(inv >> 16), ib = (int)(inv & 0xffffu);
+            if ((sUsedA[ia >> 5] >> (ia & 31)) & 1u) continue;
+            if ((sUsedB[ib >> 5] >> (ib & 31)) & 1u) continue;
+            sUsedA[ia >> 5] |= 1u << (ia & 31);
+            sUsedB[ib >> 5] |= 1u << (ib & 31);
+            hp_connection c;
+            c.cid1 = base_a + ia; // peak ids == index in the ordered all_peaks list
+            c.cid2 = base_b + ib;
+            c.score = __uint_as_float((unsigned)(k >> 32));
+            conn[nconn++] = c;
+        }
+        *conn_cnt = nconn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: get_humans + filter + conversion; one warp per frame
+// ---------------------------------------------------------------------------------------------
+struct AssembleParams {
+    int pcap, hcap, UW, UH;
+    const int* part_base; const int* px; const int* py; const float* pscore;
+    const hp_connection* conn; const int* conn_cnt;
+    hp_human* humans;  // [N,hcap]
+    int* human_cnt;    // [N]
+    int* flags;
+    int max_refs;      // smem capacity for partial humans
+};
+
+struct HumanRef { // paf.cpp:19-37 (id == position in the vector, kept implicit)
+    int parts[HP_N_PARTS];
+    float score;
+    int n_parts;
+};
+
+__global__ void __launch_bounds__(32) paf_assemble_kernel(const AssembleParams p)
+{
+    extern __shared__ HumanRef sRef[];
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const int* pbase = p.part_base + frame * (HP_N_PARTS + 1);
+    const int n_peaks = pbase[HP_N_PARTS];
+    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
+    const float* pscore = p.pscore + peak_off;
+    const int* px = p.px + peak_off;
+    const int* py = p.py + peak_off;
+    int nh = 0;
+
+    for (int pair_id = 0; pair_id < HP_N_PAIRS; ++pair_id) {
+        const int part1 = c_pairs[pair_id][0], part2 = c_pairs[pair_id][1];
+        const int ncn = p.conn_cnt[frame * HP_N_PAIRS + pair_id];
+        const hp_connection* conns = p.conn + ((size_t)frame * HP_N_PAIRS + pair_id) * p.pcap;
+        for (int ci = 0; ci < ncn; ++ci) {
+            const hp_connection cn = conns[ci];
+            // touches (paf.cpp:33-36) evaluated for 32 humans at a time; first two hits in vector order
+            int t0 = -1, t1 = -1, nt = 0;
+            for (int hb = 0; hb < nh && nt < 2; hb += 32) {
+                const int h = hb + lane;
+                const bool touch = (h < nh) && (sRef[h].parts[part1] == cn.cid1 || sRef[h].parts[part2] == cn.cid2);
+                unsigned b = __ballot_sync(0xffffffffu, touch);
+                while (b && nt < 2) {
+                    const int l = __ffs(b) - 1;
+                    if (nt == 0) t0 = hb + l; else t1 = hb + l;
+                    ++nt;
+                    b &= b - 1;
+                }
+            }
+            int delta = 0;
+            if (lane == 0) {
+                if (nt == 1) { // paf.cpp:172-178
+                    HumanRef& h1 = sRef[t0];
+                    if (h1.parts[part2] != cn.cid2) {
+                        h1.parts[part2] = cn.cid2;
+                        ++h1.n_parts;
+                        h1.score = __fadd_rn(h1.score, __fadd_rn(pscore[cn.cid2], cn.score));
+                    }
+                } else if (nt >= 2) { // paf.cpp:179-210
+                    HumanRef& h1 = sRef[t0];
+                    const HumanRef& h2 = sRef[t1];
+                    int membership = 0;
+                    for (int i = 0; i < HP_N_PARTS; ++i)
+                        if (h1.parts[i] > 0 && h2.parts[i] > 0) membership = 2; // `id > 0` quirk (paf.cpp:185)
+                    if (membership == 0) {
+                        for (int i = 0; i < HP_N_PARTS; ++i) h1.parts[i] += h2.parts[i] + 1; // paf.cpp:193
+                        h1.n_parts += h2.n_parts;
+                        h1.score = __fadd_rn(h1.score, h2.score);
+                        h1.score = __fadd_rn(h1.score, cn.score);
+                        for (int h = t1; h + 1 < nh; ++h) sRef[h] = sRef[h + 1]; // vector::erase (paf.cpp:201-205)
+                        delta = -1;
+                    } else {
+                        h1.parts[part2] = cn.cid2;
+                        h1.n_parts += 1;
+                        h1.score = __fadd_rn(h1.score, __fadd_rn(pscore[cn.cid2], cn.score));
+                    }
+                } else if (pair_id <= 16) { // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
+                    if (nh < p.max_refs) {
+                        HumanRef& h = sRef[nh];
+                        for (int i = 0; i < HP_N_PARTS; ++i) h.parts[i] = -1;
+                        h.parts[part1] = cn.cid1;
+                        h.parts[part2] = cn.cid2;
+                        h.n_parts = 2;
+                        h.score = __fadd_rn(__fadd_rn(pscore[cn.cid1], pscore[cn.cid2]), cn.score);
+                        delta = 1;
+                    } else {
+                        atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
+                    }
+                }
+            }
+            __syncwarp();
+            nh += __shfl_sync(0xffffffffu, delta, 0);
+        }
+    }
+
+    // filter (paf.cpp:226-230, stable like remove_if) + conversion to human_t (paf.cpp:359-372)
+    int no = 0;
+    for (int hb = 0; hb < nh; hb += 32) {
+        const int h = hb + lane;
+        bool keep = false;
+        if (h < nh) {
+            const HumanRef& r = sRef[h];
+            keep = !(r.n_parts < THRESH_PART_CNT || __fdiv_rn(r.score, (float)r.n_parts) < 0.4f);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        const int idx = no + __popc(b & ((1u << lane) - 1u));
+        if (keep) {
+            if (idx < p.hcap) {
+                const HumanRef& r = sRef[h];
+                hp_human* o = p.humans + (size_t)frame * p.hcap + idx;
+                o->score = r.score;
+                for (int i = 0; i < HP_N_PARTS; ++i) {
+                    const int id = r.parts[i];
+                    hp_body_part bp;
+                    bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
+                    // ids fabricated by the `+=` merge quirk would be an out-of-bounds read (UB) in the
+                    // reference; like the oracle, such parts are reported absent.
+                    if (id != -1 && id >= 0 && id < n_peaks) {
+                        bp.has_value = 1;
+                        bp.score = pscore[id];
+                        bp.x = __fdiv_rn((float)px[id], (float)p.UW);
+                        bp.y = __fdiv_rn((float)py[id], (float)p.UH);
+                    }
+                    o->parts[i] = bp;
+                }
+            } else {
+                atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
+            }
+        }
+        no += __popc(b);
+    }
+    if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// OpenCV resize.cpp, INTER_AREA with dst >= src ("area_mode" 2-tap interpolation):
+//   inv = dst/src (double), scale = 1/inv, sx = floor(dx*scale),
+//   fx = (float)((dx+1) - (sx+1)*inv); fx = fx <= 0 ? 0 : fx - floor(fx); clamp at the last source px.
+void area_up_table(int src, int dst, std::vector<int>& idx, std::vector<float>& frac)
+{
+    idx.resize(dst);
+    frac.resize(dst);
+    const double inv = (double)dst / (double)src;
+    const double scale = 1.0 / inv;
+    for (int d = 0; d < dst; ++d) {
+        int s = (int)floor(d * scale);
+        float f = (float)((double)(d + 1) - (double)(s + 1) * inv);
+        f = f <= 0.f ? 0.f : f - floorf(f);
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= src - 1) { f = 0.f; s = src - 1; }
+        idx[d] = s;
+        frac[d] = f;
+    }
+}
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T> struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+} // namespace
+
+struct hp_paf {
+    int device = 0;
+    float conf_thresh = 0.05f, paf_thresh = 0.05f;
+    int res_w = -1, res_h = -1; // user resolution (-1 = reference default, fixed at the first call like paf.cpp:314-315)
+    int pcap = 128, ccap = 2048, hcap = 64, max_refs = 256;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+
+    // geometry of the current buffers
+    int N = 0, c_conf = 0, c_paf = 0, H = 0, W = 0, UH = 0, UW = 0;
+    int cap_pcap = 0, cap_ccap = 0, cap_hcap = 0, cap_N = 0;
+
+    DevBuf<int> xi, yi;
+    DevBuf<float> xf, yf;
+    DevBuf<int> counters; // [N*18 peak_cnt | N*19 conn_cnt | N human_cnt | N flags]
+    DevBuf<int> raw_key, part_base, px, py;
+    DevBuf<float> raw_score, pscore;
+    DevBuf<unsigned long long> cand, cand_sorted;
+    DevBuf<hp_connection> conn;
+    DevBuf<hp_human> humans;
+    DevBuf<float> in_conf, in_paf; // device staging for host inputs
+    PinnedBuf<float> pin_in;
+    PinnedBuf<hp_human> pin_humans;
+    PinnedBuf<int> pin_counts; // [N human_cnt | N flags]
+    int last_N = 0;
+    cudaStream_t last_stream = nullptr;
+    int limb_stage_bytes = 0;
+
+    int* peak_cnt() { return counters.p; }
+    int* conn_cnt() { return counters.p + (size_t)cap_N * HP_N_PARTS; }
+    int* human_cnt() { return counters.p + (size_t)cap_N * (HP_N_PARTS + HP_N_PAIRS); }
+    int* flags() { return counters.p + (size_t)cap_N * (HP_N_PARTS + HP_N_PAIRS + 1); }
+};
+
+namespace {
+
+int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
+{
+    if (N <= 0 || H <= 0 || W <= 0 || c_conf < HP_N_PARTS || c_paf < 2 * HP_N_PAIRS) {
+        hpb::set_error("hp_paf: bad tensor shape N=%d conf=[%d,%d,%d] paf=[%d,%d,%d] (need >=18 / >=38 channels)",
+                       N, c_conf, H, W, c_paf, H, W);
+        return HP_ERR_ARG;
+    }
+    // paf.cpp:311-315: dims() of the [C,H,W] view are bound to (C, fw, fh): fw = H, fh = W, and the
+    // default resolution is cv::Size(width = fw*4, height = fh*4).  Fixed at the first call.
+    if (p->res_w == -1 || p->res_h == -1) {
+        p->res_w = H * 4;
+        p->res_h = W * 4;
+    }
+    const int UW = p->res_w, UH = p->res_h;
+    if (UW < W || UH < H) {
+        hpb::set_error("hp_paf: resolution %dx%d smaller than the feature map %dx%d is not supported "
+                       "(true INTER_AREA down-scaling is not on the reference's default path)", UW, UH, W, H);
+        return HP_ERR_UNSUPPORTED;
+    }
+    if (p->pcap > MAX_PCAP) p->pcap = MAX_PCAP;
+    const bool geo_changed = (H != p->H || W != p->W || UH != p->UH || UW != p->UW);
+    if (geo_changed) {
+        std::vector<int> idx;
+        std::vector<float> fr;
+        area_up_table(W, UW, idx, fr);
+        HP_CUDA_TRY(p->xi.ensure(UW));
+        HP_CUDA_TRY(p->xf.ensure(UW));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->xi.p, idx.data(), UW * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->xf.p, fr.data(), UW * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(p->stream)); // idx/fr are stack vectors
+        area_up_table(H, UH, idx, fr);
+        HP_CUDA_TRY(p->yi.ensure(UH));
+        HP_CUDA_TRY(p->yf.ensure(UH));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->yi.p, idx.data(), UH * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->yf.p, fr.data(), UH * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
+    p->H = H; p->W = W; p->UH = UH; p->UW = UW; p->c_conf = c_conf; p->c_paf = c_paf;
+    if (N > p->cap_N || p->pcap != p->cap_pcap || p->ccap != p->cap_ccap || p->hcap != p->cap_hcap) {
+        const int cN = std::max(N, p->cap_N);
+        p->cap_N = cN;
+        p->cap_pcap = p->pcap; p->cap_ccap = p->ccap; p->cap_hcap = p->hcap;
+        HP_CUDA_TRY(p->counters.ensure((size_t)cN * (HP_N_PARTS + HP_N_PAIRS + 2)));
+        HP_CUDA_TRY(p->raw_key.ensure((size_t)cN * HP_N_PARTS * p->pcap));
+        HP_CUDA_TRY(p->raw_score.ensure((size_t)cN * HP_N_PARTS * p->pcap));
+        HP_CUDA_TRY(p->part_base.ensure((size_t)cN * (HP_N_PARTS + 1)));
+        HP_CUDA_TRY(p->px.ensure((size_t)cN * HP_N_PARTS * p->pcap));
+        HP_CUDA_TRY(p->py.ensure((size_t)cN * HP_N_PARTS * p->pcap));
+        HP_CUDA_TRY(p->pscore.ensure((size_t)cN * HP_N_PARTS * p->pcap));
+        HP_CUDA_TRY(p->cand.ensure((size_t)cN * HP_N_PAIRS * p->ccap));
+        HP_CUDA_TRY(p->cand_sorted.ensure((size_t)cN * HP_N_PAIRS * p->ccap));
+        HP_CUDA_TRY(p->conn.ensure((size_t)cN * HP_N_PAIRS * p->pcap));
+        HP_CUDA_TRY(p->humans.ensure((size_t)cN * p->hcap));
+        HP_CUDA_TRY(p->pin_humans.ensure((size_t)cN * p->hcap));
+        HP_CUDA_TRY(p->pin_counts.ensure((size_t)cN * 2));
+    }
+    p->N = N;
+    return HP_OK;
+}
+
+int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, cudaStream_t st)
+{
+    const int UH = p->UH, UW = p->UW;
+    HP_CUDA_TRY(cudaMemsetAsync(p->counters.p, 0, (size_t)p->cap_N * (HP_N_PARTS + HP_N_PAIRS + 2) * sizeof(int), st));
+
+    PeakParams k1;
+    k1.conf = d_conf; k1.c_conf = p->c_conf; k1.H = p->H; k1.W = p->W; k1.UH = UH; k1.UW = UW;
+    k1.xi = p->xi.p; k1.xf = p->xf.p; k1.yi = p->yi.p; k1.yf = p->yf.p;
+    k1.thresh = p->conf_thresh;
+    k1.skip_below = (p->conf_thresh > 0.f) ? p->conf_thresh * (1.f - 1e-5f) : -INFINITY;
+    k1.tiles_x = (UW + TW - 1) / TW;
+    k1.pcap = p->pcap;
+    k1.peak_cnt = p->peak_cnt(); k1.raw_key = p->raw_key.p; k1.raw_score = p->raw_score.p; k1.flags = p->flags();
+    k1.n8 = UW & ~7;
+    k1.n4 = (UW - k1.n8 >= 4) ? k1.n8 + 4 : k1.n8;
+    const int tiles_y = (UH + TH - 1) / TH;
+    dim3 g1(k1.tiles_x * tiles_y, HP_N_PARTS, N);
+    paf_peaks_kernel<<<g1, K1_THREADS, 0, st>>>(k1);
+
+    OrderParams k2;
+    k2.pcap = p->pcap; k2.UW = UW; k2.peak_cnt = p->peak_cnt(); k2.raw_key = p->raw_key.p; k2.raw_score = p->raw_score.p;
+    k2.part_base = p->part_base.p; k2.px = p->px.p; k2.py = p->py.p; k2.pscore = p->pscore.p;
+    paf_order_kernel<<<dim3(HP_N_PARTS, N), 128, p->pcap * sizeof(int), st>>>(k2);
+
+    LimbParams k3;
+    k3.paf = d_paf; k3.c_paf = p->c_paf; k3.H = p->H; k3.W = p->W; k3.UH = UH; k3.UW = UW;
+    k3.xi = p->xi.p; k3.xf = p->xf.p; k3.yi = p->yi.p; k3.yf = p->yf.p;
+    k3.paf_thresh = p->paf_thresh;
+    k3.feat_height = p->W; // m_feature_size = cv::Size(fw, fh) with fh = W (paf.cpp:329); .height -> get_connections (:354)
+    k3.pcap = p->pcap; k3.ccap = p->ccap;
+    k3.part_base = p->part_base.p; k3.px = p->px.p; k3.py = p->py.p; k3.pscore = p->pscore.p;
+    k3.cand = p->cand.p; k3.cand_sorted = p->cand_sorted.p; k3.conn = p->conn.p; k3.conn_cnt = p->conn_cnt();
+    k3.flags = p->flags();
+    const int want = 2 * p->H * p->W * (int)sizeof(float);
+    k3.stage_bytes = (want <= p->limb_stage_bytes) ? want : 0;
+    paf_limb_kernel<<<dim3(HP_N_PAIRS, N), K3_THREADS, k3.stage_bytes, st>>>(k3);
+
+    AssembleParams k4;
+    k4.pcap = p->pcap; k4.hcap = p->hcap; k4.UW = UW; k4.UH = UH;
+    k4.part_base = p->part_base.p; k4.px = p->px.p; k4.py = p->py.p; k4.pscore = p->pscore.p;
+    k4.conn = p->conn.p; k4.conn_cnt = p->conn_cnt();
+    k4.humans = p->humans.p; k4.human_cnt = p->human_cnt(); k4.flags = p->flags(); k4.max_refs = p->max_refs;
+    paf_assemble_kernel<<<N, 32, p->max_refs * sizeof(HumanRef), st>>>(k4);
+    HP_CUDA_TRY(cudaGetLastError());
+    p->launches += 4;
+    p->last_N = N;
+    p->last_stream = st;
+    return HP_OK;
+}
+
+int fetch_results(hp_paf* p, hp_human* out, int cap, int* n_out, int N)
+{
+    if (N != p->last_N || !out || !n_out || cap < 0) {
+        hpb::set_error("hp_paf_fetch: N=%d does not match the last processed batch (%d) or null output", N, p->last_N);
+        return HP_ERR_ARG;
+    }
+    cudaStream_t st = p->last_stream;
+    HP_CUDA_TRY(cudaMemcpyAsync(p->pin_counts.p, p->human_cnt(), sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(p->pin_counts.p + N, p->flags(), sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(p->pin_humans.p, p->humans.p, sizeof(hp_human) * (size_t)N * p->hcap, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaStreamSynchronize(st));
+    int flags = 0;
+    for (int f = 0; f < N; ++f) flags |= p->pin_counts.p[N + f];
+    if (flags) {
+        hpb::set_error("hp_paf: internal capacity exceeded (flags=%d: 1 peaks/part>%d, 2 candidates/limb>%d, 4 humans>%d)",
+                       flags, p->pcap, p->ccap, p->hcap);
+        return HP_ERR_CAPACITY;
+    }
+    for (int f = 0; f < N; ++f) {
+        const int n = p->pin_counts.p[f];
+        if (n > cap) {
+            hpb::set_error("hp_paf: frame %d has %d humans but the caller's capacity is %d", f, n, cap);
+            return HP_ERR_CAPACITY;
+        }
+        n_out[f] = n;
+        memcpy(out + (size_t)f * cap, p->pin_humans.p + (size_t)f * p->hcap, sizeof(hp_human) * n);
+    }
+    return HP_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int hp_paf_create(hp_paf** out, float conf_thresh, float paf_thresh, int res_w, int res_h, int device)
+{
+    if (!out) { hpb::set_error("hp_paf_create: null out"); return HP_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        hpb::set_error("hp_paf_create: no CUDA device (this library has no CPU fallback)");
+        return HP_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { hpb::set_error("hp_paf_create: device %d out of range (%d devices)", device, ndev); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(device));
+    hp_paf* p = new hp_paf();
+    p->device = device;
+    p->conf_thresh = conf_thresh;
+    p->paf_thresh = paf_thresh;
+    p->res_w = res_w;
+    p->res_h = res_h;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete p; hpb::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return HP_ERR_CUDA; }
+    // opt in to a large dynamic shared-memory carve-out for staging the two PAF channels of a limb
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    int stage = max_optin - 4096;
+    if (stage > 160 * 1024) stage = 160 * 1024;
+    if (stage > 0 && cudaFuncSetAttribute(paf_limb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage) == cudaSuccess)
+        p->limb_stage_bytes = stage;
+    else
+        cudaGetLastError();
+    *out = p;
+    return HP_OK;
+}
+
+void hp_paf_destroy(hp_paf* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    p->xi.release(); p->yi.release(); p->xf.release(); p->yf.release(); p->counters.release();
+    p->raw_key.release(); p->part_base.release(); p->px.release(); p->py.release();
+    p->raw_score.release(); p->pscore.release(); p->cand.release(); p->cand_sorted.release();
+    p->conn.release(); p->humans.release(); p->in_conf.release(); p->in_paf.release();
+    p->pin_in.release(); p->pin_humans.release(); p->pin_counts.release();
+    delete p;
+}
+
+int hp_paf_set_conf_thresh(hp_paf* p, float t) { if (!p) return HP_ERR_ARG; p->conf_thresh = t; return HP_OK; }
+int hp_paf_set_paf_thresh(hp_paf* p, float t) { if (!p) return HP_ERR_ARG; p->paf_thresh = t; return HP_OK; }
+
+int hp_paf_set_capacity(hp_paf* p, int max_peaks_per_part, int max_candidates_per_limb, int max_humans)
+{
+    if (!p) return HP_ERR_ARG;
+    if (max_peaks_per_part > 0) p->pcap = std::min(max_peaks_per_part, MAX_PCAP);
+    if (max_candidates_per_limb > 0) p->ccap = max_candidates_per_limb;
+    if (max_humans > 0) {
+        p->hcap = max_humans;
+        p->max_refs = std::min(std::max(256, 2 * max_humans), 560); // 560 * 80 B < 48 KB static dynamic-smem limit
+    }
+    return HP_OK;
+}
+
+int hp_paf_process_device(hp_paf* p, const float* d_conf, const float* d_paf, int N, int c_conf, int c_paf, int H, int W, void* stream)
+{
+    if (!p || !d_conf || !d_paf) { hpb::set_error("hp_paf_process_device: null argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_geometry(p, N, c_conf, c_paf, H, W);
+    if (rc) return rc;
+    return launch_pipeline(p, d_conf, d_paf, N, stream ? (cudaStream_t)stream : p->stream);
+}
+
+int hp_paf_fetch(hp_paf* p, hp_human* out, int cap, int* n_out, int N)
+{
+    if (!p) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    return fetch_results(p, out, cap, n_out, N);
+}
+
+int hp_paf_process_host_batched(hp_paf* p, const float* conf, const float* paf, int N, int c_conf, int c_paf, int H, int W,
+                                hp_human* out, int cap, int* n_out)
+{
+    if (!p || !conf || !paf || !out || !n_out) { hpb::set_error("hp_paf_process_host: null argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        int rc = ensure_geometry(p, N, c_conf, c_paf, H, W);
+        if (rc) return rc;
+        const size_t n_conf = (size_t)N * c_conf * H * W, n_paf = (size_t)N * c_paf * H * W;
+        HP_CUDA_TRY(p->in_conf.ensure(n_conf));
+        HP_CUDA_TRY(p->in_paf.ensure(n_paf));
+        HP_CUDA_TRY(p->pin_in.ensure(n_conf + n_paf));
+        memcpy(p->pin_in.p, conf, n_conf * sizeof(float));
+        memcpy(p->pin_in.p + n_conf, paf, n_paf * sizeof(float));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->in_conf.p, p->pin_in.p, n_conf * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->in_paf.p, p->pin_in.p + n_conf, n_paf * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        rc = launch_pipeline(p, p->in_conf.p, p->in_paf.p, N, p->stream);
+        if (rc) return rc;
+        rc = fetch_results(p, out, cap, n_out, N);
+        if (rc != HP_ERR_CAPACITY) return rc;
+        // the reference is unbounded: grow whichever internal capacity overflowed and retry
+        int flags = 0;
+        for (int f = 0; f < N; ++f) flags |= p->pin_counts.p[N + f];
+        if (!flags) return rc; // the caller's own `cap` was too small
+        if ((flags & FLAG_PEAK_OVERFLOW) && p->pcap >= MAX_PCAP) return rc;
+        if (flags & FLAG_PEAK_OVERFLOW) p->pcap = std::min(p->pcap * 4, MAX_PCAP);
+        if (flags & FLAG_CAND_OVERFLOW) p->ccap *= 4;
+        if (flags & FLAG_HUMAN_OVERFLOW) {
+            if (p->hcap >= 280) return rc;
+            hp_paf_set_capacity(p, 0, 0, std::min(p->hcap * 2, 280));
+        }
+    }
+    return HP_ERR_CAPACITY;
+}
+
+int hp_paf_process_host(hp_paf* p, const float* conf, const float* paf, int c_conf, int c_paf, int H, int W,
+                        hp_human* out, int cap, int* n_out)
+{
+    return hp_paf_process_host_batched(p, conf, paf, 1, c_conf, c_paf, H, W, out, cap, n_out);
+}
+
+int hp_paf_debug_peaks(hp_paf* p, int frame, hp_peak* out, int cap, int* n_out)
+{
+    if (!p || frame < 0 || frame >= p->last_N || !out || !n_out) { hpb::set_error("hp_paf_debug_peaks: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    HP_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
+    int base[HP_N_PARTS + 1];
+    HP_CUDA_TRY(cudaMemcpy(base, p->part_base.p + (size_t)frame * (HP_N_PARTS + 1), sizeof(base), cudaMemcpyDeviceToHost));
+    const int n = base[HP_N_PARTS];
+    *n_out = n;
+    if (n > cap) { hpb::set_error("hp_paf_debug_peaks: %d peaks > cap %d", n, cap); return HP_ERR_CAPACITY; }
+    std::vector<int> x(n), y(n);
+    std::vector<float> s(n);
+    const size_t off = (size_t)frame * HP_N_PARTS * p->pcap;
+    if (n) {
+        HP_CUDA_TRY(cudaMemcpy(x.data(), p->px.p + off, n * sizeof(int), cudaMemcpyDeviceToHost));
+        HP_CUDA_TRY(cudaMemcpy(y.data(), p->py.p + off, n * sizeof(int), cudaMemcpyDeviceToHost));
+        HP_CUDA_TRY(cudaMemcpy(s.data(), p->pscore.p + off, n * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    int part = 0;
+    for (int i = 0; i < n; ++i) {
+        while (part < HP_N_PARTS - 1 && i >= base[part + 1]) ++part;
+        out[i].part_id = part; out[i].x = x[i]; out[i].y = y[i]; out[i].score = s[i]; out[i].id = i;
+    }
+    return HP_OK;
+}
+
+int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* out, int cap, int* n_out)
+{
+    if (!p || frame < 0 || frame >= p->last_N || pair_id < 0 || pair_id >= HP_N_PAIRS || !out || !n_out) {
+        hpb::set_error("hp_paf_debug_connections: bad argument");
+        return HP_ERR_ARG;
+    }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    HP_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
+    int n = 0;
+    HP_CUDA_TRY(cudaMemcpy(&n, p->conn_cnt() + frame * HP_N_PAIRS + pair_id, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > cap) { hpb::set_error("hp_paf_debug_connections: %d > cap %d", n, cap); return HP_ERR_CAPACITY; }
+    if (n) HP_CUDA_TRY(cudaMemcpy(out, p->conn.p + ((size_t)frame * HP_N_PAIRS + pair_id) * p->pcap, n * sizeof(hp_connection), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+long long hp_paf_launch_count(const hp_paf* p) { return p ? p->launches : 0; }
+
+} // extern "C"
