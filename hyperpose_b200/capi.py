@@ -85,11 +85,15 @@ class PafParser:
         check(lib().hp_paf_create(C.byref(self._h), conf_thresh, paf_thresh, resolution_size[0], resolution_size[1], device))
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().hp_paf_destroy(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hp_paf_destroy(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def set_conf_thresh(self, t):
         check(lib().hp_paf_set_conf_thresh(self._h, t))

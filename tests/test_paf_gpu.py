@@ -72,7 +72,7 @@ def test_random_shapes_vs_oracle(seed):
     """ragged / odd geometries: every column class of the separable filter, reflect borders on tiny maps"""
     rng = np.random.default_rng(seed)
     hf = int(rng.integers(5, 60))
-    wf = int(rng.integers(5, 90))
+    wf = int(rng.integers(max(5, (hf + 3) // 4), min(90, 4 * hf) + 1))   # default resolution must up-scale both axes
     P = int(rng.integers(0, 6))
     conf, paf = syn.make_frame_tensors(seed, P, hf, wf)
     orc = oracle.oracle_process(conf, paf)
@@ -129,6 +129,15 @@ def test_bad_rank_is_rejected():
         parser.process(np.zeros((19, 46), np.float32), np.zeros((38, 46, 54), np.float32))
     with pytest.raises(capi.HyperposeError):
         parser.process(np.zeros((10, 46, 54), np.float32), np.zeros((38, 46, 54), np.float32))
+    parser.close()
+
+
+def test_downscaling_resolution_is_rejected_not_approximated():
+    # default resolution of a 9x70 map is 36 wide (< 70): true INTER_AREA down-scaling is not implemented
+    parser = capi.PafParser()
+    with pytest.raises(capi.HyperposeError) as e:
+        parser.process(np.zeros((19, 9, 70), np.float32), np.zeros((38, 9, 70), np.float32))
+    assert e.value.status == capi.HP_ERR_UNSUPPORTED
     parser.close()
 
 
