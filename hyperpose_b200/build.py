@@ -18,6 +18,7 @@ EXACT_FLAGS = ["-fmad=false"]
 # (source, extra flags)
 SOURCES = [
     ("paf_parser.cu", EXACT_FLAGS),
+    ("engine.cu", []),
     ("common.cpp", []),
 ]
 
@@ -52,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 f.write(r.stderr)
             rebuilt = True
     if rebuilt or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs  # static cudart (nvcc default); the driver API is reached via cudaGetDriverEntryPoint
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

@@ -151,3 +151,136 @@ class PafParser:
     @property
     def launch_count(self) -> int:
         return int(lib().hp_paf_launch_count(self._h))
+
+
+# ---------------------------------------------------------------------------------------------
+# DNN engine
+# ---------------------------------------------------------------------------------------------
+EXPORTS += [
+    "hp_engine_create", "hp_engine_destroy", "hp_engine_info", "hp_engine_infer_u8_host", "hp_engine_infer_u8_device",
+    "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_sync",
+    "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
+    "hp_pose_run_u8_host",
+]
+
+
+def _bind_engine(L):
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.hp_engine_create.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+    L.hp_engine_destroy.argtypes = [vp]
+    L.hp_engine_destroy.restype = None
+    L.hp_engine_info.argtypes = [vp, ip, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_double)]
+    L.hp_engine_infer_u8_host.argtypes = [vp, vp, C.c_int]
+    L.hp_engine_infer_u8_device.argtypes = [vp, vp, C.c_int, vp]
+    L.hp_engine_infer_f32_host.argtypes = [vp, vp, C.c_int]
+    L.hp_engine_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.hp_engine_read_outputs_host.argtypes = [vp, vp, vp, C.c_int]
+    L.hp_engine_sync.argtypes = [vp]
+    L.hp_engine_launch_count.argtypes = [vp]
+    L.hp_engine_launch_count.restype = C.c_longlong
+    L.hp_engine_debug_read_buffer.argtypes = [vp, C.c_int, vp, C.c_int, ip, ip, ip]
+    L.hp_engine_debug_write_buffer.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.hp_engine_debug_run_ops.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.hp_pose_run_u8_host.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, ip]
+
+
+class Engine:
+    """Mirror of hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141):
+    Engine(model_pack, input_size=(w, h), max_batch_size, factor=1/255, flip_rgb=True); inference(frames)."""
+
+    def __init__(self, pack: bytes, input_size, max_batch_size: int = 8, factor: float = 1.0 / 255, flip_rgb: bool = True,
+                 device: int = 0):
+        L = lib()
+        if not getattr(L, "_engine_bound", False):
+            _bind_engine(L)
+            L._engine_bound = True
+        self._h = C.c_void_p()
+        self._pack = pack
+        check(L.hp_engine_create(C.byref(self._h), pack, len(pack), int(input_size[0]), int(input_size[1]), max_batch_size,
+                                 factor, 1 if flip_rgb else 0, device))
+        v = [C.c_int() for _ in range(7)]
+        fl = C.c_double()
+        check(L.hp_engine_info(self._h, *[C.byref(x) for x in v], C.byref(fl)))
+        (self.in_w, self.in_h, self.max_batch, self.c_conf, self.c_paf, self.out_h, self.out_w) = [x.value for x in v]
+        self.flops_per_frame = fl.value
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hp_engine_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def max_batch_size(self):
+        return self.max_batch
+
+    def input_size(self):
+        return (self.in_w, self.in_h)
+
+    def infer_u8(self, frames: np.ndarray):
+        """frames u8[N,in_h,in_w,3] (BGR, already network-sized).  Asynchronous; outputs stay on the device."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 4 and frames.shape[1:] == (self.in_h, self.in_w, 3), frames.shape
+        check(lib().hp_engine_infer_u8_host(self._h, frames.ctypes.data, frames.shape[0]))
+        self._last_n = frames.shape[0]
+
+    def infer_u8_device(self, d_ptr: int, n: int, stream: int = 0):
+        check(lib().hp_engine_infer_u8_device(self._h, d_ptr, n, stream))
+        self._last_n = n
+
+    def infer_f32(self, nchw: np.ndarray):
+        nchw = np.ascontiguousarray(nchw, np.float32)
+        check(lib().hp_engine_infer_f32_host(self._h, nchw.ctypes.data, nchw.shape[0]))
+        self._last_n = nchw.shape[0]
+
+    def inference(self, frames: np.ndarray):
+        """tensorrt::inference(std::vector<cv::Mat>): returns per image [conf[C,h,w], paf[2L,h,w]] host tensors
+        (ordered by name: conf < paf, src/tensorrt.cpp:405)."""
+        self.infer_u8(frames)
+        conf, paf = self.read_outputs(frames.shape[0])
+        return [[conf[i], paf[i]] for i in range(frames.shape[0])]
+
+    def read_outputs(self, n: int):
+        conf = np.empty((n, self.c_conf, self.out_h, self.out_w), np.float32)
+        paf = np.empty((n, self.c_paf, self.out_h, self.out_w), np.float32)
+        check(lib().hp_engine_read_outputs_host(self._h, conf.ctypes.data, paf.ctypes.data, n))
+        return conf, paf
+
+    def device_outputs(self):
+        a, b, s = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().hp_engine_outputs(self._h, C.byref(a), C.byref(b), C.byref(s)))
+        return a.value, b.value, (s.value or 0)
+
+    def sync(self):
+        check(lib().hp_engine_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().hp_engine_launch_count(self._h))
+
+    def debug_read_buffer(self, buf: int, n: int) -> np.ndarray:
+        H, W, Cc = C.c_int(), C.c_int(), C.c_int()
+        check(lib().hp_engine_debug_read_buffer(self._h, buf, None, n, C.byref(H), C.byref(W), C.byref(Cc)))
+        out = np.empty((n, H.value, W.value, Cc.value), np.float16)
+        check(lib().hp_engine_debug_read_buffer(self._h, buf, out.ctypes.data, n, C.byref(H), C.byref(W), C.byref(Cc)))
+        return out
+
+    def debug_write_buffer(self, buf: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr, np.float16)
+        check(lib().hp_engine_debug_write_buffer(self._h, buf, arr.ctypes.data, arr.shape[0]))
+
+    def debug_run_ops(self, first: int, last: int, n: int):
+        check(lib().hp_engine_debug_run_ops(self._h, first, last, n))
+
+    def run_pose(self, parser: "PafParser", frames: np.ndarray, cap: int = 128):
+        """hp_pose_run_u8_host: frames in, humans out (list of N structured arrays)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        N = frames.shape[0]
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_pose_run_u8_host(self._h, parser._h, frames.ctypes.data, N, out.ctypes.data, cap, n))
+        return [out[i, :n[i]].copy() for i in range(N)]

@@ -1,0 +1,396 @@
+// conv_tcgen05.cuh -- implicit-GEMM convolution on the sm_100a 5th-gen tensor cores.
+//
+// Replaces the TensorRT-executed CNN of the reference (IExecutionContext::executeV2,
+// src/tensorrt.cpp:387-396; layer shapes from hyperpose/Model/backbones.py:447-509 and
+// hyperpose/Model/openpose/model/openpose.py:36-199).
+//
+//   D[128 pixels, BN out-channels] += A[128 pixels, 64 in-channels] * B[BN, 64]^T
+//   summed over (filter tap r,s) x (64-channel chunk): one "k-step" per (r, s, chunk).
+//
+// * activations are fp16 NHWC; the A tile of a k-step is ONE 4-D TMA box {64 ch, BW, BH, 1}
+//   fetched at spatial offset (s - pad, r - pad): out-of-image elements are zero-filled by the
+//   TMA unit, which implements "SAME" padding with no im2col buffer in HBM;
+// * weights are fp16 [G][Cout_pad][R][S][Cin_g] (K-major); the B tile is a 2-D TMA box {64, BN};
+// * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes;
+// * accumulators live in TMEM (2 x BN fp32 columns, double-buffered so the epilogue of tile i
+//   overlaps the MMAs of tile i+1);
+// * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+//   (single elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue
+//   (tcgen05.ld -> bias + PReLU/ReLU -> fp16 NHWC (or fp32 NCHW for the parser) stores).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hpb {
+
+constexpr int CONV_BLOCK_M = 128;   // pixels per tile == TMEM lanes == UMMA M
+constexpr int CONV_BLOCK_K = 64;    // fp16 channels per k-step == one 128-byte swizzle row
+constexpr int CONV_UMMA_K = 16;     // K of one tcgen05.mma.kind::f16
+constexpr int CONV_MAX_STAGES = 8;
+constexpr int CONV_THREADS = 256;
+constexpr int CONV_A_BYTES = CONV_BLOCK_M * CONV_BLOCK_K * 2; // 16 KiB
+
+enum ConvOutMode : int {
+    OUT_F16_NHWC = 0,       // fp16, out[pixel * ld + ch_off + g * cout_g + n]
+    OUT_F32_NCHW_SPLIT = 1, // fp32 planar; channels [0,split) -> out, [split,cout_g) -> out2 (conf / paf for the parser)
+};
+
+struct ConvParams {
+    int Nb, H, W;              // batch, spatial size (stride 1, "SAME" padding: output size == input size)
+    int R, S;                  // filter taps
+    int groups, cin_g;         // cin_g: multiple of 64
+    int cout_g, cout_g_pad;    // real / padded (multiple of BN) output channels per group
+    int BN;                    // tile N == UMMA N (multiple of 16, <= 256)
+    int BH, BW;                // pixel tile, BH * BW == 128
+    int tiles_h, tiles_w;
+    int in_ch_off;             // first input channel inside the input buffer
+    int num_stages;
+    int tmem_cols;             // power of two >= 2 * BN
+    const float* bias;         // [groups * cout_g_pad]
+    const float* alpha;        // [groups * cout_g_pad]   y = v > 0 ? v : alpha * v   (0 => ReLU, 1 => linear)
+    int out_mode;
+    void* out; void* out2;
+    int out_ld, out_ch_off;    // NHWC: channels per pixel of the output buffer / first channel written
+    int split;                 // NCHW_SPLIT: channels [0,split) go to out, the rest to out2
+};
+
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc];  accumulate = 0 overwrites D
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (count 1) on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 (sm_100)
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, A/B = fp16 K-major, D = fp32:
+//   [4,6) c_format = 1 (F32) | [7,10) a_format = 0 (F16) | [10,13) b_format = 0 (F16)
+//   [15] a_major = 0 (K) | [16] b_major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ inline uint32_t make_idesc_f16(int M, int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+} // namespace ptx
+
+struct ConvTile {
+    int nb, h0, w0, g, n0;
+};
+
+__device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int tile, int n_tiles_g)
+{
+    ConvTile t;
+    const int n_tiles_total = p.groups * n_tiles_g;
+    const int nt = tile % n_tiles_total;
+    int mt = tile / n_tiles_total;
+    t.g = nt / n_tiles_g;
+    t.n0 = (nt - t.g * n_tiles_g) * p.BN;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    t.nb = mt / p.tiles_h;
+    t.h0 = th * p.BH;
+    t.w0 = tw * p.BW;
+    return t;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle atoms shared by TMA and UMMA
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.BN * CONV_BLOCK_K * 2;
+    const int stage_bytes = CONV_A_BYTES + b_bytes;
+    uint8_t* bar_base = smem + (size_t)p.num_stages * stage_bytes;
+    uint64_t* full_bar = (uint64_t*)bar_base;                  // [stages]  TMA -> MMA
+    uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;          // [stages]  MMA -> TMA
+    uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;         // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;                      // [2]       epilogue -> MMA
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_g = p.cout_g_pad / p.BN;
+    const int total_tiles = p.Nb * p.tiles_h * p.tiles_w * p.groups * n_tiles_g;
+    const int chunks = p.cin_g / CONV_BLOCK_K;
+    const int ksteps = p.R * p.S * chunks;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.num_stages; ++i) {
+            ptx::mbar_init(ptx::smem_u32(full_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(empty_bar + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4); // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int pad_h = p.R / 2, pad_w = p.S / 2;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const ConvTile t = decode_tile(p, tile, n_tiles_g);
+                const int a_ch0 = p.in_ch_off + t.g * p.cin_g;
+                const int b_row = t.g * p.cout_g_pad + t.n0;
+                int kcol = 0;
+                for (int r = 0; r < p.R; ++r)
+                    for (int s = 0; s < p.S; ++s)
+                        for (int c = 0; c < chunks; ++c, kcol += CONV_BLOCK_K) {
+                            ptx::mbar_wait(ptx::smem_u32(empty_bar + stage), phase ^ 1);
+                            const uint32_t fb = ptx::smem_u32(full_bar + stage);
+                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                            ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                            ptx::tma_load_4d(ptx::smem_u32(sa), &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K,
+                                             t.w0 + s - pad_w, t.h0 + r - pad_h, t.nb);
+                            ptx::tma_load_2d(ptx::smem_u32(sa + CONV_A_BYTES), &tmap_b, fb, kcol, b_row);
+                            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1); // epilogue drained this accumulator
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(sa + CONV_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k) {
+                        // advancing K by 16 fp16 = 32 bytes inside the 128-byte swizzled row: +2 in the (>>4) address field
+                        ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(ptx::smem_u32(empty_bar + stage)); // frees the smem slot when these MMAs retire
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc)); // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM -> registers -> global =====================
+        const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may access
+        const int row = ew * 32 + lane;           // accumulator row == pixel index inside the tile
+        const int ph = row / p.BW, pw = row - ph * p.BW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const ConvTile t = decode_tile(p, tile, n_tiles_g);
+            const int h = t.h0 + ph, w = t.w0 + pw;
+            const bool in_img = (h < p.H) && (w < p.W);
+            ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
+            const float* bias = p.bias + t.g * p.cout_g_pad + t.n0;
+            const float* alpha = p.alpha + t.g * p.cout_g_pad + t.n0;
+            const int n_valid = min(p.BN, p.cout_g - t.n0); // real (unpadded) channels of this tile
+            const size_t pix = ((size_t)t.nb * p.H + h) * p.W + w;
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                if (c0 >= n_valid) break; // warp-uniform: the remaining columns are padding
+                uint32_t v[16];
+                ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v); // warp-collective: executed by all lanes
+                ptx::tmem_ld_wait();
+                if (!in_img) continue;
+                float y[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float a = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
+                    y[j] = a > 0.f ? a : a * __ldg(alpha + c0 + j);
+                }
+                if (p.out_mode == OUT_F16_NHWC) {
+                    __half* o = (__half*)p.out + pix * p.out_ld + p.out_ch_off + t.g * p.cout_g + t.n0 + c0;
+                    const int nv = min(16, n_valid - c0);
+                    if (nv == 16 && ((uintptr_t)o & 15) == 0) {
+                        uint4 q0, q1;
+                        __half2 h2;
+                        h2 = __floats2half2_rn(y[0], y[1]);   q0.x = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[2], y[3]);   q0.y = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[4], y[5]);   q0.z = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[6], y[7]);   q0.w = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[8], y[9]);   q1.x = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[10], y[11]); q1.y = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[12], y[13]); q1.z = *(uint32_t*)&h2;
+                        h2 = __floats2half2_rn(y[14], y[15]); q1.w = *(uint32_t*)&h2;
+                        ((uint4*)o)[0] = q0;
+                        ((uint4*)o)[1] = q1;
+                    } else {
+                        for (int j = 0; j < nv; ++j) o[j] = __float2half_rn(y[j]);
+                    }
+                } else {
+                    const int nv = min(16, n_valid - c0);
+                    for (int j = 0; j < nv; ++j) {
+                        const int ch = t.n0 + c0 + j;
+                        if (ch < p.split) {
+                            ((float*)p.out)[(((size_t)t.nb * p.split + ch) * p.H + h) * p.W + w] = y[j];
+                        } else {
+                            const int c2 = ch - p.split, n2 = p.cout_g - p.split;
+                            ((float*)p.out2)[(((size_t)t.nb * n2 + c2) * p.H + h) * p.W + w] = y[j];
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+inline size_t conv_smem_bytes(int BN, int stages)
+{
+    return 1024 /*alignment slack*/ + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (2 * CONV_MAX_STAGES + 4) * 8 + 16;
+}
+
+} // namespace hpb

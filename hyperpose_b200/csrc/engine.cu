@@ -1,0 +1,586 @@
+// engine.cu -- the DNN engine: replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
+// src/tensorrt.cpp:121-471).  No TensorRT: the network is a flat list of ops (pack_format.h) executed as
+// hand-written sm_100a kernels on one stream:
+//   OP_IM2COL3  : frame pre-processing fused with the first layer's patch gather
+//                 (nhwc_images_append_nchw_batch, src/data.cpp:21-51: u8 HWC BGR -> x*factor, R/B swap;
+//                  vgg mean subtraction, hyperpose/Model/backbones.py:455,497-498)
+//   OP_CONV     : conv_tcgen05_kernel (conv_tcgen05.cuh)
+//   OP_MAXPOOL2 : 2x2/2 max-pool on fp16 NHWC
+// Activations stay on the device in fp16 NHWC; only the final conf/paf maps are produced as fp32 NCHW
+// (the layout hyperpose::parser::paf consumes, src/tensorrt.cpp:398-431) and they, too, stay on the device
+// for the parser hand-off.  Precision: fp16 operands, fp32 accumulation (same mantissa as TF32).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/hyperpose_b200.h"
+#include "common.h"
+#include "conv_tcgen05.cuh"
+#include "pack_format.h"
+
+namespace {
+using namespace hpb;
+
+// ---------------------------------------------------------------------------------------------
+// helper kernels
+// ---------------------------------------------------------------------------------------------
+
+// One thread per pixel: gathers the 3x3x3 neighbourhood (k = (r*3+s)*3 + c, c = model channel) into 64 fp16
+// channels (27 values + zeros).  SAME padding pads the *normalised* input with zeros.
+//   u8 path : v = (float)((double)u8 * factor) (data.cpp:48); model channel c reads byte (flip ? 2-c : c)
+//   f32 path: input is already scaled NCHW (tensorrt::inference(const std::vector<float>&, size_t))
+template <bool U8>
+__global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
+                                                      int N, int H, int W, double factor, int flip, float m0, float m1, float m2)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * H * W;
+    if (idx >= total) return;
+    const int w = (int)(idx % W);
+    const int h = (int)((idx / W) % H);
+    const int n = (int)(idx / ((size_t)W * H));
+    const float mean[3] = { m0, m1, m2 };
+    __align__(16) __half vals[64];
+#pragma unroll
+    for (int k = 27; k < 64; ++k) vals[k] = __float2half_rn(0.f);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int hh = h + r - 1, ww = w + s - 1;
+            const bool ok = (hh >= 0 && hh < H && ww >= 0 && ww < W);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = 0.f;
+                if (ok) {
+                    if (U8) {
+                        const uint8_t* px = (const uint8_t*)in + (((size_t)n * H + hh) * W + ww) * 3;
+                        v = (float)((double)px[flip ? 2 - c : c] * factor) - mean[c];
+                    } else {
+                        v = ((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c];
+                    }
+                }
+                vals[(r * 3 + s) * 3 + c] = __float2half_rn(v);
+            }
+        }
+    uint4* o = (uint4*)(out + idx * 64);
+    const uint4* v4 = (const uint4*)vals;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = v4[i];
+}
+
+// 2x2 stride-2 max pool, NHWC fp16, 8 channels per thread; SAME semantics (window clipped at the border).
+__global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                                       int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = C / 8;
+    const size_t total = (size_t)N * OH * OW * cv;
+    if (idx >= total) return;
+    const int c8 = (int)(idx % cv);
+    size_t t = idx / cv;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    const int h0 = oh * 2, w0 = ow * 2;
+    const int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+    auto ld = [&](int h, int w) { return *(const uint4*)(in + (((size_t)n * H + h) * W + w) * C_in_ld + c8 * 8); };
+    uint4 a = ld(h0, w0), b = ld(h0, w1), c = ld(h1, w0), d = ld(h1, w1);
+    uint4 r;
+    __half2* ra = (__half2*)&a; __half2* rb = (__half2*)&b; __half2* rc = (__half2*)&c; __half2* rd = (__half2*)&d;
+    __half2* rr = (__half2*)&r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rr[i] = __hmax2(__hmax2(ra[i], rb[i]), __hmax2(rc[i], rd[i]));
+    *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * C_out_ld + c8 * 8) = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps (driver entry point fetched at run time: no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// activations [N,H,W,C] fp16: dims (C, W, H, N), box (64, BW, BH, 1), 128B swizzle, zero OOB fill
+int make_tmap_act(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int BH, int BW)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
+    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+    cuuint64_t strides[3] = { (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2 };
+    cuuint32_t box[4] = { 64, (cuuint32_t)BW, (cuuint32_t)BH, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d (N=%d H=%d W=%d C=%d box %dx%d)", (int)r, N, H, W, C, BH, BW); return HP_ERR_CUDA; }
+    return HP_OK;
+}
+// weights [rows, K] fp16 K-major: dims (K, rows), box (64, BN)
+int make_tmap_wgt(CUtensorMap* m, const __half* base, int rows, int K, int BN)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
+    cuuint64_t dims[2] = { (cuuint64_t)K, (cuuint64_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)K * 2 };
+    cuuint32_t box[2] = { 64, (cuuint32_t)BN };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d (rows=%d K=%d BN=%d)", (int)r, rows, K, BN); return HP_ERR_CUDA; }
+    return HP_OK;
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int pick_bn(int cout_g)
+{
+    if (cout_g <= 16) return 16;
+    if (cout_g <= 32) return 32;
+    if (cout_g <= 48) return 48;
+    if (cout_g <= 64) return 64;
+    if (cout_g <= 96) return 96;
+    if (cout_g <= 128) return 128;
+    if (cout_g % 256 == 0) return 256;
+    if (cout_g % 128 == 0) return 128;
+    return 256;
+}
+
+void pick_tile(int H, int W, int* BH, int* BW)
+{
+    static const int cand[][2] = { { 8, 16 }, { 16, 8 }, { 4, 32 }, { 32, 4 }, { 2, 64 }, { 1, 128 } };
+    long best = -1;
+    for (auto& c : cand) {
+        const long cover = (long)round_up(H, c[0]) * round_up(W, c[1]);
+        if (best < 0 || cover < best) { best = cover; *BH = c[0]; *BW = c[1]; }
+    }
+}
+
+struct ConvPlan {
+    ConvParams prm;
+    CUtensorMap tmap_a, tmap_b;
+    __half* d_w = nullptr;
+    float* d_bias = nullptr;
+    float* d_alpha = nullptr;
+    int grid = 0;
+    size_t smem = 0;
+    int built_for_N = 0;
+    double flops_per_frame = 0;
+};
+
+struct EngOp {
+    PackOp po;
+    ConvPlan plan; // OP_CONV only
+};
+
+struct EngBuffer {
+    int channels = 0, down = 0, H = 0, W = 0;
+    __half* d = nullptr;
+};
+
+} // namespace
+
+struct hp_engine {
+    int device = 0;
+    int in_h = 0, in_w = 0, max_batch = 0;
+    double factor = 1.0 / 255;
+    int flip_rgb = 1;
+    int num_sms = 148;
+    PackHeader hdr;
+    std::vector<EngBuffer> bufs;
+    std::vector<EngOp> ops;
+    float* d_conf = nullptr;
+    float* d_paf = nullptr;
+    int out_h = 0, out_w = 0;
+    uint8_t* d_frames = nullptr;   // [max_batch, in_h, in_w, 3]
+    float* d_input_f32 = nullptr;  // [max_batch, 3, in_h, in_w] (lazily)
+    uint8_t* pin_frames = nullptr;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    double flops_per_frame = 0;
+    int last_N = 0;
+};
+
+namespace {
+
+int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
+{
+    const PackOp& po = op.po;
+    ConvPlan& pl = op.plan;
+    const EngBuffer& ib = e->bufs[po.in_buf];
+    const int G = (int)po.groups;
+    int R = (int)po.R, S = (int)po.S, cin_g = (int)po.cin_g;
+    const int cout_g = (int)po.cout_g;
+    const bool im2col = po.im2col_input != 0;
+    if (im2col && (G != 1 || R * S * cin_g > 64)) { set_error("engine: bad im2col conv"); return HP_ERR_ARG; }
+    if (!im2col && G > 1 && cin_g % 64 != 0) { set_error("engine: grouped conv needs cin_g %% 64 == 0 (got %d)", cin_g); return HP_ERR_UNSUPPORTED; }
+    // effective GEMM view
+    const int eR = im2col ? 1 : R, eS = im2col ? 1 : S;
+    const int ecin = im2col ? 64 : round_up(cin_g, 64);
+    if ((int)po.in_ch_off + (G - 1) * ecin + ecin > ib.channels) {
+        set_error("engine: conv reads channels [%d,%d) of a %d-channel buffer", po.in_ch_off, po.in_ch_off + G * ecin, ib.channels);
+        return HP_ERR_ARG;
+    }
+    const int BN = pick_bn(cout_g);
+    const int cout_pad = round_up(cout_g, BN);
+    const int K = eR * eS * ecin;
+    // repack fp32 [G][cout][cin][R][S] -> fp16 [G][cout_pad][R][S][cin_pad]
+    std::vector<__half> w((size_t)G * cout_pad * K, __float2half(0.f));
+    std::vector<float> bias((size_t)G * cout_pad, 0.f), alpha((size_t)G * cout_pad, 0.f);
+    const float* W = blob + po.w_off;
+    for (int g = 0; g < G; ++g)
+        for (int o = 0; o < cout_g; ++o) {
+            bias[(size_t)g * cout_pad + o] = blob[po.b_off + (size_t)g * cout_g + o];
+            alpha[(size_t)g * cout_pad + o] = blob[po.a_off + (size_t)g * cout_g + o];
+            for (int c = 0; c < cin_g; ++c)
+                for (int r = 0; r < R; ++r)
+                    for (int s = 0; s < S; ++s) {
+                        const float v = W[((((size_t)g * cout_g + o) * cin_g + c) * R + r) * S + s];
+                        const size_t k = im2col ? (size_t)((r * S + s) * cin_g + c) : ((size_t)(r * S + s) * ecin + c);
+                        w[((size_t)g * cout_pad + o) * K + k] = __float2half_rn(v);
+                    }
+        }
+    HP_CUDA_TRY(cudaMalloc(&pl.d_w, w.size() * sizeof(__half)));
+    HP_CUDA_TRY(cudaMalloc(&pl.d_bias, bias.size() * sizeof(float)));
+    HP_CUDA_TRY(cudaMalloc(&pl.d_alpha, alpha.size() * sizeof(float)));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_alpha, alpha.data(), alpha.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    ConvParams& p = pl.prm;
+    memset(&p, 0, sizeof(p));
+    p.Nb = e->max_batch; p.H = ib.H; p.W = ib.W;
+    p.R = eR; p.S = eS; p.groups = G; p.cin_g = ecin;
+    p.cout_g = cout_g; p.cout_g_pad = cout_pad; p.BN = BN;
+    pick_tile(p.H, p.W, &p.BH, &p.BW);
+    p.tiles_h = (p.H + p.BH - 1) / p.BH;
+    p.tiles_w = (p.W + p.BW - 1) / p.BW;
+    p.in_ch_off = (int)po.in_ch_off;
+    const int stage_bytes = CONV_A_BYTES + BN * CONV_BLOCK_K * 2;
+    p.num_stages = std::min(CONV_MAX_STAGES, (200 * 1024) / stage_bytes);
+    int tc = 32;
+    while (tc < 2 * BN) tc *= 2;
+    p.tmem_cols = tc;
+    p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.out_mode = (int)po.out_mode;
+    if (po.out_mode == OUT_F32_NCHW_SPLIT) {
+        p.out = e->d_conf; p.out2 = e->d_paf; p.split = (int)po.split;
+        if ((int)po.split != (int)e->hdr.conf_channels || cout_g - (int)po.split != (int)e->hdr.paf_channels || G != 1) {
+            set_error("engine: output conv must produce conf(%u)+paf(%u) channels", e->hdr.conf_channels, e->hdr.paf_channels);
+            return HP_ERR_ARG;
+        }
+    } else {
+        const EngBuffer& ob = e->bufs[po.out_buf];
+        if (ob.H != ib.H || ob.W != ib.W || (int)po.out_ch_off + G * cout_g > ob.channels) { set_error("engine: conv output buffer mismatch"); return HP_ERR_ARG; }
+        p.out = ob.d; p.out_ld = ob.channels; p.out_ch_off = (int)po.out_ch_off;
+    }
+    int rc = make_tmap_act(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, p.BH, p.BW);
+    if (rc) return rc;
+    rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
+    if (rc) return rc;
+    pl.smem = conv_smem_bytes(BN, p.num_stages);
+    pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
+    return HP_OK;
+}
+
+int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
+{
+    ConvPlan& pl = op.plan;
+    ConvParams p = pl.prm;
+    p.Nb = N;
+    const int n_tiles = N * p.tiles_h * p.tiles_w * p.groups * (p.cout_g_pad / p.BN);
+    const int grid = std::min(e->num_sms, n_tiles);
+    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, p);
+    e->launches++;
+    return HP_OK;
+}
+
+int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0, int last = -1)
+{
+    if (last < 0) last = (int)e->ops.size() - 1;
+    for (int oi = first; oi <= last; ++oi) {
+        EngOp& op = e->ops[oi];
+        const PackOp& po = op.po;
+        if (po.type == OP_IM2COL3) {
+            EngBuffer& ob = e->bufs[po.out_buf];
+            const size_t total = (size_t)N * ob.H * ob.W;
+            const int blocks = (int)((total + 255) / 256);
+            if (u8_input)
+                im2col3_kernel<true><<<blocks, 256, 0, st>>>(e->d_frames, ob.d, N, ob.H, ob.W, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2]);
+            else
+                im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, ob.H, ob.W, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2]);
+            e->launches++;
+        } else if (po.type == OP_MAXPOOL2) {
+            EngBuffer& ib = e->bufs[po.in_buf];
+            EngBuffer& ob = e->bufs[po.out_buf];
+            const int C = (int)po.cout_g;
+            const size_t total = (size_t)N * ob.H * ob.W * (C / 8);
+            maxpool2_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W);
+            e->launches++;
+        } else if (po.type == OP_CONV) {
+            launch_conv(e, op, N, st);
+        }
+    }
+    HP_CUDA_TRY(cudaGetLastError());
+    e->last_N = N;
+    return HP_OK;
+}
+
+void free_engine(hp_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& b : e->bufs) if (b.d) cudaFree(b.d);
+    for (auto& o : e->ops) {
+        if (o.plan.d_w) cudaFree(o.plan.d_w);
+        if (o.plan.d_bias) cudaFree(o.plan.d_bias);
+        if (o.plan.d_alpha) cudaFree(o.plan.d_alpha);
+    }
+    if (e->d_conf) cudaFree(e->d_conf);
+    if (e->d_paf) cudaFree(e->d_paf);
+    if (e->d_frames) cudaFree(e->d_frames);
+    if (e->d_input_f32) cudaFree(e->d_input_f32);
+    if (e->pin_frames) cudaFreeHost(e->pin_frames);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+} // namespace
+
+extern "C" {
+
+int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
+                     double factor, int flip_rgb, int device)
+{
+    if (!out || !pack) { set_error("hp_engine_create: null argument"); return HP_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("hp_engine_create: no CUDA device (this library has no CPU fallback)");
+        return HP_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev || in_w <= 0 || in_h <= 0 || max_batch <= 0) { set_error("hp_engine_create: bad device/size/batch"); return HP_ERR_ARG; }
+    if (pack_bytes < sizeof(PackHeader)) { set_error("hp_engine_create: pack too small"); return HP_ERR_ARG; }
+    PackHeader hdr;
+    memcpy(&hdr, pack, sizeof(hdr));
+    if (memcmp(hdr.magic, PACK_MAGIC, 8) != 0 || hdr.version != PACK_VERSION) { set_error("hp_engine_create: not an HPB2PACK v%u model pack", PACK_VERSION); return HP_ERR_ARG; }
+    const size_t need = sizeof(PackHeader) + hdr.n_buffers * sizeof(PackBuffer) + hdr.n_ops * sizeof(PackOp) + hdr.blob_floats * sizeof(float);
+    if (pack_bytes < need) { set_error("hp_engine_create: truncated pack (%zu < %zu bytes)", pack_bytes, need); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("hp_engine_create: device is sm_%d%d; this engine is tcgen05/TMA code for sm_100a only", prop.major, prop.minor); return HP_ERR_UNSUPPORTED; }
+
+    hp_engine* e = new hp_engine();
+    e->device = device; e->in_h = in_h; e->in_w = in_w; e->max_batch = max_batch;
+    e->factor = factor; e->flip_rgb = flip_rgb; e->hdr = hdr; e->num_sms = prop.multiProcessorCount;
+    const uint8_t* ptr = (const uint8_t*)pack + sizeof(PackHeader);
+    const PackBuffer* pb = (const PackBuffer*)ptr;
+    const PackOp* pops = (const PackOp*)(ptr + hdr.n_buffers * sizeof(PackBuffer));
+    std::vector<float> blob(hdr.blob_floats);
+    memcpy(blob.data(), (const uint8_t*)pops + hdr.n_ops * sizeof(PackOp), hdr.blob_floats * sizeof(float));
+
+    int rc = HP_OK;
+    auto fail = [&](int code) { free_engine(e); return code; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(HP_ERR_CUDA); }
+    e->bufs.resize(hdr.n_buffers);
+    for (uint32_t i = 0; i < hdr.n_buffers; ++i) {
+        EngBuffer& b = e->bufs[i];
+        b.channels = (int)pb[i].channels; b.down = (int)pb[i].down_shift;
+        b.H = in_h; b.W = in_w;
+        for (int d = 0; d < b.down; ++d) { b.H = (b.H + 1) / 2; b.W = (b.W + 1) / 2; }
+        if (b.channels % 8) { set_error("engine: buffer %u has %d channels (need a multiple of 8)", i, b.channels); return fail(HP_ERR_ARG); }
+        const size_t bytes = (size_t)max_batch * b.H * b.W * b.channels * sizeof(__half);
+        if (cudaMalloc(&b.d, bytes) != cudaSuccess) { set_error("engine: cudaMalloc(%zu) failed", bytes); return fail(HP_ERR_CUDA); }
+        cudaMemset(b.d, 0, bytes); // padding channels must read as zero
+    }
+    e->out_h = in_h; e->out_w = in_w;
+    for (uint32_t d = 0; d < hdr.out_down_shift; ++d) { e->out_h = (e->out_h + 1) / 2; e->out_w = (e->out_w + 1) / 2; }
+    if (cudaMalloc(&e->d_conf, (size_t)max_batch * hdr.conf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->d_paf, (size_t)max_batch * hdr.paf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&e->d_frames, (size_t)max_batch * in_h * in_w * 3) != cudaSuccess ||
+        cudaMallocHost(&e->pin_frames, (size_t)max_batch * in_h * in_w * 3) != cudaSuccess) {
+        set_error("engine: output/frame allocation failed");
+        return fail(HP_ERR_CUDA);
+    }
+    e->ops.resize(hdr.n_ops);
+    size_t max_smem = 0;
+    for (uint32_t i = 0; i < hdr.n_ops; ++i) {
+        e->ops[i].po = pops[i];
+        const PackOp& po = pops[i];
+        if ((po.type != OP_IM2COL3 && po.in_buf >= hdr.n_buffers) || (po.out_mode != OUT_F32_NCHW_SPLIT && po.out_buf >= hdr.n_buffers)) {
+            set_error("engine: op %u references a missing buffer", i);
+            return fail(HP_ERR_ARG);
+        }
+        if (po.type == OP_CONV) {
+            rc = build_conv_plan(e, e->ops[i], blob.data());
+            if (rc) return fail(rc);
+            max_smem = std::max(max_smem, e->ops[i].plan.smem);
+            e->flops_per_frame += e->ops[i].plan.flops_per_frame;
+        } else if (po.type == OP_IM2COL3) {
+            if (e->bufs[po.out_buf].channels != 64 || e->bufs[po.out_buf].down != 0) { set_error("engine: im2col buffer must be 64 channels at full resolution"); return fail(HP_ERR_ARG); }
+        } else if (po.type == OP_MAXPOOL2) {
+            if (po.cout_g % 8 || e->bufs[po.out_buf].down != e->bufs[po.in_buf].down + 1) { set_error("engine: bad maxpool op %u", i); return fail(HP_ERR_ARG); }
+        } else {
+            set_error("engine: unknown op type %u", po.type);
+            return fail(HP_ERR_UNSUPPORTED);
+        }
+    }
+    if (max_smem > 0 && cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
+        set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
+        return fail(HP_ERR_CUDA);
+    }
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    *out = e;
+    return HP_OK;
+}
+
+void hp_engine_destroy(hp_engine* e) { free_engine(e); }
+
+int hp_engine_info(const hp_engine* e, int* in_w, int* in_h, int* max_batch, int* c_conf, int* c_paf, int* out_h, int* out_w, double* flops_per_frame)
+{
+    if (!e) return HP_ERR_ARG;
+    if (in_w) *in_w = e->in_w;
+    if (in_h) *in_h = e->in_h;
+    if (max_batch) *max_batch = e->max_batch;
+    if (c_conf) *c_conf = (int)e->hdr.conf_channels;
+    if (c_paf) *c_paf = (int)e->hdr.paf_channels;
+    if (out_h) *out_h = e->out_h;
+    if (out_w) *out_w = e->out_w;
+    if (flops_per_frame) *flops_per_frame = e->flops_per_frame;
+    return HP_OK;
+}
+
+// frames: HOST u8 [N, in_h, in_w, 3] (already network-sized, BGR like cv::Mat).  Asynchronous on the engine stream.
+int hp_engine_infer_u8_host(hp_engine* e, const uint8_t* frames, int N)
+{
+    if (!e || !frames) { set_error("hp_engine_infer_u8_host: null argument"); return HP_ERR_ARG; }
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)N * e->in_h * e->in_w * 3;
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); // pin_frames may still feed the previous batch
+    memcpy(e->pin_frames, frames, bytes);
+    HP_CUDA_TRY(cudaMemcpyAsync(e->d_frames, e->pin_frames, bytes, cudaMemcpyHostToDevice, e->stream));
+    return run_graph(e, N, true, e->stream);
+}
+
+// frames: DEVICE u8 [N, in_h, in_w, 3]; stream: cudaStream_t or NULL for the engine's own stream.
+int hp_engine_infer_u8_device(hp_engine* e, const uint8_t* d_frames, int N, void* stream)
+{
+    if (!e || !d_frames) { set_error("hp_engine_infer_u8_device: null argument"); return HP_ERR_ARG; }
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    HP_CUDA_TRY(cudaMemcpyAsync(e->d_frames, d_frames, (size_t)N * e->in_h * e->in_w * 3, cudaMemcpyDeviceToDevice, st));
+    return run_graph(e, N, true, st);
+}
+
+// tensorrt::inference(const std::vector<float>&, size_t) (src/tensorrt.cpp:364): HOST f32 NCHW, already scaled.
+int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N)
+{
+    if (!e || !nchw) { set_error("hp_engine_infer_f32_host: null argument"); return HP_ERR_ARG; }
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t n = (size_t)e->max_batch * 3 * e->in_h * e->in_w;
+    if (!e->d_input_f32) HP_CUDA_TRY(cudaMalloc(&e->d_input_f32, n * sizeof(float)));
+    HP_CUDA_TRY(cudaMemcpyAsync(e->d_input_f32, nchw, (size_t)N * 3 * e->in_h * e->in_w * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    return run_graph(e, N, false, e->stream);
+}
+
+int hp_engine_outputs(hp_engine* e, const float** d_conf, const float** d_paf, void** stream)
+{
+    if (!e) return HP_ERR_ARG;
+    if (d_conf) *d_conf = e->d_conf;
+    if (d_paf) *d_paf = e->d_paf;
+    if (stream) *stream = (void*)e->stream;
+    return HP_OK;
+}
+
+// D2H of the last batch's outputs: conf[N,c_conf,h,w], paf[N,c_paf,h,w] (what tensorrt::inference returns per image)
+int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N)
+{
+    if (!e || N <= 0 || N > e->max_batch) { set_error("hp_engine_read_outputs_host: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t plane = (size_t)e->out_h * e->out_w;
+    if (conf) HP_CUDA_TRY(cudaMemcpyAsync(conf, e->d_conf, N * e->hdr.conf_channels * plane * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (paf) HP_CUDA_TRY(cudaMemcpyAsync(paf, e->d_paf, N * e->hdr.paf_channels * plane * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return HP_OK;
+}
+
+int hp_engine_sync(hp_engine* e)
+{
+    if (!e) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return HP_OK;
+}
+
+// test hook: copies activation buffer `buf` (fp16 NHWC, N frames) to the host
+int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int* H, int* W, int* C)
+{
+    if (!e || buf < 0 || buf >= (int)e->bufs.size()) { set_error("hp_engine_debug_read_buffer: bad buffer"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const EngBuffer& b = e->bufs[buf];
+    if (H) *H = b.H;
+    if (W) *W = b.W;
+    if (C) *C = b.channels;
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (out_f16) HP_CUDA_TRY(cudaMemcpy(out_f16, b.d, (size_t)N * b.H * b.W * b.channels * sizeof(__half), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+int hp_engine_debug_write_buffer(hp_engine* e, int buf, const void* in_f16, int N)
+{
+    if (!e || buf < 0 || buf >= (int)e->bufs.size() || !in_f16 || N <= 0 || N > e->max_batch) { set_error("hp_engine_debug_write_buffer: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const EngBuffer& b = e->bufs[buf];
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    HP_CUDA_TRY(cudaMemcpy(b.d, in_f16, (size_t)N * b.H * b.W * b.channels * sizeof(__half), cudaMemcpyHostToDevice));
+    return HP_OK;
+}
+
+int hp_engine_debug_run_ops(hp_engine* e, int first_op, int last_op, int N)
+{
+    if (!e || first_op < 0 || last_op >= (int)e->ops.size() || first_op > last_op || N <= 0 || N > e->max_batch) { set_error("hp_engine_debug_run_ops: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    int rc = run_graph(e, N, true, e->stream, first_op, last_op);
+    if (rc) return rc;
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return HP_OK;
+}
+
+long long hp_engine_launch_count(const hp_engine* e) { return e ? e->launches : 0; }
+
+// End-to-end pose call: HOST u8 frames -> humans on the host, one stream, tensors never leave the device in between
+// (operator API sequence engine.inference(batch) + parser.process(packet) per image,
+//  examples/operator_api_batched_images_paf.example.cpp:64-74).
+int hp_pose_run_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, hp_human* out, int cap, int* n_out)
+{
+    int rc = hp_engine_infer_u8_host(e, frames, N);
+    if (rc) return rc;
+    rc = hp_paf_process_device(parser, e->d_conf, e->d_paf, N, (int)e->hdr.conf_channels, (int)e->hdr.paf_channels, e->out_h, e->out_w, (void*)e->stream);
+    if (rc) return rc;
+    return hp_paf_fetch(parser, out, cap, n_out, N);
+}
+
+} // extern "C"

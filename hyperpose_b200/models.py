@@ -1,0 +1,210 @@
+"""Model graphs + the HPB2PACK writer (host-side logic; numpy only).
+
+The reference's C++ engine consumes .onnx/.uff/.trt files downloaded from Google Drive
+(scripts/downloader.py:11-21; none in the tree, no network).  This module rebuilds the same
+layer tables from the reference's Python model definitions and serialises them, together with
+seeded random-init weights, into the flat pack `hp_engine_create` loads
+(hyperpose_b200/csrc/pack_format.h).  A converter from real trained weights only has to fill
+`Graph.add_conv(..., weight=..., bias=..., alpha=...)` with the trained arrays.
+
+Graphs:
+  * openpose_vgg19  -- hyperpose/Model/backbones.py:447-509 (VGG-19 first 10 convs, 3 max-pools)
+                       + hyperpose/Model/openpose/model/openpose.py:36-47 (CPM 512->256->128),
+                       :119-154 (init stage), :156-199 (5 refinement stages, 7x7 convs, PReLU).
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+OP_IM2COL3, OP_CONV, OP_MAXPOOL2 = 1, 2, 3
+OUT_F16_NHWC, OUT_F32_NCHW_SPLIT = 0, 1
+PACK_MAGIC = b"HPB2PACK"
+PACK_VERSION = 1
+
+
+@dataclass
+class Op:
+    type: int
+    in_buf: int = 0
+    out_buf: int = 0
+    in_ch_off: int = 0
+    out_ch_off: int = 0
+    R: int = 1
+    S: int = 1
+    groups: int = 1
+    cin_g: int = 0
+    cout_g: int = 0
+    out_mode: int = OUT_F16_NHWC
+    split: int = 0
+    im2col_input: int = 0
+    weight: np.ndarray | None = None   # [G, cout_g, cin_g, R, S] float32
+    bias: np.ndarray | None = None     # [G*cout_g]
+    alpha: np.ndarray | None = None    # [G*cout_g]  PReLU slope; 0 = ReLU, 1 = linear
+    name: str = ""
+
+
+@dataclass
+class Graph:
+    name: str
+    conf_channels: int = 19
+    paf_channels: int = 38
+    out_down_shift: int = 3
+    mean: tuple = (0.0, 0.0, 0.0)
+    buffers: list = field(default_factory=list)   # (channels, down_shift)
+    ops: list = field(default_factory=list)
+
+    def add_buffer(self, channels: int, down_shift: int) -> int:
+        assert channels % 8 == 0
+        self.buffers.append((channels, down_shift))
+        return len(self.buffers) - 1
+
+    def add_im2col(self, out_buf: int, name="im2col") -> None:
+        self.ops.append(Op(OP_IM2COL3, out_buf=out_buf, name=name))
+
+    def add_maxpool(self, in_buf: int, out_buf: int, channels: int, name="pool") -> None:
+        self.ops.append(Op(OP_MAXPOOL2, in_buf=in_buf, out_buf=out_buf, cout_g=channels, name=name))
+
+    def add_conv(self, in_buf, out_buf, weight, bias, alpha, in_ch_off=0, out_ch_off=0, out_mode=OUT_F16_NHWC, split=0,
+                 im2col_input=0, name="conv") -> None:
+        G, cout_g, cin_g, R, S = weight.shape
+        self.ops.append(Op(OP_CONV, in_buf, out_buf, in_ch_off, out_ch_off, R, S, G, cin_g, cout_g, out_mode, split, im2col_input,
+                           np.ascontiguousarray(weight, np.float32), np.ascontiguousarray(bias, np.float32).reshape(-1),
+                           np.ascontiguousarray(alpha, np.float32).reshape(-1), name))
+
+    # ---- serialisation (layout of pack_format.h) ----
+    def to_pack(self) -> bytes:
+        blob = []
+        off = 0
+        op_recs = []
+        for op in self.ops:
+            w_off = b_off = a_off = 0
+            if op.type == OP_CONV:
+                w_off = off; blob.append(op.weight.reshape(-1)); off += op.weight.size
+                b_off = off; blob.append(op.bias); off += op.bias.size
+                a_off = off; blob.append(op.alpha); off += op.alpha.size
+            op_recs.append(struct.pack("<14I3Q", op.type, op.in_buf, op.out_buf, op.in_ch_off, op.out_ch_off, op.R, op.S, op.groups,
+                                       op.cin_g, op.cout_g, op.out_mode, op.split, op.im2col_input, 0, w_off, b_off, a_off))
+        blob_arr = np.concatenate(blob).astype("<f4") if blob else np.zeros(0, "<f4")
+        hdr = struct.pack("<8s6I3f5IQ", PACK_MAGIC, PACK_VERSION, len(self.buffers), len(self.ops), self.conf_channels,
+                          self.paf_channels, self.out_down_shift, *[float(m) for m in self.mean], 0, 0, 0, 0, 0, blob_arr.size)
+        bufs = b"".join(struct.pack("<2I", c, d) for c, d in self.buffers)
+        return hdr + bufs + b"".join(op_recs) + blob_arr.tobytes()
+
+    def flops_per_frame(self, in_h: int, in_w: int) -> float:
+        total = 0.0
+        for op in self.ops:
+            if op.type != OP_CONV:
+                continue
+            _, d = self.buffers[op.in_buf]
+            h, w = in_h, in_w
+            for _ in range(d):
+                h, w = (h + 1) // 2, (w + 1) // 2
+            total += 2.0 * h * w * op.groups * op.cout_g * op.cin_g * op.R * op.S
+        return total
+
+
+def _he(rng, G, cout, cin, R, S, gain=2.0):
+    std = np.sqrt(gain / (cin * R * S))
+    return (rng.standard_normal((G, cout, cin, R, S)) * std).astype(np.float32)
+
+
+def _block_diag(w_a: np.ndarray, w_b: np.ndarray) -> np.ndarray:
+    """two [1,co,ci,R,S] branch weights -> one dense [1, co_a+co_b, ci_a+ci_b, R, S] block-diagonal conv"""
+    _, ca, ia, R, S = w_a.shape
+    _, cb, ib, _, _ = w_b.shape
+    w = np.zeros((1, ca + cb, ia + ib, R, S), np.float32)
+    w[0, :ca, :ia] = w_a[0]
+    w[0, ca:, ia:] = w_b[0]
+    return w
+
+
+def openpose_vgg19(seed: int = 0, n_stages: int = 6) -> Graph:
+    """OpenPose-COCO on VGG-19 (BASELINE.json config 3).  Random-init weights (He-normal, seeded).
+
+    Both branches of a stage (conf: L2, paf: L1) are executed together: their first layers share the
+    input and are merged into one conv (cout 256); later layers run as a 2-group conv; the two 1x1
+    output convs are fused into one block-diagonal conv writing [conf | paf] straight into the next
+    stage's concat buffer (openpose.py:74: concat([features, conf, paf])).
+    """
+    rng = np.random.default_rng(seed)
+    g = Graph("openpose_vgg19", 19, 38, 3, mean=tuple(np.array([103.939, 116.779, 123.68]) / 255.0))  # backbones.py:455
+    relu = lambda n: np.zeros(n, np.float32)
+    prelu = lambda n: rng.uniform(0.1, 0.4, n).astype(np.float32)
+    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    # ---- VGG-19 front (backbones.py:461-476) ----
+    b_col = g.add_buffer(64, 0)
+    g.add_im2col(b_col)
+    cur = g.add_buffer(64, 0)
+    g.add_conv(b_col, cur, _he(rng, 1, 64, 3, 3, 3), b_(64), relu(64), im2col_input=1, name="conv1_1")
+    nxt = g.add_buffer(64, 0)
+    g.add_conv(cur, nxt, _he(rng, 1, 64, 64, 3, 3), b_(64), relu(64), name="conv1_2")
+    cur = g.add_buffer(64, 1); g.add_maxpool(nxt, cur, 64, "maxpool_1")
+    for i, (ci, co) in enumerate([(64, 128), (128, 128)]):
+        nxt = g.add_buffer(co, 1); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv2_{i+1}"); cur = nxt
+    nxt = g.add_buffer(128, 2); g.add_maxpool(cur, nxt, 128, "maxpool_2"); cur = nxt
+    for i, (ci, co) in enumerate([(128, 256), (256, 256), (256, 256), (256, 256)]):
+        nxt = g.add_buffer(co, 2); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv3_{i+1}"); cur = nxt
+    nxt = g.add_buffer(256, 3); g.add_maxpool(cur, nxt, 256, "maxpool_3"); cur = nxt
+    for i, (ci, co) in enumerate([(256, 512), (512, 512)]):
+        nxt = g.add_buffer(co, 3); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv4_{i+1}"); cur = nxt
+    # ---- CPM (openpose.py:36-39) ----
+    nxt = g.add_buffer(256, 3); g.add_conv(cur, nxt, _he(rng, 1, 256, 512, 3, 3), b_(256), relu(256), name="cpm_1"); cur = nxt
+    cat = g.add_buffer(192, 3)   # [features 128 | conf 19 | paf 38 | 7 zero pad]: the refinement stages' input
+    g.add_conv(cur, cat, _he(rng, 1, 128, 256, 3, 3), b_(128), relu(128), name="cpm_2")
+    ta = g.add_buffer(256, 3)
+    tb = g.add_buffer(256, 3)
+    wide = g.add_buffer(1024, 3)
+
+    def out_conv(in_buf, cin_each, last, name):
+        w = _block_diag(_he(rng, 1, 19, cin_each, 1, 1, 1.0), _he(rng, 1, 38, cin_each, 1, 1, 1.0))
+        if last:
+            g.add_conv(in_buf, 0, w, b_(57), prelu(57), out_mode=OUT_F32_NCHW_SPLIT, split=19, name=name)
+        else:
+            g.add_conv(in_buf, cat, w, b_(57), prelu(57), out_ch_off=128, name=name)
+
+    # ---- init stage (openpose.py:119-154): 3x(3x3,128) + 1x1x512 + 1x1x{19,38}, PReLU after every conv ----
+    w0 = np.concatenate([_he(rng, 1, 128, 128, 3, 3), _he(rng, 1, 128, 128, 3, 3)], axis=1)
+    g.add_conv(cat, ta, w0, b_(256), prelu(256), name="init_1")
+    g.add_conv(ta, tb, _he(rng, 2, 128, 128, 3, 3), b_(256), prelu(256), name="init_2")
+    g.add_conv(tb, ta, _he(rng, 2, 128, 128, 3, 3), b_(256), prelu(256), name="init_3")
+    g.add_conv(ta, wide, _he(rng, 2, 512, 128, 1, 1), b_(1024), prelu(1024), name="init_4")
+    out_conv(wide, 512, n_stages == 1, "init_out")
+    # ---- refinement stages (openpose.py:156-199): 5x(7x7,128) + 1x1x128 + 1x1x{19,38} ----
+    for s in range(1, n_stages):
+        w0 = np.concatenate([_he(rng, 1, 128, 185, 7, 7), _he(rng, 1, 128, 185, 7, 7)], axis=1)
+        g.add_conv(cat, ta, w0, b_(256), prelu(256), name=f"ref{s}_1")
+        src, dst = ta, tb
+        for k in range(2, 6):
+            g.add_conv(src, dst, _he(rng, 2, 128, 128, 7, 7), b_(256), prelu(256), name=f"ref{s}_{k}")
+            src, dst = dst, src
+        g.add_conv(src, dst, _he(rng, 2, 128, 128, 1, 1), b_(256), prelu(256), name=f"ref{s}_6")
+        out_conv(dst, 128, s == n_stages - 1, f"ref{s}_out")
+    return g
+
+
+def tiny_test_net(seed: int = 0) -> Graph:
+    """small graph exercising every op type / conv variant (tests only need seconds):
+    im2col conv, 3x3, maxpool, merged + grouped 7x7, 185->192 padded input, block-diagonal split output."""
+    rng = np.random.default_rng(seed)
+    g = Graph("tiny", 19, 38, 1, mean=(0.4, 0.45, 0.5))
+    relu = lambda n: np.zeros(n, np.float32)
+    prelu = lambda n: rng.uniform(0.1, 0.4, n).astype(np.float32)
+    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
+    b0 = g.add_buffer(64, 0); g.add_im2col(b0)
+    b1 = g.add_buffer(64, 0); g.add_conv(b0, b1, _he(rng, 1, 64, 3, 3, 3), b_(64), relu(64), im2col_input=1, name="c1")
+    b2 = g.add_buffer(64, 1); g.add_maxpool(b1, b2, 64)
+    cat = g.add_buffer(192, 1)
+    g.add_conv(b2, cat, _he(rng, 1, 128, 64, 3, 3), b_(128), relu(128), name="c2")
+    ta = g.add_buffer(256, 1); tb = g.add_buffer(256, 1)
+    w = _block_diag(_he(rng, 1, 19, 128, 1, 1, 1.0), _he(rng, 1, 38, 128, 1, 1, 1.0))
+    g.add_conv(cat, ta, np.concatenate([_he(rng, 1, 128, 128, 3, 3), _he(rng, 1, 128, 128, 3, 3)], axis=1), b_(256), prelu(256), name="m1")
+    g.add_conv(ta, cat, w, b_(57), prelu(57), out_ch_off=128, name="o1")
+    g.add_conv(cat, ta, np.concatenate([_he(rng, 1, 128, 185, 7, 7), _he(rng, 1, 128, 185, 7, 7)], axis=1), b_(256), prelu(256), name="r1")
+    g.add_conv(ta, tb, _he(rng, 2, 128, 128, 7, 7), b_(256), prelu(256), name="r2")
+    g.add_conv(tb, ta, _he(rng, 2, 128, 128, 1, 1), b_(256), prelu(256), name="r3")
+    g.add_conv(ta, 0, w.copy(), b_(57), prelu(57), out_mode=OUT_F32_NCHW_SPLIT, split=19, name="out")
+    return g

@@ -101,6 +101,44 @@ int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* o
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long hp_paf_launch_count(const hp_paf* p);
 
+/* ------------------------------------------------------------------------------------------
+ * DNN engine -- replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
+ * src/tensorrt.cpp:121-471).  The model file is a flat "HPB2PACK" pack (hyperpose_b200/csrc/pack_format.h,
+ * written by hyperpose_b200/models.py) instead of .onnx/.uff/.trt (utility/model.hpp:13-32).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hp_engine hp_engine;
+
+/* tensorrt::tensorrt(model, input_size(w,h), max_batch_size, keep_ratio, dtype, factor, flip_rgb)
+ * (tensorrt.hpp:44-74).  pack/pack_bytes: model pack image in host memory. */
+int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
+                     double factor, int flip_rgb, int device);
+void hp_engine_destroy(hp_engine* e);
+/* max_batch_size() / input_size() (tensorrt.hpp:81-85) + output geometry; any pointer may be NULL */
+int hp_engine_info(const hp_engine* e, int* in_w, int* in_h, int* max_batch, int* c_conf, int* c_paf, int* out_h, int* out_w,
+                   double* flops_per_frame);
+/* tensorrt::inference(std::vector<cv::Mat>) (tensorrt.cpp:436-461) after the resize step: HOST u8
+ * [N,in_h,in_w,3] BGR frames.  N > max_batch -> HP_ERR_BATCH (std::logic_error in the reference).
+ * Asynchronous: outputs stay on the device (hp_engine_outputs / hp_engine_read_outputs_host). */
+int hp_engine_infer_u8_host(hp_engine* e, const uint8_t* frames, int N);
+int hp_engine_infer_u8_device(hp_engine* e, const uint8_t* d_frames, int N, void* stream);
+/* tensorrt::inference(const std::vector<float>&, size_t) (tensorrt.cpp:364-434): HOST f32 NCHW, pre-scaled */
+int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N);
+/* device pointers of the fp32 NCHW outputs conf[N,c_conf,h,w] / paf[N,c_paf,h,w] and the engine stream */
+int hp_engine_outputs(hp_engine* e, const float** d_conf, const float** d_paf, void** stream);
+/* the reference's per-image D2H of every output (tensorrt.cpp:398-431), as two contiguous host tensors */
+int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N);
+int hp_engine_sync(hp_engine* e);
+long long hp_engine_launch_count(const hp_engine* e);
+/* test hooks: read / write an activation buffer (fp16 NHWC), run a sub-range [first,last] of the op list */
+int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int* H, int* W, int* C);
+int hp_engine_debug_write_buffer(hp_engine* e, int buf, const void* in_f16, int N);
+int hp_engine_debug_run_ops(hp_engine* e, int first_op, int last_op, int N);
+
+/* engine.inference(batch) + parser.process(packet) for every image of the batch
+ * (examples/operator_api_batched_images_paf.example.cpp:64-74) as ONE call: host u8 frames in,
+ * human_t records out, conf/paf never leave the device. */
+int hp_pose_run_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, hp_human* out, int cap, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,51 @@
+"""Plain PyTorch reference executor for hyperpose_b200.models.Graph (tests only).
+
+The backbone is a floating-point kernel, so its checker is a torch fp32 reference of the same ops
+(F.conv2d / max_pool2d / PReLU), as the reference's TensorRT FP32 engine would compute them.
+`emulate_fp16=True` additionally rounds weights and stored activations to fp16 exactly where the
+engine does (fp16 operands, fp32 accumulation), which isolates kernel bugs from precision."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from hyperpose_b200 import models
+
+
+def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb=True, emulate_fp16=False, device="cuda",
+              upto=None):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, H, W, _ = frames_u8.shape
+    q = (lambda t: t.half().float()) if emulate_fp16 else (lambda t: t)
+    bufs = []
+    for (c, d) in g.buffers:
+        h, w = H, W
+        for _ in range(d):
+            h, w = (h + 1) // 2, (w + 1) // 2
+        bufs.append(torch.zeros(N, c, h, w, device=device))
+    conf = paf = None
+    for oi, op in enumerate(g.ops):
+        if upto is not None and oi > upto:
+            break
+        if op.type == models.OP_IM2COL3:
+            x = (frames_u8.astype(np.float64) * factor).astype(np.float32)          # data.cpp:48
+            if flip_rgb:
+                x = x[..., ::-1]
+            x = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2))).to(device)
+            x = x - torch.tensor(g.mean, dtype=torch.float32, device=device).view(1, 3, 1, 1)
+            bufs[op.out_buf][:, :3] = q(x)
+        elif op.type == models.OP_MAXPOOL2:
+            x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + op.cout_g]
+            bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + op.cout_g] = F.max_pool2d(x, 2, 2, ceil_mode=True)
+        elif op.type == models.OP_CONV:
+            G, co, ci, R, S = op.weight.shape
+            x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + G * ci]
+            w = q(torch.from_numpy(op.weight.reshape(G * co, ci, R, S)).to(device))
+            y = F.conv2d(x, w, torch.from_numpy(op.bias).to(device), padding=(R // 2, S // 2), groups=G)
+            a = torch.from_numpy(op.alpha).to(device).view(1, -1, 1, 1)
+            y = torch.where(y > 0, y, y * a)
+            if op.out_mode == models.OUT_F32_NCHW_SPLIT:
+                conf, paf = y[:, :op.split].contiguous(), y[:, op.split:].contiguous()
+            else:
+                bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + G * co] = q(y)
+    return conf, paf, bufs
