@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s end-to-end (conv + PAF parse), OpenPose-COCO VGG-19 368x656, batch 16 per GPU.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU parser (oracle/_ref) on the host cores
+
+One "step" = one pass of the hot path over one batch of 16 synthetic frames per GPU (weak scaling:
+frames shard across GPUs): frame pre-processing + every conv of OpenPose-VGG19 (random-init
+weights of the real architecture) + the PAF parse of the batch (+ for N>1 the NCCL gather of the
+keypoint records to rank 0).  Because random weights give structureless heat-maps, seeded synthetic
+crowd tensors are copied over the backbone's outputs after the last conv (hp_engine_set_output_override,
+SURVEY 8d) -- all conv work is still executed; this is stated in config.parse_input.
+
+  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather)
+  e2e   : the public host call hp_pose_run_u8_host -- pinned host frames H2D, human_t records D2H, every step
+  roofline : the conv kernel (dominant): algorithmic FLOPs / CUDA-event time of the conv launches, measured in
+             the timed region on the launching stream, vs the measured cuBLAS bf16 peak
+  cpu_baseline : the reference's CPU parser timed on this host (parse stage only: the reference never runs
+             the convs on a CPU; its engine is TensorRT)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IN_H, IN_W = 368, 656
+HF, WF = 46, 82
+BATCH = 16
+PERSONS = (10, 20)                   # synthetic crowd per frame (SURVEY 8d cfg4 recipe on cfg3 geometry)
+ALGO_FLOPS_PER_FRAME = 484.6e9       # OpenPose-VGG19 (6 stages) @368x656, 2*MAC
+N_INPUT_SETS = 12                    # 12 x 11.6 MB of distinct frames > 126 MB L2
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def crowd_tensors(seed: int):
+    from hyperpose_b200 import synthetic as syn
+    return syn.make_batch_tensors(seed, BATCH, PERSONS, HF, WF)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own src/paf.cpp (oracle/_ref) or the oracle port, parse stage only
+# ------------------------------------------------------------------------------------------------
+def cpu_parse_rate(conf, paf, seconds: float, threads: int):
+    """frames/s of the CPU parser on the host cores; one parser replica per thread, frames round-robin
+    (the reference's stream API does exactly this: stream.hpp:139,365-373)."""
+    import oracle
+    kind = "reference" if oracle.ref_available() else "port"
+    n = conf.shape[0]
+    counts = [0] * threads
+    stop = time.time() + seconds
+
+    def work(t):
+        if kind == "reference":
+            rp = oracle.RefParser()
+            fn = lambda i: rp.process(conf[i], paf[i])
+        else:
+            fn = lambda i: oracle.oracle_process(conf[i], paf[i])
+        i = t
+        fn(i % n)  # first call allocates (paf.cpp:321-332): not timed
+        t0 = time.time()
+        while time.time() < stop:
+            fn(i % n)
+            i += threads
+            counts[t] += 1
+        return time.time() - t0
+
+    t_start = time.time()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = time.time() - t_start
+    return sum(counts) / max(wall, 1e-9), kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this host.  Only the PAF parse can run
+    (its convs are TensorRT-on-GPU, src/tensorrt.cpp:387-396, not buildable here); each step parses one 16-frame
+    batch of the arm's synthetic workload with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    conf, paf = crowd_tensors(1000)
+    cores = os.cpu_count() or 1
+    threads = min(cores, BATCH)
+    kind = "reference" if oracle.ref_available() else "port"
+    parsers = [oracle.RefParser() if kind == "reference" else None for _ in range(threads)]
+
+    def step():
+        def work(t):
+            for i in range(t, BATCH, threads):
+                if kind == "reference":
+                    parsers[t].process(conf[i], paf[i])
+                else:
+                    oracle.oracle_process(conf[i], paf[i])
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for th in ths: th.start()
+        for th in ths: th.join()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    fps = BATCH * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "frames/sec end-to-end (conv+PAF parse) OpenPose-COCO 368x656", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: OpenPose-COCO VGG-19 368x656 batch 16 -- PAF parse stage only (reference convs are TensorRT, not runnable on CPU)",
+                   "frames_per_step": BATCH, "persons_per_frame": list(PERSONS)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} x 16 synthetic 46x82 crowd frames, parse stage only, {threads} threads of {cores} host cores"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hyperpose_b200 import capi, models, synthetic as syn
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    graph = models.openpose_vgg19(seed=0)
+    pack = graph.to_pack()
+    engine = capi.Engine(pack, (IN_W, IN_H), max_batch_size=BATCH, device=local_rank)
+    del pack
+    parser = capi.PafParser(0.05, 0.05, device=local_rank)
+    HCAP = 64
+    parser.set_capacity(peaks_per_part=128, candidates_per_limb=2048, humans=HCAP)
+
+    # inputs: N_INPUT_SETS distinct batches of frames (device + pinned host), one set of crowd tensors per rank
+    rng_seed = 2 + 1000 * rank
+    frames_host = [torch.from_numpy(syn.make_frames_u8(rng_seed + i, BATCH, IN_H, IN_W)).pin_memory() for i in range(N_INPUT_SETS)]
+    frames_dev = [f.to(dev) for f in frames_host]
+    conf_np, paf_np = crowd_tensors(1000 + rank)
+    d_conf = torch.from_numpy(conf_np).to(dev)
+    d_paf = torch.from_numpy(paf_np).to(dev)
+    engine.set_output_override(d_conf.data_ptr(), d_paf.data_ptr())
+    out_conf_ptr, out_paf_ptr, _ = engine.device_outputs()
+
+    st = torch.cuda.Stream(device=dev)
+    rec_bytes = capi.HUMAN_DT.itemsize
+    res_humans = torch.zeros(BATCH * HCAP * rec_bytes, dtype=torch.uint8, device=dev)
+    res_counts = torch.zeros(BATCH, dtype=torch.int32, device=dev)
+    if world > 1:
+        gather_h = torch.zeros(world * res_humans.numel(), dtype=torch.uint8, device=dev)
+        gather_c = torch.zeros(world * BATCH, dtype=torch.int32, device=dev)
+
+    def gather_results():
+        parser.copy_results_device(res_humans.data_ptr(), res_counts.data_ptr(), BATCH, HCAP, st.cuda_stream)
+        if world > 1:
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(gather_h, res_humans)
+                dist.all_gather_into_tensor(gather_c, res_counts)
+
+    def step_device(i):
+        engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
+        parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
+        gather_results()
+
+    def step_host(i):
+        humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
+        if world > 1:
+            gather_results()
+            st.synchronize()
+        return humans
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = engine.launch_count + parser.launch_count
+        if profile:
+            engine.set_profiling(True)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        t0 = time.time()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(st)
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        ms_dev = e0.elapsed_time(e1)
+        if profile:
+            engine.set_profiling(False)
+        launches = engine.launch_count + parser.launch_count - l0
+        barrier()
+        ms = max(ms_dev, 0.0)
+        # host-synchronous paths are bounded by wall clock, device-async ones by the stream events: take the larger
+        ms = max(ms, wall * 1e3) if fn is step_host else ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    # sanity: the device path and the host path agree with each other before anything is timed
+    step_device(0)
+    torch.cuda.synchronize()
+    ref_h = parser.fetch(BATCH, cap=HCAP)
+    host_h = step_host(0)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(ref_h, host_h)), "device and host paths disagree"
+    n_humans = sum(len(h) for h in host_h)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_device, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    prof_ms, prof_ty, prof_fl, prof_runs = engine.get_profile()
+    ms_e2e, _ = timed(step_host, max(3, args.steps // 2), max(3, args.warmup))
+    e2e_steps = max(3, args.steps // 2)
+
+    frames_total = world * BATCH * args.steps
+    value = frames_total / (ms_total / 1e3)
+    e2e_value = world * BATCH * e2e_steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        conv_ms = float(prof_ms[prof_ty == models.OP_CONV].sum())
+        other_ms = float(prof_ms[prof_ty != models.OP_CONV].sum())
+        n_conv = int((prof_ty == models.OP_CONV).sum())
+        algo_flops = ALGO_FLOPS_PER_FRAME * BATCH
+        achieved = algo_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+            except Exception:
+                traffic = None
+        # bounded CPU baseline (rank 0, N=1 only): ~12 s of the reference parser on the host cores
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            threads = min(cores, BATCH)
+            rate, kind = cpu_parse_rate(conf_np, paf_np, 12.0, threads)
+            cpu = {"value": rate, "unit": "frames/s", "cores": threads, "kind": kind,
+                   "sample": f"12 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's 16 synthetic 46x82 crowd frames, "
+                             f"{threads} threads of {cores} host cores; parse stage only (reference convs are TensorRT, no CPU path)"}
+        layers = [{"op": i, "name": graph.ops[i].name, "type": int(prof_ty[i]), "ms": float(prof_ms[i]),
+                   "tflops": (float(prof_fl[i]) * BATCH / (prof_ms[i] / 1e3) / 1e12 if prof_ms[i] > 0 and prof_fl[i] > 0 else None)}
+                  for i in range(len(prof_ms))]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_layers_n{world}.json"), "w") as f:
+            json.dump({"ms_per_step": ms_total / args.steps, "conv_ms": conv_ms, "other_engine_ms": other_ms, "profiled_runs": prof_runs, "layers": layers}, f, indent=1)
+        h2d = BATCH * IN_H * IN_W * 3
+        d2h = BATCH * HCAP * rec_bytes + BATCH * 8
+        line = {
+            "metric": "frames/sec end-to-end (conv+PAF parse) OpenPose-COCO 368x656", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate (conv); f32/f64 (parse)", "data": "synthetic",
+            "config": {"workload": "cfg3: OpenPose-COCO VGG-19 368x656, batch 16 per GPU, frame-sharded",
+                       "global_batch": world * BATCH, "input": "u8 frames 368x656x3, random (default_rng)",
+                       "weights": "random-init (He-normal, seed 0) of the reference architecture (484.6 GFLOP/frame)",
+                       "parse_input": f"synthetic crowd tensors ({PERSONS[0]}-{PERSONS[1]} persons/frame, {n_humans} humans/batch) copied over the conv outputs after the last conv",
+                       "l2": f"{N_INPUT_SETS} distinct input batches rotated ({N_INPUT_SETS * BATCH * IN_H * IN_W * 3 / 1e6:.0f} MB > L2); activations (>1 GB/step) stream through",
+                       "parallelism": f"dp{world} (frames shard; NCCL all-gather of keypoint records only)" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "hp_pose_run_u8_host (pinned host frames in, human_t records out, synchronous per batch)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "kernel": "conv_tcgen05_kernel", "launches_per_step": n_conv,
+                         "algorithmic_flops_per_step": algo_flops, "kernel_ms_per_step": conv_ms,
+                         "kernel_share_of_step": conv_ms / (ms_total / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    engine.close()
+    parser.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

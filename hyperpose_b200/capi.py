@@ -29,7 +29,7 @@ EXPORTS = [
     "hp_last_error", "hp_device_count", "hp_version",
     "hp_paf_create", "hp_paf_destroy", "hp_paf_set_conf_thresh", "hp_paf_set_paf_thresh", "hp_paf_set_capacity",
     "hp_paf_process_host", "hp_paf_process_host_batched", "hp_paf_process_device", "hp_paf_fetch",
-    "hp_paf_debug_peaks", "hp_paf_debug_connections", "hp_paf_launch_count",
+    "hp_paf_debug_peaks", "hp_paf_debug_connections", "hp_paf_launch_count", "hp_paf_copy_results_device",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
         L.hp_paf_debug_connections.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, ip]
         L.hp_paf_launch_count.argtypes = [vp]
         L.hp_paf_launch_count.restype = C.c_longlong
+        L.hp_paf_copy_results_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -152,6 +153,9 @@ class PafParser:
     def launch_count(self) -> int:
         return int(lib().hp_paf_launch_count(self._h))
 
+    def copy_results_device(self, d_humans_ptr: int, d_counts_ptr: int, N: int, cap: int, stream: int = 0):
+        check(lib().hp_paf_copy_results_device(self._h, d_humans_ptr, d_counts_ptr, N, cap, stream))
+
 
 # ---------------------------------------------------------------------------------------------
 # DNN engine
@@ -160,7 +164,7 @@ EXPORTS += [
     "hp_engine_create", "hp_engine_destroy", "hp_engine_info", "hp_engine_infer_u8_host", "hp_engine_infer_u8_device",
     "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_sync",
     "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
-    "hp_pose_run_u8_host",
+    "hp_pose_run_u8_host", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
 ]
 
 
@@ -182,6 +186,9 @@ def _bind_engine(L):
     L.hp_engine_debug_write_buffer.argtypes = [vp, C.c_int, vp, C.c_int]
     L.hp_engine_debug_run_ops.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.hp_pose_run_u8_host.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, ip]
+    L.hp_engine_set_output_override.argtypes = [vp, vp, vp]
+    L.hp_engine_set_profiling.argtypes = [vp, C.c_int]
+    L.hp_engine_get_profile.argtypes = [vp, vp, vp, vp, C.c_int, ip, C.POINTER(C.c_longlong)]
 
 
 class Engine:
@@ -275,6 +282,20 @@ class Engine:
 
     def debug_run_ops(self, first: int, last: int, n: int):
         check(lib().hp_engine_debug_run_ops(self._h, first, last, n))
+
+    def set_output_override(self, d_conf_ptr: int, d_paf_ptr: int):
+        check(lib().hp_engine_set_output_override(self._h, d_conf_ptr, d_paf_ptr))
+
+    def set_profiling(self, enable: bool):
+        check(lib().hp_engine_set_profiling(self._h, 1 if enable else 0))
+
+    def get_profile(self):
+        """-> (ms_per_op[n], op_type[n], flops_per_frame_per_op[n], runs)"""
+        cap = 1024
+        ms = np.zeros(cap, np.float64); ty = np.zeros(cap, np.int32); fl = np.zeros(cap, np.float64)
+        n, runs = C.c_int(), C.c_longlong()
+        check(lib().hp_engine_get_profile(self._h, ms.ctypes.data, ty.ctypes.data, fl.ctypes.data, cap, C.byref(n), C.byref(runs)))
+        return ms[:n.value], ty[:n.value], fl[:n.value], runs.value
 
     def run_pose(self, parser: "PafParser", frames: np.ndarray, cap: int = 128):
         """hp_pose_run_u8_host: frames in, humans out (list of N structured arrays)."""

@@ -216,6 +216,15 @@ struct hp_engine {
     long long launches = 0;
     double flops_per_frame = 0;
     int last_N = 0;
+    // benchmark hook: synthetic conf/paf copied over the outputs after the last conv
+    const float* override_conf = nullptr;
+    const float* override_paf = nullptr;
+    // per-op CUDA-event profiling (bench.py roofline leg)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;       // n_ops + 1 events
+    std::vector<double> op_ms_sum;     // accumulated per op
+    long long profiled_runs = 0;
+    bool ev_pending = false;
 };
 
 namespace {
@@ -312,9 +321,26 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     return HP_OK;
 }
 
+void collect_profile(hp_engine* e)
+{
+    if (!e->ev_pending) return;
+    cudaEventSynchronize(e->ev.back());
+    for (size_t i = 0; i + 1 < e->ev.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->op_ms_sum[i] += ms;
+    }
+    e->profiled_runs++;
+    e->ev_pending = false;
+}
+
 int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0, int last = -1)
 {
     if (last < 0) last = (int)e->ops.size() - 1;
+    const bool prof = e->profiling && first == 0 && last == (int)e->ops.size() - 1;
+    if (prof) {
+        collect_profile(e); // folds the previous run's events in (synchronises on its last event only)
+        cudaEventRecord(e->ev[0], st);
+    }
     for (int oi = first; oi <= last; ++oi) {
         EngOp& op = e->ops[oi];
         const PackOp& po = op.po;
@@ -337,6 +363,13 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
         } else if (po.type == OP_CONV) {
             launch_conv(e, op, N, st);
         }
+        if (prof) cudaEventRecord(e->ev[oi + 1], st);
+    }
+    if (prof) e->ev_pending = true;
+    if (e->override_conf && e->override_paf && last == (int)e->ops.size() - 1) {
+        const size_t plane = (size_t)e->out_h * e->out_w;
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_conf, e->override_conf, N * e->hdr.conf_channels * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_paf, e->override_paf, N * e->hdr.paf_channels * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     HP_CUDA_TRY(cudaGetLastError());
     e->last_N = N;
@@ -359,6 +392,7 @@ void free_engine(hp_engine* e)
     if (e->d_frames) cudaFree(e->d_frames);
     if (e->d_input_f32) cudaFree(e->d_input_f32);
     if (e->pin_frames) cudaFreeHost(e->pin_frames);
+    for (auto& ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -477,9 +511,16 @@ int hp_engine_infer_u8_host(hp_engine* e, const uint8_t* frames, int N)
     if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
     HP_CUDA_TRY(cudaSetDevice(e->device));
     const size_t bytes = (size_t)N * e->in_h * e->in_w * 3;
-    HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); // pin_frames may still feed the previous batch
-    memcpy(e->pin_frames, frames, bytes);
-    HP_CUDA_TRY(cudaMemcpyAsync(e->d_frames, e->pin_frames, bytes, cudaMemcpyHostToDevice, e->stream));
+    cudaPointerAttributes attr;
+    const bool pinned = (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+    if (!pinned) cudaGetLastError();
+    if (pinned) { // page-locked caller memory: DMA straight from it
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_frames, frames, bytes, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); // pin_frames may still feed the previous batch
+        memcpy(e->pin_frames, frames, bytes);
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_frames, e->pin_frames, bytes, cudaMemcpyHostToDevice, e->stream));
+    }
     return run_graph(e, N, true, e->stream);
 }
 
@@ -570,6 +611,50 @@ int hp_engine_debug_run_ops(hp_engine* e, int first_op, int last_op, int N)
 }
 
 long long hp_engine_launch_count(const hp_engine* e) { return e ? e->launches : 0; }
+
+int hp_engine_set_output_override(hp_engine* e, const float* d_conf, const float* d_paf)
+{
+    if (!e) return HP_ERR_ARG;
+    e->override_conf = d_conf;
+    e->override_paf = d_paf;
+    return HP_OK;
+}
+
+int hp_engine_set_profiling(hp_engine* e, int enable)
+{
+    if (!e) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    if (enable && e->ev.empty()) {
+        e->ev.resize(e->ops.size() + 1);
+        for (auto& ev : e->ev) HP_CUDA_TRY(cudaEventCreate(&ev));
+    }
+    if (enable) {
+        e->op_ms_sum.assign(e->ops.size(), 0.0);
+        e->profiled_runs = 0;
+        e->ev_pending = false;
+    } else {
+        collect_profile(e);
+    }
+    e->profiling = enable != 0;
+    return HP_OK;
+}
+
+int hp_engine_get_profile(hp_engine* e, double* ms_per_op, int* op_type, double* flops_per_op, int cap, int* n_ops, long long* runs)
+{
+    if (!e) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    collect_profile(e);
+    const int n = (int)e->ops.size();
+    if (n_ops) *n_ops = n;
+    if (runs) *runs = e->profiled_runs;
+    if (cap < n) { set_error("hp_engine_get_profile: cap %d < %d ops", cap, n); return HP_ERR_CAPACITY; }
+    for (int i = 0; i < n; ++i) {
+        if (ms_per_op) ms_per_op[i] = (e->profiled_runs && i < (int)e->op_ms_sum.size()) ? e->op_ms_sum[i] / e->profiled_runs : 0.0;
+        if (op_type) op_type[i] = (int)e->ops[i].po.type;
+        if (flops_per_op) flops_per_op[i] = e->ops[i].po.type == OP_CONV ? e->ops[i].plan.flops_per_frame : 0.0;
+    }
+    return HP_OK;
+}
 
 // End-to-end pose call: HOST u8 frames -> humans on the host, one stream, tensors never leave the device in between
 // (operator API sequence engine.inference(batch) + parser.process(packet) per image,

@@ -1033,4 +1033,18 @@ int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* o
 
 long long hp_paf_launch_count(const hp_paf* p) { return p ? p->launches : 0; }
 
+int hp_paf_copy_results_device(hp_paf* p, hp_human* d_humans, int* d_counts, int N, int cap, void* stream)
+{
+    if (!p || !d_humans || !d_counts || N != p->last_N || cap < p->hcap) {
+        hpb::set_error("hp_paf_copy_results_device: bad argument (N=%d last=%d cap=%d hcap=%d)", N, p ? p->last_N : -1, cap, p ? p->hcap : -1);
+        return HP_ERR_ARG;
+    }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->last_stream;
+    HP_CUDA_TRY(cudaMemcpy2DAsync(d_humans, (size_t)cap * sizeof(hp_human), p->humans.p, (size_t)p->hcap * sizeof(hp_human),
+                                  (size_t)p->hcap * sizeof(hp_human), N, cudaMemcpyDeviceToDevice, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(d_counts, p->human_cnt(), sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+    return HP_OK;
+}
+
 } // extern "C"

@@ -100,6 +100,10 @@ int hp_paf_debug_peaks(hp_paf* p, int frame, hp_peak* out, int cap, int* n_out);
 int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* out, int cap, int* n_out);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long hp_paf_launch_count(const hp_paf* p);
+/* multi-GPU gather leg: copies the last batch's records (padded to `cap` >= the parser's human capacity per
+ * frame) and counts into caller-owned DEVICE buffers, asynchronously on `stream` (NULL = the batch's stream),
+ * so they can be handed to NCCL without a host round trip. */
+int hp_paf_copy_results_device(hp_paf* p, hp_human* d_humans, int* d_counts, int N, int cap, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * DNN engine -- replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
@@ -133,6 +137,13 @@ long long hp_engine_launch_count(const hp_engine* e);
 int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int* H, int* W, int* C);
 int hp_engine_debug_write_buffer(hp_engine* e, int buf, const void* in_f16, int N);
 int hp_engine_debug_run_ops(hp_engine* e, int first_op, int last_op, int N);
+
+/* benchmark hook: after the last conv of every run, copy these DEVICE tensors over the engine's
+ * conf/paf outputs, so that random-init weights still give the parser a realistic load.  NULL disables it. */
+int hp_engine_set_output_override(hp_engine* e, const float* d_conf, const float* d_paf);
+/* per-op CUDA-event timing on the engine's launching stream (bench.py roofline leg) */
+int hp_engine_set_profiling(hp_engine* e, int enable);
+int hp_engine_get_profile(hp_engine* e, double* ms_per_op, int* op_type, double* flops_per_op, int cap, int* n_ops, long long* runs);
 
 /* engine.inference(batch) + parser.process(packet) for every image of the batch
  * (examples/operator_api_batched_images_paf.example.cpp:64-74) as ONE call: host u8 frames in,
