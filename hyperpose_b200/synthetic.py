@@ -39,7 +39,7 @@ def random_skeletons(rng: np.random.Generator, n_persons: int, height: int, widt
     for p in range(n_persons):
         ph = rng.uniform(0.55, 0.9) * height            # person height in pixels
         pw = ph * rng.uniform(0.75, 0.95)
-        x0 = rng.uniform(-0.1 * pw, width - 0.9 * pw)
+        x0 = rng.uniform(-0.1 * pw, max(-0.1 * pw + 1.0, width - 0.9 * pw))
         y0 = rng.uniform(0.0, max(1.0, height - ph))
         jit = rng.normal(0.0, 0.012, size=(N_PARTS, 2))
         pts = (_TEMPLATE + jit) * np.array([pw, ph]) + np.array([x0, y0])
