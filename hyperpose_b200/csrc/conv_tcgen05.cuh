@@ -54,6 +54,7 @@ struct ConvParams {
     void* out; void* out2;
     int out_ld, out_ch_off;    // NHWC: channels per pixel of the output buffer / first channel written
     int split;                 // NCHW_SPLIT: channels [0,split) go to out, the rest to out2
+    int tma_store;             // 1: fp16 NHWC output goes through swizzled smem staging + TMA tensor stores (BN % 64 == 0)
 };
 
 namespace ptx {
@@ -120,6 +121,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
 {
@@ -215,7 +236,8 @@ __device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int tile, i
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_o, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms shared by TMA and UMMA
@@ -228,6 +250,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;         // [2]       MMA -> epilogue
     uint64_t* tempty_bar = tfull_bar + 2;                      // [2]       epilogue -> MMA
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    // two 16 KiB staging tiles (128 pixels x 64 channels fp16, 128B-swizzled) for the TMA-store epilogue
+    uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_g = p.cout_g_pad / p.BN;
@@ -238,6 +262,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
+        if (p.tma_store) ptx::prefetch_tmap(&tmap_o);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.num_stages; ++i) {
@@ -318,6 +343,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int ph = row / p.BW, pw = row - ph * p.BW;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t stage_ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvTile t = decode_tile(p, tile, n_tiles_g);
             const int h = t.h0 + ph, w = t.w0 + pw;
@@ -329,6 +355,44 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const float* alpha = p.alpha + t.g * p.cout_g_pad + t.n0;
             const int n_valid = min(p.BN, p.cout_g - t.n0); // real (unpadded) channels of this tile
             const size_t pix = ((size_t)t.nb * p.H + h) * p.W + w;
+            if (p.tma_store) {
+                // 64 channels at a time: registers -> swizzled smem tile -> one TMA tensor store (coalesced, clipped
+                // at the image border by the TMA unit); double-buffered so the store of sub-tile k overlaps the
+                // TMEM reads of sub-tile k+1.
+                const bool leader = (warp == 4 && lane == 0);
+                for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                    uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
+                    if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
+                    ptx::named_bar_sync(1, 128);
+                    const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c0 = sub * 64 + q * 16;
+                        uint32_t v[16];
+                        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                        ptx::tmem_ld_wait();
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float a0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
+                            float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
+                            a0 = a0 > 0.f ? a0 : a0 * __ldg(alpha + c0 + 2 * j);
+                            a1 = a1 > 0.f ? a1 : a1 * __ldg(alpha + c0 + 2 * j + 1);
+                            const __half2 h2 = __floats2half2_rn(a0, a1);
+                            pk[j] = *(const uint32_t*)&h2;
+                        }
+                        const int ch0 = q * 2; // 16-byte chunk index inside the 128-byte row
+                        ptx::st_shared_v4(srow + (uint32_t)(((ch0) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                        ptx::st_shared_v4(srow + (uint32_t)(((ch0 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                    }
+                    ptx::fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    ptx::named_bar_sync(1, 128);
+                    if (leader) {
+                        ptx::tma_store_4d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.w0, t.h0, t.nb);
+                        ptx::bulk_commit_group();
+                    }
+                }
+            } else
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
                 if (c0 >= n_valid) break; // warp-uniform: the remaining columns are padding
                 uint32_t v[16];
@@ -378,6 +442,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && warp == 4 && lane == 0) ptx::bulk_wait_group_read<0>(); // smem must outlive the last stores
     }
 
     ptx::tc_fence_before();
@@ -388,9 +453,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
-inline size_t conv_smem_bytes(int BN, int stages)
+constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
+constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 4) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
+inline size_t conv_smem_bytes(int BN, int stages, bool tma_store)
 {
-    return 1024 /*alignment slack*/ + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (2 * CONV_MAX_STAGES + 4) * 8 + 16;
+    return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0);
+}
+inline int conv_pick_stages(int BN, bool tma_store)
+{
+    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - (tma_store ? 2 * CONV_A_BYTES : 0);
+    const int st = (int)(avail / (size_t)(CONV_A_BYTES + BN * CONV_BLOCK_K * 2));
+    return st > CONV_MAX_STAGES ? CONV_MAX_STAGES : st;
 }
 
 } // namespace hpb

@@ -175,7 +175,7 @@ void pick_tile(int H, int W, int* BH, int* BW)
 
 struct ConvPlan {
     ConvParams prm;
-    CUtensorMap tmap_a, tmap_b;
+    CUtensorMap tmap_a, tmap_b, tmap_o;
     __half* d_w = nullptr;
     float* d_bias = nullptr;
     float* d_alpha = nullptr;
@@ -282,8 +282,9 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     p.tiles_h = (p.H + p.BH - 1) / p.BH;
     p.tiles_w = (p.W + p.BW - 1) / p.BW;
     p.in_ch_off = (int)po.in_ch_off;
-    const int stage_bytes = CONV_A_BYTES + BN * CONV_BLOCK_K * 2;
-    p.num_stages = std::min(CONV_MAX_STAGES, (200 * 1024) / stage_bytes);
+    // TMA-store epilogue whenever whole 64-channel sub-tiles map onto the output buffer
+    p.tma_store = (po.out_mode == OUT_F16_NHWC && BN % 64 == 0 && (G == 1 || cout_g % 64 == 0)) ? 1 : 0;
+    p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
     int tc = 32;
     while (tc < 2 * BN) tc *= 2;
     p.tmem_cols = tc;
@@ -304,7 +305,17 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     if (rc) return rc;
     rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
     if (rc) return rc;
-    pl.smem = conv_smem_bytes(BN, p.num_stages);
+    memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
+    if (p.tma_store) {
+        const EngBuffer& ob = e->bufs[po.out_buf];
+        if ((int)po.out_ch_off + (G - 1) * cout_g + cout_pad > ob.channels) p.tma_store = 0; // padded sub-tile would leave the buffer
+        else {
+            rc = make_tmap_act(&pl.tmap_o, ob.d, e->max_batch, ob.H, ob.W, ob.channels, p.BH, p.BW);
+            if (rc) return rc;
+        }
+        p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
+    }
+    pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0);
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
     return HP_OK;
 }
@@ -316,7 +327,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     p.Nb = N;
     const int n_tiles = N * p.tiles_h * p.tiles_w * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms, n_tiles);
-    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, p);
+    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
     e->launches++;
     return HP_OK;
 }

@@ -1,7 +1,7 @@
 """scratch timing of the parser kernels (device-resident inputs); not the bench."""
 import sys, time
 import numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from hyperpose_b200 import capi, synthetic as syn
 for (hf, wf, P, N) in [(46, 82, (3, 9), 16), (46, 54, (10, 20), 32), (46, 82, (3, 9), 64)]:
     conf, paf = syn.make_batch_tensors(21, N, P, hf, wf)
