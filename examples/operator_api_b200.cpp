@@ -1,0 +1,38 @@
+// examples/operator_api_b200.cpp -- the reference's operator-API call sequence
+// (examples/operator_api_batched_images_paf.example.cpp:58-74: engine.inference(batch), then
+// parser.process(packet[0], packet[1]) per image) against the B200 drop-in, using only the reference's
+// public headers.  Frames are synthetic (no OpenCV image I/O here); the model is an HPB2PACK file.
+//   usage: operator_api_b200 <model.pack> <width> <height> <batch>
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include <random>
+
+#include <hyperpose/operator/dnn/tensorrt.hpp>
+#include <hyperpose/operator/parser/paf.hpp>
+
+int main(int argc, char** argv)
+{
+    if (argc < 5) { std::cerr << "usage: " << argv[0] << " model.pack width height batch\n"; return 2; }
+    const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), n = std::atoi(argv[4]);
+    namespace hp = hyperpose;
+    hp::dnn::tensorrt engine(hp::dnn::tensorrt_serialized{ argv[1] }, { w, h }, n);
+    hp::parser::paf parser{};
+    std::mt19937 rng(1);
+    std::vector<cv::Mat> batch;
+    for (int i = 0; i < n; ++i) {
+        cv::Mat m(cv::Size(w, h), CV_8UC3);
+        for (size_t k = 0; k < m.total() * 3; ++k) m.data[k] = (unsigned char)(rng() & 0xff);
+        batch.push_back(m);
+    }
+    auto beg = std::chrono::high_resolution_clock::now();
+    auto packets = engine.inference(batch);
+    size_t humans = 0;
+    for (auto&& packet : packets) {
+        std::cout << packet[0] << ' ' << packet[1] << '\n';
+        humans += parser.process(packet[0], packet[1]).size();
+    }
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - beg).count();
+    std::cout << batch.size() << " images got processed. FPS = " << 1000. * batch.size() / ms << " humans = " << humans << '\n';
+    return 0;
+}

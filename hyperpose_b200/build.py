@@ -61,5 +61,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_cpp_example(ref_root: str = "/root/reference") -> str | None:
+    """Compiles the C++ drop-in (hyperpose_api/*.cpp) + examples/operator_api_b200.cpp against the reference's
+    UNCHANGED public headers.  Needs the reference tree (headers are not copied into this repo); returns the
+    binary path, or None when the reference is absent (GPU box: the prebuilt binary travels with the snapshot)."""
+    exe = os.path.join(ROOT, "examples", "operator_api_b200")
+    if not os.path.isdir(os.path.join(ref_root, "include", "hyperpose")):
+        return exe if os.path.exists(exe) else None
+    api = os.path.join(CSRC, "hyperpose_api")
+    srcs = [os.path.join(api, "paf.cpp"), os.path.join(api, "tensorrt.cpp"), os.path.join(ROOT, "examples", "operator_api_b200.cpp")]
+    if _newer(srcs + [LIB], exe):
+        cmd = ["g++", "-std=c++17", "-O2", "-DHP_B200_STANDALONE", "-I" + os.path.join(CSRC, "shim"), "-I" + os.path.join(ref_root, "include"),
+               "-I" + os.path.join(ROOT, "include")] + srcs + ["-L" + PKG, "-lhyperpose_b200", "-Wl,-rpath,$ORIGIN/../hyperpose_b200", "-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("C++ drop-in failed to compile against the reference headers")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,146 @@
+// hyperpose_api/tensorrt.cpp -- hyperpose::dnn::tensorrt implemented on the B200 C ABI (no TensorRT).
+//
+// Drop-in replacement for the reference's src/tensorrt.cpp (same seam as src/fake/fake_tensorrt.cpp),
+// compiled against the UNCHANGED include/hyperpose/operator/dnn/tensorrt.hpp.  All three constructors
+// accept the path of an HPB2PACK model pack (hyperpose_b200/models.py) in place of the .uff/.onnx/.trt file;
+// a file that is not a pack is a fatal error, like an unparsable model in the reference (tensorrt.cpp:141-158).
+// inference() returns, per image, the outputs ordered by name (conf < paf, tensorrt.cpp:405) as host
+// feature_map_t objects with shape [C,H,W], exactly as the reference does.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+
+#include <hyperpose/operator/dnn/tensorrt.hpp>
+
+#include "hyperpose_b200.h"
+
+namespace hyperpose {
+namespace dnn {
+
+    namespace {
+        [[noreturn]] void die(const std::string& what)
+        {
+            std::cerr << "[HyperPose::ERROR  ] " << what << ": " << hp_last_error() << '\n';
+            std::exit(1);
+        }
+        hp_engine* load_engine(const std::string& path, cv::Size input_size, int max_batch, double factor, bool flip_rgb)
+        {
+            std::ifstream f(path, std::ios::binary | std::ios::ate);
+            if (!f) die("cannot open model pack " + path);
+            const std::streamsize n = f.tellg();
+            f.seekg(0);
+            std::vector<char> blob((size_t)n);
+            if (!f.read(blob.data(), n)) die("cannot read model pack " + path);
+            hp_engine* e = nullptr;
+            if (hp_engine_create(&e, blob.data(), blob.size(), input_size.width, input_size.height, max_batch, factor, flip_rgb ? 1 : 0, 0) != HP_OK)
+                die("hp_engine_create(" + path + ")");
+            return e;
+        }
+    }
+
+    struct tensorrt::cuda_dep {
+        hp_engine* engine = nullptr;
+        int c_conf = 0, c_paf = 0, out_h = 0, out_w = 0;
+        ~cuda_dep() { hp_engine_destroy(engine); }
+    };
+
+    tensorrt::tensorrt(const uff& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type, double factor, bool flip_rgb)
+        : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
+        , m_cuda_dep(std::make_unique<cuda_dep>())
+    {
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        _create_binding_buffers();
+    }
+    tensorrt::tensorrt(const onnx& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type, double factor, bool flip_rgb)
+        : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
+        , m_cuda_dep(std::make_unique<cuda_dep>())
+    {
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        _create_binding_buffers();
+    }
+    tensorrt::tensorrt(const tensorrt_serialized& m, cv::Size input_size, int max_batch_size, bool keep_ratio, double factor, bool flip_rgb)
+        : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
+        , m_cuda_dep(std::make_unique<cuda_dep>())
+    {
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        _create_binding_buffers();
+    }
+
+    void tensorrt::_create_binding_buffers()
+    {
+        hp_engine_info(m_cuda_dep->engine, nullptr, nullptr, nullptr, &m_cuda_dep->c_conf, &m_cuda_dep->c_paf, &m_cuda_dep->out_h, &m_cuda_dep->out_w, nullptr);
+    }
+
+    void tensorrt::_batching(std::vector<cv::Mat>&, std::vector<float>&) {} // batching happens on the GPU (im2col3_kernel)
+
+    namespace {
+        std::vector<internal_t> collect(hp_engine* e, size_t batch, int cc, int cp, int oh, int ow)
+        {
+            const size_t plane = (size_t)oh * ow;
+            std::vector<float> conf(batch * cc * plane), paf(batch * cp * plane);
+            if (hp_engine_read_outputs_host(e, conf.data(), paf.data(), (int)batch) != HP_OK) die("hp_engine_read_outputs_host");
+            std::vector<internal_t> ret(batch);
+            for (size_t j = 0; j < batch; ++j) {
+                std::unique_ptr<char[]> a(new char[cc * plane * sizeof(float)]), b(new char[cp * plane * sizeof(float)]);
+                std::memcpy(a.get(), conf.data() + j * cc * plane, cc * plane * sizeof(float));
+                std::memcpy(b.get(), paf.data() + j * cp * plane, cp * plane * sizeof(float));
+                ret[j].emplace_back("conf", std::move(a), std::vector<int>{ cc, oh, ow });
+                ret[j].emplace_back("paf", std::move(b), std::vector<int>{ cp, oh, ow });
+            }
+            return ret;
+        }
+    }
+
+    std::vector<internal_t> tensorrt::inference(const std::vector<float>& buffer, size_t batch_size)
+    {
+        const int rc = hp_engine_infer_f32_host(m_cuda_dep->engine, buffer.data(), (int)batch_size);
+        if (rc == HP_ERR_BATCH) throw std::logic_error(hp_last_error());
+        if (rc != HP_OK) die("hp_engine_infer_f32_host");
+        return collect(m_cuda_dep->engine, batch_size, m_cuda_dep->c_conf, m_cuda_dep->c_paf, m_cuda_dep->out_h, m_cuda_dep->out_w);
+    }
+
+    std::vector<internal_t> tensorrt::inference(std::vector<cv::Mat> batch)
+    {
+        if (batch.size() > (size_t)m_max_batch_size)
+            throw std::logic_error("Input batch size overflow: Yours@" + std::to_string(batch.size()) + " Max@" + std::to_string(m_max_batch_size));
+        const size_t frame = (size_t)m_inp_size.width * m_inp_size.height * 3;
+        std::vector<uint8_t> host(batch.size() * frame);
+        for (size_t i = 0; i < batch.size(); ++i) {
+            const cv::Mat& m = batch[i];
+            if (m.type() != CV_8UC3 || m.cols != m_inp_size.width || m.rows != m_inp_size.height || !m.isContinuous()) {
+                // the reference resizes on the CPU here (cv::resize / non_scaling_resize, tensorrt.cpp:446-451);
+                // a GPU resize is the next row of the hot-path table (DESIGN.md "what comes next")
+                std::cerr << "[HyperPose::ERROR  ] B200 engine: frames must be CV_8UC3 at the network size ("
+                          << m_inp_size.width << "x" << m_inp_size.height << ")\n";
+                std::exit(-1);
+            }
+            std::memcpy(host.data() + i * frame, m.data, frame);
+        }
+        if (hp_engine_infer_u8_host(m_cuda_dep->engine, host.data(), (int)batch.size()) != HP_OK) die("hp_engine_infer_u8_host");
+        return collect(m_cuda_dep->engine, batch.size(), m_cuda_dep->c_conf, m_cuda_dep->c_paf, m_cuda_dep->out_h, m_cuda_dep->out_w);
+    }
+
+    void tensorrt::save(const std::string) {} // the pack already is the serialised engine
+
+    tensorrt::~tensorrt() = default;
+
+} // namespace dnn
+
+// member-wise constructor + printer of feature_map_t (include/hyperpose/utility/data.hpp:22,28): in a full
+// integration these come from the reference's own src/data.cpp; they are repeated here only so that this
+// translation unit links stand-alone (tests, the B200 example) without OpenCV.
+#ifdef HP_B200_STANDALONE
+feature_map_t::feature_map_t(std::string name, std::unique_ptr<char[]>&& tensor, std::vector<int> shape)
+    : m_name(std::move(name)), m_data(std::move(tensor)), m_shape(std::move(shape))
+{
+}
+std::ostream& operator<<(std::ostream& out, const feature_map_t& map)
+{
+    out << map.m_name << ":[";
+    for (auto& s : map.m_shape) out << s << ", ";
+    return out << ']';
+}
+#endif
+} // namespace hyperpose

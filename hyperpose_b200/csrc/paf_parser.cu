@@ -718,6 +718,7 @@ struct hp_paf {
     int last_N = 0;
     cudaStream_t last_stream = nullptr;
     int limb_stage_bytes = 0;
+    int assemble_max_refs = 560; // 560 * 80 B < 48 KB (no opt-in needed); raised at create when the device allows
 
     int* peak_cnt() { return counters.p; }
     int* conn_cnt() { return counters.p + (size_t)cap_N * HP_N_PARTS; }
@@ -900,6 +901,11 @@ int hp_paf_create(hp_paf** out, float conf_thresh, float paf_thresh, int res_w, 
         p->limb_stage_bytes = stage;
     else
         cudaGetLastError();
+    int refs_bytes = std::min(max_optin - 2048, 200 * 1024);
+    if (refs_bytes > 48 * 1024 && cudaFuncSetAttribute(paf_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, refs_bytes) == cudaSuccess)
+        p->assemble_max_refs = refs_bytes / (int)sizeof(HumanRef);
+    else
+        cudaGetLastError();
     *out = p;
     return HP_OK;
 }
@@ -927,7 +933,8 @@ int hp_paf_set_capacity(hp_paf* p, int max_peaks_per_part, int max_candidates_pe
     if (max_candidates_per_limb > 0) p->ccap = max_candidates_per_limb;
     if (max_humans > 0) {
         p->hcap = max_humans;
-        p->max_refs = std::min(std::max(256, 2 * max_humans), 560); // 560 * 80 B < 48 KB static dynamic-smem limit
+        // partial humans (paf.cpp:152 `human_refs`) live in shared memory: 80 B each, up to the opted-in carve-out
+        p->max_refs = std::min(std::max(256, 4 * max_humans), p->assemble_max_refs);
     }
     return HP_OK;
 }
@@ -953,7 +960,7 @@ int hp_paf_process_host_batched(hp_paf* p, const float* conf, const float* paf, 
 {
     if (!p || !conf || !paf || !out || !n_out) { hpb::set_error("hp_paf_process_host: null argument"); return HP_ERR_ARG; }
     HP_CUDA_TRY(cudaSetDevice(p->device));
-    for (int attempt = 0; attempt < 6; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         int rc = ensure_geometry(p, N, c_conf, c_paf, H, W);
         if (rc) return rc;
         const size_t n_conf = (size_t)N * c_conf * H * W, n_paf = (size_t)N * c_paf * H * W;
@@ -976,8 +983,8 @@ int hp_paf_process_host_batched(hp_paf* p, const float* conf, const float* paf, 
         if (flags & FLAG_PEAK_OVERFLOW) p->pcap = std::min(p->pcap * 4, MAX_PCAP);
         if (flags & FLAG_CAND_OVERFLOW) p->ccap *= 4;
         if (flags & FLAG_HUMAN_OVERFLOW) {
-            if (p->hcap >= 280) return rc;
-            hp_paf_set_capacity(p, 0, 0, std::min(p->hcap * 2, 280));
+            if (p->hcap >= 4096 && p->max_refs >= p->assemble_max_refs) return rc; // > ~2500 partial humans in one frame
+            hp_paf_set_capacity(p, 0, 0, std::min(p->hcap * 4, 4096));
         }
     }
     return HP_ERR_CAPACITY;
