@@ -55,6 +55,7 @@ struct ConvParams {
     int out_ld, out_ch_off;    // NHWC: channels per pixel of the output buffer / first channel written
     int split;                 // NCHW_SPLIT: channels [0,split) go to out, the rest to out2
     int tma_store;             // 1: fp16 NHWC output goes through swizzled smem staging + TMA tensor stores (BN % 64 == 0)
+    int swap_ab;               // 1: conv_tcgen05_swap_kernel (cout_g_pad == 128, TMA store)
 };
 
 namespace ptx {
@@ -450,6 +451,186 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Swapped-operand variant for layers whose group has exactly 128 (padded) output channels
+// (the 2-group 7x7 refinement convs: 68 % of the model's FLOPs).  With M = 128 pixels, N = 128 channels
+// one MMA reads 4 KiB (A) + 4 KiB (B) of shared memory per 64 tensor cycles = the full 128 B/clk smem
+// bandwidth (ncu: sm__mem_tensor_cycles_active 78 %).  Here the roles are swapped:
+//   D^T[128 channels, 256 pixels] += W[128 ch, 64 k] * X[256 px, 64 k]^T
+// i.e. UMMA M = 128 (channels), N = 256 (two independent 128-pixel tiles): 4 + 8 KiB per 128 cycles = 96 B/clk.
+// TMEM lanes are channels, columns are pixels; the epilogue transposes through the swizzled staging tiles
+// (one 2-byte shared store per value) before the same TMA tensor store.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void decode_mtile(const ConvParams& p, int mt, int& nb, int& h0, int& w0)
+{
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    nb = mt / p.tiles_h; // >= Nb for the dummy half of an odd last pair: every TMA access is then out of bounds
+    h0 = th * p.BH;
+    w0 = tw * p.BW;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_o, const ConvParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int W_BYTES = 128 * CONV_BLOCK_K * 2;          // 16 KiB weight tile (128 channels x 64 k)
+    constexpr int STAGE_BYTES = W_BYTES + 2 * CONV_A_BYTES;  // + two 128-pixel activation tiles = 48 KiB
+    uint8_t* bar_base = smem + (size_t)p.num_stages * STAGE_BYTES;
+    uint64_t* full_bar = (uint64_t*)bar_base;
+    uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023); // 2 x 16 KiB
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = p.Nb * p.tiles_h * p.tiles_w;
+    const int pairs = (m_tiles + 1) / 2;
+    const int total_tiles = pairs * p.groups;
+    const int chunks = p.cin_g / CONV_BLOCK_K;
+    const int ksteps = p.R * p.S * chunks;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_o);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.num_stages; ++i) {
+            ptx::mbar_init(ptx::smem_u32(full_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(empty_bar + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512u);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int pad_h = p.R / 2, pad_w = p.S / 2;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int g = tile % p.groups, pair = tile / p.groups;
+                int nb0, h00, w00, nb1, h01, w01;
+                decode_mtile(p, 2 * pair, nb0, h00, w00);
+                decode_mtile(p, 2 * pair + 1, nb1, h01, w01);
+                const int a_ch0 = p.in_ch_off + g * p.cin_g;
+                const int b_row = g * p.cout_g_pad;
+                int kcol = 0;
+                for (int r = 0; r < p.R; ++r)
+                    for (int s = 0; s < p.S; ++s)
+                        for (int c = 0; c < chunks; ++c, kcol += CONV_BLOCK_K) {
+                            ptx::mbar_wait(ptx::smem_u32(empty_bar + stage), phase ^ 1);
+                            const uint32_t fb = ptx::smem_u32(full_bar + stage);
+                            const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                            ptx::mbar_expect_tx(fb, (uint32_t)STAGE_BYTES);
+                            ptx::tma_load_2d(sw, &tmap_b, fb, kcol, b_row);
+                            ptx::tma_load_4d(sw + W_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, w00 + s - pad_w, h00 + r - pad_h, nb0);
+                            ptx::tma_load_4d(sw + W_BYTES + CONV_A_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, w01 + s - pad_w, h01 + r - pad_h, nb1);
+                            if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_f16(128, 256);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t dw = ptx::make_sw128_kmajor_desc(sw);           // "A" operand: weights, M = 128 channels
+                    const uint64_t dx = ptx::make_sw128_kmajor_desc(sw + W_BYTES); // "B" operand: 256 pixel rows
+#pragma unroll
+                    for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
+                        ptx::umma_f16(d_tmem, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(ptx::smem_u32(empty_bar + stage));
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int ch = ew * 32 + lane;                 // TMEM lane == output channel inside the group
+        const bool leader = (warp == 4 && lane == 0);
+        uint8_t* sbuf = out_stage + (ch >> 6) * CONV_A_BYTES; // staging tile of this channel's 64-channel half
+        const uint32_t sbase = ptx::smem_u32(sbuf) + (uint32_t)((ch & 7) * 2);
+        const int chunk = (ch & 63) >> 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int g = tile % p.groups, pair = tile / p.groups;
+            const float bias = __ldg(p.bias + g * p.cout_g_pad + ch);
+            const float alpha = __ldg(p.alpha + g * p.cout_g_pad + ch);
+            ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 256);
+            for (int half = 0; half < 2; ++half) {
+                int nb, h0, w0;
+                decode_mtile(p, 2 * pair + half, nb, h0, w0);
+                if (leader) ptx::bulk_wait_group_read<0>(); // previous stores have drained both staging tiles
+                ptx::named_bar_sync(1, 128);
+#pragma unroll 2
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t v[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(half * 128 + q * 16), v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int px = q * 16 + j;
+                        float a = __uint_as_float(v[j]) + bias;
+                        a = a > 0.f ? a : a * alpha;
+                        const __half hv = __float2half_rn(a);
+                        const uint32_t addr = sbase + (uint32_t)(px * 128 + ((chunk ^ (px & 7)) * 16));
+                        asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*(const unsigned short*)&hv) : "memory");
+                    }
+                }
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(1, 128);
+                if (leader) {
+                    const int c0 = p.out_ch_off + g * p.cout_g;
+                    ptx::tma_store_4d(&tmap_o, ptx::smem_u32(out_stage), c0, w0, h0, nb);
+                    ptx::tma_store_4d(&tmap_o, ptx::smem_u32(out_stage + CONV_A_BYTES), c0 + 64, w0, h0, nb);
+                    ptx::bulk_commit_group();
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (leader) ptx::bulk_wait_group_read<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512u);
     }
 }
 

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -315,7 +316,10 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         }
         p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
     }
-    pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0);
+    // swapped-operand kernel: one 128-channel N tile per group, enough k-steps to amortise the transposing epilogue
+    p.swap_ab = (p.tma_store && cout_pad == 128 && cout_g == 128 && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
+    if (p.swap_ab) p.num_stages = conv_pick_stages(256, true); // stage = 16 KiB weights + 2 x 16 KiB pixels
+    pl.smem = conv_smem_bytes(p.swap_ab ? 256 : BN, p.num_stages, p.tma_store != 0);
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
     return HP_OK;
 }
@@ -325,6 +329,12 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     ConvPlan& pl = op.plan;
     ConvParams p = pl.prm;
     p.Nb = N;
+    if (p.swap_ab) {
+        const int n_tiles = (N * p.tiles_h * p.tiles_w + 1) / 2 * p.groups;
+        conv_tcgen05_swap_kernel<<<std::min(e->num_sms, n_tiles), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
+        e->launches++;
+        return HP_OK;
+    }
     const int n_tiles = N * p.tiles_h * p.tiles_w * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms, n_tiles);
     conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
@@ -490,7 +500,8 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             return fail(HP_ERR_UNSUPPORTED);
         }
     }
-    if (max_smem > 0 && cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
+    if (max_smem > 0 && (cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+                         cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
         return fail(HP_ERR_CUDA);
     }
