@@ -7,9 +7,10 @@
 //   D[128 pixels, BN out-channels] += A[128 pixels, 64 in-channels] * B[BN, 64]^T
 //   summed over (filter tap r,s) x (64-channel chunk): one "k-step" per (r, s, chunk).
 //
-// * activations are fp16 NHWC; the A tile of a k-step is ONE 4-D TMA box {64 ch, BW, BH, 1}
-//   fetched at spatial offset (s - pad, r - pad): out-of-image elements are zero-filled by the
-//   TMA unit, which implements "SAME" padding with no im2col buffer in HBM;
+// * activations are fp16 NHWC; the A tile of a k-step is ONE im2col-mode TMA load
+//   (cp.async.bulk.tensor.4d...im2col): 128 consecutive output pixels (in n,h,w order, wrapping over rows
+//   and images inside the TMA unit) x 64 channels at filter offset (s, r); out-of-image elements are
+//   zero-filled by the TMA unit = "SAME" padding, no im2col buffer in HBM and no tile padding waste;
 // * weights are fp16 [G][Cout_pad][R][S][Cin_g] (K-major); the B tile is a 2-D TMA box {64, BN};
 // * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes;
 // * accumulators live in TMEM (2 x BN fp32 columns, double-buffered so the epilogue of tile i
@@ -43,8 +44,7 @@ struct ConvParams {
     int groups, cin_g;         // cin_g: multiple of 64
     int cout_g, cout_g_pad;    // real / padded (multiple of BN) output channels per group
     int BN;                    // tile N == UMMA N (multiple of 16, <= 256)
-    int BH, BW;                // pixel tile, BH * BW == 128
-    int tiles_h, tiles_w;
+    int m_tiles;               // ceil(Nb * H * W / 128): a tile is 128 CONSECUTIVE output pixels in (n, h, w) order
     int in_ch_off;             // first input channel inside the input buffer
     int num_stages;
     int tmem_cols;             // power of two >= 2 * BN
@@ -115,6 +115,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// im2col-mode load: {c, w, h, n} = channel + base pixel (output pixel minus padding); {offw, offh} = filter tap
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n, int offw, int offh)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)offw), "h"((unsigned short)offh)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1)
 {
@@ -216,7 +228,7 @@ __host__ __device__ inline uint32_t make_idesc_f16(int M, int N)
 } // namespace ptx
 
 struct ConvTile {
-    int nb, h0, w0, g, n0;
+    int p0, g, n0; // first output pixel (flattened n,h,w), group, first output channel of the tile
 };
 
 __device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int tile, int n_tiles_g)
@@ -224,16 +236,25 @@ __device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int tile, i
     ConvTile t;
     const int n_tiles_total = p.groups * n_tiles_g;
     const int nt = tile % n_tiles_total;
-    int mt = tile / n_tiles_total;
+    const int mt = tile / n_tiles_total;
     t.g = nt / n_tiles_g;
     t.n0 = (nt - t.g * n_tiles_g) * p.BN;
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    t.nb = mt / p.tiles_h;
-    t.h0 = th * p.BH;
-    t.w0 = tw * p.BW;
+    t.p0 = mt * CONV_BLOCK_M;
     return t;
+}
+
+struct PixelPos {
+    int n, h, w;
+};
+__device__ __forceinline__ PixelPos unflatten(const ConvParams& p, int px)
+{
+    PixelPos q;
+    const int hw = p.H * p.W;
+    q.n = px / hw;
+    const int rem = px - q.n * hw;
+    q.h = rem / p.W;
+    q.w = rem - q.h * p.W;
+    return q;
 }
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
@@ -256,7 +277,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_g = p.cout_g_pad / p.BN;
-    const int total_tiles = p.Nb * p.tiles_h * p.tiles_w * p.groups * n_tiles_g;
+    const int total_tiles = p.m_tiles * p.groups * n_tiles_g;
     const int chunks = p.cin_g / CONV_BLOCK_K;
     const int ksteps = p.R * p.S * chunks;
 
@@ -290,6 +311,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int pad_h = p.R / 2, pad_w = p.S / 2;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const ConvTile t = decode_tile(p, tile, n_tiles_g);
+                const PixelPos q0 = unflatten(p, t.p0);
                 const int a_ch0 = p.in_ch_off + t.g * p.cin_g;
                 const int b_row = t.g * p.cout_g_pad + t.n0;
                 int kcol = 0;
@@ -300,8 +322,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             const uint32_t fb = ptx::smem_u32(full_bar + stage);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                            ptx::tma_load_4d(ptx::smem_u32(sa), &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K,
-                                             t.w0 + s - pad_w, t.h0 + r - pad_h, t.nb);
+                            ptx::tma_load_im2col_4d(ptx::smem_u32(sa), &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K,
+                                                    q0.w - pad_w, q0.h - pad_h, q0.n, s, r);
                             ptx::tma_load_2d(ptx::smem_u32(sa + CONV_A_BYTES), &tmap_b, fb, kcol, b_row);
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         }
@@ -341,21 +363,22 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may access
         const int row = ew * 32 + lane;           // accumulator row == pixel index inside the tile
-        const int ph = row / p.BW, pw = row - ph * p.BW;
+        const int total_px = p.Nb * p.H * p.W;
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t stage_ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvTile t = decode_tile(p, tile, n_tiles_g);
-            const int h = t.h0 + ph, w = t.w0 + pw;
-            const bool in_img = (h < p.H) && (w < p.W);
+            const bool in_img = (t.p0 + row) < total_px;
+            const PixelPos q = unflatten(p, in_img ? t.p0 + row : 0);
+            const int h = q.h, w = q.w;
             ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
             const float* bias = p.bias + t.g * p.cout_g_pad + t.n0;
             const float* alpha = p.alpha + t.g * p.cout_g_pad + t.n0;
             const int n_valid = min(p.BN, p.cout_g - t.n0); // real (unpadded) channels of this tile
-            const size_t pix = ((size_t)t.nb * p.H + h) * p.W + w;
+            const size_t pix = (size_t)(t.p0 + row);
             if (p.tma_store) {
                 // 64 channels at a time: registers -> swizzled smem tile -> one TMA tensor store (coalesced, clipped
                 // at the image border by the TMA unit); double-buffered so the store of sub-tile k overlaps the
@@ -389,7 +412,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
                     ptx::named_bar_sync(1, 128);
                     if (leader) {
-                        ptx::tma_store_4d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.w0, t.h0, t.nb);
+                        ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
                         ptx::bulk_commit_group();
                     }
                 }
@@ -430,10 +453,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < nv; ++j) {
                         const int ch = t.n0 + c0 + j;
                         if (ch < p.split) {
-                            ((float*)p.out)[(((size_t)t.nb * p.split + ch) * p.H + h) * p.W + w] = y[j];
+                            ((float*)p.out)[(((size_t)q.n * p.split + ch) * p.H + h) * p.W + w] = y[j];
                         } else {
                             const int c2 = ch - p.split, n2 = p.cout_g - p.split;
-                            ((float*)p.out2)[(((size_t)t.nb * n2 + c2) * p.H + h) * p.W + w] = y[j];
+                            ((float*)p.out2)[(((size_t)q.n * n2 + c2) * p.H + h) * p.W + w] = y[j];
                         }
                     }
                 }
@@ -464,16 +487,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // TMEM lanes are channels, columns are pixels; the epilogue transposes through the swizzled staging tiles
 // (one 2-byte shared store per value) before the same TMA tensor store.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void decode_mtile(const ConvParams& p, int mt, int& nb, int& h0, int& w0)
-{
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    nb = mt / p.tiles_h; // >= Nb for the dummy half of an odd last pair: every TMA access is then out of bounds
-    h0 = th * p.BH;
-    w0 = tw * p.BW;
-}
-
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_o, const ConvParams p)
@@ -491,8 +504,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023); // 2 x 16 KiB
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = p.Nb * p.tiles_h * p.tiles_w;
-    const int pairs = (m_tiles + 1) / 2;
+    const int pairs = (p.m_tiles + 1) / 2;
     const int total_tiles = pairs * p.groups;
     const int chunks = p.cin_g / CONV_BLOCK_K;
     const int ksteps = p.R * p.S * chunks;
@@ -526,9 +538,10 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int pad_h = p.R / 2, pad_w = p.S / 2;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int g = tile % p.groups, pair = tile / p.groups;
-                int nb0, h00, w00, nb1, h01, w01;
-                decode_mtile(p, 2 * pair, nb0, h00, w00);
-                decode_mtile(p, 2 * pair + 1, nb1, h01, w01);
+                // the second half of an odd last pair starts past the last pixel: the TMA unit zero-fills whatever lies
+                // beyond the tensor and the epilogue never stores it
+                const PixelPos q0 = unflatten(p, 2 * pair * CONV_BLOCK_M);
+                const PixelPos q1 = unflatten(p, (2 * pair + 1) * CONV_BLOCK_M);
                 const int a_ch0 = p.in_ch_off + g * p.cin_g;
                 const int b_row = g * p.cout_g_pad;
                 int kcol = 0;
@@ -540,8 +553,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
                             ptx::mbar_expect_tx(fb, (uint32_t)STAGE_BYTES);
                             ptx::tma_load_2d(sw, &tmap_b, fb, kcol, b_row);
-                            ptx::tma_load_4d(sw + W_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, w00 + s - pad_w, h00 + r - pad_h, nb0);
-                            ptx::tma_load_4d(sw + W_BYTES + CONV_A_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, w01 + s - pad_w, h01 + r - pad_h, nb1);
+                            ptx::tma_load_im2col_4d(sw + W_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, q0.w - pad_w, q0.h - pad_h, q0.n, s, r);
+                            ptx::tma_load_im2col_4d(sw + W_BYTES + CONV_A_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, q1.w - pad_w, q1.h - pad_h, q1.n, s, r);
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         }
             }
@@ -590,8 +603,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 256);
             for (int half = 0; half < 2; ++half) {
-                int nb, h0, w0;
-                decode_mtile(p, 2 * pair + half, nb, h0, w0);
+                const int p0 = (2 * pair + half) * CONV_BLOCK_M;
                 if (leader) ptx::bulk_wait_group_read<0>(); // previous stores have drained both staging tiles
                 ptx::named_bar_sync(1, 128);
 #pragma unroll 2
@@ -611,10 +623,10 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 ptx::fence_proxy_async();
                 ptx::named_bar_sync(1, 128);
-                if (leader) {
+                if (leader && p0 < p.Nb * p.H * p.W) {
                     const int c0 = p.out_ch_off + g * p.cout_g;
-                    ptx::tma_store_4d(&tmap_o, ptx::smem_u32(out_stage), c0, w0, h0, nb);
-                    ptx::tma_store_4d(&tmap_o, ptx::smem_u32(out_stage + CONV_A_BYTES), c0 + 64, w0, h0, nb);
+                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(out_stage), c0, p0);
+                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(out_stage + CONV_A_BYTES), c0 + 64, p0);
                     ptx::bulk_commit_group();
                 }
             }

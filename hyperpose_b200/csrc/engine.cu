@@ -120,18 +120,45 @@ PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-// activations [N,H,W,C] fp16: dims (C, W, H, N), box (64, BW, BH, 1), 128B swizzle, zero OOB fill
-int make_tmap_act(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int BH, int BW)
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                     cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+// activations [N,H,W,C] fp16 in im2col mode: 128 consecutive output pixels x 64 channels per load; the bounding box
+// [-pad, dim - pad) holds one base position per output pixel, filter taps are the im2col offsets of the copy instruction
+// (semantics verified on hardware with tools/probe_im2col.cu)
+int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int R, int S)
+{
+    static PFN_encodeIm2col enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            enc = (PFN_encodeIm2col)p;
+    }
+    if (!enc) { set_error("cuTensorMapEncodeIm2col entry point not available"); return HP_ERR_CUDA; }
+    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+    cuuint64_t strides[3] = { (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2 };
+    const int pad_w = S / 2, pad_h = R / 2;
+    int lower[2] = { -pad_w, -pad_h };
+    int upper[2] = { pad_w - (S - 1), pad_h - (R - 1) };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, lower, upper, 64, CONV_BLOCK_M, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed: %d (N=%d H=%d W=%d C=%d R=%d S=%d)", (int)r, N, H, W, C, R, S); return HP_ERR_CUDA; }
+    return HP_OK;
+}
+// output [N*H*W, C] fp16 as a 2-D tensor: dims (C, pixels), box (64, 128), 128B swizzle (TMA store clips at the last pixel)
+int make_tmap_out(CUtensorMap* m, const __half* base, size_t pixels, int C)
 {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
-    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
-    cuuint64_t strides[3] = { (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2 };
-    cuuint32_t box[4] = { 64, (cuuint32_t)BW, (cuuint32_t)BH, 1 };
-    cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    cuuint64_t dims[2] = { (cuuint64_t)C, (cuuint64_t)pixels };
+    cuuint64_t strides[1] = { (cuuint64_t)C * 2 };
+    cuuint32_t box[2] = { 64, CONV_BLOCK_M };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation) failed: %d (N=%d H=%d W=%d C=%d box %dx%d)", (int)r, N, H, W, C, BH, BW); return HP_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed: %d (pixels=%zu C=%d)", (int)r, pixels, C); return HP_ERR_CUDA; }
     return HP_OK;
 }
 // weights [rows, K] fp16 K-major: dims (K, rows), box (64, BN)
@@ -162,16 +189,6 @@ int pick_bn(int cout_g)
     if (cout_g % 256 == 0) return 256;
     if (cout_g % 128 == 0) return 128;
     return 256;
-}
-
-void pick_tile(int H, int W, int* BH, int* BW)
-{
-    static const int cand[][2] = { { 8, 16 }, { 16, 8 }, { 4, 32 }, { 32, 4 }, { 2, 64 }, { 1, 128 } };
-    long best = -1;
-    for (auto& c : cand) {
-        const long cover = (long)round_up(H, c[0]) * round_up(W, c[1]);
-        if (best < 0 || cover < best) { best = cover; *BH = c[0]; *BW = c[1]; }
-    }
 }
 
 struct ConvPlan {
@@ -279,9 +296,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     p.Nb = e->max_batch; p.H = ib.H; p.W = ib.W;
     p.R = eR; p.S = eS; p.groups = G; p.cin_g = ecin;
     p.cout_g = cout_g; p.cout_g_pad = cout_pad; p.BN = BN;
-    pick_tile(p.H, p.W, &p.BH, &p.BW);
-    p.tiles_h = (p.H + p.BH - 1) / p.BH;
-    p.tiles_w = (p.W + p.BW - 1) / p.BW;
+    p.m_tiles = (int)(((size_t)e->max_batch * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
     p.in_ch_off = (int)po.in_ch_off;
     // TMA-store epilogue whenever whole 64-channel sub-tiles map onto the output buffer
     p.tma_store = (po.out_mode == OUT_F16_NHWC && BN % 64 == 0 && (G == 1 || cout_g % 64 == 0)) ? 1 : 0;
@@ -302,7 +317,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         if (ob.H != ib.H || ob.W != ib.W || (int)po.out_ch_off + G * cout_g > ob.channels) { set_error("engine: conv output buffer mismatch"); return HP_ERR_ARG; }
         p.out = ob.d; p.out_ld = ob.channels; p.out_ch_off = (int)po.out_ch_off;
     }
-    int rc = make_tmap_act(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, p.BH, p.BW);
+    int rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS);
     if (rc) return rc;
     rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
     if (rc) return rc;
@@ -311,7 +326,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         const EngBuffer& ob = e->bufs[po.out_buf];
         if ((int)po.out_ch_off + (G - 1) * cout_g + cout_pad > ob.channels) p.tma_store = 0; // padded sub-tile would leave the buffer
         else {
-            rc = make_tmap_act(&pl.tmap_o, ob.d, e->max_batch, ob.H, ob.W, ob.channels, p.BH, p.BW);
+            rc = make_tmap_out(&pl.tmap_o, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels);
             if (rc) return rc;
         }
         p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
@@ -329,13 +344,14 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     ConvPlan& pl = op.plan;
     ConvParams p = pl.prm;
     p.Nb = N;
+    p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
     if (p.swap_ab) {
-        const int n_tiles = (N * p.tiles_h * p.tiles_w + 1) / 2 * p.groups;
+        const int n_tiles = (p.m_tiles + 1) / 2 * p.groups;
         conv_tcgen05_swap_kernel<<<std::min(e->num_sms, n_tiles), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
         e->launches++;
         return HP_OK;
     }
-    const int n_tiles = N * p.tiles_h * p.tiles_w * p.groups * (p.cout_g_pad / p.BN);
+    const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms, n_tiles);
     conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
     e->launches++;
