@@ -55,7 +55,8 @@ struct ConvParams {
     int out_ld, out_ch_off;    // NHWC: channels per pixel of the output buffer / first channel written
     int split;                 // NCHW_SPLIT: channels [0,split) go to out, the rest to out2
     int tma_store;             // 1: fp16 NHWC output goes through swizzled smem staging + TMA tensor stores (BN % 64 == 0)
-    int swap_ab;               // 1: conv_tcgen05_swap_kernel (cout_g_pad == 128, TMA store)
+    int swap_ab;               // 1: conv_tcgen05_swap_kernel (cout_g_pad % 128 == 0, TMA store)
+    int npx;                   // swap kernel: pixels per unit (UMMA N), multiple of 16, 128 < npx <= 256
 };
 
 namespace ptx {
@@ -478,24 +479,28 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Swapped-operand variant for layers whose group has exactly 128 (padded) output channels
-// (the 2-group 7x7 refinement convs: 68 % of the model's FLOPs).  With M = 128 pixels, N = 128 channels
-// one MMA reads 4 KiB (A) + 4 KiB (B) of shared memory per 64 tensor cycles = the full 128 B/clk smem
-// bandwidth (ncu: sm__mem_tensor_cycles_active 78 %).  Here the roles are swapped:
-//   D^T[128 channels, 256 pixels] += W[128 ch, 64 k] * X[256 px, 64 k]^T
-// i.e. UMMA M = 128 (channels), N = 256 (two independent 128-pixel tiles): 4 + 8 KiB per 128 cycles = 96 B/clk.
-// TMEM lanes are channels, columns are pixels; the epilogue transposes through the swizzled staging tiles
-// (one 2-byte shared store per value) before the same TMA tensor store.
+// Swapped-operand variant for layers whose output channels come in blocks of 128 and whose k-loop is long
+// (the 7x7 refinement convs: 68 % of the model's FLOPs, and the 3x3 init convs).
+//   D^T[128 channels, NPX pixels] += W[128 ch, 64 k] * X[NPX px, 64 k]^T        (UMMA M = 128, N = NPX <= 256)
+// Why: (1) with M = 128 pixels x N = 128 channels one MMA reads 4 + 4 KiB of shared memory per 64 tensor cycles,
+// the full 128 B/clk (ncu: sm__mem_tensor_cycles_active 78 %); with N = NPX >= 192 pixels it is <= 107 B/clk.
+// (2) NPX is free (any multiple of 16), so the unit size is chosen per layer to fill the last wave of the
+// persistent grid: 46x82x16 pixels x 2 groups at NPX = 256 is 472 units = 3.19 waves of 148 CTAs (4 rounds),
+// at NPX = 208 it is 582 units = 3.93 waves (4 rounds of a 19 % smaller unit).
+// One im2col TMA load brings the NPX consecutive pixels of a unit.  TMEM lanes are channels, columns are pixels;
+// the epilogue transposes through the swizzled staging tiles (one 2-byte shared store per value) and issues
+// TMA stores of rows [0,128) and [128,NPX) (second tensor map with an NPX-128 row box).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_o, const ConvParams p)
+                         const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int W_BYTES = 128 * CONV_BLOCK_K * 2;          // 16 KiB weight tile (128 channels x 64 k)
-    constexpr int STAGE_BYTES = W_BYTES + 2 * CONV_A_BYTES;  // + two 128-pixel activation tiles = 48 KiB
-    uint8_t* bar_base = smem + (size_t)p.num_stages * STAGE_BYTES;
+    const int npx = p.npx;
+    const int stage_bytes = W_BYTES + npx * 128;             // + NPX pixel rows of 128 B
+    uint8_t* bar_base = smem + (size_t)p.num_stages * stage_bytes;
     uint64_t* full_bar = (uint64_t*)bar_base;
     uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;
@@ -504,8 +509,11 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023); // 2 x 16 KiB
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pairs = (p.m_tiles + 1) / 2;
-    const int total_tiles = pairs * p.groups;
+    const int total_px = p.Nb * p.H * p.W;
+    const int units = (total_px + npx - 1) / npx;
+    const int c_tiles = p.cout_g_pad / 128;                  // 128-channel blocks per group
+    const int gc = p.groups * c_tiles;
+    const int total_tiles = units * gc;
     const int chunks = p.cin_g / CONV_BLOCK_K;
     const int ksteps = p.R * p.S * chunks;
 
@@ -513,6 +521,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         ptx::prefetch_tmap(&tmap_o);
+        ptx::prefetch_tmap(&tmap_o2);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.num_stages; ++i) {
@@ -537,31 +546,29 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             const int pad_h = p.R / 2, pad_w = p.S / 2;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int g = tile % p.groups, pair = tile / p.groups;
-                // the second half of an odd last pair starts past the last pixel: the TMA unit zero-fills whatever lies
-                // beyond the tensor and the epilogue never stores it
-                const PixelPos q0 = unflatten(p, 2 * pair * CONV_BLOCK_M);
-                const PixelPos q1 = unflatten(p, (2 * pair + 1) * CONV_BLOCK_M);
+                const int sub = tile % gc, unit = tile / gc;
+                const int g = sub / c_tiles, ct = sub - g * c_tiles;
+                // pixels past the last image are zero-filled by the TMA unit and never stored
+                const PixelPos q0 = unflatten(p, unit * npx);
                 const int a_ch0 = p.in_ch_off + g * p.cin_g;
-                const int b_row = g * p.cout_g_pad;
+                const int b_row = g * p.cout_g_pad + ct * 128;
                 int kcol = 0;
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
                         for (int c = 0; c < chunks; ++c, kcol += CONV_BLOCK_K) {
                             ptx::mbar_wait(ptx::smem_u32(empty_bar + stage), phase ^ 1);
                             const uint32_t fb = ptx::smem_u32(full_bar + stage);
-                            const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                            ptx::mbar_expect_tx(fb, (uint32_t)STAGE_BYTES);
+                            const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+                            ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
                             ptx::tma_load_2d(sw, &tmap_b, fb, kcol, b_row);
                             ptx::tma_load_im2col_4d(sw + W_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, q0.w - pad_w, q0.h - pad_h, q0.n, s, r);
-                            ptx::tma_load_im2col_4d(sw + W_BYTES + CONV_A_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, q1.w - pad_w, q1.h - pad_h, q1.n, s, r);
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         }
             }
         }
     } else if (warp == 1) {
         if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_f16(128, 256);
+            const uint32_t idesc = ptx::make_idesc_f16(128, npx);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -573,9 +580,9 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int ks = 0; ks < ksteps; ++ks) {
                     ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
                     ptx::tc_fence_after();
-                    const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t dw = ptx::make_sw128_kmajor_desc(sw);           // "A" operand: weights, M = 128 channels
-                    const uint64_t dx = ptx::make_sw128_kmajor_desc(sw + W_BYTES); // "B" operand: 256 pixel rows
+                    const uint64_t dx = ptx::make_sw128_kmajor_desc(sw + W_BYTES); // "B" operand: NPX pixel rows
 #pragma unroll
                     for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
                         ptx::umma_f16(d_tmem, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
@@ -588,7 +595,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;
-        const int ch = ew * 32 + lane;                 // TMEM lane == output channel inside the group
+        const int ch = ew * 32 + lane;                 // TMEM lane == output channel inside the 128-channel block
         const bool leader = (warp == 4 && lane == 0);
         uint8_t* sbuf = out_stage + (ch >> 6) * CONV_A_BYTES; // staging tile of this channel's 64-channel half
         const uint32_t sbase = ptx::smem_u32(sbuf) + (uint32_t)((ch & 7) * 2);
@@ -596,18 +603,19 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int g = tile % p.groups, pair = tile / p.groups;
-            const float bias = __ldg(p.bias + g * p.cout_g_pad + ch);
-            const float alpha = __ldg(p.alpha + g * p.cout_g_pad + ch);
+            const int sub = tile % gc, unit = tile / gc;
+            const int g = sub / c_tiles, ct = sub - g * c_tiles;
+            const float bias = __ldg(p.bias + g * p.cout_g_pad + ct * 128 + ch);
+            const float alpha = __ldg(p.alpha + g * p.cout_g_pad + ct * 128 + ch);
             ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 256);
-            for (int half = 0; half < 2; ++half) {
-                const int p0 = (2 * pair + half) * CONV_BLOCK_M;
+            for (int half = 0; half * 128 < npx; ++half) {
+                const int rows = min(128, npx - half * 128);
+                const int p0 = unit * npx + half * 128;
                 if (leader) ptx::bulk_wait_group_read<0>(); // previous stores have drained both staging tiles
                 ptx::named_bar_sync(1, 128);
-#pragma unroll 2
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q * 16 < rows; ++q) {
                     uint32_t v[16];
                     ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(half * 128 + q * 16), v);
                     ptx::tmem_ld_wait();
@@ -623,10 +631,11 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 ptx::fence_proxy_async();
                 ptx::named_bar_sync(1, 128);
-                if (leader && p0 < p.Nb * p.H * p.W) {
-                    const int c0 = p.out_ch_off + g * p.cout_g;
-                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(out_stage), c0, p0);
-                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(out_stage + CONV_A_BYTES), c0 + 64, p0);
+                if (leader && p0 < total_px) {
+                    const int c0 = p.out_ch_off + g * p.cout_g + ct * 128;
+                    const CUtensorMap* tm = (rows == 128) ? &tmap_o : &tmap_o2;
+                    ptx::tma_store_2d(tm, ptx::smem_u32(out_stage), c0, p0);
+                    ptx::tma_store_2d(tm, ptx::smem_u32(out_stage + CONV_A_BYTES), c0 + 64, p0);
                     ptx::bulk_commit_group();
                 }
             }
@@ -651,6 +660,26 @@ constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGE
 inline size_t conv_smem_bytes(int BN, int stages, bool tma_store)
 {
     return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0);
+}
+inline size_t conv_swap_smem_bytes(int npx, int stages) { return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + npx * 128) + 2 * CONV_A_BYTES; }
+inline int conv_swap_pick_stages(int npx)
+{
+    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - 2 * CONV_A_BYTES;
+    const int st = (int)(avail / (size_t)(CONV_A_BYTES + npx * 128));
+    return st > CONV_MAX_STAGES ? CONV_MAX_STAGES : st;
+}
+// unit size that fills the last wave of the persistent grid best: minimise rounds x (npx + fixed per-unit cost)
+inline int conv_swap_pick_npx(long total_px, int gc, int num_sms)
+{
+    int best = 256;
+    long best_cost = -1;
+    for (int npx = 256; npx >= 144; npx -= 16) {
+        const long units = (total_px + npx - 1) / npx * gc;
+        const long rounds = (units + num_sms - 1) / num_sms;
+        const long cost = rounds * (npx + 6) + (npx < 192 ? rounds * (192 - npx) / 4 : 0); // small units: smem operand feed
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = npx; }
+    }
+    return best;
 }
 inline int conv_pick_stages(int BN, bool tma_store)
 {

@@ -126,7 +126,7 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 // activations [N,H,W,C] fp16 in im2col mode: 128 consecutive output pixels x 64 channels per load; the bounding box
 // [-pad, dim - pad) holds one base position per output pixel, filter taps are the im2col offsets of the copy instruction
 // (semantics verified on hardware with tools/probe_im2col.cu)
-int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int R, int S)
+int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int R, int S, int pixels_per_load = CONV_BLOCK_M)
 {
     static PFN_encodeIm2col enc = nullptr;
     if (!enc) {
@@ -142,19 +142,19 @@ int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W
     int lower[2] = { -pad_w, -pad_h };
     int upper[2] = { pad_w - (S - 1), pad_h - (R - 1) };
     cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, lower, upper, 64, CONV_BLOCK_M, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, lower, upper, 64, (cuuint32_t)pixels_per_load, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed: %d (N=%d H=%d W=%d C=%d R=%d S=%d)", (int)r, N, H, W, C, R, S); return HP_ERR_CUDA; }
     return HP_OK;
 }
 // output [N*H*W, C] fp16 as a 2-D tensor: dims (C, pixels), box (64, 128), 128B swizzle (TMA store clips at the last pixel)
-int make_tmap_out(CUtensorMap* m, const __half* base, size_t pixels, int C)
+int make_tmap_out(CUtensorMap* m, const __half* base, size_t pixels, int C, int rows = CONV_BLOCK_M)
 {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
     cuuint64_t dims[2] = { (cuuint64_t)C, (cuuint64_t)pixels };
     cuuint64_t strides[1] = { (cuuint64_t)C * 2 };
-    cuuint32_t box[2] = { 64, CONV_BLOCK_M };
+    cuuint32_t box[2] = { 64, (cuuint32_t)rows };
     cuuint32_t estr[2] = { 1, 1 };
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -193,7 +193,7 @@ int pick_bn(int cout_g)
 
 struct ConvPlan {
     ConvParams prm;
-    CUtensorMap tmap_a, tmap_b, tmap_o;
+    CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2;
     __half* d_w = nullptr;
     float* d_bias = nullptr;
     float* d_alpha = nullptr;
@@ -331,10 +331,26 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         }
         p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
     }
-    // swapped-operand kernel: one 128-channel N tile per group, enough k-steps to amortise the transposing epilogue
-    p.swap_ab = (p.tma_store && cout_pad == 128 && cout_g == 128 && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
-    if (p.swap_ab) p.num_stages = conv_pick_stages(256, true); // stage = 16 KiB weights + 2 x 16 KiB pixels
-    pl.smem = conv_smem_bytes(p.swap_ab ? 256 : BN, p.num_stages, p.tma_store != 0);
+    // swapped-operand kernel: output channels in blocks of 128, enough k-steps to amortise the transposing epilogue
+    memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
+    // (restricted to one 128-channel block per group: with several blocks every block would re-fetch the same pixels
+    //  through L2, which the 2x larger L2->SM traffic does not pay for on the merged 256-channel layers)
+    p.swap_ab = (p.tma_store && cout_pad == 128 && cout_g == cout_pad && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
+    if (p.swap_ab) {
+        const EngBuffer& ob = e->bufs[po.out_buf];
+        const long total_px = (long)e->max_batch * ib.H * ib.W;
+        p.npx = getenv("HPB_NPX") ? atoi(getenv("HPB_NPX")) : conv_swap_pick_npx(total_px, G * (cout_pad / 128), e->num_sms);
+        p.num_stages = conv_swap_pick_stages(p.npx);
+        rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS, p.npx);
+        if (rc) return rc;
+        rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, 128);
+        if (rc) return rc;
+        rc = make_tmap_out(&pl.tmap_o2, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels, p.npx > 128 ? p.npx - 128 : 128);
+        if (rc) return rc;
+        pl.smem = conv_swap_smem_bytes(p.npx, p.num_stages);
+    } else {
+        pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0);
+    }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
     return HP_OK;
 }
@@ -346,8 +362,9 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     p.Nb = N;
     p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
     if (p.swap_ab) {
-        const int n_tiles = (p.m_tiles + 1) / 2 * p.groups;
-        conv_tcgen05_swap_kernel<<<std::min(e->num_sms, n_tiles), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
+        const long total_px = (long)N * p.H * p.W;
+        const int n_tiles = (int)((total_px + p.npx - 1) / p.npx) * p.groups * (p.cout_g_pad / 128);
+        conv_tcgen05_swap_kernel<<<std::min(e->num_sms, n_tiles), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, p);
         e->launches++;
         return HP_OK;
     }
