@@ -164,7 +164,7 @@ EXPORTS += [
     "hp_engine_create", "hp_engine_destroy", "hp_engine_info", "hp_engine_infer_u8_host", "hp_engine_infer_u8_device",
     "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_sync",
     "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
-    "hp_pose_run_u8_host", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
+    "hp_pose_run_u8_host", "hp_engine_stage_frame_u8", "hp_engine_infer_staged", "hp_engine_debug_read_frames", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
 ]
 
 
@@ -186,6 +186,9 @@ def _bind_engine(L):
     L.hp_engine_debug_write_buffer.argtypes = [vp, C.c_int, vp, C.c_int]
     L.hp_engine_debug_run_ops.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.hp_pose_run_u8_host.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, ip]
+    L.hp_engine_stage_frame_u8.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    L.hp_engine_infer_staged.argtypes = [vp, C.c_int]
+    L.hp_engine_debug_read_frames.argtypes = [vp, vp, C.c_int]
     L.hp_engine_set_output_override.argtypes = [vp, vp, vp]
     L.hp_engine_set_profiling.argtypes = [vp, C.c_int]
     L.hp_engine_get_profile.argtypes = [vp, vp, vp, vp, C.c_int, ip, C.POINTER(C.c_longlong)]
@@ -234,6 +237,21 @@ class Engine:
         assert frames.ndim == 4 and frames.shape[1:] == (self.in_h, self.in_w, 3), frames.shape
         check(lib().hp_engine_infer_u8_host(self._h, frames.ctypes.data, frames.shape[0]))
         self._last_n = frames.shape[0]
+
+    def stage_frame(self, slot: int, frame: np.ndarray, keep_ratio: bool = False):
+        """one u8 HWC3 frame of ANY size -> GPU resize (cv::resize / non_scaling_resize) into batch slot `slot`"""
+        frame = np.ascontiguousarray(frame, np.uint8)
+        assert frame.ndim == 3 and frame.shape[2] == 3
+        check(lib().hp_engine_stage_frame_u8(self._h, slot, frame.ctypes.data, frame.shape[0], frame.shape[1], 1 if keep_ratio else 0))
+
+    def infer_staged(self, n: int):
+        check(lib().hp_engine_infer_staged(self._h, n))
+        self._last_n = n
+
+    def debug_read_frames(self, n: int) -> np.ndarray:
+        out = np.empty((n, self.in_h, self.in_w, 3), np.uint8)
+        check(lib().hp_engine_debug_read_frames(self._h, out.ctypes.data, n))
+        return out
 
     def infer_u8_device(self, d_ptr: int, n: int, stream: int = 0):
         check(lib().hp_engine_infer_u8_device(self._h, d_ptr, n, stream))

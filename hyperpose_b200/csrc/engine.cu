@@ -77,6 +77,40 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ i
     for (int i = 0; i < 8; ++i) o[i] = v4[i];
 }
 
+// cv::resize(INTER_LINEAR) on CV_8UC3 frames (src/tensorrt.cpp:451), OpenCV's 11-bit fixed-point bilinear:
+//   rows: S = src[sx]*a0 + src[sx+1]*a1 (a = round(coef*2048)); out = (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2
+// x fractions are clamped at the borders, y keeps the fraction and clips the two row indices (resize.cpp).
+// An exact 2x reduction is INTER_AREA in OpenCV: (a+b+c+d+2)>>2.  Pixels outside the resized region (letterbox,
+// non_scaling_resize src/data.cpp:53-69) are set to 0.  One thread per destination pixel.
+__global__ void __launch_bounds__(256) resize_u8c3_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                                                          int rh, int rw, const int* __restrict__ xi, const short* __restrict__ xa,
+                                                          const int* __restrict__ yi, const short* __restrict__ ya, int area2x)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= dh * dw) return;
+    const int y = idx / dw, x = idx - y * dw;
+    uint8_t* o = dst + (size_t)idx * 3;
+    if (y >= rh || x >= rw) { o[0] = 0; o[1] = 0; o[2] = 0; return; }
+    if (area2x) {
+        const uint8_t* p = src + ((size_t)(2 * y) * sw + 2 * x) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((p[c] + p[3 + c] + p[(size_t)sw * 3 + c] + p[(size_t)sw * 3 + 3 + c] + 2) >> 2);
+        return;
+    }
+    const int x0 = xi[x], x1 = min(x0 + 1, sw - 1);
+    const int y0 = min(max(yi[y], 0), sh - 1), y1 = min(max(yi[y] + 1, 0), sh - 1);
+    const int a0 = xa[2 * x], a1 = xa[2 * x + 1], b0 = ya[2 * y], b1 = ya[2 * y + 1];
+    const uint8_t* r0 = src + (size_t)y0 * sw * 3;
+    const uint8_t* r1 = src + (size_t)y1 * sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int S0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+        const int S1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+        const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
 // 2x2 stride-2 max pool, NHWC fp16, 8 channels per thread; SAME semantics (window clipped at the border).
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                                                        int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW)
@@ -234,6 +268,11 @@ struct hp_engine {
     long long launches = 0;
     double flops_per_frame = 0;
     int last_N = 0;
+    // frame staging with on-device resize (arbitrary-size frames)
+    uint8_t* d_src = nullptr; size_t d_src_bytes = 0;
+    uint8_t* pin_src = nullptr; size_t pin_src_bytes = 0;
+    int* d_rz_xi = nullptr; short* d_rz_xa = nullptr; int* d_rz_yi = nullptr; short* d_rz_ya = nullptr;
+    int rz_sh = -1, rz_sw = -1, rz_rh = 0, rz_rw = 0, rz_keep = -1, rz_area = 0;
     // benchmark hook: synthetic conf/paf copied over the outputs after the last conv
     const float* override_conf = nullptr;
     const float* override_paf = nullptr;
@@ -446,6 +485,12 @@ void free_engine(hp_engine* e)
     if (e->d_frames) cudaFree(e->d_frames);
     if (e->d_input_f32) cudaFree(e->d_input_f32);
     if (e->pin_frames) cudaFreeHost(e->pin_frames);
+    if (e->d_src) cudaFree(e->d_src);
+    if (e->pin_src) cudaFreeHost(e->pin_src);
+    if (e->d_rz_xi) cudaFree(e->d_rz_xi);
+    if (e->d_rz_xa) cudaFree(e->d_rz_xa);
+    if (e->d_rz_yi) cudaFree(e->d_rz_yi);
+    if (e->d_rz_ya) cudaFree(e->d_rz_ya);
     for (auto& ev : e->ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -600,6 +645,106 @@ int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N)
     if (!e->d_input_f32) HP_CUDA_TRY(cudaMalloc(&e->d_input_f32, n * sizeof(float)));
     HP_CUDA_TRY(cudaMemcpyAsync(e->d_input_f32, nchw, (size_t)N * 3 * e->in_h * e->in_w * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     return run_graph(e, N, false, e->stream);
+}
+
+// Stages ONE host frame of arbitrary size into batch slot `slot`: H2D of the original pixels, then the reference's
+// resize step on the GPU -- cv::resize(INTER_LINEAR) or, with keep_ratio, non_scaling_resize (src/tensorrt.cpp:446-451).
+int hp_engine_stage_frame_u8(hp_engine* e, int slot, const uint8_t* frame, int src_h, int src_w, int keep_ratio)
+{
+    if (!e || !frame || slot < 0 || slot >= e->max_batch || src_h <= 0 || src_w <= 0) { set_error("hp_engine_stage_frame_u8: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)src_h * src_w * 3;
+    uint8_t* dst = e->d_frames + (size_t)slot * e->in_h * e->in_w * 3;
+    if (src_h == e->in_h && src_w == e->in_w) { // already network-sized: both resize variants are the identity
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (e->pin_src_bytes < bytes) {
+            if (e->pin_src) cudaFreeHost(e->pin_src);
+            HP_CUDA_TRY(cudaMallocHost(&e->pin_src, bytes));
+            e->pin_src_bytes = bytes;
+        }
+        memcpy(e->pin_src, frame, bytes);
+        HP_CUDA_TRY(cudaMemcpyAsync(dst, e->pin_src, bytes, cudaMemcpyHostToDevice, e->stream));
+        return HP_OK;
+    }
+    if (src_h != e->rz_sh || src_w != e->rz_sw || keep_ratio != e->rz_keep) {
+        int rh = e->in_h, rw = e->in_w;
+        if (keep_ratio) { // non_scaling_resize (src/data.cpp:53-69)
+            const double h1 = e->in_w * (src_h / (double)src_w);
+            const double w2 = e->in_h * (src_w / (double)src_h);
+            if (h1 <= e->in_h) { rw = e->in_w; rh = (int)h1; } else { rw = (int)w2; rh = e->in_h; }
+            if (rh <= 0 || rw <= 0) { set_error("hp_engine_stage_frame_u8: degenerate letterbox"); return HP_ERR_ARG; }
+        }
+        auto table = [](int src, int dst, bool clamp, std::vector<int>& idx, std::vector<short>& coef) {
+            idx.resize(dst); coef.resize(2 * (size_t)dst);
+            const double inv = (double)dst / (double)src, scale = 1.0 / inv;
+            for (int d = 0; d < dst; ++d) {
+                float f = (float)((d + 0.5) * scale - 0.5);
+                int s = (int)floorf(f);
+                f -= (float)s;
+                if (clamp) {
+                    if (s < 0) { f = 0.f; s = 0; }
+                    if (s >= src - 1) { f = 0.f; s = src - 1; }
+                }
+                idx[d] = s;
+                coef[2 * d] = (short)lrintf((1.f - f) * 2048.f);   // saturate_cast<short>(float): round half to even
+                coef[2 * d + 1] = (short)lrintf(f * 2048.f);
+            }
+        };
+        std::vector<int> xi, yi; std::vector<short> xa, ya;
+        table(src_w, rw, true, xi, xa);
+        table(src_h, rh, false, yi, ya);
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (!e->d_rz_xi) {
+            HP_CUDA_TRY(cudaMalloc(&e->d_rz_xi, e->in_w * sizeof(int)));
+            HP_CUDA_TRY(cudaMalloc(&e->d_rz_xa, e->in_w * 2 * sizeof(short)));
+            HP_CUDA_TRY(cudaMalloc(&e->d_rz_yi, e->in_h * sizeof(int)));
+            HP_CUDA_TRY(cudaMalloc(&e->d_rz_ya, e->in_h * 2 * sizeof(short)));
+        }
+        HP_CUDA_TRY(cudaMemcpy(e->d_rz_xi, xi.data(), rw * sizeof(int), cudaMemcpyHostToDevice));
+        HP_CUDA_TRY(cudaMemcpy(e->d_rz_xa, xa.data(), rw * 2 * sizeof(short), cudaMemcpyHostToDevice));
+        HP_CUDA_TRY(cudaMemcpy(e->d_rz_yi, yi.data(), rh * sizeof(int), cudaMemcpyHostToDevice));
+        HP_CUDA_TRY(cudaMemcpy(e->d_rz_ya, ya.data(), rh * 2 * sizeof(short), cudaMemcpyHostToDevice));
+        e->rz_sh = src_h; e->rz_sw = src_w; e->rz_keep = keep_ratio; e->rz_rh = rh; e->rz_rw = rw;
+        e->rz_area = (src_h == 2 * rh && src_w == 2 * rw) ? 1 : 0;
+    }
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); // pin_src / d_src may still feed the previous frame
+    if (e->pin_src_bytes < bytes) {
+        if (e->pin_src) cudaFreeHost(e->pin_src);
+        HP_CUDA_TRY(cudaMallocHost(&e->pin_src, bytes));
+        e->pin_src_bytes = bytes;
+    }
+    if (e->d_src_bytes < bytes) {
+        if (e->d_src) cudaFree(e->d_src);
+        HP_CUDA_TRY(cudaMalloc(&e->d_src, bytes));
+        e->d_src_bytes = bytes;
+    }
+    memcpy(e->pin_src, frame, bytes);
+    HP_CUDA_TRY(cudaMemcpyAsync(e->d_src, e->pin_src, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int total = e->in_h * e->in_w;
+    resize_u8c3_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(e->d_src, src_h, src_w, dst, e->in_h, e->in_w, e->rz_rh, e->rz_rw,
+                                                                 e->d_rz_xi, e->d_rz_xa, e->d_rz_yi, e->d_rz_ya, e->rz_area);
+    e->launches++;
+    HP_CUDA_TRY(cudaGetLastError());
+    return HP_OK;
+}
+
+// runs the network on the N frames staged by hp_engine_stage_frame_u8
+int hp_engine_infer_staged(hp_engine* e, int N)
+{
+    if (!e) return HP_ERR_ARG;
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    return run_graph(e, N, true, e->stream);
+}
+
+// test hook: the staged (resized) u8 frames back on the host
+int hp_engine_debug_read_frames(hp_engine* e, uint8_t* out, int N)
+{
+    if (!e || !out || N <= 0 || N > e->max_batch) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    HP_CUDA_TRY(cudaMemcpy(out, e->d_frames, (size_t)N * e->in_h * e->in_w * 3, cudaMemcpyDeviceToHost));
+    return HP_OK;
 }
 
 int hp_engine_outputs(hp_engine* e, const float** d_conf, const float** d_paf, void** stream)

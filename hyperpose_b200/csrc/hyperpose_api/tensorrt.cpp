@@ -105,20 +105,17 @@ namespace dnn {
     {
         if (batch.size() > (size_t)m_max_batch_size)
             throw std::logic_error("Input batch size overflow: Yours@" + std::to_string(batch.size()) + " Max@" + std::to_string(m_max_batch_size));
-        const size_t frame = (size_t)m_inp_size.width * m_inp_size.height * 3;
-        std::vector<uint8_t> host(batch.size() * frame);
+        // Step 1 of the reference (cv::resize / non_scaling_resize on the CPU, tensorrt.cpp:446-451) runs on the GPU,
+        // bit-exact with OpenCV's 8-bit bilinear; step 2 (_batching, NHWC->NCHW) is fused into the first conv's gather.
         for (size_t i = 0; i < batch.size(); ++i) {
             const cv::Mat& m = batch[i];
-            if (m.type() != CV_8UC3 || m.cols != m_inp_size.width || m.rows != m_inp_size.height || !m.isContinuous()) {
-                // the reference resizes on the CPU here (cv::resize / non_scaling_resize, tensorrt.cpp:446-451);
-                // a GPU resize is the next row of the hot-path table (DESIGN.md "what comes next")
-                std::cerr << "[HyperPose::ERROR  ] B200 engine: frames must be CV_8UC3 at the network size ("
-                          << m_inp_size.width << "x" << m_inp_size.height << ")\n";
+            if (m.type() != CV_8UC3 || !m.isContinuous() || m.empty()) {
+                std::cerr << "[HyperPose::ERROR  ] B200 engine: frames must be continuous CV_8UC3\n";
                 std::exit(-1);
             }
-            std::memcpy(host.data() + i * frame, m.data, frame);
+            if (hp_engine_stage_frame_u8(m_cuda_dep->engine, (int)i, m.data, m.rows, m.cols, m_keep_ratio ? 1 : 0) != HP_OK) die("hp_engine_stage_frame_u8");
         }
-        if (hp_engine_infer_u8_host(m_cuda_dep->engine, host.data(), (int)batch.size()) != HP_OK) die("hp_engine_infer_u8_host");
+        if (hp_engine_infer_staged(m_cuda_dep->engine, (int)batch.size()) != HP_OK) die("hp_engine_infer_staged");
         return collect(m_cuda_dep->engine, batch.size(), m_cuda_dep->c_conf, m_cuda_dep->c_paf, m_cuda_dep->out_h, m_cuda_dep->out_w);
     }
 

@@ -125,6 +125,12 @@ int hp_engine_info(const hp_engine* e, int* in_w, int* in_h, int* max_batch, int
  * Asynchronous: outputs stay on the device (hp_engine_outputs / hp_engine_read_outputs_host). */
 int hp_engine_infer_u8_host(hp_engine* e, const uint8_t* frames, int N);
 int hp_engine_infer_u8_device(hp_engine* e, const uint8_t* d_frames, int N, void* stream);
+/* The resize step of tensorrt::inference (tensorrt.cpp:446-451) on the GPU: stages ONE host frame of any size into
+ * batch slot `slot` -- cv::resize(INTER_LINEAR) or, with keep_ratio, non_scaling_resize (src/data.cpp:53-69),
+ * bit-exact with OpenCV's 8-bit fixed-point bilinear.  hp_engine_infer_staged then runs the network on N slots. */
+int hp_engine_stage_frame_u8(hp_engine* e, int slot, const uint8_t* frame, int src_h, int src_w, int keep_ratio);
+int hp_engine_infer_staged(hp_engine* e, int N);
+int hp_engine_debug_read_frames(hp_engine* e, uint8_t* out, int N);
 /* tensorrt::inference(const std::vector<float>&, size_t) (tensorrt.cpp:364-434): HOST f32 NCHW, pre-scaled */
 int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N);
 /* device pointers of the fp32 NCHW outputs conf[N,c_conf,h,w] / paf[N,c_paf,h,w] and the engine stream */

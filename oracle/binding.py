@@ -71,6 +71,10 @@ def load_oracle():
         lib.orc_gauss17_kernel.restype = fp
         lib.orc_area_up_tab.restype = None
         lib.orc_area_up_tab.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), fp]
+        u8p = C.POINTER(C.c_uint8)
+        for fn in (lib.orc_resize_linear_u8c3, lib.orc_letterbox_u8c3):
+            fn.restype = C.c_int
+            fn.argtypes = [u8p, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
         _orc = lib
     return _orc
 
@@ -93,6 +97,19 @@ def area_up_tab(src: int, dst: int):
     fr = np.empty(dst, np.float32)
     load_oracle().orc_area_up_tab(src, dst, idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(fr))
     return idx, fr
+
+
+def resize_linear_u8(img: np.ndarray, dh: int, dw: int, letterbox: bool = False) -> np.ndarray:
+    """cv::resize(INTER_LINEAR) on u8 HWC3 (letterbox=True: non_scaling_resize, src/data.cpp:53-69)"""
+    img = np.ascontiguousarray(img, np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3
+    out = np.empty((dh, dw, 3), np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    fn = load_oracle().orc_letterbox_u8c3 if letterbox else load_oracle().orc_resize_linear_u8c3
+    rc = fn(img.ctypes.data_as(u8p), img.shape[0], img.shape[1], out.ctypes.data_as(u8p), dh, dw)
+    if rc:
+        raise ValueError(f"resize rc={rc}")
+    return out
 
 
 def gaussian17(img: np.ndarray) -> np.ndarray:

@@ -392,3 +392,84 @@ done:
     free(up_conf); free(up_paf); free(smoothed); free(pooled);
     return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame resize of tensorrt::inference(std::vector<cv::Mat>) (src/tensorrt.cpp:446-451):
+ * cv::resize(mat, mat, size) = INTER_LINEAR on CV_8UC3, and non_scaling_resize (src/data.cpp:53-69).
+ * Restates OpenCV's 8-bit fixed-point bilinear path (resize.cpp: INTER_RESIZE_COEF_BITS = 11,
+ * HResizeLinear / VResizeLinear<uchar,int,short>), including the exact-2x shortcut to INTER_AREA.
+ * Pinned bit-exactly against cv2 4.13.0 (tests/golden/cv_pin.npz, tests/test_oracle_cv_pin.py).
+ * ---------------------------------------------------------------------------------------------- */
+static int cv_round_half_even(float v) { return (int)lrintf(v); } /* saturate_cast<short>(float) = cvRound */
+
+void orc_linear_tab(int src, int dst, int clamp_frac, int32_t* idx, int16_t* coef /* [dst][2] */)
+{
+    const double inv = (double)dst / (double)src;
+    const double scale = 1.0 / inv;
+    for (int d = 0; d < dst; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (clamp_frac) { /* x direction: resize.cpp clamps the fraction at the borders ... */
+            if (s < 0) { f = 0.f; s = 0; }
+            if (s >= src - 1) { f = 0.f; s = src - 1; }
+        } /* ... the y direction keeps the fraction and clips the two row indices instead */
+        idx[d] = s;
+        coef[2 * d] = (int16_t)cv_round_half_even((1.f - f) * 2048.f);
+        coef[2 * d + 1] = (int16_t)cv_round_half_even(f * 2048.f);
+    }
+}
+
+int orc_resize_linear_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw)
+{
+    if (sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0) return -1;
+    if (sh == dh && sw == dw) { memcpy(dst, src, (size_t)sh * sw * 3); return 0; }
+    if (sh == 2 * dh && sw == 2 * dw) { /* INTER_LINEAR with integer scale 2 is switched to INTER_AREA: (a+b+c+d+2)>>2 */
+        for (int y = 0; y < dh; ++y)
+            for (int x = 0; x < dw; ++x)
+                for (int c = 0; c < 3; ++c) {
+                    const uint8_t* p = src + ((size_t)(2 * y) * sw + 2 * x) * 3 + c;
+                    dst[((size_t)y * dw + x) * 3 + c] = (uint8_t)((p[0] + p[3] + p[(size_t)sw * 3] + p[(size_t)sw * 3 + 3] + 2) >> 2);
+                }
+        return 0;
+    }
+    int32_t* xi = (int32_t*)malloc(sizeof(int32_t) * dw); int16_t* xa = (int16_t*)malloc(sizeof(int16_t) * 2 * dw);
+    int32_t* yi = (int32_t*)malloc(sizeof(int32_t) * dh); int16_t* ya = (int16_t*)malloc(sizeof(int16_t) * 2 * dh);
+    orc_linear_tab(sw, dw, 1, xi, xa);
+    orc_linear_tab(sh, dh, 0, yi, ya);
+    for (int y = 0; y < dh; ++y) {
+        int y0 = yi[y], y1 = yi[y] + 1;
+        y0 = y0 < 0 ? 0 : (y0 > sh - 1 ? sh - 1 : y0);
+        y1 = y1 < 0 ? 0 : (y1 > sh - 1 ? sh - 1 : y1);
+        const int b0 = ya[2 * y], b1 = ya[2 * y + 1];
+        for (int x = 0; x < dw; ++x) {
+            const int x0 = xi[x], x1 = x0 + 1 < sw ? x0 + 1 : sw - 1;
+            const int a0 = xa[2 * x], a1 = xa[2 * x + 1];
+            for (int c = 0; c < 3; ++c) {
+                const int S0 = src[((size_t)y0 * sw + x0) * 3 + c] * a0 + src[((size_t)y0 * sw + x1) * 3 + c] * a1;
+                const int S1 = src[((size_t)y1 * sw + x0) * 3 + c] * a0 + src[((size_t)y1 * sw + x1) * 3 + c] * a1;
+                int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+                dst[((size_t)y * dw + x) * 3 + c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+        }
+    }
+    free(xi); free(xa); free(yi); free(ya);
+    return 0;
+}
+
+/* non_scaling_resize (src/data.cpp:53-69): fit inside dst keeping the aspect ratio, pad right/bottom with 0 */
+int orc_letterbox_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw)
+{
+    const double h1 = dw * (sh / (double)sw);
+    const double w2 = dh * (sw / (double)sh);
+    int rh, rw;
+    if (h1 <= dh) { rw = dw; rh = (int)h1; } else { rw = (int)w2; rh = dh; }
+    if (rh <= 0 || rw <= 0) return -1;
+    uint8_t* tmp = (uint8_t*)malloc((size_t)rh * rw * 3);
+    int rc = orc_resize_linear_u8c3(src, sh, sw, tmp, rh, rw);
+    memset(dst, 0, (size_t)dh * dw * 3);
+    for (int y = 0; y < rh; ++y) memcpy(dst + (size_t)y * dw * 3, tmp + (size_t)y * rw * 3, (size_t)rw * 3);
+    free(tmp);
+    return rc;
+}

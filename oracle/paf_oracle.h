@@ -54,6 +54,11 @@ int orc_paf_process(const float* conf, const float* paf, int c_conf, int c_paf, 
                     orc_peak* peaks, int peak_cap, int* n_peaks,
                     orc_conn* conns /* [19][conn_cap] */, int conn_cap, int* n_conns /* [19] */);
 
+/* cv::resize(INTER_LINEAR) on CV_8UC3 (src/tensorrt.cpp:451) and non_scaling_resize (src/data.cpp:53-69) */
+int orc_resize_linear_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
+int orc_letterbox_u8c3(const uint8_t* src, int sh, int sw, uint8_t* dst, int dh, int dw);
+void orc_linear_tab(int src, int dst, int clamp_frac, int32_t* idx, int16_t* coef);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,11 @@ FRAME_CASES = [
 ]
 
 
+# (src_h, src_w, dst_h, dst_w) of the frame-resize pin
+RESIZE_CASES = [(360, 640, 368, 656), (480, 640, 368, 656), (720, 1280, 368, 656), (736, 1312, 368, 656), (100, 80, 368, 432),
+                (1080, 1920, 368, 656), (368, 656, 368, 656), (300, 500, 207, 344), (37, 53, 64, 48)]
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -64,6 +69,14 @@ def main():
         out[f"big{i}_dims"] = np.array([sh, sw, dh, dw])
         out[f"big{i}_up_sha"] = np.array(sha(up))
         out[f"big{i}_blur_sha"] = np.array(sha(cv2.GaussianBlur(up, (17, 17), 3.0)))
+    # cv::resize(INTER_LINEAR) on u8 frames (src/tensorrt.cpp:451) and the letterbox path (src/data.cpp:53-69)
+    for i, (sh, sw, dh, dw) in enumerate(RESIZE_CASES):
+        img = np.random.default_rng(200 + i).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        out[f"rz{i}_sha"] = np.array(sha(cv2.resize(img, (dw, dh))))
+        h1 = dw * (sh / float(sw)); w2 = dh * (sw / float(sh))
+        rw, rh = (dw, int(h1)) if h1 <= dh else (int(w2), dh)
+        lb = cv2.copyMakeBorder(cv2.resize(img, (rw, rh)), 0, dh - rh, 0, dw - rw, cv2.BORDER_CONSTANT, value=(0, 0, 0))
+        out[f"lb{i}_sha"] = np.array(sha(lb))
     np.savez_compressed(os.path.join(HERE, "cv_pin.npz"), **out)
 
     ref = {}

@@ -139,3 +139,26 @@ def test_output_override_hook_and_profile():
     ms, ty, fl, runs = eng.get_profile()
     assert runs == 1 and len(ms) == len(g.ops) and ms[ty == models.OP_CONV].sum() > 0
     eng.close(); parser.close()
+
+
+@pytest.mark.parametrize("src_hw,keep", [((90, 150), False), ((128, 192), False), ((200, 120), True), ((48, 200), True), ((64, 96), False)])
+def test_gpu_frame_resize_bit_exact_vs_oracle(src_hw, keep):
+    """A1: the resize step of tensorrt::inference (cv::resize INTER_LINEAR / non_scaling_resize) on the GPU,
+    bit-exact against the oracle restatement that is pinned to cv2 (tests/test_oracle_cv_pin.py)"""
+    g = models.tiny_test_net(0)
+    H, W = 64, 96
+    eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=2)
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, (src_hw[0], src_hw[1], 3), dtype=np.uint8) for _ in range(2)]
+    for i, f in enumerate(frames):
+        eng.stage_frame(i, f, keep_ratio=keep)
+    got = eng.debug_read_frames(2)
+    for i, f in enumerate(frames):
+        want = oracle.resize_linear_u8(f, H, W, letterbox=keep)
+        assert np.array_equal(got[i], want), f"frame {i}: {np.abs(got[i].astype(int) - want.astype(int)).max()}"
+    eng.infer_staged(2)
+    c1, p1 = eng.read_outputs(2)
+    eng.infer_u8(got)
+    c2, p2 = eng.read_outputs(2)
+    assert np.array_equal(c1, c2) and np.array_equal(p1, p2)
+    eng.close()
