@@ -37,16 +37,19 @@ using namespace hpb;
 // channels (27 values + zeros).  SAME padding pads the *normalised* input with zeros.
 //   u8 path : v = (float)((double)u8 * factor) (data.cpp:48); model channel c reads byte (flip ? 2-c : c)
 //   f32 path: input is already scaled NCHW (tensorrt::inference(const std::vector<float>&, size_t))
+// stride 2 (MobileNet stem): output pixel (oh, ow) gathers rows 2*oh - pad + r with TF "SAME" padding
+// (pad_before = max((OH-1)*2 + 3 - H, 0) / 2, i.e. 0 for even H).
 template <bool U8>
 __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
-                                                      int N, int H, int W, double factor, int flip, float m0, float m1, float m2)
+                                                      int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
+                                                      int stride, int OH, int OW, int pad_h, int pad_w)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * H * W;
+    const size_t total = (size_t)N * OH * OW;
     if (idx >= total) return;
-    const int w = (int)(idx % W);
-    const int h = (int)((idx / W) % H);
-    const int n = (int)(idx / ((size_t)W * H));
+    const int w = (int)(idx % OW) * stride - pad_w + 1; // "+1": the tap loop below uses (r - 1, s - 1)
+    const int h = (int)((idx / OW) % OH) * stride - pad_h + 1;
+    const int n = (int)(idx / ((size_t)OW * OH));
     const float mean[3] = { m0, m1, m2 };
     __align__(16) __half vals[64];
 #pragma unroll
@@ -109,6 +112,55 @@ __global__ void __launch_bounds__(256) resize_u8c3_kernel(const uint8_t* __restr
         const int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
         o[c] = (uint8_t)min(max(v, 0), 255);
     }
+}
+
+// depthwise KxK conv (K in {1,3}) + bias + PReLU on fp16 NHWC, 8 channels per thread (one 16-byte load per tap),
+// fp32 accumulation.  HBM-bound: reads each input element ~once (taps hit L1/L2), writes the output once.
+// Reference layers: DepthwiseConv2d + BatchNorm2d(act) of separable_block (hyperpose/Model/backbones.py:240-248), BN folded.
+__global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
+                                                     const float* __restrict__ w /*[K*K][C]*/, const float* __restrict__ bias,
+                                                     const float* __restrict__ alpha, int N, int H, int W, int C, int K, int stride,
+                                                     int OH, int OW, int pad_h, int pad_w)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = C / 8;
+    const size_t total = (size_t)N * OH * OW * cv;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % cv) * 8;
+    size_t t = idx / cv;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < K; ++r) {
+        const int h = oh * stride - pad_h + r;
+        if (h < 0 || h >= H) continue;
+        for (int s = 0; s < K; ++s) {
+            const int x = ow * stride - pad_w + s;
+            if (x < 0 || x >= W) continue;
+            const uint4 v = *(const uint4*)(in + (((size_t)n * H + h) * W + x) * in_ld + c0);
+            const __half2* h2 = (const __half2*)&v;
+            const float4 w0 = __ldg((const float4*)(w + (size_t)(r * K + s) * C + c0));
+            const float4 w1 = __ldg((const float4*)(w + (size_t)(r * K + s) * C + c0 + 4));
+            const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
+            acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
+            acc[2] = fmaf(b.x, w0.z, acc[2]); acc[3] = fmaf(b.y, w0.w, acc[3]);
+            acc[4] = fmaf(c.x, w1.x, acc[4]); acc[5] = fmaf(c.y, w1.y, acc[5]);
+            acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
+        }
+    }
+    uint4 o;
+    __half2* oh2 = (__half2*)&o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float y0 = acc[2 * j] + __ldg(bias + c0 + 2 * j), y1 = acc[2 * j + 1] + __ldg(bias + c0 + 2 * j + 1);
+        y0 = y0 > 0.f ? y0 : y0 * __ldg(alpha + c0 + 2 * j);
+        y1 = y1 > 0.f ? y1 : y1 * __ldg(alpha + c0 + 2 * j + 1);
+        oh2[j] = __floats2half2_rn(y0, y1);
+    }
+    *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * out_ld + c0) = o;
 }
 
 // 2x2 stride-2 max pool, NHWC fp16, 8 channels per thread; SAME semantics (window clipped at the border).
@@ -239,8 +291,17 @@ struct ConvPlan {
 
 struct EngOp {
     PackOp po;
-    ConvPlan plan; // OP_CONV only
+    ConvPlan plan;              // OP_CONV only
+    float* d_dw = nullptr;      // OP_DWCONV: [K*K][C] weights | bias[C] | alpha[C]
 };
+
+// TF "SAME": out = ceil(in / stride), pad_before = max((out - 1) * stride + k - in, 0) / 2
+inline int same_pad_before(int in, int k, int stride)
+{
+    const int out = (in + stride - 1) / stride;
+    const int total = std::max((out - 1) * stride + k - in, 0);
+    return total / 2;
+}
 
 struct EngBuffer {
     int channels = 0, down = 0, H = 0, W = 0;
@@ -441,10 +502,23 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& ob = e->bufs[po.out_buf];
             const size_t total = (size_t)N * ob.H * ob.W;
             const int blocks = (int)((total + 255) / 256);
+            const int stride = po.stride ? (int)po.stride : 1;
+            const int ph = same_pad_before(e->in_h, 3, stride), pw = same_pad_before(e->in_w, 3, stride);
             if (u8_input)
-                im2col3_kernel<true><<<blocks, 256, 0, st>>>(e->d_frames, ob.d, N, ob.H, ob.W, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2]);
+                im2col3_kernel<true><<<blocks, 256, 0, st>>>(e->d_frames, ob.d, N, e->in_h, e->in_w, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
+                                                            stride, ob.H, ob.W, ph, pw);
             else
-                im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, ob.H, ob.W, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2]);
+                im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, e->in_h, e->in_w, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
+                                                             stride, ob.H, ob.W, ph, pw);
+            e->launches++;
+        } else if (po.type == OP_DWCONV) {
+            EngBuffer& ib = e->bufs[po.in_buf];
+            EngBuffer& ob = e->bufs[po.out_buf];
+            const int C = (int)po.cout_g, K = (int)po.R, stride = po.stride ? (int)po.stride : 1;
+            const size_t total = (size_t)N * ob.H * ob.W * (C / 8);
+            dwconv_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels,
+                                                                   op.d_dw, op.d_dw + (size_t)K * K * C, op.d_dw + (size_t)K * K * C + C, N, ib.H, ib.W, C, K, stride,
+                                                                   ob.H, ob.W, same_pad_before(ib.H, K, stride), same_pad_before(ib.W, K, stride));
             e->launches++;
         } else if (po.type == OP_MAXPOOL2) {
             EngBuffer& ib = e->bufs[po.in_buf];
@@ -479,6 +553,7 @@ void free_engine(hp_engine* e)
         if (o.plan.d_w) cudaFree(o.plan.d_w);
         if (o.plan.d_bias) cudaFree(o.plan.d_bias);
         if (o.plan.d_alpha) cudaFree(o.plan.d_alpha);
+        if (o.d_dw) cudaFree(o.d_dw);
     }
     if (e->d_conf) cudaFree(e->d_conf);
     if (e->d_paf) cudaFree(e->d_paf);
@@ -570,7 +645,30 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             max_smem = std::max(max_smem, e->ops[i].plan.smem);
             e->flops_per_frame += e->ops[i].plan.flops_per_frame;
         } else if (po.type == OP_IM2COL3) {
-            if (e->bufs[po.out_buf].channels != 64 || e->bufs[po.out_buf].down != 0) { set_error("engine: im2col buffer must be 64 channels at full resolution"); return fail(HP_ERR_ARG); }
+            const int stride = po.stride ? (int)po.stride : 1;
+            if (e->bufs[po.out_buf].channels != 64 || e->bufs[po.out_buf].down != (stride == 2 ? 1 : 0) || stride > 2) { set_error("engine: im2col buffer must be 64 channels at the stem resolution"); return fail(HP_ERR_ARG); }
+        } else if (po.type == OP_DWCONV) {
+            const int C = (int)po.cout_g, K = (int)po.R, stride = po.stride ? (int)po.stride : 1;
+            const EngBuffer& ib = e->bufs[po.in_buf];
+            const EngBuffer& ob = e->bufs[po.out_buf];
+            if (C % 8 || (K != 1 && K != 3) || po.S != po.R || stride < 1 || stride > 2 || ob.down != ib.down + (stride == 2 ? 1 : 0) ||
+                (int)po.in_ch_off + C > ib.channels || (int)po.out_ch_off + C > ob.channels || po.in_ch_off % 8 || po.out_ch_off % 8) {
+                set_error("engine: bad depthwise op %u", i);
+                return fail(HP_ERR_ARG);
+            }
+            // blob W[C][K][K] -> device [K*K][C] (tap-major so that 8 consecutive channels are one 32-byte load)
+            std::vector<float> w((size_t)K * K * C + 2 * (size_t)C);
+            for (int c = 0; c < C; ++c) {
+                for (int t = 0; t < K * K; ++t) w[(size_t)t * C + c] = blob[po.w_off + (size_t)c * K * K + t];
+                w[(size_t)K * K * C + c] = blob[po.b_off + c];
+                w[(size_t)K * K * C + C + c] = blob[po.a_off + c];
+            }
+            if (cudaMalloc(&e->ops[i].d_dw, w.size() * sizeof(float)) != cudaSuccess ||
+                cudaMemcpy(e->ops[i].d_dw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("engine: depthwise weight upload failed");
+                return fail(HP_ERR_CUDA);
+            }
+            e->flops_per_frame += 2.0 * ob.H * ob.W * C * K * K;
         } else if (po.type == OP_MAXPOOL2) {
             if (po.cout_g % 8 || e->bufs[po.out_buf].down != e->bufs[po.in_buf].down + 1) { set_error("engine: bad maxpool op %u", i); return fail(HP_ERR_ARG); }
         } else {

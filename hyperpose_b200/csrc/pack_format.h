@@ -14,7 +14,8 @@ constexpr uint32_t PACK_VERSION = 1;
 enum PackOpType : uint32_t {
     OP_IM2COL3 = 1, // network input (u8 HWC frames or f32 NCHW) -> [N,H,W,64] fp16: 3x3x3 patches (27 values + 37 zeros), minus mean
     OP_CONV = 2,    // stride-1 SAME convolution + bias + PReLU (alpha 0 = ReLU, alpha 1 = linear)
-    OP_MAXPOOL2 = 3 // 2x2 stride-2 max-pool, SAME (ceil) semantics
+    OP_MAXPOOL2 = 3, // 2x2 stride-2 max-pool, SAME (ceil) semantics
+    OP_DWCONV = 4    // depthwise KxK (K = 1 or 3) conv, stride 1/2, TF "SAME" padding, + bias + PReLU; HBM-bound CUDA-core kernel
 };
 
 struct PackHeader {
@@ -41,8 +42,9 @@ struct PackOp {
     uint32_t out_mode;              // ConvOutMode; OUT_F32_NCHW_SPLIT writes the engine's conf/paf outputs
     uint32_t split;
     uint32_t im2col_input;          // 1: this conv consumes an OP_IM2COL3 buffer (R*S*cin_g <= 64 packed as one 64-ch k-step)
-    uint32_t reserved;
+    uint32_t stride;                // OP_IM2COL3 / OP_DWCONV: 1 or 2 (0 = 1)
     uint64_t w_off, b_off, a_off;   // float offsets into the blob: W[G][cout_g][cin_g][R][S], bias[G*cout_g], alpha[G*cout_g]
+                                    // OP_DWCONV: W[C][R][S], bias[C], alpha[C] with C = cout_g
 };
 
 static_assert(sizeof(PackHeader) == 72 && sizeof(PackBuffer) == 8 && sizeof(PackOp) == 80, "pack layout");

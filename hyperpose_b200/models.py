@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-OP_IM2COL3, OP_CONV, OP_MAXPOOL2 = 1, 2, 3
+OP_IM2COL3, OP_CONV, OP_MAXPOOL2, OP_DWCONV = 1, 2, 3, 4
 OUT_F16_NHWC, OUT_F32_NCHW_SPLIT = 0, 1
 PACK_MAGIC = b"HPB2PACK"
 PACK_VERSION = 1
@@ -40,7 +40,8 @@ class Op:
     out_mode: int = OUT_F16_NHWC
     split: int = 0
     im2col_input: int = 0
-    weight: np.ndarray | None = None   # [G, cout_g, cin_g, R, S] float32
+    stride: int = 1
+    weight: np.ndarray | None = None   # [G, cout_g, cin_g, R, S] float32 (OP_DWCONV: [C, K, K])
     bias: np.ndarray | None = None     # [G*cout_g]
     alpha: np.ndarray | None = None    # [G*cout_g]  PReLU slope; 0 = ReLU, 1 = linear
     name: str = ""
@@ -61,8 +62,16 @@ class Graph:
         self.buffers.append((channels, down_shift))
         return len(self.buffers) - 1
 
-    def add_im2col(self, out_buf: int, name="im2col") -> None:
-        self.ops.append(Op(OP_IM2COL3, out_buf=out_buf, name=name))
+    def add_im2col(self, out_buf: int, stride: int = 1, name="im2col") -> None:
+        self.ops.append(Op(OP_IM2COL3, out_buf=out_buf, stride=stride, name=name))
+
+    def add_dwconv(self, in_buf, out_buf, weight, bias, alpha, stride=1, in_ch_off=0, out_ch_off=0, name="dw") -> None:
+        """depthwise KxK conv (K in {1,3}) + bias + PReLU; weight [C, K, K]"""
+        C, K, K2 = weight.shape
+        assert K == K2 and K in (1, 3) and C % 8 == 0
+        self.ops.append(Op(OP_DWCONV, in_buf, out_buf, in_ch_off, out_ch_off, K, K, 1, C, C, stride=stride,
+                           weight=np.ascontiguousarray(weight, np.float32), bias=np.ascontiguousarray(bias, np.float32).reshape(-1),
+                           alpha=np.ascontiguousarray(alpha, np.float32).reshape(-1), name=name))
 
     def add_maxpool(self, in_buf: int, out_buf: int, channels: int, name="pool") -> None:
         self.ops.append(Op(OP_MAXPOOL2, in_buf=in_buf, out_buf=out_buf, cout_g=channels, name=name))
@@ -71,8 +80,8 @@ class Graph:
                  im2col_input=0, name="conv") -> None:
         G, cout_g, cin_g, R, S = weight.shape
         self.ops.append(Op(OP_CONV, in_buf, out_buf, in_ch_off, out_ch_off, R, S, G, cin_g, cout_g, out_mode, split, im2col_input,
-                           np.ascontiguousarray(weight, np.float32), np.ascontiguousarray(bias, np.float32).reshape(-1),
-                           np.ascontiguousarray(alpha, np.float32).reshape(-1), name))
+                           weight=np.ascontiguousarray(weight, np.float32), bias=np.ascontiguousarray(bias, np.float32).reshape(-1),
+                           alpha=np.ascontiguousarray(alpha, np.float32).reshape(-1), name=name))
 
     # ---- serialisation (layout of pack_format.h) ----
     def to_pack(self) -> bytes:
@@ -81,12 +90,12 @@ class Graph:
         op_recs = []
         for op in self.ops:
             w_off = b_off = a_off = 0
-            if op.type == OP_CONV:
+            if op.type in (OP_CONV, OP_DWCONV):
                 w_off = off; blob.append(op.weight.reshape(-1)); off += op.weight.size
                 b_off = off; blob.append(op.bias); off += op.bias.size
                 a_off = off; blob.append(op.alpha); off += op.alpha.size
             op_recs.append(struct.pack("<14I3Q", op.type, op.in_buf, op.out_buf, op.in_ch_off, op.out_ch_off, op.R, op.S, op.groups,
-                                       op.cin_g, op.cout_g, op.out_mode, op.split, op.im2col_input, 0, w_off, b_off, a_off))
+                                       op.cin_g, op.cout_g, op.out_mode, op.split, op.im2col_input, op.stride, w_off, b_off, a_off))
         blob_arr = np.concatenate(blob).astype("<f4") if blob else np.zeros(0, "<f4")
         hdr = struct.pack("<8s6I3f5IQ", PACK_MAGIC, PACK_VERSION, len(self.buffers), len(self.ops), self.conf_channels,
                           self.paf_channels, self.out_down_shift, *[float(m) for m in self.mean], 0, 0, 0, 0, 0, blob_arr.size)
@@ -96,13 +105,16 @@ class Graph:
     def flops_per_frame(self, in_h: int, in_w: int) -> float:
         total = 0.0
         for op in self.ops:
-            if op.type != OP_CONV:
+            if op.type not in (OP_CONV, OP_DWCONV):
                 continue
-            _, d = self.buffers[op.in_buf]
+            _, d = self.buffers[op.out_buf if op.type == OP_DWCONV or op.out_mode == OUT_F16_NHWC else op.in_buf]
             h, w = in_h, in_w
             for _ in range(d):
                 h, w = (h + 1) // 2, (w + 1) // 2
-            total += 2.0 * h * w * op.groups * op.cout_g * op.cin_g * op.R * op.S
+            if op.type == OP_DWCONV:
+                total += 2.0 * h * w * op.cout_g * op.R * op.S
+            else:
+                total += 2.0 * h * w * op.groups * op.cout_g * op.cin_g * op.R * op.S
         return total
 
 
@@ -183,6 +195,106 @@ def openpose_vgg19(seed: int = 0, n_stages: int = 6) -> Graph:
             src, dst = dst, src
         g.add_conv(src, dst, _he(rng, 2, 128, 128, 1, 1), b_(256), prelu(256), name=f"ref{s}_6")
         out_conv(dst, 128, s == n_stages - 1, f"ref{s}_out")
+    return g
+
+
+def _bn_fold(rng, n):
+    """random inference-time BatchNorm -> (scale, shift): y = scale * x + shift"""
+    gamma = rng.uniform(0.8, 1.2, n); beta = rng.normal(0, 0.05, n); mean = rng.normal(0, 0.05, n); var = rng.uniform(0.8, 1.2, n)
+    scale = gamma / np.sqrt(var + 1e-5)
+    return scale.astype(np.float32), (beta - mean * scale).astype(np.float32)
+
+
+def _r64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6) -> Graph:
+    """OpenPose on MobilenetThin (BASELINE.json config 2): hyperpose/Model/backbones.py:240-297 (3x3/2 stem + 11
+    depthwise-separable blocks, three scales concatenated to 1152 channels at stride 8) and
+    hyperpose/Model/openpose/model/mbv2_th_openpose.py:106-158 (init + 5 refinement stages of separable blocks).
+    Inference-time BatchNorm is folded (random statistics): depthwise conv + BN + ReLU -> one OP_DWCONV;
+    1x1 conv + BN (+ReLU) -> one OP_CONV.  The stem is Conv(act=relu) followed by BatchNorm(act=relu)
+    (mbv2_th_openpose.py:160-166), which cannot be folded through the inner ReLU: conv(+bias, ReLU) then a 1x1
+    depthwise affine + ReLU.  Both branches of a stage run together (grouped 1x1 convs, block-diagonal output conv)."""
+    rng = np.random.default_rng(seed)
+    g = Graph("mobilenet_thin_openpose", 19, 38, 3, mean=(0.0, 0.0, 0.0))
+    relu = lambda n: np.zeros(n, np.float32)
+    lin = lambda n: np.ones(n, np.float32)
+
+    def dw(in_buf, out_buf, C, K, stride=1, in_off=0, out_off=0, name="dw"):
+        w = (rng.standard_normal((C, K, K)) * np.sqrt(2.0 / (K * K))).astype(np.float32)
+        sc, sh = _bn_fold(rng, C)
+        g.add_dwconv(in_buf, out_buf, w * sc[:, None, None], sh, relu(C), stride=stride, in_ch_off=in_off, out_ch_off=out_off, name=name)
+
+    def pw(in_buf, out_buf, groups, cin_g, cout_g, act=True, out_off=0, cin_real=None, name="pw", **kw):
+        w = _he(rng, groups, cout_g, cin_g, 1, 1, 2.0 if act else 1.0)
+        if cin_real is not None:
+            w[:, :, cin_real:] = 0
+        sc, sh = _bn_fold(rng, groups * cout_g)
+        w = w * sc.reshape(groups, cout_g, 1, 1, 1)
+        g.add_conv(in_buf, out_buf, w, sh, relu(groups * cout_g) if act else lin(groups * cout_g), out_ch_off=out_off, name=name, **kw)
+
+    # ---- stem: conv 3x3/2 3->32 (+bias, ReLU), BN, ReLU ----
+    b_col = g.add_buffer(64, 1); g.add_im2col(b_col, stride=2)
+    b0 = g.add_buffer(64, 1)
+    g.add_conv(b_col, b0, _he(rng, 1, 32, 3, 3, 3), (rng.standard_normal(32) * 0.05).astype(np.float32), relu(32), im2col_input=1, name="convblock_0")
+    sc, sh = _bn_fold(rng, 32)
+    b0b = g.add_buffer(64, 1)
+    g.add_dwconv(b0, b0b, sc.reshape(32, 1, 1), sh, relu(32), name="convblock_0_bn")
+    cur, cur_off, cur_c, cur_d = b0b, 0, 32, 1
+    cat_c = _r64(1152 + 57)
+    cat = g.add_buffer(cat_c, 3)   # [maxpool(block3) 128 | block7 512 | block11 512 | conf 19 | paf 38 | 7 zero]
+    # (n_filter, stride) of convblock_1..11 at scale_size 8 (backbones.py:264-275)
+    blocks = [(64, 1), (128, 2), (128, 1), (256, 2), (256, 1), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1), (512, 1)]
+    for i, (co, st) in enumerate(blocks, start=1):
+        d_out = cur_d + (1 if st == 2 else 0)
+        t = g.add_buffer(_r64(cur_c), d_out)
+        dw(cur, t, cur_c, 3, stride=st, in_off=cur_off, name=f"convblock_{i}_dw")
+        if i in (7, 11):     # concat_list[1] / [2] (backbones.py:288,293): written straight into the concat buffer
+            off = 128 if i == 7 else 640
+            pw(t, cat, 1, _r64(cur_c), co, out_off=off, cin_real=cur_c, name=f"convblock_{i}_pw")
+            cur, cur_off = cat, off
+        else:
+            nxt = g.add_buffer(_r64(co), d_out)
+            pw(t, nxt, 1, _r64(cur_c), co, cin_real=cur_c, name=f"convblock_{i}_pw")
+            cur, cur_off = nxt, 0
+        if i == 3:           # concat_list[0] = maxpool(x) (backbones.py:283)
+            g.add_maxpool(cur, cat, 128, "maxpool")
+        cur_c, cur_d = co, d_out
+    _dw_orig = dw
+
+    def stage(cin_real, mid, last, name):
+        """two branches of 5 separable blocks (mbv2_th_openpose.py:111-158) executed together"""
+        C = cat_c
+        wide = g.add_buffer(2 * C, 3)
+        for br in range(2):
+            wd = (rng.standard_normal((C, 3, 3)) * np.sqrt(2.0 / 9)).astype(np.float32)
+            wd[cin_real:] = 0
+            sc, sh = _bn_fold(rng, C)
+            sh[cin_real:] = 0
+            g.add_dwconv(cat, wide, wd * sc[:, None, None], sh, relu(C), out_ch_off=br * C, name=f"{name}_1_dw{br}")
+        a = g.add_buffer(256, 3); b = g.add_buffer(256, 3)
+        pw(wide, a, 2, C, 128, cin_real=cin_real, name=f"{name}_1_pw")
+        for k in (2, 3):
+            _dw_orig(a, b, 256, 3, name=f"{name}_{k}_dw")
+            pw(b, a, 2, 128, 128, name=f"{name}_{k}_pw")
+        _dw_orig(a, b, 256, 1, name=f"{name}_4_dw")
+        m = g.add_buffer(2 * mid, 3)
+        pw(b, m, 2, 128, mid, name=f"{name}_4_pw")
+        m2 = g.add_buffer(2 * mid, 3)
+        _dw_orig(m, m2, 2 * mid, 1, name=f"{name}_5_dw")
+        w = _block_diag(_he(rng, 1, 19, mid, 1, 1, 1.0), _he(rng, 1, 38, mid, 1, 1, 1.0))
+        sc, sh = _bn_fold(rng, 57)
+        w = w * sc.reshape(1, 57, 1, 1, 1)
+        if last:
+            g.add_conv(m2, 0, w, sh, lin(57), out_mode=OUT_F32_NCHW_SPLIT, split=19, name=f"{name}_out")
+        else:
+            g.add_conv(m2, cat, w, sh, lin(57), out_ch_off=1152, name=f"{name}_out")
+
+    stage(1152, 512, n_stages == 1, "init")
+    for s_ in range(1, n_stages):
+        stage(1209, 128, s_ == n_stages - 1, f"ref{s_}")
     return g
 
 

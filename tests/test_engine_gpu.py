@@ -71,6 +71,29 @@ def test_openpose_vgg19_small_resolution():
     eng.close()
 
 
+@pytest.mark.parametrize("hw,N", [((96, 128), 2), ((72, 88), 1)])
+def test_mobilenet_thin_openpose(hw, N):
+    """BASELINE config 2 architecture (MobilenetThin + separable-block heads): depthwise 3x3/1x1 (stride 1/2, TF SAME),
+    stride-2 stem, three-scale concat, grouped 1x1 convs -- every buffer and both outputs vs torch"""
+    H, W = hw
+    g = models.mobilenet_thin_openpose(0, n_stages=3)
+    frames = syn.make_frames_u8(4, N, H, W)
+    eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+    eng.infer_u8(frames)
+    conf, paf = eng.read_outputs(N)
+    rconf, rpaf, rbufs = torch_ref.run_graph(g, frames, emulate_fp16=True)
+    for bi in range(1, len(g.buffers)):
+        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        _check(got, rbufs[bi].cpu().numpy(), 4e-3, 4e-3, f"buffer {bi}")
+    _check(conf, rconf.cpu().numpy(), 4e-3, 4e-3, "conf")
+    _check(paf, rpaf.cpu().numpy(), 4e-3, 4e-3, "paf")
+    fconf, fpaf, _ = torch_ref.run_graph(g, frames, emulate_fp16=False)
+    d1, m1 = _check(conf, fconf.cpu().numpy(), 3e-2, 2e-3, "conf vs fp32")
+    d2, m2 = _check(paf, fpaf.cpu().numpy(), 3e-2, 2e-3, "paf vs fp32")
+    print(f"mobilenet-thin fp16 budget: conf {d1:.2e}/{m1:.2e} paf {d2:.2e}/{m2:.2e}")
+    eng.close()
+
+
 def test_f32_nchw_entry_matches_u8_entry():
     """tensorrt::inference(const std::vector<float>&, n): pre-scaled NCHW floats give the same outputs"""
     g = models.tiny_test_net(2)

@@ -24,6 +24,17 @@ def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb
             h, w = (h + 1) // 2, (w + 1) // 2
         bufs.append(torch.zeros(N, c, h, w, device=device))
     conf = paf = None
+    img, img_stride = None, 1
+
+    def same_pad(x, k, stride):
+        """TF 'SAME': out = ceil(in/stride); pad_before = total // 2"""
+        pads = []
+        for dim in (x.shape[3], x.shape[2]):   # F.pad order: W first, then H
+            out = (dim + stride - 1) // stride
+            total = max((out - 1) * stride + k - dim, 0)
+            pads += [total // 2, total - total // 2]
+        return F.pad(x, pads)
+
     for oi, op in enumerate(g.ops):
         if upto is not None and oi > upto:
             break
@@ -33,19 +44,32 @@ def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb
                 x = x[..., ::-1]
             x = torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2))).to(device)
             x = x - torch.tensor(g.mean, dtype=torch.float32, device=device).view(1, 3, 1, 1)
-            bufs[op.out_buf][:, :3] = q(x)
+            img, img_stride = q(x), op.stride
+            if op.stride == 1:
+                bufs[op.out_buf][:, :3] = img
         elif op.type == models.OP_MAXPOOL2:
             x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + op.cout_g]
             bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + op.cout_g] = F.max_pool2d(x, 2, 2, ceil_mode=True)
         elif op.type == models.OP_CONV:
             G, co, ci, R, S = op.weight.shape
-            x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + G * ci]
             w = q(torch.from_numpy(op.weight.reshape(G * co, ci, R, S)).to(device))
-            y = F.conv2d(x, w, torch.from_numpy(op.bias).to(device), padding=(R // 2, S // 2), groups=G)
+            if op.im2col_input:
+                y = F.conv2d(same_pad(img, R, img_stride), w, torch.from_numpy(op.bias).to(device), stride=img_stride)
+            else:
+                x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + G * ci]
+                y = F.conv2d(x, w, torch.from_numpy(op.bias).to(device), padding=(R // 2, S // 2), groups=G)
             a = torch.from_numpy(op.alpha).to(device).view(1, -1, 1, 1)
             y = torch.where(y > 0, y, y * a)
             if op.out_mode == models.OUT_F32_NCHW_SPLIT:
                 conf, paf = y[:, :op.split].contiguous(), y[:, op.split:].contiguous()
             else:
                 bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + G * co] = q(y)
+        elif op.type == models.OP_DWCONV:
+            C, K, _ = op.weight.shape
+            x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + C]
+            w = torch.from_numpy(op.weight.reshape(C, 1, K, K)).to(device)      # depthwise weights stay fp32 in the engine
+            y = F.conv2d(same_pad(x, K, op.stride), w, torch.from_numpy(op.bias).to(device), stride=op.stride, groups=C)
+            a = torch.from_numpy(op.alpha).to(device).view(1, -1, 1, 1)
+            y = torch.where(y > 0, y, y * a)
+            bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + C] = q(y)
     return conf, paf, bufs
