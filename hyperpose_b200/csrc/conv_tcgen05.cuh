@@ -57,6 +57,9 @@ struct ConvParams {
     int tma_store;             // 1: fp16 NHWC output goes through swizzled smem staging + TMA tensor stores (BN % 64 == 0)
     int swap_ab;               // 1: conv_tcgen05_swap_kernel (cout_g_pad % 128 == 0, TMA store)
     int npx;                   // swap kernel: pixels per unit (UMMA N), multiple of 16, 128 < npx <= 256
+    const __half* res;         // residual input [pixels, res_ld] (+ res_ch_off), or nullptr
+    int res_ld, res_ch_off;
+    int res_mode;              // 1: y = act(v + res)   2: y = act(v) + res
 };
 
 namespace ptx {
@@ -397,12 +400,27 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
                         ptx::tmem_ld_wait();
                         uint32_t pk[8];
+                        __half2 rs[8];
+                        if (p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
+                            if (in_img) {
+                                const uint4* rp = (const uint4*)(p.res + pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0);
+                                *(uint4*)&rs[0] = __ldg(rp);
+                                *(uint4*)&rs[4] = __ldg(rp + 1);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) rs[j] = __floats2half2_rn(0.f, 0.f);
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float a0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
                             float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
+                            float r0 = 0.f, r1 = 0.f;
+                            if (p.res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
+                            if (p.res_mode == 1) { a0 += r0; a1 += r1; }
                             a0 = a0 > 0.f ? a0 : a0 * __ldg(alpha + c0 + 2 * j);
                             a1 = a1 > 0.f ? a1 : a1 * __ldg(alpha + c0 + 2 * j + 1);
+                            if (p.res_mode == 2) { a0 += r0; a1 += r1; }
                             const __half2 h2 = __floats2half2_rn(a0, a1);
                             pk[j] = *(const uint32_t*)&h2;
                         }
@@ -427,8 +445,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 float y[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float a = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
-                    y[j] = a > 0.f ? a : a * __ldg(alpha + c0 + j);
+                    float a = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
+                    float r = 0.f;
+                    if (p.res_mode && c0 + j < n_valid) r = __half2float(p.res[pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0 + j]);
+                    if (p.res_mode == 1) a += r;
+                    a = a > 0.f ? a : a * __ldg(alpha + c0 + j);
+                    if (p.res_mode == 2) a += r;
+                    y[j] = a;
                 }
                 if (p.out_mode == OUT_F16_NHWC) {
                     __half* o = (__half*)p.out + pix * p.out_ld + p.out_ch_off + t.g * p.cout_g + t.n0 + c0;

@@ -33,48 +33,46 @@ using namespace hpb;
 // helper kernels
 // ---------------------------------------------------------------------------------------------
 
-// One thread per pixel: gathers the 3x3x3 neighbourhood (k = (r*3+s)*3 + c, c = model channel) into 64 fp16
-// channels (27 values + zeros).  SAME padding pads the *normalised* input with zeros.
+// One thread per (output pixel, 64-channel chunk): gathers the RxRx3 neighbourhood (k = (r*R+s)*3 + c, c = model channel)
+// into roundup(R*R*3, 64) fp16 channels.  SAME padding pads the *normalised* input with zeros.
 //   u8 path : v = (float)((double)u8 * factor) (data.cpp:48); model channel c reads byte (flip ? 2-c : c)
 //   f32 path: input is already scaled NCHW (tensorrt::inference(const std::vector<float>&, size_t))
-// stride 2 (MobileNet stem): output pixel (oh, ow) gathers rows 2*oh - pad + r with TF "SAME" padding
-// (pad_before = max((OH-1)*2 + 3 - H, 0) / 2, i.e. 0 for even H).
+// stride 2 (MobileNet / ResNet stems): TF "SAME" padding, pad_before = max((OH-1)*2 + R - H, 0) / 2.
 template <bool U8>
 __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
                                                       int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
-                                                      int stride, int OH, int OW, int pad_h, int pad_w)
+                                                      int stride, int OH, int OW, int pad_h, int pad_w, int R, int chunks)
 {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * OH * OW;
-    if (idx >= total) return;
-    const int w = (int)(idx % OW) * stride - pad_w + 1; // "+1": the tap loop below uses (r - 1, s - 1)
-    const int h = (int)((idx / OW) % OH) * stride - pad_h + 1;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * OH * OW * chunks;
+    if (gid >= total) return;
+    const int chunk = (int)(gid % chunks);
+    const size_t idx = gid / chunks;
+    const int w0 = (int)(idx % OW) * stride - pad_w;
+    const int h0 = (int)((idx / OW) % OH) * stride - pad_h;
     const int n = (int)(idx / ((size_t)OW * OH));
     const float mean[3] = { m0, m1, m2 };
+    const int kmax = R * R * 3;
     __align__(16) __half vals[64];
-#pragma unroll
-    for (int k = 27; k < 64; ++k) vals[k] = __float2half_rn(0.f);
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int hh = h + r - 1, ww = w + s - 1;
-            const bool ok = (hh >= 0 && hh < H && ww >= 0 && ww < W);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float v = 0.f;
-                if (ok) {
-                    if (U8) {
-                        const uint8_t* px = (const uint8_t*)in + (((size_t)n * H + hh) * W + ww) * 3;
-                        v = (float)((double)px[flip ? 2 - c : c] * factor) - mean[c];
-                    } else {
-                        v = ((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c];
-                    }
+#pragma unroll 4
+    for (int j = 0; j < 64; ++j) {
+        const int k = chunk * 64 + j;
+        float v = 0.f;
+        if (k < kmax) {
+            const int c = k % 3, rs = k / 3, s = rs % R, r = rs / R;
+            const int hh = h0 + r, ww = w0 + s;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                if (U8) {
+                    const uint8_t* px = (const uint8_t*)in + (((size_t)n * H + hh) * W + ww) * 3;
+                    v = (float)((double)px[flip ? 2 - c : c] * factor) - mean[c];
+                } else {
+                    v = ((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c];
                 }
-                vals[(r * 3 + s) * 3 + c] = __float2half_rn(v);
             }
         }
-    uint4* o = (uint4*)(out + idx * 64);
+        vals[j] = __float2half_rn(v);
+    }
+    uint4* o = (uint4*)(out + (idx * chunks + chunk) * 64);
     const uint4* v4 = (const uint4*)vals;
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = v4[i];
@@ -163,9 +161,9 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ 
     *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * out_ld + c0) = o;
 }
 
-// 2x2 stride-2 max pool, NHWC fp16, 8 channels per thread; SAME semantics (window clipped at the border).
+// KxK (K = 2 or 3) stride-2 max pool, NHWC fp16, 8 channels per thread; TF "SAME" semantics (window clipped at the border).
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                                                       int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW)
+                                                       int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW, int K, int pad_h, int pad_w)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cv = C / 8;
@@ -176,16 +174,26 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict_
     const int ow = (int)(t % OW); t /= OW;
     const int oh = (int)(t % OH);
     const int n = (int)(t / OH);
-    const int h0 = oh * 2, w0 = ow * 2;
-    const int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
-    auto ld = [&](int h, int w) { return *(const uint4*)(in + (((size_t)n * H + h) * W + w) * C_in_ld + c8 * 8); };
-    uint4 a = ld(h0, w0), b = ld(h0, w1), c = ld(h1, w0), d = ld(h1, w1);
-    uint4 r;
-    __half2* ra = (__half2*)&a; __half2* rb = (__half2*)&b; __half2* rc = (__half2*)&c; __half2* rd = (__half2*)&d;
-    __half2* rr = (__half2*)&r;
+    __half2 m[4];
+    bool first = true;
+    for (int r = 0; r < K; ++r) {
+        const int h = oh * 2 - pad_h + r;
+        if (h < 0 || h >= H) continue;
+        for (int s = 0; s < K; ++s) {
+            const int w = ow * 2 - pad_w + s;
+            if (w < 0 || w >= W) continue;
+            const uint4 v = *(const uint4*)(in + (((size_t)n * H + h) * W + w) * C_in_ld + c8 * 8);
+            const __half2* hv = (const __half2*)&v;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rr[i] = __hmax2(__hmax2(ra[i], rb[i]), __hmax2(rc[i], rd[i]));
-    *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * C_out_ld + c8 * 8) = r;
+            for (int i = 0; i < 4; ++i) m[i] = first ? hv[i] : __hmax2(m[i], hv[i]);
+            first = false;
+        }
+    }
+    uint4 r4;
+    __half2* rr = (__half2*)&r4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rr[i] = m[i];
+    *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * C_out_ld + c8 * 8) = r4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -356,11 +364,11 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     int R = (int)po.R, S = (int)po.S, cin_g = (int)po.cin_g;
     const int cout_g = (int)po.cout_g;
     const bool im2col = po.im2col_input != 0;
-    if (im2col && (G != 1 || R * S * cin_g > 64)) { set_error("engine: bad im2col conv"); return HP_ERR_ARG; }
+    if (im2col && (G != 1 || R * S * cin_g > ib.channels)) { set_error("engine: bad im2col conv"); return HP_ERR_ARG; }
     if (!im2col && G > 1 && cin_g % 64 != 0) { set_error("engine: grouped conv needs cin_g %% 64 == 0 (got %d)", cin_g); return HP_ERR_UNSUPPORTED; }
     // effective GEMM view
     const int eR = im2col ? 1 : R, eS = im2col ? 1 : S;
-    const int ecin = im2col ? 64 : round_up(cin_g, 64);
+    const int ecin = im2col ? round_up(R * S * cin_g, 64) : round_up(cin_g, 64);
     if ((int)po.in_ch_off + (G - 1) * ecin + ecin > ib.channels) {
         set_error("engine: conv reads channels [%d,%d) of a %d-channel buffer", po.in_ch_off, po.in_ch_off + G * ecin, ib.channels);
         return HP_ERR_ARG;
@@ -417,6 +425,12 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         if (ob.H != ib.H || ob.W != ib.W || (int)po.out_ch_off + G * cout_g > ob.channels) { set_error("engine: conv output buffer mismatch"); return HP_ERR_ARG; }
         p.out = ob.d; p.out_ld = ob.channels; p.out_ch_off = (int)po.out_ch_off;
     }
+    if (po.res_mode) {
+        if (po.out_mode != OUT_F16_NHWC || po.res_buf >= e->bufs.size()) { set_error("engine: bad residual"); return HP_ERR_ARG; }
+        const EngBuffer& rb = e->bufs[po.res_buf];
+        if (rb.H != ib.H || rb.W != ib.W || (int)po.res_ch_off + G * cout_g > rb.channels || po.res_ch_off % 8 || cout_g % 16) { set_error("engine: residual buffer mismatch"); return HP_ERR_ARG; }
+        p.res = rb.d; p.res_ld = rb.channels; p.res_ch_off = (int)po.res_ch_off; p.res_mode = (int)po.res_mode;
+    }
     int rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS);
     if (rc) return rc;
     rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
@@ -435,7 +449,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
     // (restricted to one 128-channel block per group: with several blocks every block would re-fetch the same pixels
     //  through L2, which the 2x larger L2->SM traffic does not pay for on the merged 256-channel layers)
-    p.swap_ab = (p.tma_store && cout_pad == 128 && cout_g == cout_pad && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
+    p.swap_ab = (p.tma_store && !po.res_mode && cout_pad == 128 && cout_g == cout_pad && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
     if (p.swap_ab) {
         const EngBuffer& ob = e->bufs[po.out_buf];
         const long total_px = (long)e->max_batch * ib.H * ib.W;
@@ -500,16 +514,18 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
         const PackOp& po = op.po;
         if (po.type == OP_IM2COL3) {
             EngBuffer& ob = e->bufs[po.out_buf];
-            const size_t total = (size_t)N * ob.H * ob.W;
+            const int R = po.R ? (int)po.R : 3;
+            const int chunks = ob.channels / 64;
+            const size_t total = (size_t)N * ob.H * ob.W * chunks;
             const int blocks = (int)((total + 255) / 256);
             const int stride = po.stride ? (int)po.stride : 1;
-            const int ph = same_pad_before(e->in_h, 3, stride), pw = same_pad_before(e->in_w, 3, stride);
+            const int ph = same_pad_before(e->in_h, R, stride), pw = same_pad_before(e->in_w, R, stride);
             if (u8_input)
                 im2col3_kernel<true><<<blocks, 256, 0, st>>>(e->d_frames, ob.d, N, e->in_h, e->in_w, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
-                                                            stride, ob.H, ob.W, ph, pw);
+                                                            stride, ob.H, ob.W, ph, pw, R, chunks);
             else
                 im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, e->in_h, e->in_w, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
-                                                             stride, ob.H, ob.W, ph, pw);
+                                                             stride, ob.H, ob.W, ph, pw, R, chunks);
             e->launches++;
         } else if (po.type == OP_DWCONV) {
             EngBuffer& ib = e->bufs[po.in_buf];
@@ -525,7 +541,9 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& ob = e->bufs[po.out_buf];
             const int C = (int)po.cout_g;
             const size_t total = (size_t)N * ob.H * ob.W * (C / 8);
-            maxpool2_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W);
+            const int K = po.R ? (int)po.R : 2;
+            maxpool2_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W,
+                                                                     K, same_pad_before(ib.H, K, 2), same_pad_before(ib.W, K, 2));
             e->launches++;
         } else if (po.type == OP_CONV) {
             launch_conv(e, op, N, st);
@@ -646,7 +664,11 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             e->flops_per_frame += e->ops[i].plan.flops_per_frame;
         } else if (po.type == OP_IM2COL3) {
             const int stride = po.stride ? (int)po.stride : 1;
-            if (e->bufs[po.out_buf].channels != 64 || e->bufs[po.out_buf].down != (stride == 2 ? 1 : 0) || stride > 2) { set_error("engine: im2col buffer must be 64 channels at the stem resolution"); return fail(HP_ERR_ARG); }
+            const int R = po.R ? (int)po.R : 3;
+            if (e->bufs[po.out_buf].channels != round_up(R * R * 3, 64) || e->bufs[po.out_buf].down != (stride == 2 ? 1 : 0) || stride > 2 || (R != 3 && R != 7)) {
+                set_error("engine: im2col buffer must hold roundup(R*R*3,64) channels at the stem resolution");
+                return fail(HP_ERR_ARG);
+            }
         } else if (po.type == OP_DWCONV) {
             const int C = (int)po.cout_g, K = (int)po.R, stride = po.stride ? (int)po.stride : 1;
             const EngBuffer& ib = e->bufs[po.in_buf];
@@ -670,7 +692,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             }
             e->flops_per_frame += 2.0 * ob.H * ob.W * C * K * K;
         } else if (po.type == OP_MAXPOOL2) {
-            if (po.cout_g % 8 || e->bufs[po.out_buf].down != e->bufs[po.in_buf].down + 1) { set_error("engine: bad maxpool op %u", i); return fail(HP_ERR_ARG); }
+            if (po.cout_g % 8 || e->bufs[po.out_buf].down != e->bufs[po.in_buf].down + 1 || (po.R != 0 && po.R != 2 && po.R != 3)) { set_error("engine: bad maxpool op %u", i); return fail(HP_ERR_ARG); }
         } else {
             set_error("engine: unknown op type %u", po.type);
             return fail(HP_ERR_UNSUPPORTED);

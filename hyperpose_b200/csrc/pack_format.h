@@ -9,12 +9,13 @@
 namespace hpb {
 
 constexpr char PACK_MAGIC[8] = { 'H', 'P', 'B', '2', 'P', 'A', 'C', 'K' };
-constexpr uint32_t PACK_VERSION = 1;
+constexpr uint32_t PACK_VERSION = 2;
 
 enum PackOpType : uint32_t {
-    OP_IM2COL3 = 1, // network input (u8 HWC frames or f32 NCHW) -> [N,H,W,64] fp16: 3x3x3 patches (27 values + 37 zeros), minus mean
+    OP_IM2COL3 = 1, // network input (u8 HWC frames or f32 NCHW) -> [N,OH,OW,roundup(R*R*3,64)] fp16: RxRx3 patches (k = (r*R+s)*3+c) + zeros,
+                    // minus mean; R in {3,7}, stride 1/2, TF "SAME" padding
     OP_CONV = 2,    // stride-1 SAME convolution + bias + PReLU (alpha 0 = ReLU, alpha 1 = linear)
-    OP_MAXPOOL2 = 3, // 2x2 stride-2 max-pool, SAME (ceil) semantics
+    OP_MAXPOOL2 = 3, // RxR (R = 2 or 3) stride-2 max-pool, TF "SAME" semantics (out = ceil(in/2), window clipped at the border)
     OP_DWCONV = 4    // depthwise KxK (K = 1 or 3) conv, stride 1/2, TF "SAME" padding, + bias + PReLU; HBM-bound CUDA-core kernel
 };
 
@@ -43,10 +44,13 @@ struct PackOp {
     uint32_t split;
     uint32_t im2col_input;          // 1: this conv consumes an OP_IM2COL3 buffer (R*S*cin_g <= 64 packed as one 64-ch k-step)
     uint32_t stride;                // OP_IM2COL3 / OP_DWCONV: 1 or 2 (0 = 1)
+    uint32_t res_buf, res_ch_off;   // OP_CONV residual input (fp16 NHWC buffer of the output's geometry)
+    uint32_t res_mode;              // 0 none | 1 y = act(conv + bias + res) (ResNet) | 2 y = act(conv + bias) + res (LW-OpenPose blocks)
+    uint32_t reserved2;
     uint64_t w_off, b_off, a_off;   // float offsets into the blob: W[G][cout_g][cin_g][R][S], bias[G*cout_g], alpha[G*cout_g]
                                     // OP_DWCONV: W[C][R][S], bias[C], alpha[C] with C = cout_g
 };
 
-static_assert(sizeof(PackHeader) == 72 && sizeof(PackBuffer) == 8 && sizeof(PackOp) == 80, "pack layout");
+static_assert(sizeof(PackHeader) == 72 && sizeof(PackBuffer) == 8 && sizeof(PackOp) == 96, "pack layout");
 
 } // namespace hpb

@@ -22,7 +22,7 @@ import numpy as np
 OP_IM2COL3, OP_CONV, OP_MAXPOOL2, OP_DWCONV = 1, 2, 3, 4
 OUT_F16_NHWC, OUT_F32_NCHW_SPLIT = 0, 1
 PACK_MAGIC = b"HPB2PACK"
-PACK_VERSION = 1
+PACK_VERSION = 2
 
 
 @dataclass
@@ -41,6 +41,9 @@ class Op:
     split: int = 0
     im2col_input: int = 0
     stride: int = 1
+    res_buf: int = 0
+    res_ch_off: int = 0
+    res_mode: int = 0                  # 1: act(conv + res)   2: act(conv) + res
     weight: np.ndarray | None = None   # [G, cout_g, cin_g, R, S] float32 (OP_DWCONV: [C, K, K])
     bias: np.ndarray | None = None     # [G*cout_g]
     alpha: np.ndarray | None = None    # [G*cout_g]  PReLU slope; 0 = ReLU, 1 = linear
@@ -62,8 +65,8 @@ class Graph:
         self.buffers.append((channels, down_shift))
         return len(self.buffers) - 1
 
-    def add_im2col(self, out_buf: int, stride: int = 1, name="im2col") -> None:
-        self.ops.append(Op(OP_IM2COL3, out_buf=out_buf, stride=stride, name=name))
+    def add_im2col(self, out_buf: int, stride: int = 1, ksize: int = 3, name="im2col") -> None:
+        self.ops.append(Op(OP_IM2COL3, out_buf=out_buf, R=ksize, S=ksize, stride=stride, name=name))
 
     def add_dwconv(self, in_buf, out_buf, weight, bias, alpha, stride=1, in_ch_off=0, out_ch_off=0, name="dw") -> None:
         """depthwise KxK conv (K in {1,3}) + bias + PReLU; weight [C, K, K]"""
@@ -73,15 +76,16 @@ class Graph:
                            weight=np.ascontiguousarray(weight, np.float32), bias=np.ascontiguousarray(bias, np.float32).reshape(-1),
                            alpha=np.ascontiguousarray(alpha, np.float32).reshape(-1), name=name))
 
-    def add_maxpool(self, in_buf: int, out_buf: int, channels: int, name="pool") -> None:
-        self.ops.append(Op(OP_MAXPOOL2, in_buf=in_buf, out_buf=out_buf, cout_g=channels, name=name))
+    def add_maxpool(self, in_buf: int, out_buf: int, channels: int, name="pool", ksize: int = 2) -> None:
+        self.ops.append(Op(OP_MAXPOOL2, in_buf=in_buf, out_buf=out_buf, R=ksize, S=ksize, cout_g=channels, name=name))
 
     def add_conv(self, in_buf, out_buf, weight, bias, alpha, in_ch_off=0, out_ch_off=0, out_mode=OUT_F16_NHWC, split=0,
-                 im2col_input=0, name="conv") -> None:
+                 im2col_input=0, name="conv", res_buf=0, res_ch_off=0, res_mode=0) -> None:
         G, cout_g, cin_g, R, S = weight.shape
         self.ops.append(Op(OP_CONV, in_buf, out_buf, in_ch_off, out_ch_off, R, S, G, cin_g, cout_g, out_mode, split, im2col_input,
                            weight=np.ascontiguousarray(weight, np.float32), bias=np.ascontiguousarray(bias, np.float32).reshape(-1),
-                           alpha=np.ascontiguousarray(alpha, np.float32).reshape(-1), name=name))
+                           alpha=np.ascontiguousarray(alpha, np.float32).reshape(-1), name=name,
+                           res_buf=res_buf, res_ch_off=res_ch_off, res_mode=res_mode))
 
     # ---- serialisation (layout of pack_format.h) ----
     def to_pack(self) -> bytes:
@@ -94,8 +98,9 @@ class Graph:
                 w_off = off; blob.append(op.weight.reshape(-1)); off += op.weight.size
                 b_off = off; blob.append(op.bias); off += op.bias.size
                 a_off = off; blob.append(op.alpha); off += op.alpha.size
-            op_recs.append(struct.pack("<14I3Q", op.type, op.in_buf, op.out_buf, op.in_ch_off, op.out_ch_off, op.R, op.S, op.groups,
-                                       op.cin_g, op.cout_g, op.out_mode, op.split, op.im2col_input, op.stride, w_off, b_off, a_off))
+            op_recs.append(struct.pack("<18I3Q", op.type, op.in_buf, op.out_buf, op.in_ch_off, op.out_ch_off, op.R, op.S, op.groups,
+                                       op.cin_g, op.cout_g, op.out_mode, op.split, op.im2col_input, op.stride,
+                                       op.res_buf, op.res_ch_off, op.res_mode, 0, w_off, b_off, a_off))
         blob_arr = np.concatenate(blob).astype("<f4") if blob else np.zeros(0, "<f4")
         hdr = struct.pack("<8s6I3f5IQ", PACK_MAGIC, PACK_VERSION, len(self.buffers), len(self.ops), self.conf_channels,
                           self.paf_channels, self.out_down_shift, *[float(m) for m in self.mean], 0, 0, 0, 0, 0, blob_arr.size)
@@ -295,6 +300,97 @@ def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6) -> Graph:
     stage(1152, 512, n_stages == 1, "init")
     for s_ in range(1, n_stages):
         stage(1209, 128, s_ == n_stages - 1, f"ref{s_}")
+    return g
+
+
+def resnet50_lw_openpose(seed: int = 0) -> Graph:
+    """Lightweight-OpenPose head on ResNet-50 at stride 8 (BASELINE.json config 4):
+    hyperpose/Model/backbones.py:587-698 (7x7/2 stem, 3x3/2 max-pool, 16 bottleneck blocks; block_3_1 / block_4_1 keep
+    stride 1 when scale_size == 8, :598-601) + hyperpose/Model/openpose/model/lw_openpose.py:106-191 (CPM, init stage,
+    one refinement stage with residual blocks).  BatchNorm folded; residual adds run in the conv epilogue
+    (ResNet: relu(conv + res); LW blocks: relu(bn(conv)) + res).  The two stride-2 convs of block_2_1 are computed at
+    stride 1 and sub-sampled by a one-hot depthwise 3x3/2 (centre tap of the TF-SAME window) / 1x1/2 op -- exact."""
+    rng = np.random.default_rng(seed)
+    g = Graph("resnet50_lw_openpose", 19, 38, 3, mean=(0.0, 0.0, 0.0))
+    relu = lambda n: np.zeros(n, np.float32)
+    lin = lambda n: np.ones(n, np.float32)
+    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", **kw):
+        w = _he(rng, 1, co, ci, k, k, 2.0 if act else 1.0)
+        sc, sh = _bn_fold(rng, co)
+        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh, relu(co) if act else lin(co), name=name, **kw)
+
+    def subsample(in_buf, out_buf, C, centre3: bool, name):
+        """x[2i(+1)] picker: one-hot depthwise op with stride 2 (see docstring)"""
+        w = np.zeros((C, 3, 3), np.float32) if centre3 else np.ones((C, 1, 1), np.float32)
+        if centre3:
+            w[:, 1, 1] = 1.0
+        g.add_dwconv(in_buf, out_buf, w, np.zeros(C, np.float32), lin(C), stride=2, name=name)
+
+    col = g.add_buffer(192, 1); g.add_im2col(col, stride=2, ksize=7)
+    c1 = g.add_buffer(64, 1)
+    w = _he(rng, 1, 64, 3, 7, 7); sc, sh = _bn_fold(rng, 64)
+    g.add_conv(col, c1, w * sc.reshape(1, 64, 1, 1, 1), sh, relu(64), im2col_input=1, name="conv1+bn1")
+    x = g.add_buffer(64, 2); g.add_maxpool(c1, x, 64, "maxpool_1", ksize=3)
+    cur, cur_c, cur_d = x, 64, 2
+    layout = [(64, 3, 1), (128, 4, 2), (256, 6, 1), (512, 3, 1)]     # (n_filter, blocks, stride of the first block) at scale_size 8
+    for bi, (nf, nblk, st0) in enumerate(layout, start=1):
+        for k in range(1, nblk + 1):
+            st = st0 if k == 1 else 1
+            name = f"block_{bi}_{k}"
+            d_out = cur_d + (1 if st == 2 else 0)
+            # residual path (backbones.py:676-682)
+            if st != 1 or cur_c != 4 * nf:
+                src = cur
+                if st == 2:
+                    src = g.add_buffer(_r64(cur_c), d_out); subsample(cur, src, cur_c, False, f"{name}_ds_sub")
+                res = g.add_buffer(4 * nf, d_out)
+                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds")
+            else:
+                res = cur
+            a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1")
+            b = g.add_buffer(_r64(nf), cur_d); conv_bn(a, b, nf, nf, 3, name=f"{name}_conv2")
+            if st == 2:
+                b2 = g.add_buffer(_r64(nf), d_out); subsample(b, b2, nf, True, f"{name}_conv2_sub"); b = b2
+            out = g.add_buffer(4 * nf, d_out)
+            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", res_buf=res, res_mode=1)   # relu(x + res)
+            cur, cur_c, cur_d = out, 4 * nf, d_out
+
+    def lw_conv(in_buf, out_buf, ci, co, k, act=True, name="c", **kw):      # Conv2d(+bias, relu)
+        g.add_conv(in_buf, out_buf, _he(rng, 1, co, ci, k, k, 2.0 if act else 1.0), b_(co), relu(co) if act else lin(co), name=name, **kw)
+
+    def lw_block(in_buf, out_buf, ci, co, k, name, **kw):                   # conv_block: Conv2d(+bias) + BN + relu (lw_openpose.py:193-199)
+        w = _he(rng, 1, co, ci, k, k); sc, sh = _bn_fold(rng, co)
+        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh + b_(co) * sc, relu(co), name=name, **kw)
+
+    # ---- CPM (lw_openpose.py:106-121) ----
+    t0 = g.add_buffer(128, 3); lw_conv(cur, t0, 2048, 128, 1, name="cpm_init")
+    t1 = g.add_buffer(128, 3); lw_block(t0, t1, 128, 128, 3, "cpm_b1")
+    t2 = g.add_buffer(128, 3); lw_block(t1, t2, 128, 128, 3, "cpm_b2")
+    t3 = g.add_buffer(128, 3); lw_block(t2, t3, 128, 128, 3, "cpm_b3", res_buf=t0, res_mode=2)          # x + main_block(x)
+    cat = g.add_buffer(192, 3)                                                                            # [cpm 128 | conf 19 | paf 38 | 7]
+    lw_conv(t3, cat, 128, 128, 3, name="cpm_end")
+    # ---- init stage (:123-149) ----
+    i1 = g.add_buffer(128, 3); lw_conv(cat, i1, 128, 128, 3, name="init_1")
+    i2 = g.add_buffer(128, 3); lw_conv(i1, i2, 128, 128, 3, name="init_2")
+    i3 = g.add_buffer(128, 3); lw_conv(i2, i3, 128, 128, 3, name="init_3")
+    wide = g.add_buffer(1024, 3)
+    g.add_conv(i3, wide, np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024), relu(1024), name="init_4")
+    g.add_conv(wide, cat, _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57), lin(57), out_ch_off=128, name="init_out")
+    # ---- refinement stage (:151-191): 5 residual blocks, then 1x1x512 + 1x1x{19,38} ----
+    src, ci = cat, 185
+    for k in range(1, 6):
+        r0 = g.add_buffer(128, 3)
+        w = _he(rng, 1, 128, ci, 1, 1)
+        g.add_conv(src, r0, w, b_(128), relu(128), name=f"ref_b{k}_init")
+        r1 = g.add_buffer(128, 3); lw_block(r0, r1, 128, 128, 3, f"ref_b{k}_c1")
+        r2 = g.add_buffer(128, 3); lw_block(r1, r2, 128, 128, 3, f"ref_b{k}_c2", res_buf=r0, res_mode=2)
+        src, ci = r2, 128
+    wide2 = g.add_buffer(1024, 3)
+    g.add_conv(src, wide2, np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024), relu(1024), name="ref_4")
+    g.add_conv(wide2, 0, _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57), lin(57),
+               out_mode=OUT_F32_NCHW_SPLIT, split=19, name="ref_out")
     return g
 
 

@@ -94,6 +94,29 @@ def test_mobilenet_thin_openpose(hw, N):
     eng.close()
 
 
+@pytest.mark.parametrize("hw,N", [((96, 128), 2), ((72, 104), 1)])
+def test_resnet50_lw_openpose(hw, N):
+    """BASELINE config 4 architecture (ResNet-50 stride 8 + Lightweight-OpenPose head): 7x7/2 stem, 3x3/2 max-pool,
+    bottleneck residual epilogues (both add orders), exact stride-2 sub-sampling -- every buffer and both outputs vs torch"""
+    H, W = hw
+    g = models.resnet50_lw_openpose(0)
+    frames = syn.make_frames_u8(6, N, H, W)
+    eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+    eng.infer_u8(frames)
+    conf, paf = eng.read_outputs(N)
+    rconf, rpaf, rbufs = torch_ref.run_graph(g, frames, emulate_fp16=True)
+    for bi in range(1, len(g.buffers)):
+        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        _check(got, rbufs[bi].cpu().numpy(), 6e-3, 6e-3, f"buffer {bi}")
+    _check(conf, rconf.cpu().numpy(), 6e-3, 6e-3, "conf")
+    _check(paf, rpaf.cpu().numpy(), 6e-3, 6e-3, "paf")
+    fconf, fpaf, _ = torch_ref.run_graph(g, frames, emulate_fp16=False)
+    d1, m1 = _check(conf, fconf.cpu().numpy(), 3e-2, 2e-3, "conf vs fp32")
+    d2, m2 = _check(paf, fpaf.cpu().numpy(), 3e-2, 2e-3, "paf vs fp32")
+    print(f"resnet50-lw fp16 budget: conf {d1:.2e}/{m1:.2e} paf {d2:.2e}/{m2:.2e}")
+    eng.close()
+
+
 def test_f32_nchw_entry_matches_u8_entry():
     """tensorrt::inference(const std::vector<float>&, n): pre-scaled NCHW floats give the same outputs"""
     g = models.tiny_test_net(2)

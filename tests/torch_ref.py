@@ -49,7 +49,15 @@ def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb
                 bufs[op.out_buf][:, :3] = img
         elif op.type == models.OP_MAXPOOL2:
             x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + op.cout_g]
-            bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + op.cout_g] = F.max_pool2d(x, 2, 2, ceil_mode=True)
+            K = op.R if op.R else 2
+            # TF SAME max-pool: pad with -inf (window clipped at the border)
+            pads = []
+            for dim in (x.shape[3], x.shape[2]):
+                out = (dim + 1) // 2
+                total = max((out - 1) * 2 + K - dim, 0)
+                pads += [total // 2, total - total // 2]
+            xp = F.pad(x, pads, value=float("-inf"))
+            bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + op.cout_g] = F.max_pool2d(xp, K, 2)
         elif op.type == models.OP_CONV:
             G, co, ci, R, S = op.weight.shape
             w = q(torch.from_numpy(op.weight.reshape(G * co, ci, R, S)).to(device))
@@ -59,7 +67,12 @@ def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb
                 x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + G * ci]
                 y = F.conv2d(x, w, torch.from_numpy(op.bias).to(device), padding=(R // 2, S // 2), groups=G)
             a = torch.from_numpy(op.alpha).to(device).view(1, -1, 1, 1)
+            res = bufs[op.res_buf][:, op.res_ch_off:op.res_ch_off + G * co] if op.res_mode else None
+            if op.res_mode == 1:
+                y = y + res
             y = torch.where(y > 0, y, y * a)
+            if op.res_mode == 2:
+                y = y + res
             if op.out_mode == models.OUT_F32_NCHW_SPLIT:
                 conf, paf = y[:, :op.split].contiguous(), y[:, op.split:].contiguous()
             else:
