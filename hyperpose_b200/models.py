@@ -316,8 +316,8 @@ def resnet50_lw_openpose(seed: int = 0) -> Graph:
     lin = lambda n: np.ones(n, np.float32)
     b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
 
-    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", **kw):
-        w = _he(rng, 1, co, ci, k, k, 2.0 if act else 1.0)
+    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", gain=None, **kw):
+        w = _he(rng, 1, co, ci, k, k, gain if gain is not None else (2.0 if act else 1.0))
         sc, sh = _bn_fold(rng, co)
         g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh, relu(co) if act else lin(co), name=name, **kw)
 
@@ -346,7 +346,7 @@ def resnet50_lw_openpose(seed: int = 0) -> Graph:
                 if st == 2:
                     src = g.add_buffer(_r64(cur_c), d_out); subsample(cur, src, cur_c, False, f"{name}_ds_sub")
                 res = g.add_buffer(4 * nf, d_out)
-                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds")
+                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds", gain=0.5)
             else:
                 res = cur
             a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1")
@@ -354,7 +354,9 @@ def resnet50_lw_openpose(seed: int = 0) -> Graph:
             if st == 2:
                 b2 = g.add_buffer(_r64(nf), d_out); subsample(b, b2, nf, True, f"{name}_conv2_sub"); b = b2
             out = g.add_buffer(4 * nf, d_out)
-            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", res_buf=res, res_mode=1)   # relu(x + res)
+            # (small gain on the residual branch, like a trained net's near-zero last gamma: keeps the random-init
+            #  activations of 16 stacked blocks inside the fp16 range)
+            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", gain=0.1, res_buf=res, res_mode=1)   # relu(x + res)
             cur, cur_c, cur_d = out, 4 * nf, d_out
 
     def lw_conv(in_buf, out_buf, ci, co, k, act=True, name="c", **kw):      # Conv2d(+bias, relu)
