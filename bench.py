@@ -13,7 +13,8 @@ keypoint records to rank 0).  Because random weights give structureless heat-map
 crowd tensors are copied over the backbone's outputs after the last conv (hp_engine_set_output_override,
 SURVEY 8d) -- all conv work is still executed; this is stated in config.parse_input.
 
-  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather)
+  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather);
+          two-stream software pipeline: parse + gather of batch i overlap the convs of batch i+1
   e2e   : the public host call hp_pose_run_u8_host -- pinned host frames H2D, human_t records D2H, every step
   roofline : the conv kernel (dominant): algorithmic FLOPs / CUDA-event time of the conv launches, measured in
              the timed region on the launching stream, vs the measured cuBLAS bf16 peak
@@ -35,12 +36,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IN_H, IN_W = 368, 656
-HF, WF = 46, 82
-BATCH = 16
-PERSONS = (10, 20)                   # synthetic crowd per frame (SURVEY 8d cfg4 recipe on cfg3 geometry)
-ALGO_FLOPS_PER_FRAME = 484.6e9       # OpenPose-VGG19 (6 stages) @368x656, 2*MAC
-N_INPUT_SETS = 12                    # 12 x 11.6 MB of distinct frames > 126 MB L2
+# workloads (BASELINE.json configs).  The default -- and the only one the headline metric is quoted on -- is cfg3.
+WORKLOADS = {
+    "cfg3": dict(name="cfg3: OpenPose-COCO VGG-19 368x656, batch 16 per GPU, frame-sharded", graph="openpose_vgg19", in_h=368, in_w=656,
+                 batch=16, persons=(10, 20), algo_flops=484.6e9, arch="OpenPose-VGG19 (6 stages), 484.6 GFLOP/frame"),
+    "cfg2": dict(name="cfg2: Lightweight-OpenPose (MobilenetThin) 368x432, batch 8", graph="mobilenet_thin_openpose", in_h=368, in_w=432,
+                 batch=8, persons=(1, 5), algo_flops=22.3e9, arch="MobilenetThin-OpenPose (6 stages), 22.3 GFLOP/frame"),
+    "cfg4": dict(name="cfg4: OpenPose-ResNet50 (LW-OpenPose head, stride 8) 368x432, batch 32 per GPU, synthetic crowd", graph="resnet50_lw_openpose",
+                 in_h=368, in_w=432, batch=32, persons=(10, 20), algo_flops=136.7e9, arch="ResNet50 + LW-OpenPose head, 136.7 GFLOP/frame"),
+}
+IN_H, IN_W, HF, WF, BATCH, PERSONS, ALGO_FLOPS_PER_FRAME = 368, 656, 46, 82, 16, (10, 20), 484.6e9
+WL = WORKLOADS["cfg3"]
+N_INPUT_SETS = 12                    # distinct input batches rotated so that the frames alone exceed the 126 MB L2
+
+
+def select_workload(key):
+    global IN_H, IN_W, HF, WF, BATCH, PERSONS, ALGO_FLOPS_PER_FRAME, WL
+    WL = WORKLOADS[key]
+    IN_H, IN_W, BATCH, PERSONS, ALGO_FLOPS_PER_FRAME = WL["in_h"], WL["in_w"], WL["batch"], WL["persons"], WL["algo_flops"]
+    HF, WF = IN_H // 8, IN_W // 8
+
+
+def METRIC():
+    return "frames/sec end-to-end (conv+PAF parse) OpenPose-COCO 368x656" if WL is WORKLOADS["cfg3"] else f"frames/sec end-to-end (conv+PAF parse) {WL['name']}"
 
 
 def load_peaks():
@@ -178,13 +196,13 @@ def run_reference(args):
     dt = time.time() - t0
     fps = BATCH * args.steps / dt
     line = {
-        "impl": "reference", "metric": "frames/sec end-to-end (conv+PAF parse) OpenPose-COCO 368x656", "value": fps, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC(), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg3: OpenPose-COCO VGG-19 368x656 batch 16 -- PAF parse stage only (reference convs are TensorRT, not runnable on CPU)",
+        "config": {"workload": WL["name"] + " -- PAF parse stage only (reference convs are TensorRT, not runnable on CPU)",
                    "frames_per_step": BATCH, "persons_per_frame": list(PERSONS)},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
-                         "sample": f"{args.steps} x 16 synthetic 46x82 crowd frames, parse stage only, {threads} threads of {cores} host cores"},
+                         "sample": f"{args.steps} x {BATCH} synthetic {HF}x{WF} crowd frames, parse stage only, {threads} threads of {cores} host cores"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,7 +223,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    graph = models.openpose_vgg19(seed=0)
+    graph = getattr(models, WL["graph"])(seed=0)
     pack = graph.to_pack()
     engine = capi.Engine(pack, (IN_W, IN_H), max_batch_size=BATCH, device=local_rank)
     del pack
@@ -235,10 +253,37 @@ def run_ours(args):
             with torch.cuda.stream(st):
                 sharding.gather_records(res_humans, res_counts, world)   # NCCL all-gather of ~300 KB per rank
 
+    # Software pipeline of the device-resident path: the PAF parse (+ the keypoint gather) of batch i runs on a second
+    # stream while the convs of batch i+1 run on the first.  The engine's conf/paf outputs are snapshotted (D2D, 14 MB)
+    # on the conv stream so that batch i+1 may overwrite them; events order snapshot <-> parse in both directions.
+    st2 = torch.cuda.Stream(device=dev)
+    snap_conf = torch.empty(BATCH * 19 * HF * WF, dtype=torch.float32, device=dev)
+    snap_paf = torch.empty(BATCH * 38 * HF * WF, dtype=torch.float32, device=dev)
+    ev_ready = torch.cuda.Event()
+    ev_parsed = torch.cuda.Event()
+    n_conf, n_paf = snap_conf.numel() * 4, snap_paf.numel() * 4
+    cudart = torch.cuda.cudart()
+    state = {"first": True}
+
     def step_device(i):
         engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
-        parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
-        gather_results()
+        if not state["first"]:
+            st.wait_event(ev_parsed)                  # the previous parse has finished reading the snapshot
+        state["first"] = False
+        with torch.cuda.stream(st):
+            cudart.cudaMemcpyAsync(snap_conf.data_ptr(), out_conf_ptr, n_conf, 3, st.cuda_stream)   # 3 = cudaMemcpyDeviceToDevice
+            cudart.cudaMemcpyAsync(snap_paf.data_ptr(), out_paf_ptr, n_paf, 3, st.cuda_stream)
+        ev_ready.record(st)
+        st2.wait_event(ev_ready)
+        parser.process_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, 19, 38, HF, WF, st2.cuda_stream)
+        parser.copy_results_device(res_humans.data_ptr(), res_counts.data_ptr(), BATCH, HCAP, st2.cuda_stream)
+        if world > 1:
+            with torch.cuda.stream(st2):
+                sharding.gather_records(res_humans, res_counts, world)   # NCCL all-gather of ~300 KB per rank
+        ev_parsed.record(st2)
+
+    def drain_device():
+        st.wait_event(ev_parsed)                      # the timed region ends when the last parse/gather has finished
 
     def step_host(i):
         humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
@@ -264,6 +309,8 @@ def run_ours(args):
         t0 = time.time()
         for i in range(steps):
             fn(warmup + i)
+        if fn is step_device:
+            drain_device()
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.time() - t0
@@ -283,6 +330,7 @@ def run_ours(args):
     # sanity: the device path and the host path agree with each other before anything is timed
     step_device(0)
     torch.cuda.synchronize()
+    state["first"] = True
     ref_h = parser.fetch(BATCH, cap=HCAP)
     host_h = step_host(0)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(ref_h, host_h)), "device and host paths disagree"
@@ -323,7 +371,7 @@ def run_ours(args):
             threads = min(cores, BATCH)
             rate, kind = cpu_parse_rate(conf_np, paf_np, 12.0, threads)
             cpu = {"value": rate, "unit": "frames/s", "cores": threads, "kind": kind,
-                   "sample": f"12 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's 16 synthetic 46x82 crowd frames, "
+                   "sample": f"12 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's {BATCH} synthetic {HF}x{WF} crowd frames, "
                              f"{threads} threads of {cores} host cores; parse stage only (reference convs are TensorRT, no CPU path)"}
         layers = [{"op": i, "name": graph.ops[i].name, "type": int(prof_ty[i]), "ms": float(prof_ms[i]),
                    "tflops": (float(prof_fl[i]) * BATCH / (prof_ms[i] / 1e3) / 1e12 if prof_ms[i] > 0 and prof_fl[i] > 0 else None)}
@@ -334,13 +382,13 @@ def run_ours(args):
         h2d = BATCH * IN_H * IN_W * 3
         d2h = BATCH * HCAP * rec_bytes + BATCH * 8
         line = {
-            "metric": "frames/sec end-to-end (conv+PAF parse) OpenPose-COCO 368x656", "value": value, "unit": "frames/s",
+            "metric": METRIC(), "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 accumulate (conv); f32/f64 (parse)", "data": "synthetic",
-            "config": {"workload": "cfg3: OpenPose-COCO VGG-19 368x656, batch 16 per GPU, frame-sharded",
-                       "global_batch": world * BATCH, "input": "u8 frames 368x656x3, random (default_rng)",
-                       "weights": "random-init (He-normal, seed 0) of the reference architecture (484.6 GFLOP/frame)",
+            "config": {"workload": WL["name"],
+                       "global_batch": world * BATCH, "input": f"u8 frames {IN_H}x{IN_W}x3, random (default_rng)",
+                       "weights": "random-init (He-normal, seed 0) of the reference architecture: " + WL["arch"],
                        "parse_input": f"synthetic crowd tensors ({PERSONS[0]}-{PERSONS[1]} persons/frame, {n_humans} humans/batch) copied over the conv outputs after the last conv",
                        "l2": f"{N_INPUT_SETS} distinct input batches rotated ({N_INPUT_SETS * BATCH * IN_H * IN_W * 3 / 1e6:.0f} MB > L2); activations (>1 GB/step) stream through",
                        "parallelism": f"dp{world} (frames shard; NCCL all-gather of keypoint records only)" if world > 1 else "single GPU"},
@@ -370,7 +418,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline cfg3)")
     args = ap.parse_args()
+    select_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
