@@ -261,8 +261,6 @@ def run_ours(args):
     snap_paf = torch.empty(BATCH * 38 * HF * WF, dtype=torch.float32, device=dev)
     ev_ready = torch.cuda.Event()
     ev_parsed = torch.cuda.Event()
-    n_conf, n_paf = snap_conf.numel() * 4, snap_paf.numel() * 4
-    cudart = torch.cuda.cudart()
     state = {"first": True}
 
     def step_device(i):
@@ -270,9 +268,7 @@ def run_ours(args):
         if not state["first"]:
             st.wait_event(ev_parsed)                  # the previous parse has finished reading the snapshot
         state["first"] = False
-        with torch.cuda.stream(st):
-            cudart.cudaMemcpyAsync(snap_conf.data_ptr(), out_conf_ptr, n_conf, 3, st.cuda_stream)   # 3 = cudaMemcpyDeviceToDevice
-            cudart.cudaMemcpyAsync(snap_paf.data_ptr(), out_paf_ptr, n_paf, 3, st.cuda_stream)
+        engine.copy_outputs_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, st.cuda_stream)
         ev_ready.record(st)
         st2.wait_event(ev_ready)
         parser.process_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, 19, 38, HF, WF, st2.cuda_stream)

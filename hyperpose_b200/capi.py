@@ -162,7 +162,7 @@ class PafParser:
 # ---------------------------------------------------------------------------------------------
 EXPORTS += [
     "hp_engine_create", "hp_engine_destroy", "hp_engine_info", "hp_engine_infer_u8_host", "hp_engine_infer_u8_device",
-    "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_sync",
+    "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_copy_outputs_device", "hp_engine_sync",
     "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
     "hp_pose_run_u8_host", "hp_engine_stage_frame_u8", "hp_engine_infer_staged", "hp_engine_debug_read_frames", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
 ]
@@ -180,6 +180,7 @@ def _bind_engine(L):
     L.hp_engine_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.hp_engine_read_outputs_host.argtypes = [vp, vp, vp, C.c_int]
     L.hp_engine_sync.argtypes = [vp]
+    L.hp_engine_copy_outputs_device.argtypes = [vp, vp, vp, C.c_int, vp]
     L.hp_engine_launch_count.argtypes = [vp]
     L.hp_engine_launch_count.restype = C.c_longlong
     L.hp_engine_debug_read_buffer.argtypes = [vp, C.c_int, vp, C.c_int, ip, ip, ip]
@@ -282,6 +283,9 @@ class Engine:
 
     def sync(self):
         check(lib().hp_engine_sync(self._h))
+
+    def copy_outputs_device(self, d_conf_ptr: int, d_paf_ptr: int, n: int, stream: int = 0):
+        check(lib().hp_engine_copy_outputs_device(self._h, d_conf_ptr, d_paf_ptr, n, stream))
 
     @property
     def launch_count(self) -> int:

@@ -888,6 +888,19 @@ int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N)
     return HP_OK;
 }
 
+// D2D snapshot of the last batch's outputs into caller-owned device tensors, asynchronously on `stream`
+// (lets a pipelined caller parse batch i on another stream while batch i+1 overwrites the engine's outputs)
+int hp_engine_copy_outputs_device(hp_engine* e, float* d_conf, float* d_paf, int N, void* stream)
+{
+    if (!e || !d_conf || !d_paf || N <= 0 || N > e->max_batch) { set_error("hp_engine_copy_outputs_device: bad argument"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    const size_t plane = (size_t)e->out_h * e->out_w;
+    HP_CUDA_TRY(cudaMemcpyAsync(d_conf, e->d_conf, N * e->hdr.conf_channels * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(d_paf, e->d_paf, N * e->hdr.paf_channels * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return HP_OK;
+}
+
 int hp_engine_sync(hp_engine* e)
 {
     if (!e) return HP_ERR_ARG;

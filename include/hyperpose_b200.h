@@ -137,6 +137,8 @@ int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N);
 int hp_engine_outputs(hp_engine* e, const float** d_conf, const float** d_paf, void** stream);
 /* the reference's per-image D2H of every output (tensorrt.cpp:398-431), as two contiguous host tensors */
 int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N);
+/* asynchronous D2D snapshot of the outputs into caller-owned device tensors (software-pipelined callers) */
+int hp_engine_copy_outputs_device(hp_engine* e, float* d_conf, float* d_paf, int N, void* stream);
 int hp_engine_sync(hp_engine* e);
 long long hp_engine_launch_count(const hp_engine* e);
 /* test hooks: read / write an activation buffer (fp16 NHWC), run a sub-range [first,last] of the op list */
