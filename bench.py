@@ -13,8 +13,7 @@ keypoint records to rank 0).  Because random weights give structureless heat-map
 crowd tensors are copied over the backbone's outputs after the last conv (hp_engine_set_output_override,
 SURVEY 8d) -- all conv work is still executed; this is stated in config.parse_input.
 
-  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather);
-          two-stream software pipeline: parse + gather of batch i overlap the convs of batch i+1
+  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather)
   e2e   : the public host call hp_pose_run_u8_host -- pinned host frames H2D, human_t records D2H, every step
   roofline : the conv kernel (dominant): algorithmic FLOPs / CUDA-event time of the conv launches, measured in
              the timed region on the launching stream, vs the measured cuBLAS bf16 peak
@@ -253,6 +252,8 @@ def run_ours(args):
             with torch.cuda.stream(st):
                 sharding.gather_records(res_humans, res_counts, world)   # NCCL all-gather of ~300 KB per rank
 
+    # Optional (--pipeline; OFF by default: measured SLOWER, 2070 vs 2221 frames/s -- the parser's many small CTAs delay
+    # the start of the next persistent conv kernel's CTAs, whose static tile assignment then runs unbalanced).
     # Software pipeline of the device-resident path: the PAF parse (+ the keypoint gather) of batch i runs on a second
     # stream while the convs of batch i+1 run on the first.  The engine's conf/paf outputs are snapshotted (D2D, 14 MB)
     # on the conv stream so that batch i+1 may overwrite them; events order snapshot <-> parse in both directions.
@@ -263,7 +264,14 @@ def run_ours(args):
     ev_parsed = torch.cuda.Event()
     state = {"first": True}
 
+    def step_device_serial(i):
+        engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
+        parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
+        gather_results()
+
     def step_device(i):
+        if not args.pipeline:
+            return step_device_serial(i)
         engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
         if not state["first"]:
             st.wait_event(ev_parsed)                  # the previous parse has finished reading the snapshot
@@ -279,7 +287,8 @@ def run_ours(args):
         ev_parsed.record(st2)
 
     def drain_device():
-        st.wait_event(ev_parsed)                      # the timed region ends when the last parse/gather has finished
+        if args.pipeline:
+            st.wait_event(ev_parsed)                      # the timed region ends when the last parse/gather has finished
 
     def step_host(i):
         humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
@@ -414,6 +423,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", action="store_true", help="two-stream software pipeline (parse of batch i overlaps convs of batch i+1)")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline cfg3)")
     args = ap.parse_args()
     select_workload(args.workload)
