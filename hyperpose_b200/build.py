@@ -19,6 +19,7 @@ EXACT_FLAGS = ["-fmad=false"]
 SOURCES = [
     ("paf_parser.cu", EXACT_FLAGS),
     ("engine.cu", []),
+    ("pifpaf_decoder.cu", EXACT_FLAGS),
     ("common.cpp", []),
 ]
 

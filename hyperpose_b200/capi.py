@@ -327,3 +327,50 @@ class Engine:
         n = (C.c_int * N)()
         check(lib().hp_pose_run_u8_host(self._h, parser._h, frames.ctypes.data, N, out.ctypes.data, cap, n))
         return [out[i, :n[i]].copy() for i in range(N)]
+
+
+# ---------------------------------------------------------------------------------------------
+# OpenPifPaf decoder
+# ---------------------------------------------------------------------------------------------
+EXPORTS += ["hp_pifpaf_create", "hp_pifpaf_destroy", "hp_pifpaf_process_host", "hp_pifpaf_process_device", "hp_pifpaf_fetch",
+            "hp_pifpaf_launch_count"]
+
+
+class PifPafParser:
+    """Mirror of hyperpose::parser::pifpaf (include/hyperpose/operator/parser/pifpaf.hpp:8-26): PifPafParser(h, w, thresh)."""
+
+    def __init__(self, net_h: int, net_w: int, thresh: float = 0.1, device: int = 0):
+        L = lib()
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        L.hp_pifpaf_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_float, C.c_int]
+        L.hp_pifpaf_destroy.argtypes = [vp]
+        L.hp_pifpaf_destroy.restype = None
+        L.hp_pifpaf_process_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip]
+        L.hp_pifpaf_process_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.hp_pifpaf_fetch.argtypes = [vp, vp, C.c_int, ip, C.c_int]
+        self._h = C.c_void_p()
+        check(L.hp_pifpaf_create(C.byref(self._h), net_h, net_w, thresh, device))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hp_pifpaf_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process_batch(self, pif: np.ndarray, paf: np.ndarray, cap: int = 128):
+        """pif[N,17,5,h,w], paf[N,19,9,h,w] host tensors -> list of N HUMAN_DT arrays"""
+        pif = np.ascontiguousarray(pif, np.float32)
+        paf = np.ascontiguousarray(paf, np.float32)
+        N, _, _, h, w = pif.shape
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_pifpaf_process_host(self._h, pif.ctypes.data, paf.ctypes.data, N, h, w, out.ctypes.data, cap, n))
+        return [out[i, :n[i]].copy() for i in range(N)]
+
+    def process(self, pif: np.ndarray, paf: np.ndarray, cap: int = 128):
+        return self.process_batch(pif[None], paf[None], cap)[0]

@@ -118,3 +118,54 @@ def make_frames_u8(seed: int, n_frames: int, height: int, width: int) -> np.ndar
     """u8[N,height,width,3] BGR frames (cfg2 default_rng(1), cfg3 default_rng(2))."""
     rng = np.random.default_rng(seed)
     return rng.integers(0, 256, size=(n_frames, height, width, 3), dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# OpenPifPaf fields (BASELINE config 5; SURVEY 8d cfg5 recipe)
+# ---------------------------------------------------------------------------------------------
+# 17 COCO keypoints in OpenPifPaf order; 19 bones, 1-based (src/pifpaf_decoder/openpifpaf_postprocessor.cpp:64-84)
+PIFPAF_BONES = [(16, 14), (14, 12), (17, 15), (15, 13), (12, 13), (6, 12), (7, 13), (6, 7), (6, 8), (7, 9), (8, 10), (9, 11),
+                (2, 3), (1, 2), (1, 3), (2, 4), (3, 5), (4, 6), (5, 7)]
+# (x, y) of the 17 keypoints in a unit person box: nose, l/r eye, l/r ear, l/r shoulder, l/r elbow, l/r wrist, l/r hip, l/r knee, l/r ankle
+_PIF_TEMPLATE = np.array([
+    (0.50, 0.08), (0.54, 0.05), (0.46, 0.05), (0.59, 0.08), (0.41, 0.08), (0.64, 0.20), (0.36, 0.20), (0.70, 0.37),
+    (0.30, 0.37), (0.73, 0.52), (0.27, 0.52), (0.58, 0.53), (0.42, 0.53), (0.59, 0.73), (0.41, 0.73), (0.60, 0.93), (0.40, 0.93)])
+
+
+def make_pifpaf_fields(seed: int, n_persons, h: int = 49, w: int = 49):
+    """(pif f32[17,5,h,w] = {conf, x, y, b, scale}, paf f32[19,9,h,w] = {conf, x1, y1, x2, y2, b1, b2, s1, s2}); all
+    coordinates / scales absolute, in feature-cell units (the decoder multiplies by its stride 8,
+    openpifpaf_postprocessor.cpp:326-328,726-730)."""
+    rng = np.random.default_rng(seed)
+    if isinstance(n_persons, tuple):
+        n_persons = int(rng.integers(n_persons[0], n_persons[1] + 1))
+    pif = np.zeros((17, 5, h, w), np.float32)
+    paf = np.zeros((19, 9, h, w), np.float32)
+    pif[:, 0] = rng.uniform(0.0, 0.05, (17, h, w))          # background confidences stay below every threshold
+    paf[:, 0] = rng.uniform(0.0, 0.05, (19, h, w))
+    pif[:, 4] = 1.0
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    for _ in range(n_persons):
+        ph = rng.uniform(0.45, 0.9) * h
+        pw = ph * rng.uniform(0.6, 0.8)
+        x0 = rng.uniform(0.0, max(1.0, w - pw)); y0 = rng.uniform(0.0, max(1.0, h - ph))
+        pts = (_PIF_TEMPLATE + rng.normal(0, 0.01, (17, 2))) * np.array([pw, ph]) + np.array([x0, y0])
+        scale = float(rng.uniform(1.0, 1.5))
+        for k, (cx, cy) in enumerate(pts):
+            m = ((xx - cx) ** 2 + (yy - cy) ** 2) <= 2.3 ** 2
+            n = int(m.sum())
+            if n == 0:
+                continue
+            pif[k, 0][m] = rng.uniform(0.85, 0.95, n)
+            pif[k, 1][m] = cx + rng.normal(0, 0.02, n)
+            pif[k, 2][m] = cy + rng.normal(0, 0.02, n)
+            pif[k, 3][m] = rng.uniform(0.2, 0.4, n)
+            pif[k, 4][m] = scale + rng.normal(0, 0.02, n)
+        for b, (j1, j2) in enumerate(PIFPAF_BONES):
+            (x1, y1), (x2, y2) = pts[j1 - 1], pts[j2 - 1]
+            for t in np.linspace(0.0, 1.0, 9):
+                cx, cy = int(round(x1 + t * (x2 - x1))), int(round(y1 + t * (y2 - y1)))
+                if 0 <= cx < w and 0 <= cy < h:
+                    paf[b, :, cy, cx] = (rng.uniform(0.85, 0.95), x1 + rng.normal(0, 0.02), y1 + rng.normal(0, 0.02),
+                                         x2 + rng.normal(0, 0.02), y2 + rng.normal(0, 0.02), 0.3, 0.3, scale, scale)
+    return pif, paf

@@ -106,6 +106,21 @@ long long hp_paf_launch_count(const hp_paf* p);
 int hp_paf_copy_results_device(hp_paf* p, hp_human* d_humans, int* d_counts, int N, int cap, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * OpenPifPaf decoder -- replaces hyperpose::parser::pifpaf (include/hyperpose/operator/parser/pifpaf.hpp:8-26,
+ * src/pifpaf.cpp:7-95, src/pifpaf_decoder/openpifpaf_postprocessor.cpp).
+ * Tensors: pif[N,17,5,h,w] = {conf,x,y,b,scale}, paf[N,19,9,h,w] = {conf,x1,y1,x2,y2,b1,b2,s1,s2}, feature-cell units.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hp_pifpaf hp_pifpaf;
+/* pifpaf::pifpaf(int h, int w, float thresh = 0.1) (pifpaf.hpp:10-13) */
+int hp_pifpaf_create(hp_pifpaf** out, int net_h, int net_w, float thresh, int device);
+void hp_pifpaf_destroy(hp_pifpaf* p);
+/* pifpaf::process (pifpaf.hpp:14; defined with the (paf, pif) argument order at src/pifpaf.cpp:7): HOST tensors, N frames */
+int hp_pifpaf_process_host(hp_pifpaf* p, const float* pif, const float* paf, int N, int h, int w, hp_human* out, int cap, int* n_out);
+int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_paf, int N, int h, int w, void* stream);
+int hp_pifpaf_fetch(hp_pifpaf* p, hp_human* out, int cap, int* n_out, int N);
+long long hp_pifpaf_launch_count(const hp_pifpaf* p);
+
+/* ------------------------------------------------------------------------------------------
  * DNN engine -- replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
  * src/tensorrt.cpp:121-471).  The model file is a flat "HPB2PACK" pack (hyperpose_b200/csrc/pack_format.h,
  * written by hyperpose_b200/models.py) instead of .onnx/.uff/.trt (utility/model.hpp:13-32).

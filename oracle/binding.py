@@ -195,3 +195,32 @@ class RefParser:
             self.close()
         except Exception:
             pass
+
+
+_refpp = None
+
+
+def pifpaf_ref_available() -> bool:
+    if os.path.isdir("/root/reference/src"):
+        build()
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_pifpaf.so"))
+
+
+def ref_pifpaf_process(pif: np.ndarray, paf: np.ndarray, net_h: int, net_w: int, thresh: float = 0.1, cap: int = 256) -> np.ndarray:
+    """The reference's own hyperpose::parser::pifpaf (src/pifpaf.cpp + src/pifpaf_decoder compiled verbatim) on one frame."""
+    global _refpp
+    if _refpp is None:
+        if not pifpaf_ref_available():
+            raise FileNotFoundError("oracle/_ref/libref_pifpaf.so not built (needs /root/reference)")
+        lib = C.CDLL(os.path.join(HERE, "_ref", "libref_pifpaf.so"))
+        fp = C.POINTER(C.c_float)
+        lib.ref_pifpaf_process.restype = C.c_int
+        lib.ref_pifpaf_process.argtypes = [fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int]
+        _refpp = lib
+    pif = np.ascontiguousarray(pif, np.float32)
+    paf = np.ascontiguousarray(paf, np.float32)
+    out = np.zeros(cap, HUMAN_REC)
+    n = _refpp.ref_pifpaf_process(_fp(pif), _fp(paf), pif.shape[2], pif.shape[3], net_h, net_w, thresh, out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"ref_pifpaf_process rc={n}")
+    return out[:n].copy()

@@ -42,6 +42,11 @@ RESIZE_CASES = [(360, 640, 368, 656), (480, 640, 368, 656), (720, 1280, 368, 656
                 (1080, 1920, 368, 656), (368, 656, 368, 656), (300, 500, 207, 344), (37, 53, 64, 48)]
 
 
+# (name, seed, persons, h, w, keypoint_thresh) of the PifPaf decode pin (BASELINE config 5: 385x385 -> 49x49 fields)
+PIFPAF_CASES = [("pp_p2", 4, 2, 49, 49, 0.1), ("pp_p5", 5, 5, 49, 49, 0.1), ("pp_crowd", 6, (6, 12), 49, 49, 0.1), ("pp_empty", 7, 0, 49, 49, 0.1),
+                ("pp_rect", 8, 3, 47, 55, 0.1), ("pp_thr", 9, 4, 49, 49, 0.3), ("pp_small", 10, 2, 25, 33, 0.1)]
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -87,6 +92,12 @@ def main():
         ref[name + "_in_sha"] = np.array(sha(conf) + sha(paf))
         rp.close()
     np.savez_compressed(os.path.join(HERE, "ref_humans.npz"), **ref)
+    pp = {}
+    for (name, seed, P, h, w, thr) in PIFPAF_CASES:
+        pif, paf = syn.make_pifpaf_fields(seed, P, h, w)
+        pp[name + "_humans"] = oracle.ref_pifpaf_process(pif, paf, (h - 1) * 8 + 1, (w - 1) * 8 + 1, thr)
+        pp[name + "_in_sha"] = np.array(sha(pif) + sha(paf))
+    np.savez_compressed(os.path.join(HERE, "ref_pifpaf.npz"), **pp)
     print("wrote", os.listdir(HERE))
 
 
