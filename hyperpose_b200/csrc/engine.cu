@@ -173,6 +173,37 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ 
     *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * out_ld + c0) = o;
 }
 
+// OpenPifPaf heads (hyperpose/Model/pifpaf/model.py:215-281): raw 1x1-conv outputs [N,hc,wc,C] fp16 ->
+//   pixel_shuffle(scale 2) (pifpaf/utils.py:371-379: in-channel ((nc*2+dy)*2+dx) -> out[nc, 2h+dy, 2w+dx]), crop to 2*hc-1,
+//   reshape [fields, comps, ho, wo]; sigmoid on the confidences, softplus on the scales (inference branch, model.py:238-241,270-274);
+//   regressed vectors are offsets from the cell, the C++ decoder wants absolute cell coordinates (postprocessor.cpp:326-328):
+//   the index grid is added here (what the exported OpenPifPaf graph does).
+__global__ void __launch_bounds__(256) pifpaf_head_kernel(const __half* __restrict__ raw, int raw_ld, float* __restrict__ out, int N, int hc, int wc,
+                                                          int fields, int comps, int ho, int wo, int is_paf)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)N * fields * comps * ho * wo;
+    if (idx >= total) return;
+    const int x = (int)(idx % wo);
+    size_t t = idx / wo;
+    const int y = (int)(t % ho); t /= ho;
+    const int comp = (int)(t % comps); t /= comps;
+    const int k = (int)(t % fields);
+    const int n = (int)(t / fields);
+    const int nc = k * comps + comp;
+    const int ch = (nc * 2 + (y & 1)) * 2 + (x & 1);
+    float v = __half2float(raw[(((size_t)n * hc + (y >> 1)) * wc + (x >> 1)) * raw_ld + ch]);
+    const bool is_conf = comp == 0;
+    const bool is_scale = is_paf ? (comp == 7 || comp == 8) : (comp == 4);
+    const bool is_x = is_paf ? (comp == 1 || comp == 3) : (comp == 1);
+    const bool is_y = is_paf ? (comp == 2 || comp == 4) : (comp == 2);
+    if (is_conf) v = 1.f / (1.f + expf(-v));
+    else if (is_scale) v = v > 20.f ? v : log1pf(expf(v));
+    else if (is_x) v += (float)x;
+    else if (is_y) v += (float)y;
+    out[idx] = v;
+}
+
 // KxK (K = 2 or 3) stride-2 max pool, NHWC fp16, 8 channels per thread; TF "SAME" semantics (window clipped at the border).
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                                                        int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW, int K, int pad_h, int pad_w)
@@ -539,6 +570,13 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
                 im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, e->in_h, e->in_w, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
                                                              stride, ob.H, ob.W, ph, pw, R, chunks);
             e->launches++;
+        } else if (po.type == OP_PIFPAF_HEAD) {
+            EngBuffer& a = e->bufs[po.in_buf];
+            EngBuffer& b = e->bufs[po.res_buf];
+            const size_t t1 = (size_t)N * 17 * 5 * e->out_h * e->out_w, t2 = (size_t)N * 19 * 9 * e->out_h * e->out_w;
+            pifpaf_head_kernel<<<(int)((t1 + 255) / 256), 256, 0, st>>>(a.d, a.channels, e->d_conf, N, a.H, a.W, 17, 5, e->out_h, e->out_w, 0);
+            pifpaf_head_kernel<<<(int)((t2 + 255) / 256), 256, 0, st>>>(b.d, b.channels, e->d_paf, N, b.H, b.W, 19, 9, e->out_h, e->out_w, 1);
+            e->launches += 2;
         } else if (po.type == OP_DWCONV) {
             EngBuffer& ib = e->bufs[po.in_buf];
             EngBuffer& ob = e->bufs[po.out_buf];
@@ -653,6 +691,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
     }
     e->out_h = in_h; e->out_w = in_w;
     for (uint32_t d = 0; d < hdr.out_down_shift; ++d) { e->out_h = (e->out_h + 1) / 2; e->out_w = (e->out_w + 1) / 2; }
+    if (hdr.head_type == 1) { e->out_h = 2 * e->out_h - 1; e->out_w = 2 * e->out_w - 1; } // pixel-shuffled and cropped
     if (cudaMalloc(&e->d_conf, (size_t)max_batch * hdr.conf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&e->d_paf, (size_t)max_batch * hdr.paf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&e->d_frames, (size_t)max_batch * in_h * in_w * 3) != cudaSuccess ||
@@ -665,7 +704,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
     for (uint32_t i = 0; i < hdr.n_ops; ++i) {
         e->ops[i].po = pops[i];
         const PackOp& po = pops[i];
-        if ((po.type != OP_IM2COL3 && po.in_buf >= hdr.n_buffers) || (po.out_mode != OUT_F32_NCHW_SPLIT && po.out_buf >= hdr.n_buffers)) {
+        if ((po.type != OP_IM2COL3 && po.in_buf >= hdr.n_buffers) || (po.out_mode != OUT_F32_NCHW_SPLIT && po.type != OP_PIFPAF_HEAD && po.out_buf >= hdr.n_buffers)) {
             set_error("engine: op %u references a missing buffer", i);
             return fail(HP_ERR_ARG);
         }
@@ -705,6 +744,9 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             e->flops_per_frame += 2.0 * ob.H * ob.W * C * K * K;
         } else if (po.type == OP_MAXPOOL2) {
             if (po.cout_g % 8 || e->bufs[po.out_buf].down != e->bufs[po.in_buf].down + 1 || (po.R != 0 && po.R != 2 && po.R != 3)) { set_error("engine: bad maxpool op %u", i); return fail(HP_ERR_ARG); }
+        } else if (po.type == OP_PIFPAF_HEAD) {
+            if (hdr.head_type != 1 || po.res_buf >= hdr.n_buffers || hdr.conf_channels != 85 || hdr.paf_channels != 171 ||
+                e->bufs[po.in_buf].channels < 340 || e->bufs[po.res_buf].channels < 684) { set_error("engine: bad pifpaf head op"); return fail(HP_ERR_ARG); }
         } else {
             set_error("engine: unknown op type %u", po.type);
             return fail(HP_ERR_UNSUPPORTED);

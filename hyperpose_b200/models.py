@@ -19,7 +19,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-OP_IM2COL3, OP_CONV, OP_MAXPOOL2, OP_DWCONV = 1, 2, 3, 4
+OP_IM2COL3, OP_CONV, OP_MAXPOOL2, OP_DWCONV, OP_PIFPAF_HEAD = 1, 2, 3, 4, 5
 OUT_F16_NHWC, OUT_F32_NCHW_SPLIT = 0, 1
 PACK_MAGIC = b"HPB2PACK"
 PACK_VERSION = 2
@@ -57,6 +57,7 @@ class Graph:
     paf_channels: int = 38
     out_down_shift: int = 3
     mean: tuple = (0.0, 0.0, 0.0)
+    head_type: int = 0                 # 1: OpenPifPaf fields (pif[17,5,ho,wo] / paf[19,9,ho,wo] in the conf / paf output slots)
     buffers: list = field(default_factory=list)   # (channels, down_shift)
     ops: list = field(default_factory=list)
 
@@ -103,7 +104,7 @@ class Graph:
                                        op.res_buf, op.res_ch_off, op.res_mode, 0, w_off, b_off, a_off))
         blob_arr = np.concatenate(blob).astype("<f4") if blob else np.zeros(0, "<f4")
         hdr = struct.pack("<8s6I3f5IQ", PACK_MAGIC, PACK_VERSION, len(self.buffers), len(self.ops), self.conf_channels,
-                          self.paf_channels, self.out_down_shift, *[float(m) for m in self.mean], 0, 0, 0, 0, 0, blob_arr.size)
+                          self.paf_channels, self.out_down_shift, *[float(m) for m in self.mean], self.head_type, 0, 0, 0, 0, blob_arr.size)
         bufs = b"".join(struct.pack("<2I", c, d) for c, d in self.buffers)
         return hdr + bufs + b"".join(op_recs) + blob_arr.tobytes()
 
@@ -393,6 +394,62 @@ def resnet50_lw_openpose(seed: int = 0) -> Graph:
     g.add_conv(src, wide2, np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024), relu(1024), name="ref_4")
     g.add_conv(wide2, 0, _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57), lin(57),
                out_mode=OUT_F32_NCHW_SPLIT, split=19, name="ref_out")
+    return g
+
+
+def resnet50_pifpaf(seed: int = 0) -> Graph:
+    """OpenPifPaf on ResNet-50 (BASELINE.json config 5): hyperpose/Model/pifpaf/model.py:41-51 (Resnet50_backbone(use_pool=False,
+    scale_size=32): 7x7/2 stem, NO max-pool, stride-2 first blocks in stages 2-4 => stride 16), :215-281 (two 1x1 heads to
+    17*5*4 and 19*9*4 channels, pixel-shuffle x2, sigmoid / softplus) -> fields at stride 8, cropped to 2*h16 - 1 (49 for 385).
+    Input normalisation (x - mean) / std (model.py:38-39,58): the mean is subtracted in the patch gather, 1/std is folded
+    into the stem weights."""
+    rng = np.random.default_rng(seed)
+    mean = (0.485, 0.456, 0.406); std = np.array([0.229, 0.224, 0.225], np.float32)
+    g = Graph("resnet50_pifpaf", 85, 171, 4, mean=mean, head_type=1)
+    relu = lambda n: np.zeros(n, np.float32)
+    lin = lambda n: np.ones(n, np.float32)
+
+    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", gain=None, **kw):
+        w = _he(rng, 1, co, ci, k, k, gain if gain is not None else (2.0 if act else 1.0))
+        sc, sh = _bn_fold(rng, co)
+        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh, relu(co) if act else lin(co), name=name, **kw)
+
+    def subsample(in_buf, out_buf, C, centre3, name):
+        w = np.zeros((C, 3, 3), np.float32) if centre3 else np.ones((C, 1, 1), np.float32)
+        if centre3:
+            w[:, 1, 1] = 1.0
+        g.add_dwconv(in_buf, out_buf, w, np.zeros(C, np.float32), lin(C), stride=2, name=name)
+
+    col = g.add_buffer(192, 1); g.add_im2col(col, stride=2, ksize=7)
+    c1 = g.add_buffer(64, 1)
+    w = _he(rng, 1, 64, 3, 7, 7) / std.reshape(1, 1, 3, 1, 1); sc, sh = _bn_fold(rng, 64)
+    g.add_conv(col, c1, w * sc.reshape(1, 64, 1, 1, 1), sh, relu(64), im2col_input=1, name="conv1+bn1")
+    cur, cur_c, cur_d = c1, 64, 1
+    for bi, (nf, nblk, st0) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], start=1):
+        for k in range(1, nblk + 1):
+            st = st0 if k == 1 else 1
+            name = f"block_{bi}_{k}"
+            d_out = cur_d + (1 if st == 2 else 0)
+            if st != 1 or cur_c != 4 * nf:
+                src = cur
+                if st == 2:
+                    src = g.add_buffer(_r64(cur_c), d_out); subsample(cur, src, cur_c, False, f"{name}_ds_sub")
+                res = g.add_buffer(4 * nf, d_out)
+                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds", gain=0.5)
+            else:
+                res = cur
+            a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1")
+            b = g.add_buffer(_r64(nf), cur_d); conv_bn(a, b, nf, nf, 3, name=f"{name}_conv2")
+            if st == 2:
+                b2 = g.add_buffer(_r64(nf), d_out); subsample(b, b2, nf, True, f"{name}_conv2_sub"); b = b2
+            out = g.add_buffer(4 * nf, d_out)
+            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", gain=0.1, res_buf=res, res_mode=1)
+            cur, cur_c, cur_d = out, 4 * nf, d_out
+    # heads (model.py:229,262): 1x1 conv + bias, no activation
+    pif_raw = g.add_buffer(512, 4); paf_raw = g.add_buffer(768, 4)
+    g.add_conv(cur, pif_raw, _he(rng, 1, 340, 2048, 1, 1, 0.5), (rng.standard_normal(340) * 0.1).astype(np.float32), lin(340), name="pif_head")
+    g.add_conv(cur, paf_raw, _he(rng, 1, 684, 2048, 1, 1, 0.5), (rng.standard_normal(684) * 0.1).astype(np.float32), lin(684), name="paf_head")
+    g.ops.append(Op(OP_PIFPAF_HEAD, in_buf=pif_raw, res_buf=paf_raw, name="pifpaf_heads"))
     return g
 
 

@@ -117,6 +117,30 @@ def test_resnet50_lw_openpose(hw, N):
     eng.close()
 
 
+def test_resnet50_pifpaf_fields_and_decode():
+    """BASELINE config 5: ResNet-50 (stride 16, no max-pool) + PIF/PAF heads (pixel shuffle, crop, sigmoid/softplus, index grid)
+    vs torch, then the engine's own device-resident fields through the CUDA decoder vs the reference decoder (oracle/_ref)."""
+    g = models.resnet50_pifpaf(0)
+    H = W = 129
+    N = 2
+    frames = syn.make_frames_u8(8, N, H, W)
+    eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+    assert (eng.out_h, eng.out_w, eng.c_conf, eng.c_paf) == (17, 17, 85, 171)
+    eng.infer_u8(frames)
+    pif, paf = eng.read_outputs(N)
+    rpif, rpaf, _ = torch_ref.run_graph(g, frames, emulate_fp16=True)
+    _check(pif.reshape(N, 17, 5, 17, 17), rpif.cpu().numpy(), 8e-3, 8e-3, "pif fields")
+    _check(paf.reshape(N, 19, 9, 17, 17), rpaf.cpu().numpy(), 8e-3, 8e-3, "paf fields")
+    if oracle.pifpaf_ref_available():
+        dec = capi.PifPafParser(H, W, 0.1)
+        got = dec.process_batch(pif.reshape(N, 17, 5, 17, 17), paf.reshape(N, 19, 9, 17, 17))
+        for i in range(N):
+            want = oracle.ref_pifpaf_process(pif[i].reshape(17, 5, 17, 17), paf[i].reshape(19, 9, 17, 17), H, W, 0.1)
+            assert got[i].tobytes() == want.tobytes()
+        dec.close()
+    eng.close()
+
+
 def test_f32_nchw_entry_matches_u8_entry():
     """tensorrt::inference(const std::vector<float>&, n): pre-scaled NCHW floats give the same outputs"""
     g = models.tiny_test_net(2)

@@ -77,6 +77,23 @@ def run_graph(g: models.Graph, frames_u8: np.ndarray, factor=1.0 / 255, flip_rgb
                 conf, paf = y[:, :op.split].contiguous(), y[:, op.split:].contiguous()
             else:
                 bufs[op.out_buf][:, op.out_ch_off:op.out_ch_off + G * co] = q(y)
+        elif op.type == models.OP_PIFPAF_HEAD:
+            def head(raw, fields, comps, is_paf):
+                x = raw[:, :fields * comps * 4]
+                b, c, h, w = x.shape
+                x = x.reshape(b, c // 4, 2, 2, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b, c // 4, 2 * h, 2 * w)   # pifpaf/utils.py:371-379
+                x = x[:, :, :2 * h - 1, :2 * w - 1].reshape(b, fields, comps, 2 * h - 1, 2 * w - 1).clone()
+                gy, gx = torch.meshgrid(torch.arange(2 * h - 1, device=device), torch.arange(2 * w - 1, device=device), indexing="ij")
+                x[:, :, 0] = torch.sigmoid(x[:, :, 0])
+                for cx in ((1, 3) if is_paf else (1,)):
+                    x[:, :, cx] += gx
+                for cy in ((2, 4) if is_paf else (2,)):
+                    x[:, :, cy] += gy
+                for cs in ((7, 8) if is_paf else (4,)):
+                    x[:, :, cs] = F.softplus(x[:, :, cs])
+                return x
+            conf = head(bufs[op.in_buf], 17, 5, False)
+            paf = head(bufs[op.res_buf], 19, 9, True)
         elif op.type == models.OP_DWCONV:
             C, K, _ = op.weight.shape
             x = bufs[op.in_buf][:, op.in_ch_off:op.in_ch_off + C]
