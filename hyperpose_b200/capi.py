@@ -333,7 +333,7 @@ class Engine:
 # OpenPifPaf decoder
 # ---------------------------------------------------------------------------------------------
 EXPORTS += ["hp_pifpaf_create", "hp_pifpaf_destroy", "hp_pifpaf_process_host", "hp_pifpaf_process_device", "hp_pifpaf_fetch",
-            "hp_pifpaf_launch_count"]
+            "hp_pifpaf_launch_count", "hp_pifpaf_debug_counts", "hp_pifpaf_debug_hr"]
 
 
 class PifPafParser:
@@ -374,3 +374,15 @@ class PifPafParser:
 
     def process(self, pif: np.ndarray, paf: np.ndarray, cap: int = 128):
         return self.process_batch(pif[None], paf[None], cap)[0]
+
+    def debug_hr(self, frame: int, field: int, h: int, w: int) -> np.ndarray:
+        out = np.zeros(((h - 1) * 8 + 1, (w - 1) * 8 + 1), np.float32)
+        lib().hp_pifpaf_debug_hr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        check(lib().hp_pifpaf_debug_hr(self._h, frame, field, out.ctypes.data))
+        return out
+
+    def debug_counts(self, frame: int = 0):
+        out = (C.c_int * 7)()
+        lib().hp_pifpaf_debug_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        check(lib().hp_pifpaf_debug_counts(self._h, frame, out))
+        return dict(zip(["seeds", "anns", "kept", "flags", "nms_h", "nms_w", "caf_entries"], list(out)))

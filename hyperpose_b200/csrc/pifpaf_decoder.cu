@@ -418,6 +418,7 @@ struct GrowParams {
     float keypoint_thresh;
     int net_h, net_w;
     hp_human* humans; int hcap; int* human_cnt; int* flags;
+    int* dbg; // [N][4]: annotations grown, kept after thresholds, NMS map h, w
 };
 
 struct QItem { float score; int has; float x, y, s, v; int start, end; };
@@ -525,6 +526,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
         ++n_ann;
     }
 
+    if (lane == 0) p.dbg[frame * 4 + 0] = n_ann;
     // ---- soft NMS (:574-635) ----
     int n_keep = 0;
     if (n_ann > 0) {
@@ -532,6 +534,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
         for (int a = 0; a < n_ann; ++a)
             for (int k = 0; k < NKP; ++k) { mx = fmaxf(mx, anns[a].kp[k * 3]); my = fmaxf(my, anns[a].kp[k * 3 + 1]); }
         const int h = (int)__fadd_rn(my, 1.f), w = (int)__fadd_rn(mx, 1.f);
+        if (lane == 0) { p.dbg[frame * 4 + 2] = h; p.dbg[frame * 4 + 3] = w; }
         if (h > p.nms_h || w > p.nms_w || n_ann > 512) {
             if (lane == 0) atomicOr(p.flags + frame, PP_FLAG_NMS_DIM);
             if (lane == 0) p.human_cnt[frame] = 0;
@@ -609,6 +612,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
             }
         }
         p.human_cnt[frame] = n_out;
+        p.dbg[frame * 4 + 1] = n_keep;
     }
 }
 
@@ -628,7 +632,7 @@ struct hp_pifpaf {
     int N = 0, H = 0, W = 0;
     DBuf<float> hr, lists, in_pif, in_paf;
     DBuf<Seed> seeds_raw, seeds;
-    DBuf<int> counters; // [N seed_cnt | N*19*2 list_cnt | N human_cnt | N flags]
+    DBuf<int> counters; // [N seed_cnt | N*19*2 list_cnt | N human_cnt | N flags | N*4 dbg]
     DBuf<uint8_t> occ_grow, occ_nms;
     DBuf<Ann> anns;
     DBuf<hp_human> humans;
@@ -678,7 +682,7 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     HP_CUDA_TRY(p->lists.ensure((size_t)N * NBONE * 2 * 9 * hw));
     HP_CUDA_TRY(p->seeds_raw.ensure((size_t)N * p->seed_cap));
     HP_CUDA_TRY(p->seeds.ensure((size_t)N * p->seed_cap));
-    HP_CUDA_TRY(p->counters.ensure((size_t)N * (1 + NBONE * 2 + 2)));
+    HP_CUDA_TRY(p->counters.ensure((size_t)N * (1 + NBONE * 2 + 2 + 4)));
     HP_CUDA_TRY(p->occ_grow.ensure((size_t)N * NKP * hr_px));
     HP_CUDA_TRY(p->occ_nms.ensure((size_t)N * NKP * nms_h * nms_w));
     HP_CUDA_TRY(p->anns.ensure((size_t)N * p->ann_cap));
@@ -687,7 +691,7 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     int* list_cnt = seed_cnt + N;
     int* human_cnt = list_cnt + (size_t)N * NBONE * 2;
     int* flags = human_cnt + N;
-    HP_CUDA_TRY(cudaMemsetAsync(p->counters.p, 0, (size_t)N * (1 + NBONE * 2 + 2) * sizeof(int), st));
+    HP_CUDA_TRY(cudaMemsetAsync(p->counters.p, 0, (size_t)N * (1 + NBONE * 2 + 2 + 4) * sizeof(int), st));
     HP_CUDA_TRY(cudaMemsetAsync(p->occ_grow.p, 0, (size_t)N * NKP * hr_px, st));
     HP_CUDA_TRY(cudaMemsetAsync(p->occ_nms.p, 0, (size_t)N * NKP * nms_h * nms_w, st));
     pif_hr_kernel<<<dim3(NKP, N), 256, hw * sizeof(int), st>>>(d_pif, p->hr.p, g, 0.1f);
@@ -696,7 +700,7 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     GrowParams gp;
     gp.g = g; gp.seeds = p->seeds.p; gp.seed_cnt = seed_cnt; gp.seed_cap = p->seed_cap; gp.lists = p->lists.p; gp.list_cnt = list_cnt;
     gp.occ_grow = p->occ_grow.p; gp.occ_nms = p->occ_nms.p; gp.nms_h = nms_h; gp.nms_w = nms_w; gp.anns = p->anns.p; gp.ann_cap = p->ann_cap;
-    gp.keypoint_thresh = p->thresh; gp.net_h = p->net_h; gp.net_w = p->net_w; gp.humans = p->humans.p; gp.hcap = p->hcap; gp.human_cnt = human_cnt; gp.flags = flags;
+    gp.keypoint_thresh = p->thresh; gp.net_h = p->net_h; gp.net_w = p->net_w; gp.humans = p->humans.p; gp.hcap = p->hcap; gp.human_cnt = human_cnt; gp.flags = flags; gp.dbg = flags + N;
     pifpaf_grow_kernel<<<N, 32, 0, st>>>(gp);
     HP_CUDA_TRY(cudaGetLastError());
     p->launches += 4;
@@ -741,5 +745,34 @@ int hp_pifpaf_process_host(hp_pifpaf* p, const float* pif, const float* paf, int
 }
 
 long long hp_pifpaf_launch_count(const hp_pifpaf* p) { return p ? p->launches : 0; }
+
+// test hook: the high-resolution core map of (frame, field) of the last call, HR x WR floats
+int hp_pifpaf_debug_hr(hp_pifpaf* p, int frame, int field, float* out)
+{
+    if (!p || !out || frame < 0 || frame >= p->last_N || field < 0 || field >= NKP) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    const size_t hr_px = (size_t)((p->H - 1) * 8 + 1) * ((p->W - 1) * 8 + 1);
+    HP_CUDA_TRY(cudaMemcpy(out, p->hr.p + ((size_t)frame * NKP + field) * hr_px, hr_px * sizeof(float), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
+
+// test hook: per-frame counters of the last call: out[0] seeds, out[1] annotations grown, out[2] kept after thresholds,
+// out[3] flags, out[4..5] NMS map h, w, out[6] sum of CAF list lengths
+int hp_pifpaf_debug_counts(hp_pifpaf* p, int frame, int* out)
+{
+    if (!p || !out || frame < 0 || frame >= p->last_N) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    HP_CUDA_TRY(cudaDeviceSynchronize());
+    const int N = p->last_N;
+    std::vector<int> c((size_t)N * (1 + NBONE * 2 + 2 + 4));
+    HP_CUDA_TRY(cudaMemcpy(c.data(), p->counters.p, c.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int* list_cnt = c.data() + N; const int* human_cnt = list_cnt + (size_t)N * NBONE * 2; const int* flags = human_cnt + N; const int* dbg = flags + N;
+    out[0] = c[frame]; out[1] = dbg[frame * 4]; out[2] = dbg[frame * 4 + 1]; out[3] = flags[frame]; out[4] = dbg[frame * 4 + 2]; out[5] = dbg[frame * 4 + 3];
+    int t = 0;
+    for (int i = 0; i < NBONE * 2; ++i) t += list_cnt[(size_t)frame * NBONE * 2 + i];
+    out[6] = t;
+    return HP_OK;
+}
 
 } // extern "C"

@@ -119,6 +119,8 @@ int hp_pifpaf_process_host(hp_pifpaf* p, const float* pif, const float* paf, int
 int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_paf, int N, int h, int w, void* stream);
 int hp_pifpaf_fetch(hp_pifpaf* p, hp_human* out, int cap, int* n_out, int N);
 long long hp_pifpaf_launch_count(const hp_pifpaf* p);
+int hp_pifpaf_debug_counts(hp_pifpaf* p, int frame, int* out7);
+int hp_pifpaf_debug_hr(hp_pifpaf* p, int frame, int field, float* out);
 
 /* ------------------------------------------------------------------------------------------
  * DNN engine -- replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
