@@ -43,6 +43,8 @@ WORKLOADS = {
                  batch=8, persons=(1, 5), algo_flops=22.3e9, arch="MobilenetThin-OpenPose (6 stages), 22.3 GFLOP/frame"),
     "cfg4": dict(name="cfg4: OpenPose-ResNet50 (LW-OpenPose head, stride 8) 368x432, batch 32 per GPU, synthetic crowd", graph="resnet50_lw_openpose",
                  in_h=368, in_w=432, batch=32, persons=(10, 20), algo_flops=136.7e9, arch="ResNet50 + LW-OpenPose head, 136.7 GFLOP/frame"),
+    "cfg5": dict(name="cfg5: OpenPifPaf ResNet50 385x385, batch 16 (pif/paf field decode)", graph="resnet50_pifpaf", in_h=385, in_w=385,
+                 batch=16, persons=(2, 8), algo_flops=100.2e9, arch="ResNet50 (stride 16, no max-pool) + PIF/PAF heads, 100.2 GFLOP/frame", pifpaf=True),
 }
 IN_H, IN_W, HF, WF, BATCH, PERSONS, ALGO_FLOPS_PER_FRAME = 368, 656, 46, 82, 16, (10, 20), 484.6e9
 WL = WORKLOADS["cfg3"]
@@ -54,6 +56,8 @@ def select_workload(key):
     WL = WORKLOADS[key]
     IN_H, IN_W, BATCH, PERSONS, ALGO_FLOPS_PER_FRAME = WL["in_h"], WL["in_w"], WL["batch"], WL["persons"], WL["algo_flops"]
     HF, WF = IN_H // 8, IN_W // 8
+    if WL.get("pifpaf"):
+        HF, WF = (IN_H - 1) // 8 + 1, (IN_W - 1) // 8 + 1     # 49 x 49 fields for 385 x 385
 
 
 def METRIC():
@@ -226,15 +230,24 @@ def run_ours(args):
     pack = graph.to_pack()
     engine = capi.Engine(pack, (IN_W, IN_H), max_batch_size=BATCH, device=local_rank)
     del pack
-    parser = capi.PafParser(0.05, 0.05, device=local_rank)
-    HCAP = 64
-    parser.set_capacity(peaks_per_part=128, candidates_per_limb=2048, humans=HCAP)
+    PIFPAF = bool(WL.get("pifpaf"))
+    HCAP = 128 if PIFPAF else 64
+    if PIFPAF:
+        parser = capi.PifPafParser(IN_H, IN_W, 0.1, device=local_rank)
+    else:
+        parser = capi.PafParser(0.05, 0.05, device=local_rank)
+        parser.set_capacity(peaks_per_part=128, candidates_per_limb=2048, humans=HCAP)
 
     # inputs: N_INPUT_SETS distinct batches of frames (device + pinned host), one set of crowd tensors per rank
     rng_seed = 2 + 1000 * rank
     frames_host = [torch.from_numpy(syn.make_frames_u8(rng_seed + i, BATCH, IN_H, IN_W)).pin_memory() for i in range(N_INPUT_SETS)]
     frames_dev = [f.to(dev) for f in frames_host]
-    conf_np, paf_np = crowd_tensors(1000 + rank)
+    if PIFPAF:
+        fields = [syn.make_pifpaf_fields(1000 * (rank + 1) + i, PERSONS, HF, WF) for i in range(BATCH)]
+        conf_np = np.stack([f[0] for f in fields]).reshape(BATCH, 85, HF, WF)
+        paf_np = np.stack([f[1] for f in fields]).reshape(BATCH, 171, HF, WF)
+    else:
+        conf_np, paf_np = crowd_tensors(1000 + rank)
     d_conf = torch.from_numpy(conf_np).to(dev)
     d_paf = torch.from_numpy(paf_np).to(dev)
     engine.set_output_override(d_conf.data_ptr(), d_paf.data_ptr())
@@ -247,6 +260,8 @@ def run_ours(args):
     from hyperpose_b200 import sharding
 
     def gather_results():
+        if PIFPAF:
+            return    # config 5 is a single-GPU config: records stay in the decoder's device buffer
         parser.copy_results_device(res_humans.data_ptr(), res_counts.data_ptr(), BATCH, HCAP, st.cuda_stream)
         if world > 1:
             with torch.cuda.stream(st):
@@ -266,7 +281,10 @@ def run_ours(args):
 
     def step_device_serial(i):
         engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
-        parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
+        if PIFPAF:
+            parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, st.cuda_stream)
+        else:
+            parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
         gather_results()
 
     def step_device(i):
@@ -291,6 +309,11 @@ def run_ours(args):
             st.wait_event(ev_parsed)                      # the timed region ends when the last parse/gather has finished
 
     def step_host(i):
+        if PIFPAF:   # engine.inference(batch) + pifpaf.process per image: host frames in, humans out (fields stay on the device)
+            engine.infer_u8(frames_host[i % N_INPUT_SETS].numpy())
+            _, _, es = engine.device_outputs()
+            parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, es)
+            return parser.fetch(BATCH, cap=HCAP)
         humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
         if world > 1:
             gather_results()
@@ -371,7 +394,7 @@ def run_ours(args):
                 traffic = None
         # bounded CPU baseline (rank 0, N=1 only): ~12 s of the reference parser on the host cores
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not PIFPAF:
             cores = os.cpu_count() or 1
             threads = min(cores, BATCH)
             rate, kind = cpu_parse_rate(conf_np, paf_np, 12.0, threads)
@@ -394,7 +417,7 @@ def run_ours(args):
             "config": {"workload": WL["name"],
                        "global_batch": world * BATCH, "input": f"u8 frames {IN_H}x{IN_W}x3, random (default_rng)",
                        "weights": "random-init (He-normal, seed 0) of the reference architecture: " + WL["arch"],
-                       "parse_input": f"synthetic crowd tensors ({PERSONS[0]}-{PERSONS[1]} persons/frame, {n_humans} humans/batch) copied over the conv outputs after the last conv",
+                       "parse_input": f"synthetic {'PIF/PAF fields' if PIFPAF else 'crowd tensors'} ({PERSONS[0]}-{PERSONS[1]} persons/frame, {n_humans} humans/batch) copied over the conv outputs after the last conv",
                        "l2": f"{N_INPUT_SETS} distinct input batches rotated ({N_INPUT_SETS * BATCH * IN_H * IN_W * 3 / 1e6:.0f} MB > L2); activations (>1 GB/step) stream through",
                        "parallelism": f"dp{world} (frames shard; NCCL all-gather of keypoint records only)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

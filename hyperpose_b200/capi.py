@@ -375,6 +375,21 @@ class PifPafParser:
     def process(self, pif: np.ndarray, paf: np.ndarray, cap: int = 128):
         return self.process_batch(pif[None], paf[None], cap)[0]
 
+    def process_device(self, d_pif_ptr: int, d_paf_ptr: int, N: int, h: int, w: int, stream: int = 0):
+        check(lib().hp_pifpaf_process_device(self._h, d_pif_ptr, d_paf_ptr, N, h, w, stream))
+
+    def fetch(self, N: int, cap: int = 128):
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_pifpaf_fetch(self._h, out.ctypes.data, cap, n, N))
+        return [out[i, :n[i]].copy() for i in range(N)]
+
+    @property
+    def launch_count(self) -> int:
+        lib().hp_pifpaf_launch_count.argtypes = [C.c_void_p]
+        lib().hp_pifpaf_launch_count.restype = C.c_longlong
+        return int(lib().hp_pifpaf_launch_count(self._h))
+
     def debug_hr(self, frame: int, field: int, h: int, w: int) -> np.ndarray:
         out = np.zeros(((h - 1) * 8 + 1, (w - 1) * 8 + 1), np.float32)
         lib().hp_pifpaf_debug_hr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]

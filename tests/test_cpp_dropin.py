@@ -20,7 +20,7 @@ def test_dropin_compiles_against_unchanged_reference_headers():
     syms = subprocess.run(["nm", "-C", "--defined-only", exe], capture_output=True, text=True).stdout
     for want in ["hyperpose::parser::paf::process(", "hyperpose::parser::paf::paf(float, float, cv::Size)",
                  "hyperpose::parser::paf::set_conf_thresh(float)", "hyperpose::dnn::tensorrt::inference(std::vector<cv::Mat",
-                 "hyperpose::dnn::tensorrt::inference(std::vector<float", "hyperpose::dnn::tensorrt::save("]:
+                 "hyperpose::dnn::tensorrt::inference(std::vector<float", "hyperpose::dnn::tensorrt::save(", "hyperpose::parser::pifpaf::process("]:
         assert want in syms, want
 
 
