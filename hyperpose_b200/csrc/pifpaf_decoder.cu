@@ -178,8 +178,7 @@ __device__ __forceinline__ size_t hr_index(double fy, double fx, int HR, int WR)
 }
 
 __global__ void __launch_bounds__(256) pif_seeds_kernel(const float* __restrict__ pif, const float* __restrict__ hr, Geo g,
-                                                        Seed* __restrict__ raw, Seed* __restrict__ sorted, int* __restrict__ count, int cap,
-                                                        int* __restrict__ flags)
+                                                        Seed* __restrict__ raw, int* __restrict__ count, int cap, int* __restrict__ flags)
 {
     __shared__ int sN;
     const int frame = blockIdx.x, tid = threadIdx.x;
@@ -207,19 +206,27 @@ __global__ void __launch_bounds__(256) pif_seeds_kernel(const float* __restrict_
         }
     }
     __syncthreads();
-    int n = sN;
-    if (n > cap) { if (tid == 0) atomicOr(flags + frame, PP_FLAG_SEEDS); n = cap; }
-    Seed* dst = sorted + (size_t)frame * cap;
-    for (int i = tid; i < n; i += 256) { // rank sort (keys are distinct cells => distinct tuples unless fully equal)
-        const Seed a = out[i];
-        int rank = 0;
-        for (int q = 0; q < n; ++q) {
-            const Seed b = out[q];
-            rank += (seed_greater(b, a) || (!seed_greater(a, b) && q < i)) ? 1 : 0;
-        }
-        dst[rank] = a;
+    if (tid == 0) {
+        int n = sN;
+        if (n > cap) { atomicOr(flags + frame, PP_FLAG_SEEDS); n = cap; }
+        count[frame] = n;
     }
-    if (tid == 0) count[frame] = n;
+}
+
+// descending rank sort of the seeds (std::sort(seeds, std::greater{}), :772): one thread per seed, grid (cap/256, N)
+__global__ void __launch_bounds__(256) pif_seed_sort_kernel(const Seed* __restrict__ raw, Seed* __restrict__ sorted, const int* __restrict__ count, int cap)
+{
+    const int frame = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int n = count[frame];
+    if (i >= n) return;
+    const Seed* in = raw + (size_t)frame * cap;
+    const Seed a = in[i];
+    int rank = 0;
+    for (int q = 0; q < n; ++q) {
+        const Seed b = in[q];
+        rank += (seed_greater(b, a) || (!seed_greater(a, b) && q < i)) ? 1 : 0;
+    }
+    sorted[(size_t)frame * cap + rank] = a;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -695,7 +702,8 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     HP_CUDA_TRY(cudaMemsetAsync(p->occ_grow.p, 0, (size_t)N * NKP * hr_px, st));
     HP_CUDA_TRY(cudaMemsetAsync(p->occ_nms.p, 0, (size_t)N * NKP * nms_h * nms_w, st));
     pif_hr_kernel<<<dim3(NKP, N), 256, hw * sizeof(int), st>>>(d_pif, p->hr.p, g, 0.1f);
-    pif_seeds_kernel<<<N, 256, 0, st>>>(d_pif, p->hr.p, g, p->seeds_raw.p, p->seeds.p, seed_cnt, p->seed_cap, flags);
+    pif_seeds_kernel<<<N, 256, 0, st>>>(d_pif, p->hr.p, g, p->seeds_raw.p, seed_cnt, p->seed_cap, flags);
+    pif_seed_sort_kernel<<<dim3((p->seed_cap + 255) / 256, N), 256, 0, st>>>(p->seeds_raw.p, p->seeds.p, seed_cnt, p->seed_cap);
     caf_filter_kernel<<<dim3(NBONE, N), 256, 0, st>>>(d_paf, p->hr.p, g, p->lists.p, list_cnt);
     GrowParams gp;
     gp.g = g; gp.seeds = p->seeds.p; gp.seed_cnt = seed_cnt; gp.seed_cap = p->seed_cap; gp.lists = p->lists.p; gp.list_cnt = list_cnt;
@@ -703,7 +711,7 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     gp.keypoint_thresh = p->thresh; gp.net_h = p->net_h; gp.net_w = p->net_w; gp.humans = p->humans.p; gp.hcap = p->hcap; gp.human_cnt = human_cnt; gp.flags = flags; gp.dbg = flags + N;
     pifpaf_grow_kernel<<<N, 32, 0, st>>>(gp);
     HP_CUDA_TRY(cudaGetLastError());
-    p->launches += 4;
+    p->launches += 5;
     p->N = N; p->H = h; p->W = w; p->last_N = N;
     return HP_OK;
 }
