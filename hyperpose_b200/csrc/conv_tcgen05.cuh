@@ -263,7 +263,7 @@ __device__ __forceinline__ PixelPos unflatten(const ConvParams& p, int px)
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_o, const ConvParams p)
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms shared by TMA and UMMA
@@ -275,9 +275,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;          // [stages]  MMA -> TMA
     uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;         // [2]       MMA -> epilogue
     uint64_t* tempty_bar = tfull_bar + 2;                      // [2]       epilogue -> MMA
-    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;                        // [2]       residual TMA loads -> epilogue
+    uint32_t* tmem_slot = (uint32_t*)(res_bar + 2);
     // two 16 KiB staging tiles (128 pixels x 64 channels fp16, 128B-swizzled) for the TMA-store epilogue
     uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+    // residual epilogue (res_tma): two more 16 KiB tiles, filled by TMA loads the epilogue leader issues ahead of use
+    uint8_t* res_stage = out_stage + 2 * CONV_A_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_g = p.cout_g_pad / p.BN;
@@ -298,6 +301,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
             ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4); // one arrive per epilogue warp
+            ptx::mbar_init(ptx::smem_u32(res_bar + i), 1);
         }
         ptx::fence_barrier_init();
     }
@@ -371,6 +375,22 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t stage_ctr = 0;
+        // residual tiles: sub-tile k of this CTA's (tile, sub) sequence lands in res_stage[k & 1]; the leader keeps two in flight
+        const bool res_tma = p.res_mode != 0 && p.tma_store != 0;
+        const int subs = p.BN / 64;
+        uint32_t res_issued = 0, res_used = 0;
+        int ri_tile = blockIdx.x, ri_sub = 0;
+        auto issue_residual = [&]() { // leader only
+            if (ri_tile >= total_tiles) return;
+            const ConvTile rt = decode_tile(p, ri_tile, n_tiles_g);
+            const uint32_t rb = ptx::smem_u32(res_bar + (res_issued & 1));
+            ptx::mbar_expect_tx(rb, (uint32_t)CONV_A_BYTES);
+            ptx::tma_load_2d(ptx::smem_u32(res_stage + (res_issued & 1) * CONV_A_BYTES), &tmap_r, rb,
+                             p.res_ch_off + rt.g * p.cout_g + rt.n0 + ri_sub * 64, rt.p0);
+            ++res_issued;
+            if (++ri_sub == subs) { ri_sub = 0; ri_tile += gridDim.x; }
+        };
+        if (res_tma && warp == 4 && lane == 0) { issue_residual(); issue_residual(); }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvTile t = decode_tile(p, tile, n_tiles_g);
             const bool in_img = (t.p0 + row) < total_px;
@@ -393,6 +413,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
                     ptx::named_bar_sync(1, 128);
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
+                    const uint8_t* rrow = res_stage + (res_used & 1) * CONV_A_BYTES + row * 128;
+                    if (res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & 1)), (res_used >> 1) & 1);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int c0 = sub * 64 + q * 16;
@@ -401,7 +423,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tmem_ld_wait();
                         uint32_t pk[8];
                         __half2 rs[8];
-                        if (p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
+                        if (res_tma) { // the residual tile sits in smem in the same 128B-swizzled layout as the output tile
+                            *(uint4*)&rs[0] = *(const uint4*)(rrow + (((q * 2) ^ (row & 7)) * 16));
+                            *(uint4*)&rs[4] = *(const uint4*)(rrow + (((q * 2 + 1) ^ (row & 7)) * 16));
+                        } else if (p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
                             if (in_img) {
                                 const uint4* rp = (const uint4*)(p.res + pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0);
                                 *(uint4*)&rs[0] = __ldg(rp);
@@ -433,7 +458,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (leader) {
                         ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
                         ptx::bulk_commit_group();
+                        if (res_tma) issue_residual(); // everybody is past the barrier: res_stage[res_used & 1] is free again
                     }
+                    ++res_used;
                 }
             } else
             for (int c0 = 0; c0 < p.BN; c0 += 16) {
@@ -679,10 +706,10 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
-constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 4) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
-inline size_t conv_smem_bytes(int BN, int stages, bool tma_store)
+constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 6) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
+inline size_t conv_smem_bytes(int BN, int stages, bool tma_store, bool res_tma = false)
 {
-    return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0);
+    return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0) + (res_tma ? 2 * CONV_A_BYTES : 0);
 }
 inline size_t conv_swap_smem_bytes(int npx, int stages) { return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + npx * 128) + 2 * CONV_A_BYTES; }
 inline int conv_swap_pick_stages(int npx)
@@ -704,9 +731,9 @@ inline int conv_swap_pick_npx(long total_px, int gc, int num_sms)
     }
     return best;
 }
-inline int conv_pick_stages(int BN, bool tma_store)
+inline int conv_pick_stages(int BN, bool tma_store, bool res_tma = false)
 {
-    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - (tma_store ? 2 * CONV_A_BYTES : 0);
+    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - (tma_store ? 2 * CONV_A_BYTES : 0) - (res_tma ? 2 * CONV_A_BYTES : 0);
     const int st = (int)(avail / (size_t)(CONV_A_BYTES + BN * CONV_BLOCK_K * 2));
     return st > CONV_MAX_STAGES ? CONV_MAX_STAGES : st;
 }

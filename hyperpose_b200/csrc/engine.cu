@@ -330,7 +330,7 @@ int pick_bn(int cout_g)
 
 struct ConvPlan {
     ConvParams prm;
-    CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2;
+    CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2, tmap_r;
     __half* d_w = nullptr;
     float* d_bias = nullptr;
     float* d_alpha = nullptr;
@@ -486,7 +486,13 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
             rc = make_tmap_out(&pl.tmap_o, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels);
             if (rc) return rc;
         }
-        p.num_stages = conv_pick_stages(BN, p.tma_store != 0);
+        p.num_stages = conv_pick_stages(BN, p.tma_store != 0, p.tma_store && po.res_mode);
+    }
+    memset(&pl.tmap_r, 0, sizeof(pl.tmap_r));
+    if (p.tma_store && po.res_mode) { // residual tiles are TMA-loaded into smem ahead of the epilogue
+        const EngBuffer& rb = e->bufs[po.res_buf];
+        rc = make_tmap_out(&pl.tmap_r, rb.d, (size_t)e->max_batch * rb.H * rb.W, rb.channels);
+        if (rc) return rc;
     }
     // swapped-operand kernel: output channels in blocks of 128, enough k-steps to amortise the transposing epilogue
     memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
@@ -506,7 +512,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         if (rc) return rc;
         pl.smem = conv_swap_smem_bytes(p.npx, p.num_stages);
     } else {
-        pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0);
+        pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
     }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
     return HP_OK;
@@ -527,7 +533,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms, n_tiles);
-    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, p);
+    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
     return HP_OK;
 }
