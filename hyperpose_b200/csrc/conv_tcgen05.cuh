@@ -261,6 +261,7 @@ __device__ __forceinline__ PixelPos unflatten(const ConvParams& p, int px)
     return q;
 }
 
+template <bool kRes> // kRes: residual epilogue compiled in (ResNet / LW-OpenPose blocks); false keeps the plain epilogue lean
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p)
@@ -376,7 +377,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t acc_phase = 0;
         uint32_t stage_ctr = 0;
         // residual tiles: sub-tile k of this CTA's (tile, sub) sequence lands in res_stage[k & 1]; the leader keeps two in flight
-        const bool res_tma = p.res_mode != 0 && p.tma_store != 0;
+        const bool res_tma = kRes && p.res_mode != 0 && p.tma_store != 0;
         const int subs = p.BN / 64;
         uint32_t res_issued = 0, res_used = 0;
         int ri_tile = blockIdx.x, ri_sub = 0;
@@ -390,7 +391,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ++res_issued;
             if (++ri_sub == subs) { ri_sub = 0; ri_tile += gridDim.x; }
         };
-        if (res_tma && warp == 4 && lane == 0) { issue_residual(); issue_residual(); }
+        if (kRes && res_tma && warp == 4 && lane == 0) { issue_residual(); issue_residual(); }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvTile t = decode_tile(p, tile, n_tiles_g);
             const bool in_img = (t.p0 + row) < total_px;
@@ -414,7 +415,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::named_bar_sync(1, 128);
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
                     const uint8_t* rrow = res_stage + (res_used & 1) * CONV_A_BYTES + row * 128;
-                    if (res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & 1)), (res_used >> 1) & 1);
+                    if (kRes && res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & 1)), (res_used >> 1) & 1);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int c0 = sub * 64 + q * 16;
@@ -423,10 +424,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tmem_ld_wait();
                         uint32_t pk[8];
                         __half2 rs[8];
-                        if (res_tma) { // the residual tile sits in smem in the same 128B-swizzled layout as the output tile
+                        if (kRes && res_tma) { // the residual tile sits in smem in the same 128B-swizzled layout as the output tile
                             *(uint4*)&rs[0] = *(const uint4*)(rrow + (((q * 2) ^ (row & 7)) * 16));
                             *(uint4*)&rs[4] = *(const uint4*)(rrow + (((q * 2 + 1) ^ (row & 7)) * 16));
-                        } else if (p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
+                        } else if (kRes && p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
                             if (in_img) {
                                 const uint4* rp = (const uint4*)(p.res + pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0);
                                 *(uint4*)&rs[0] = __ldg(rp);
@@ -441,11 +442,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             float a0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
                             float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
                             float r0 = 0.f, r1 = 0.f;
-                            if (p.res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
-                            if (p.res_mode == 1) { a0 += r0; a1 += r1; }
+                            if (kRes && p.res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
+                            if (kRes && p.res_mode == 1) { a0 += r0; a1 += r1; }
                             a0 = a0 > 0.f ? a0 : a0 * __ldg(alpha + c0 + 2 * j);
                             a1 = a1 > 0.f ? a1 : a1 * __ldg(alpha + c0 + 2 * j + 1);
-                            if (p.res_mode == 2) { a0 += r0; a1 += r1; }
+                            if (kRes && p.res_mode == 2) { a0 += r0; a1 += r1; }
                             const __half2 h2 = __floats2half2_rn(a0, a1);
                             pk[j] = *(const uint32_t*)&h2;
                         }
@@ -458,7 +459,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (leader) {
                         ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
                         ptx::bulk_commit_group();
-                        if (res_tma) issue_residual(); // everybody is past the barrier: res_stage[res_used & 1] is free again
+                        if (kRes && res_tma) issue_residual(); // everybody is past the barrier: res_stage[res_used & 1] is free again
                     }
                     ++res_used;
                 }
@@ -474,10 +475,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int j = 0; j < 16; ++j) {
                     float a = __uint_as_float(v[j]) + __ldg(bias + c0 + j);
                     float r = 0.f;
-                    if (p.res_mode && c0 + j < n_valid) r = __half2float(p.res[pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0 + j]);
-                    if (p.res_mode == 1) a += r;
+                    if (kRes && p.res_mode && c0 + j < n_valid) r = __half2float(p.res[pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0 + j]);
+                    if (kRes && p.res_mode == 1) a += r;
                     a = a > 0.f ? a : a * __ldg(alpha + c0 + j);
-                    if (p.res_mode == 2) a += r;
+                    if (kRes && p.res_mode == 2) a += r;
                     y[j] = a;
                 }
                 if (p.out_mode == OUT_F16_NHWC) {

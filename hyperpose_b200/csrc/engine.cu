@@ -38,10 +38,10 @@ using namespace hpb;
 //   u8 path : v = (float)((double)u8 * factor) (data.cpp:48); model channel c reads byte (flip ? 2-c : c)
 //   f32 path: input is already scaled NCHW (tensorrt::inference(const std::vector<float>&, size_t))
 // stride 2 (MobileNet / ResNet stems): TF "SAME" padding, pad_before = max((OH-1)*2 + R - H, 0) / 2.
-template <bool U8>
+template <bool U8, int R>
 __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
                                                       int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
-                                                      int stride, int OH, int OW, int pad_h, int pad_w, int R, int chunks)
+                                                      int stride, int OH, int OW, int pad_h, int pad_w, int chunks)
 {
     // u8 path: the 3 x 256 possible results of (float)((double)u8 * factor) - mean[c], rounded to fp16, as a shared LUT
     // (bit-identical to computing them per pixel; removes 27 fp64 multiplies per pixel)
@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ i
     const int h0 = (int)((idx / OW) % OH) * stride - pad_h;
     const int n = (int)(idx / ((size_t)OW * OH));
     const float mean[3] = { m0, m1, m2 };
-    const int kmax = R * R * 3;
+    constexpr int kmax = R * R * 3;
     __align__(16) __half vals[64];
     const __half zero = __float2half_rn(0.f);
-#pragma unroll 4
+#pragma unroll
     for (int j = 0; j < 64; ++j) {
         const int k = chunk * 64 + j;
         __half hv = zero;
@@ -205,8 +205,9 @@ __global__ void __launch_bounds__(256) pifpaf_head_kernel(const __half* __restri
 }
 
 // KxK (K = 2 or 3) stride-2 max pool, NHWC fp16, 8 channels per thread; TF "SAME" semantics (window clipped at the border).
+template <int K>
 __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                                                       int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW, int K, int pad_h, int pad_w)
+                                                       int N, int H, int W, int C_in_ld, int C, int C_out_ld, int OH, int OW, int pad_h, int pad_w)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cv = C / 8;
@@ -219,9 +220,11 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict_
     const int n = (int)(t / OH);
     __half2 m[4];
     bool first = true;
+#pragma unroll
     for (int r = 0; r < K; ++r) {
         const int h = oh * 2 - pad_h + r;
         if (h < 0 || h >= H) continue;
+#pragma unroll
         for (int s = 0; s < K; ++s) {
             const int w = ow * 2 - pad_w + s;
             if (w < 0 || w >= W) continue;
@@ -533,7 +536,8 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms, n_tiles);
-    conv_tcgen05_kernel<<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    else conv_tcgen05_kernel<false><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
     return HP_OK;
 }
@@ -569,12 +573,11 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             const int blocks = (int)((total + 255) / 256);
             const int stride = po.stride ? (int)po.stride : 1;
             const int ph = same_pad_before(e->in_h, R, stride), pw = same_pad_before(e->in_w, R, stride);
-            if (u8_input)
-                im2col3_kernel<true><<<blocks, 256, 0, st>>>(e->d_frames, ob.d, N, e->in_h, e->in_w, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
-                                                            stride, ob.H, ob.W, ph, pw, R, chunks);
-            else
-                im2col3_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, ob.d, N, e->in_h, e->in_w, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
-                                                             stride, ob.H, ob.W, ph, pw, R, chunks);
+#define HP_IM2COL(U8, RR, SRC, FAC, FLIP) im2col3_kernel<U8, RR><<<blocks, 256, 0, st>>>(SRC, ob.d, N, e->in_h, e->in_w, FAC, FLIP, \
+                e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2], stride, ob.H, ob.W, ph, pw, chunks)
+            if (u8_input) { if (R == 3) HP_IM2COL(true, 3, e->d_frames, e->factor, e->flip_rgb); else HP_IM2COL(true, 7, e->d_frames, e->factor, e->flip_rgb); }
+            else          { if (R == 3) HP_IM2COL(false, 3, e->d_input_f32, 1.0, 0); else HP_IM2COL(false, 7, e->d_input_f32, 1.0, 0); }
+#undef HP_IM2COL
             e->launches++;
         } else if (po.type == OP_PIFPAF_HEAD) {
             EngBuffer& a = e->bufs[po.in_buf];
@@ -598,8 +601,12 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             const int C = (int)po.cout_g;
             const size_t total = (size_t)N * ob.H * ob.W * (C / 8);
             const int K = po.R ? (int)po.R : 2;
-            maxpool2_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W,
-                                                                     K, same_pad_before(ib.H, K, 2), same_pad_before(ib.W, K, 2));
+            if (K == 3)
+                maxpool2_kernel<3><<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W,
+                                                                            same_pad_before(ib.H, 3, 2), same_pad_before(ib.W, 3, 2));
+            else
+                maxpool2_kernel<2><<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels, ob.H, ob.W,
+                                                                            same_pad_before(ib.H, 2, 2), same_pad_before(ib.W, 2, 2));
             e->launches++;
         } else if (po.type == OP_CONV) {
             launch_conv(e, op, N, st);
@@ -758,7 +765,8 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
             return fail(HP_ERR_UNSUPPORTED);
         }
     }
-    if (max_smem > 0 && (cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+    if (max_smem > 0 && (cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+                         cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
         return fail(HP_ERR_CUDA);
