@@ -43,17 +43,6 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ i
                                                       int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
                                                       int stride, int OH, int OW, int pad_h, int pad_w, int chunks)
 {
-    // u8 path: the 3 x 256 possible results of (float)((double)u8 * factor) - mean[c], rounded to fp16, as a shared LUT
-    // (bit-identical to computing them per pixel; removes 27 fp64 multiplies per pixel)
-    __shared__ __half lut[3 * 256];
-    if (U8) {
-        for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-            const int c = i >> 8;
-            const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2);
-            lut[i] = __float2half_rn((float)((double)(i & 255) * factor) - mc);
-        }
-        __syncthreads();
-    }
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)N * OH * OW * chunks;
     if (gid >= total) return;
@@ -76,7 +65,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ i
             if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
                 if (U8) {
                     const uint8_t* px = (const uint8_t*)in + (((size_t)n * H + hh) * W + ww) * 3;
-                    hv = lut[(c << 8) + px[flip ? 2 - c : c]];
+                    hv = __float2half_rn((float)((double)px[flip ? 2 - c : c] * factor) - mean[c]);
                 } else {
                     hv = __float2half_rn(((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c]);
                 }
@@ -218,6 +207,19 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const __half* __restrict_
     const int ow = (int)(t % OW); t /= OW;
     const int oh = (int)(t % OH);
     const int n = (int)(t / OH);
+    if (K == 2) { // window rows/cols clamped to the last one: max(a, a) == a reproduces the clipped SAME window
+        const int h0 = oh * 2, w0 = ow * 2;
+        const int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+        auto ld = [&](int h, int w) { return *(const uint4*)(in + (((size_t)n * H + h) * W + w) * C_in_ld + c8 * 8); };
+        const uint4 a = ld(h0, w0), b = ld(h0, w1), c = ld(h1, w0), d = ld(h1, w1);
+        const __half2* ra = (const __half2*)&a; const __half2* rb = (const __half2*)&b; const __half2* rc = (const __half2*)&c; const __half2* rd = (const __half2*)&d;
+        uint4 r;
+        __half2* rr = (__half2*)&r;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rr[i] = __hmax2(__hmax2(ra[i], rb[i]), __hmax2(rc[i], rd[i]));
+        *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * C_out_ld + c8 * 8) = r;
+        return;
+    }
     __half2 m[4];
     bool first = true;
 #pragma unroll
