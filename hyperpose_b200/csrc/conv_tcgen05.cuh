@@ -706,6 +706,213 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem variant: the first convolution of a network (RxR x 3 channels, R in {3,7}, stride 1/2) reading the u8 frames
+// DIRECTLY.  The generic path materialises the im2col patches in HBM (128 B/pixel for 3x3: 494 MB written and read again
+// per cfg3 step); here four producer warps (one thread per pixel of the tile) gather the RxRx3 bytes of their pixel,
+// normalise (u8 * factor in double, R/B swap, - mean: src/data.cpp:21-51, backbones.py:455) and write the fp16 patch row
+// straight into the 128B-swizzled A tile that tcgen05.mma reads -- the patches never exist outside shared memory.
+// The weight tile (BN x KCH*64) is loaded once by TMA and stays resident.  Warp roles: 0-3 producers, 4-7 epilogue,
+// 8 MMA issuer + TMEM allocator.  Epilogue = bias + PReLU -> fp16 -> swizzled staging -> TMA tensor store.
+// ---------------------------------------------------------------------------------------------
+struct StemParams {
+    const uint8_t* frames; // [N, H, W, 3] u8
+    int Nb, H, W;          // input frame geometry
+    int OH, OW;            // output geometry (= ceil(H / stride))
+    int stride, pad_h, pad_w;
+    double factor; int flip;
+    float m0, m1, m2;
+    int BN;                // padded output channels (multiple of 64, <= 128), single N tile
+    int cout;
+    const float* bias; const float* alpha;
+    int out_ch_off;
+};
+
+constexpr int STEM_THREADS = 288;
+constexpr int STEM_STAGES = 3;
+
+template <int R>
+__global__ void __launch_bounds__(STEM_THREADS, 1)
+conv_stem_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o, const StemParams p)
+{
+    constexpr int KTOT = R * R * 3;
+    constexpr int KCH = (KTOT + 63) / 64;           // 64-wide k chunks (1 for 3x3, 3 for 7x7)
+    constexpr int A_BYTES = KCH * CONV_A_BYTES;     // one stage of patches: KCH tiles of 128 rows x 128 B
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                         // [STEM_STAGES][KCH][128 x 128 B]
+    uint8_t* sB = sA + (size_t)STEM_STAGES * A_BYTES;           // [KCH][BN x 128 B] weights, resident
+    uint8_t* sOut = sB + (size_t)KCH * p.BN * 128;              // 2 x 16 KiB staging
+    uint64_t* full_bar = (uint64_t*)(sOut + 2 * CONV_A_BYTES);  // [STAGES] producers -> MMA (128 arrivals)
+    uint64_t* empty_bar = full_bar + STEM_STAGES;               // [STAGES] MMA -> producers
+    uint64_t* tfull_bar = empty_bar + STEM_STAGES;              // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                       // [2]
+    uint64_t* w_bar = tempty_bar + 2;                           // weights landed
+    uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_px = p.Nb * p.OH * p.OW;
+    const int total_tiles = (total_px + CONV_BLOCK_M - 1) / CONV_BLOCK_M;
+    const int tmem_cols = p.BN <= 64 ? 128 : 256;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_o);
+        for (int i = 0; i < STEM_STAGES; ++i) {
+            ptx::mbar_init(ptx::smem_u32(full_bar + i), 128);
+            ptx::mbar_init(ptx::smem_u32(empty_bar + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4);
+        }
+        ptx::mbar_init(ptx::smem_u32(w_bar), 1);
+        ptx::fence_barrier_init();
+    }
+    // zero the patch tiles once: the k slots beyond R*R*3 are never written again and must read as 0
+    for (int i = threadIdx.x; i < STEM_STAGES * A_BYTES / 16; i += STEM_THREADS) ((uint4*)sA)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 8) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)tmem_cols);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== producers: one thread per pixel of the tile =====================
+        const int row = threadIdx.x; // 0..127
+        const float mean[3] = { p.m0, p.m1, p.m2 };
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int px = tile * CONV_BLOCK_M + row;
+            const bool valid = px < total_px;
+            int n = 0, oh = 0, ow = 0;
+            if (valid) { n = px / (p.OH * p.OW); const int rem = px - n * p.OH * p.OW; oh = rem / p.OW; ow = rem - oh * p.OW; }
+            const int h0 = oh * p.stride - p.pad_h, w0 = ow * p.stride - p.pad_w;
+            // gather + normalise into registers first (global latency), then wait for the stage and store
+            __align__(16) __half vals[((KTOT + 7) / 8) * 8];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int hh = h0 + r;
+                const bool rok = valid && hh >= 0 && hh < p.H;
+                const uint8_t* rp = p.frames + ((size_t)n * p.H + (rok ? hh : 0)) * p.W * 3;
+#pragma unroll
+                for (int s2 = 0; s2 < R; ++s2) {
+                    const int ww = w0 + s2;
+                    const bool ok = rok && ww >= 0 && ww < p.W;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float v = 0.f;
+                        if (ok) v = (float)((double)__ldg(rp + (size_t)ww * 3 + (p.flip ? 2 - c : c)) * p.factor) - mean[c];
+                        vals[(r * R + s2) * 3 + c] = __float2half_rn(v);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = KTOT; k < ((KTOT + 7) / 8) * 8; ++k) vals[k] = __float2half_rn(0.f);
+            ptx::mbar_wait(ptx::smem_u32(empty_bar + stage), phase ^ 1);
+            uint8_t* a = sA + (size_t)stage * A_BYTES;
+#pragma unroll
+            for (int q = 0; q < (KTOT + 7) / 8; ++q) { // 16-byte chunk q of the patch row
+                const int kc = q >> 3, j = q & 7;
+                const uint32_t addr = ptx::smem_u32(a + (size_t)kc * CONV_A_BYTES) + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) * 16);
+                ptx::st_shared_v4(addr, ((const uint4*)vals)[q]);
+            }
+            ptx::fence_proxy_async(); // generic-proxy writes -> visible to the tensor core (async proxy)
+            ptx::mbar_arrive(ptx::smem_u32(full_bar + stage));
+            if (++stage == STEM_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 8) {
+        // ===================== weights (once) + MMA issuer =====================
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(ptx::smem_u32(w_bar), (uint32_t)(KCH * p.BN * 128));
+            for (int kc = 0; kc < KCH; ++kc) ptx::tma_load_2d(ptx::smem_u32(sB + (size_t)kc * p.BN * 128), &tmap_b, ptx::smem_u32(w_bar), kc * 64, 0);
+            ptx::mbar_wait(ptx::smem_u32(w_bar), 0);
+            const uint32_t idesc = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+#pragma unroll
+                for (int kc = 0; kc < KCH; ++kc) {
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + (size_t)stage * A_BYTES + (size_t)kc * CONV_A_BYTES));
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + (size_t)kc * p.BN * 128));
+                    constexpr int KK = (KCH == 1) ? (KTOT + 15) / 16 : 4; // 3x3: only the first two 16-wide k slices are non-zero
+#pragma unroll
+                    for (int k = 0; k < KK; ++k) ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(ptx::smem_u32(empty_bar + stage));
+                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
+                if (++stage == STEM_STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (warps 4..7) =====================
+        const int ew = warp - 4, row = ew * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        int acc = 0; uint32_t acc_phase = 0, stage_ctr = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int p0 = tile * CONV_BLOCK_M;
+            ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                uint8_t* sbuf = sOut + (stage_ctr & 1) * CONV_A_BYTES;
+                if (leader) ptx::bulk_wait_group_read<1>();
+                ptx::named_bar_sync(1, 128);
+                const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = sub * 64 + q * 16;
+                    uint32_t v[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                    ptx::tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float a0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + c0 + 2 * j);
+                        float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + c0 + 2 * j + 1);
+                        a0 = a0 > 0.f ? a0 : a0 * __ldg(p.alpha + c0 + 2 * j);
+                        a1 = a1 > 0.f ? a1 : a1 * __ldg(p.alpha + c0 + 2 * j + 1);
+                        const __half2 h2 = __floats2half2_rn(a0, a1);
+                        pk[j] = *(const uint32_t*)&h2;
+                    }
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                }
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(1, 128);
+                if (leader) {
+                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + sub * 64, p0);
+                    ptx::bulk_commit_group();
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (leader) ptx::bulk_wait_group_read<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+}
+
+inline size_t conv_stem_smem_bytes(int R, int BN)
+{
+    const int kch = (R * R * 3 + 63) / 64;
+    return 1024 + (size_t)STEM_STAGES * kch * CONV_A_BYTES + (size_t)kch * BN * 128 + 2 * CONV_A_BYTES + (2 * STEM_STAGES + 5) * 8 + 16;
+}
+
 constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
 constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 6) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
 inline size_t conv_smem_bytes(int BN, int stages, bool tma_store, bool res_tma = false)

@@ -341,11 +341,17 @@ struct ConvPlan {
     float* d_alpha = nullptr;
     int grid = 0;
     size_t smem = 0;
+    // fused stem (u8 frames -> first conv, no im2col buffer)
+    bool stem = false;
+    int stem_R = 3;
+    StemParams sp;
+    size_t stem_smem = 0;
     int built_for_N = 0;
     double flops_per_frame = 0;
 };
 
 struct EngOp {
+    bool fused_into_stem = false; // OP_IM2COL3 whose consumer runs conv_stem_kernel: skipped for u8 input
     PackOp po;
     ConvPlan plan;              // OP_CONV only
     float* d_dw = nullptr;      // OP_DWCONV: [K*K][C] weights | bias[C] | alpha[C]
@@ -421,7 +427,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         set_error("engine: conv reads channels [%d,%d) of a %d-channel buffer", po.in_ch_off, po.in_ch_off + G * ecin, ib.channels);
         return HP_ERR_ARG;
     }
-    const int BN = pick_bn(cout_g);
+    const int BN = (im2col && cout_g <= 128) ? round_up(cout_g, 64) : pick_bn(cout_g); // stem: whole 64-channel sub-tiles
     const int cout_pad = round_up(cout_g, BN);
     const int K = eR * eS * ecin;
     // repack fp32 [G][cout][cin][R][S] -> fp16 [G][cout_pad][R][S][cin_pad]
@@ -520,12 +526,40 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
     }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
+    if (im2col && p.tma_store && cout_pad == BN && BN <= 128 && !po.res_mode && (R == 3 || R == 7) && R == S && !getenv("HPB_NO_STEM")) {
+        // locate the patch-gather op feeding this conv: its stride / tap size define the stem geometry
+        for (auto& o2 : e->ops) {
+            if (o2.po.type != OP_IM2COL3 || o2.po.out_buf != po.in_buf) continue;
+            const int stride = o2.po.stride ? (int)o2.po.stride : 1;
+            if ((int)(o2.po.R ? o2.po.R : 3) != R) break;
+            StemParams& sp = pl.sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.frames = e->d_frames; sp.Nb = e->max_batch; sp.H = e->in_h; sp.W = e->in_w; sp.OH = ib.H; sp.OW = ib.W;
+            sp.stride = stride; sp.pad_h = same_pad_before(e->in_h, R, stride); sp.pad_w = same_pad_before(e->in_w, R, stride);
+            sp.factor = e->factor; sp.flip = e->flip_rgb; sp.m0 = e->hdr.mean[0]; sp.m1 = e->hdr.mean[1]; sp.m2 = e->hdr.mean[2];
+            sp.BN = BN; sp.cout = cout_g; sp.bias = pl.d_bias; sp.alpha = pl.d_alpha; sp.out_ch_off = (int)po.out_ch_off;
+            pl.stem = true; pl.stem_R = R; pl.stem_smem = conv_stem_smem_bytes(R, BN);
+            o2.fused_into_stem = true;
+            break;
+        }
+    }
     return HP_OK;
 }
 
-int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st)
+int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
 {
     ConvPlan& pl = op.plan;
+    if (pl.stem && u8_input) {
+        StemParams sp = pl.sp;
+        sp.Nb = N;
+        const int tiles = (int)(((size_t)N * sp.OH * sp.OW + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
+        const int per_sm = pl.stem_smem <= 110 * 1024 ? 2 : 1; // two resident CTAs hide the gather latency of the 3x3 stem
+        const int grid = std::min(e->num_sms * per_sm, tiles);
+        if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        else conv_stem_kernel<7><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        e->launches++;
+        return HP_OK;
+    }
     ConvParams p = pl.prm;
     p.Nb = N;
     p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
@@ -567,7 +601,9 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
     for (int oi = first; oi <= last; ++oi) {
         EngOp& op = e->ops[oi];
         const PackOp& po = op.po;
-        if (po.type == OP_IM2COL3) {
+        if (po.type == OP_IM2COL3 && op.fused_into_stem && u8_input) {
+            // the consumer is conv_stem_kernel: patches are built in shared memory, nothing to do here
+        } else if (po.type == OP_IM2COL3) {
             EngBuffer& ob = e->bufs[po.out_buf];
             const int R = po.R ? (int)po.R : 3;
             const int chunks = ob.channels / 64;
@@ -611,7 +647,7 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
                                                                             same_pad_before(ib.H, 2, 2), same_pad_before(ib.W, 2, 2));
             e->launches++;
         } else if (po.type == OP_CONV) {
-            launch_conv(e, op, N, st);
+            launch_conv(e, op, N, st, u8_input);
         }
         if (prof) cudaEventRecord(e->ev[oi + 1], st);
     }
@@ -771,6 +807,13 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
                          cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
+        return fail(HP_ERR_CUDA);
+    }
+    size_t stem_smem = 0;
+    for (auto& o : e->ops) if (o.plan.stem) stem_smem = std::max(stem_smem, o.plan.stem_smem);
+    if (stem_smem && (cudaFuncSetAttribute(conv_stem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_smem) != cudaSuccess ||
+                      cudaFuncSetAttribute(conv_stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_smem) != cudaSuccess)) {
+        set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (stem)", stem_smem);
         return fail(HP_ERR_CUDA);
     }
     HP_CUDA_TRY(cudaDeviceSynchronize());
