@@ -526,7 +526,10 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
     }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
-    if (im2col && p.tma_store && cout_pad == BN && BN <= 128 && !po.res_mode && (R == 3 || R == 7) && R == S && !getenv("HPB_NO_STEM")) {
+    // Fused stem: a clear win for the 7x7 stems (ResNet: 0.66 ms instead of 0.64 + 0.2 ms for im2col + conv at cfg4); for the 3x3
+    // stems the 128 gather threads per CTA are latency-bound (0.56 ms vs 0.43 ms measured at cfg3), so those keep the im2col
+    // buffer unless HPB_STEM3 is set.
+    if (im2col && p.tma_store && cout_pad == BN && BN <= 128 && !po.res_mode && (R == 7 || (R == 3 && getenv("HPB_STEM3"))) && R == S && !getenv("HPB_NO_STEM")) {
         // locate the patch-gather op feeding this conv: its stride / tap size define the stem geometry
         for (auto& o2 : e->ops) {
             if (o2.po.type != OP_IM2COL3 || o2.po.out_buf != po.in_buf) continue;
