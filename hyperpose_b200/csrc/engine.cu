@@ -116,50 +116,79 @@ __global__ void __launch_bounds__(256) resize_u8c3_kernel(const uint8_t* __restr
 // depthwise KxK conv (K in {1,3}) + bias + PReLU on fp16 NHWC, 8 channels per thread (one 16-byte load per tap),
 // fp32 accumulation.  HBM-bound: reads each input element ~once (taps hit L1/L2), writes the output once.
 // Reference layers: DepthwiseConv2d + BatchNorm2d(act) of separable_block (hyperpose/Model/backbones.py:240-248), BN folded.
+// Each thread produces DW_STRIP consecutive output pixels of one row for 8 channels with a sliding window over the input
+// columns: every input column of the window is loaded once (3 x (strip*stride + K - stride) 16-byte loads per strip instead of 9 per
+// output) and the K*K*8 weights live in registers.
+constexpr int DW_STRIP = 4;
+template <int K, int stride>
 __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
                                                      const float* __restrict__ w /*[K*K][C]*/, const float* __restrict__ bias,
-                                                     const float* __restrict__ alpha, int N, int H, int W, int C, int K, int stride,
+                                                     const float* __restrict__ alpha, int N, int H, int W, int C,
                                                      int OH, int OW, int pad_h, int pad_w)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cv = C / 8;
-    const size_t total = (size_t)N * OH * OW * cv;
+    const int strips = (OW + DW_STRIP - 1) / DW_STRIP;
+    const size_t total = (size_t)N * OH * strips * cv;
     if (idx >= total) return;
     const int c0 = (int)(idx % cv) * 8;
     size_t t = idx / cv;
-    const int ow = (int)(t % OW); t /= OW;
+    const int ow0 = (int)(t % strips) * DW_STRIP; t /= strips;
     const int oh = (int)(t % OH);
     const int n = (int)(t / OH);
-    float acc[8];
+    float wt[K * K][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = 0; k < K * K; ++k) {
+        const float4 w0 = __ldg((const float4*)(w + (size_t)k * C + c0)), w1 = __ldg((const float4*)(w + (size_t)k * C + c0 + 4));
+        wt[k][0] = w0.x; wt[k][1] = w0.y; wt[k][2] = w0.z; wt[k][3] = w0.w; wt[k][4] = w1.x; wt[k][5] = w1.y; wt[k][6] = w1.z; wt[k][7] = w1.w;
+    }
+    float acc[DW_STRIP][8];
+#pragma unroll
+    for (int o = 0; o < DW_STRIP; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+    const int x_first = ow0 * stride - pad_w;
+    constexpr int ncols = (DW_STRIP - 1) * stride + K; // input columns touched by the strip
+#pragma unroll
     for (int r = 0; r < K; ++r) {
         const int h = oh * stride - pad_h + r;
         if (h < 0 || h >= H) continue;
-        for (int s = 0; s < K; ++s) {
-            const int x = ow * stride - pad_w + s;
+        const __half* rowp = in + ((size_t)n * H + h) * W * in_ld + c0;
+#pragma unroll
+        for (int ci = 0; ci < ncols; ++ci) {
+            const int x = x_first + ci;
             if (x < 0 || x >= W) continue;
-            const uint4 v = *(const uint4*)(in + (((size_t)n * H + h) * W + x) * in_ld + c0);
+            const uint4 v = *(const uint4*)(rowp + (size_t)x * in_ld);
             const __half2* h2 = (const __half2*)&v;
-            const float4 w0 = __ldg((const float4*)(w + (size_t)(r * K + s) * C + c0));
-            const float4 w1 = __ldg((const float4*)(w + (size_t)(r * K + s) * C + c0 + 4));
             const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
-            acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
-            acc[2] = fmaf(b.x, w0.z, acc[2]); acc[3] = fmaf(b.y, w0.w, acc[3]);
-            acc[4] = fmaf(c.x, w1.x, acc[4]); acc[5] = fmaf(c.y, w1.y, acc[5]);
-            acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
+            const float xv[8] = { a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y };
+#pragma unroll
+            for (int o = 0; o < DW_STRIP; ++o) {
+                const int s = ci - o * stride; // tap column of output o that reads input column ci
+                if (s < 0 || s >= K) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(xv[j], wt[r * K + s][j], acc[o][j]);
+            }
         }
     }
-    uint4 o;
-    __half2* oh2 = (__half2*)&o;
+    float bs[8], al[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float y0 = acc[2 * j] + __ldg(bias + c0 + 2 * j), y1 = acc[2 * j + 1] + __ldg(bias + c0 + 2 * j + 1);
-        y0 = y0 > 0.f ? y0 : y0 * __ldg(alpha + c0 + 2 * j);
-        y1 = y1 > 0.f ? y1 : y1 * __ldg(alpha + c0 + 2 * j + 1);
-        oh2[j] = __floats2half2_rn(y0, y1);
+    for (int j = 0; j < 8; ++j) { bs[j] = __ldg(bias + c0 + j); al[j] = __ldg(alpha + c0 + j); }
+#pragma unroll
+    for (int o = 0; o < DW_STRIP; ++o) {
+        const int ow = ow0 + o;
+        if (ow >= OW) break;
+        uint4 ov;
+        __half2* oh2 = (__half2*)&ov;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y0 = acc[o][2 * j] + bs[2 * j], y1 = acc[o][2 * j + 1] + bs[2 * j + 1];
+            y0 = y0 > 0.f ? y0 : y0 * al[2 * j];
+            y1 = y1 > 0.f ? y1 : y1 * al[2 * j + 1];
+            oh2[j] = __floats2half2_rn(y0, y1);
+        }
+        *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * out_ld + c0) = ov;
     }
-    *(uint4*)(out + (((size_t)n * OH + oh) * OW + ow) * out_ld + c0) = o;
 }
 
 // OpenPifPaf heads (hyperpose/Model/pifpaf/model.py:215-281): raw 1x1-conv outputs [N,hc,wc,C] fp16 ->
@@ -631,10 +660,14 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& ib = e->bufs[po.in_buf];
             EngBuffer& ob = e->bufs[po.out_buf];
             const int C = (int)po.cout_g, K = (int)po.R, stride = po.stride ? (int)po.stride : 1;
-            const size_t total = (size_t)N * ob.H * ob.W * (C / 8);
-            dwconv_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels,
-                                                                   op.d_dw, op.d_dw + (size_t)K * K * C, op.d_dw + (size_t)K * K * C + C, N, ib.H, ib.W, C, K, stride,
-                                                                   ob.H, ob.W, same_pad_before(ib.H, K, stride), same_pad_before(ib.W, K, stride));
+            const size_t total = (size_t)N * ob.H * ((ob.W + DW_STRIP - 1) / DW_STRIP) * (C / 8);
+            const int blocks = (int)((total + 255) / 256);
+            const float* dw = op.d_dw;
+#define HP_DW(KK, SS) dwconv_kernel<KK, SS><<<blocks, 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels, dw, \
+                dw + (size_t)KK * KK * C, dw + (size_t)KK * KK * C + C, N, ib.H, ib.W, C, ob.H, ob.W, same_pad_before(ib.H, KK, SS), same_pad_before(ib.W, KK, SS))
+            if (K == 3) { if (stride == 2) HP_DW(3, 2); else HP_DW(3, 1); }
+            else        { if (stride == 2) HP_DW(1, 2); else HP_DW(1, 1); }
+#undef HP_DW
             e->launches++;
         } else if (po.type == OP_MAXPOOL2) {
             EngBuffer& ib = e->bufs[po.in_buf];
