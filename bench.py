@@ -255,17 +255,36 @@ def run_ours(args):
 
     st = torch.cuda.Stream(device=dev)
     rec_bytes = capi.HUMAN_DT.itemsize
-    res_humans = torch.zeros(BATCH * HCAP * rec_bytes, dtype=torch.uint8, device=dev)
-    res_counts = torch.zeros(BATCH, dtype=torch.int32, device=dev)
-    from hyperpose_b200 import sharding
-
+    # keypoint records + per-frame counts of one batch in ONE buffer (a single NCCL all-gather per step), double-buffered so
+    # that the gather of batch i runs on a side stream while batch i+1 is computed
+    hum_bytes = BATCH * HCAP * rec_bytes
+    res_bufs = [torch.zeros(hum_bytes + BATCH * 4, dtype=torch.uint8, device=dev) for _ in range(2)]
+    gath_bufs = [torch.zeros(world * (hum_bytes + BATCH * 4), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    sg = torch.cuda.Stream(device=dev)
+    ev_res = [torch.cuda.Event() for _ in range(2)]
+    ev_gat = [torch.cuda.Event() for _ in range(2)]
+    gstate = {"n": 0}
     def gather_results():
         if PIFPAF:
             return    # config 5 is a single-GPU config: records stay in the decoder's device buffer
-        parser.copy_results_device(res_humans.data_ptr(), res_counts.data_ptr(), BATCH, HCAP, st.cuda_stream)
+        k = gstate["n"] & 1
+        if gstate["n"] >= 2 and world > 1:
+            st.wait_event(ev_gat[k])              # the gather that last read this buffer has finished
+        buf = res_bufs[k]
+        parser.copy_results_device(buf.data_ptr(), buf.data_ptr() + hum_bytes, BATCH, HCAP, st.cuda_stream)
         if world > 1:
-            with torch.cuda.stream(st):
-                sharding.gather_records(res_humans, res_counts, world)   # NCCL all-gather of ~300 KB per rank
+            ev_res[k].record(st)
+            sg.wait_event(ev_res[k])
+            with torch.cuda.stream(sg):
+                dist.all_gather_into_tensor(gath_bufs[k], buf)   # ~300 KB per rank, off the conv stream
+            ev_gat[k].record(sg)
+        gstate["n"] += 1
+
+    def drain_gather():
+        if world > 1 and not PIFPAF:
+            for k in range(2):
+                if gstate["n"] > k:
+                    st.wait_event(ev_gat[k])
 
     # Optional (--pipeline; OFF by default: measured SLOWER, 2070 vs 2221 frames/s -- the parser's many small CTAs delay
     # the start of the next persistent conv kernel's CTAs, whose static tile assignment then runs unbalanced).
@@ -298,10 +317,10 @@ def run_ours(args):
         ev_ready.record(st)
         st2.wait_event(ev_ready)
         parser.process_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, 19, 38, HF, WF, st2.cuda_stream)
-        parser.copy_results_device(res_humans.data_ptr(), res_counts.data_ptr(), BATCH, HCAP, st2.cuda_stream)
+        parser.copy_results_device(res_bufs[0].data_ptr(), res_bufs[0].data_ptr() + hum_bytes, BATCH, HCAP, st2.cuda_stream)
         if world > 1:
             with torch.cuda.stream(st2):
-                sharding.gather_records(res_humans, res_counts, world)   # NCCL all-gather of ~300 KB per rank
+                dist.all_gather_into_tensor(gath_bufs[0], res_bufs[0])
         ev_parsed.record(st2)
 
     def drain_device():
@@ -317,7 +336,7 @@ def run_ours(args):
         humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
         if world > 1:
             gather_results()
-            st.synchronize()
+            sg.synchronize()
         return humans
 
     def barrier():
@@ -339,6 +358,7 @@ def run_ours(args):
             fn(warmup + i)
         if fn is step_device:
             drain_device()
+        drain_gather()                                # the timed region ends when the last keypoint gather has finished
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.time() - t0
