@@ -387,10 +387,10 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        for i in range(30):                 # nvidia-smi needs ~0.3 s to deliver its first sample: keep the GPU under the same load meanwhile
-            step_device(i)
-        torch.cuda.synchronize()
-        sampler.lines.clear()               # keep only samples taken under load
+    for i in range(30):                     # (every rank: the steps contain the collective) nvidia-smi needs ~0.3 s to deliver
+        step_device(i)                      # its first sample: keep the GPUs under the same load meanwhile
+    torch.cuda.synchronize()
+    sampler.lines.clear()                   # keep only samples taken under load
     ms_total, launches = timed(step_device, args.steps, args.warmup, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     prof_ms, prof_ty, prof_fl, prof_runs = engine.get_profile()
