@@ -329,9 +329,21 @@ __device__ Blend grow_connection_blend(float x, float y, float s, const float* L
         const float d2 = __fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay));
         return (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)L[i]); // :399 (double exp, then float)
     };
-    // pass 1: maximum score and its LAST index (score >= score_1 replaces)
+    // pass 1: maximum score and its LAST index (score >= score_1 replaces).  The scores of the first 8 entries of each
+    // lane (lists up to 256 long) are kept in registers for pass 2 (the double-precision exp dominates this function).
+    float cache[8]; unsigned cache_ok = 0;
     float m1 = -1.f; int i1 = -1;
-    for (int i = lane; i < n; i += 32) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int i = lane + 32 * c;
+        cache[c] = 0.f;
+        if (i < n) {
+            bool ok; const float sc = score_of(i, ok);
+            cache[c] = sc; cache_ok |= (ok ? 1u : 0u) << c;
+            if (ok && (sc > m1 || (sc == m1 && i > i1))) { m1 = sc; i1 = i; }
+        }
+    }
+    for (int i = lane + 256; i < n; i += 32) {
         bool ok; const float sc = score_of(i, ok);
         if (ok && (sc > m1 || (sc == m1 && i > i1))) { m1 = sc; i1 = i; }
     }
@@ -347,12 +359,19 @@ __device__ Blend grow_connection_blend(float x, float y, float s, const float* L
     // pass 2: best of the others
     float mp = -1.f; int ip = -1; // prefix (i < i1): larger score, then LARGER index
     float ms = -1.f; int is = -1; // suffix (i > i1): larger score, then SMALLER index
-    for (int i = lane; i < n; i += 32) {
-        if (i == i1) continue;
-        bool ok; const float sc = score_of(i, ok);
-        if (!ok) continue;
+    auto consider = [&](int i, float sc) {
         if (i < i1) { if (sc > mp || (sc == mp && i > ip)) { mp = sc; ip = i; } }
         else        { if (sc > ms || (sc == ms && (is < 0 || i < is))) { ms = sc; is = i; } }
+    };
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int i = lane + 32 * c;
+        if (i < n && i != i1 && ((cache_ok >> c) & 1u)) consider(i, cache[c]);
+    }
+    for (int i = lane + 256; i < n; i += 32) {
+        if (i == i1) continue;
+        bool ok; const float sc = score_of(i, ok);
+        if (ok) consider(i, sc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -434,6 +453,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
 {
     __shared__ QItem q[96];     // frontier: every directed edge at most once as placeholder and once scored
     __shared__ int order[512];  // sort permutations
+    __shared__ Ann sAnn;        // the annotation being grown (copied to global memory when finished)
     const int frame = blockIdx.x, lane = threadIdx.x;
     const Geo g = p.g;
     const int hw = g.H * g.W;
@@ -449,7 +469,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
         const Seed sd = seeds[si];
         if (og.fuzz_get(sd.f, sd.y, sd.x)) continue; // :779 (warp-uniform)
         if (n_ann >= p.ann_cap) { if (lane == 0) atomicOr(p.flags + frame, PP_FLAG_ANNS); break; }
-        Ann& ann = anns[n_ann];
+        Ann& ann = sAnn;
         if (lane == 0) {
             for (int i = 0; i < NKP * 3; ++i) ann.kp[i] = 0.f;
             for (int i = 0; i < NKP; ++i) ann.js[i] = 0.f;
@@ -529,6 +549,9 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
             if (ann.kp[i * 3 + 2] == 0.f) continue;
             occ_add(og, i, g.HR, g.WR, ann.kp[i * 3], ann.kp[i * 3 + 1], ann.js[i], 2.f, 2.f, lane);
         }
+        __syncwarp();
+        for (int i = lane; i < NKP * 3; i += 32) anns[n_ann].kp[i] = sAnn.kp[i];
+        if (lane < NKP) anns[n_ann].js[lane] = sAnn.js[lane];
         __syncwarp();
         ++n_ann;
     }
