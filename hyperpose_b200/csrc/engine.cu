@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) resize_u8c3_kernel(const uint8_t* __restr
 // output) and the K*K*8 weights live in registers.
 constexpr int DW_STRIP = 4;
 template <int K, int stride>
-__global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
+__global__ void __launch_bounds__(256, 3) dwconv_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
                                                      const float* __restrict__ w /*[K*K][C]*/, const float* __restrict__ bias,
                                                      const float* __restrict__ alpha, int N, int H, int W, int C,
                                                      int OH, int OW, int pad_h, int pad_w)
@@ -153,12 +153,11 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __half* __restrict__ 
     for (int r = 0; r < K; ++r) {
         const int h = oh * stride - pad_h + r;
         if (h < 0 || h >= H) continue;
-        const __half* rowp = in + ((size_t)n * H + h) * W * in_ld + c0;
+        const __half* rowp = in + (((size_t)n * H + h) * W + x_first) * in_ld + c0;
 #pragma unroll
         for (int ci = 0; ci < ncols; ++ci) {
-            const int x = x_first + ci;
-            if (x < 0 || x >= W) continue;
-            const uint4 v = *(const uint4*)(rowp + (size_t)x * in_ld);
+            if ((unsigned)(x_first + ci) >= (unsigned)W) continue;
+            const uint4 v = *(const uint4*)(rowp + (size_t)ci * in_ld);
             const __half2* h2 = (const __half2*)&v;
             const float2 a = __half22float2(h2[0]), b = __half22float2(h2[1]), c = __half22float2(h2[2]), d = __half22float2(h2[3]);
             const float xv[8] = { a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y };
