@@ -411,7 +411,7 @@ def run_ours(args):
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "cfg3":      # the ncu capture is of the headline workload only
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_step")
             except Exception:
@@ -453,6 +453,17 @@ def run_ours(args):
                          "kernel_share_of_step": conv_ms / (ms_total / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"},
             "clocks": clocks,
         }
+        # backbone-only and parser-only rates of the same run (per GPU), and the parser against its HBM bound
+        step_ms = ms_total / args.steps
+        parse_ms = max(step_ms - conv_ms - other_ms, 1e-6)
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # (19+38)*Hf*Wf*4 B per frame for conf/PAF; (17*5+19*9)*h*w*4 B for the PIF/PAF fields
+        parse_bytes = BATCH * ((17 * 5 + 19 * 9) if PIFPAF else 57) * HF * WF * 4
+        line["breakdown"] = {"backbone_ms_per_step": conv_ms + other_ms, "backbone_frames_per_s": BATCH / ((conv_ms + other_ms) / 1e3),
+                             "parse_ms_per_step": parse_ms, "parse_frames_per_s": BATCH / (parse_ms / 1e3),
+                             "parse_hbm_frac": (parse_bytes / (parse_ms / 1e3) / 1e9 / hbm) if parse_bytes else None,
+                             "parse_algorithmic_bytes_per_step": parse_bytes,
+                             "note": "parse = step minus the engine's per-op events (parser kernels + result copy); its HBM bound counts only the network-output tensors read once"}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

@@ -2,7 +2,7 @@
 // (examples/operator_api_batched_images_paf.example.cpp:58-74: engine.inference(batch), then
 // parser.process(packet[0], packet[1]) per image) against the B200 drop-in, using only the reference's
 // public headers.  Frames are synthetic (no OpenCV image I/O here); the model is an HPB2PACK file.
-//   usage: operator_api_b200 <model.pack> <width> <height> <batch>
+//   usage: operator_api_b200 <model.pack> <width> <height> <batch> [save-as.pack]
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -17,6 +17,7 @@ int main(int argc, char** argv)
     const int w = std::atoi(argv[2]), h = std::atoi(argv[3]), n = std::atoi(argv[4]);
     namespace hp = hyperpose;
     hp::dnn::tensorrt engine(hp::dnn::tensorrt_serialized{ argv[1] }, { w, h }, n);
+    if (argc > 5) engine.save(argv[5]); // examples/gen_serialized_engine.example.cpp:44
     hp::parser::paf parser{};
     std::mt19937 rng(1);
     std::vector<cv::Mat> batch;

@@ -20,6 +20,7 @@ SOURCES = [
     ("paf_parser.cu", EXACT_FLAGS),
     ("engine.cu", []),
     ("pifpaf_decoder.cu", EXACT_FLAGS),
+    ("ppn_parser.cu", EXACT_FLAGS),
     ("common.cpp", []),
 ]
 
@@ -70,7 +71,7 @@ def build_cpp_example(ref_root: str = "/root/reference") -> str | None:
     if not os.path.isdir(os.path.join(ref_root, "include", "hyperpose")):
         return exe if os.path.exists(exe) else None
     api = os.path.join(CSRC, "hyperpose_api")
-    srcs = [os.path.join(api, "paf.cpp"), os.path.join(api, "tensorrt.cpp"), os.path.join(api, "pifpaf.cpp"),
+    srcs = [os.path.join(api, "paf.cpp"), os.path.join(api, "tensorrt.cpp"), os.path.join(api, "pifpaf.cpp"), os.path.join(api, "pose_proposal.cpp"),
             os.path.join(ROOT, "examples", "operator_api_b200.cpp")]
     if _newer(srcs + [LIB], exe):
         cmd = ["g++", "-std=c++17", "-O2", "-DHP_B200_STANDALONE", "-I" + os.path.join(CSRC, "shim"), "-I" + os.path.join(ref_root, "include"),

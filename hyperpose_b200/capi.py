@@ -401,3 +401,68 @@ class PifPafParser:
         lib().hp_pifpaf_debug_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         check(lib().hp_pifpaf_debug_counts(self._h, frame, out))
         return dict(zip(["seeds", "anns", "kept", "flags", "nms_h", "nms_w", "caf_entries"], list(out)))
+
+
+EXPORTS += ["hp_ppn_create", "hp_ppn_destroy", "hp_ppn_set_point_thresh", "hp_ppn_set_limb_thresh", "hp_ppn_set_nms_thresh",
+            "hp_ppn_process_host", "hp_ppn_process_device", "hp_ppn_fetch", "hp_ppn_launch_count"]
+
+
+class PoseProposalParser:
+    """Mirror of hyperpose::parser::pose_proposal (include/hyperpose/operator/parser/proposal_network.hpp:18-80):
+    PoseProposalParser((net_w, net_h), point_thresh=0.10, limb_thresh=0.05, nms_thresh=0.3)."""
+
+    def __init__(self, net_resolution, point_thresh: float = 0.10, limb_thresh: float = 0.05, nms_thresh: float = 0.3, device: int = 0):
+        L = lib()
+        vp, ip, ci, cf = C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_float
+        L.hp_ppn_create.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci]
+        L.hp_ppn_destroy.argtypes = [vp]
+        L.hp_ppn_destroy.restype = None
+        for f in (L.hp_ppn_set_point_thresh, L.hp_ppn_set_limb_thresh, L.hp_ppn_set_nms_thresh):
+            f.argtypes = [vp, cf]
+        L.hp_ppn_process_host.argtypes = [vp] + [vp] * 6 + [ci] * 7 + [vp, ci, ip]
+        L.hp_ppn_process_device.argtypes = [vp] + [vp] * 6 + [ci] * 7 + [vp]
+        L.hp_ppn_fetch.argtypes = [vp, vp, ci, ip, ci]
+        L.hp_ppn_launch_count.argtypes = [vp]
+        L.hp_ppn_launch_count.restype = C.c_longlong
+        self._h = C.c_void_p()
+        check(L.hp_ppn_create(C.byref(self._h), int(net_resolution[0]), int(net_resolution[1]), point_thresh, limb_thresh, nms_thresh, device))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hp_ppn_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_point_thresh(self, t: float):
+        check(lib().hp_ppn_set_point_thresh(self._h, t))
+
+    def set_limb_thresh(self, t: float):
+        check(lib().hp_ppn_set_limb_thresh(self._h, t))
+
+    def set_nms_thresh(self, t: float):
+        check(lib().hp_ppn_set_nms_thresh(self._h, t))
+
+    def process_batch(self, conf_point, x, y, w, h, edge, cap: int = 256):
+        """host tensors [N,K,gh,gw] x5 and edge [N,E,nh,nw,gh,gw] -> list of N HUMAN_DT arrays"""
+        a = [np.ascontiguousarray(t, np.float32) for t in (conf_point, x, y, w, h, edge)]
+        N, K, gh, gw = a[0].shape
+        E, nh, nw = a[5].shape[1:4]
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_ppn_process_host(self._h, *[t.ctypes.data for t in a], N, K, gh, gw, E, nh, nw, out.ctypes.data, cap, n))
+        return [out[i, :n[i]].copy() for i in range(N)]
+
+    def process(self, conf_point, conf_iou, x, y, w, h, edge, cap: int = 256):
+        """pose_proposal::process(conf_point, conf_iou, x, y, w, h, edge): one frame; conf_iou is ignored like in the
+        reference (src/pose_proposal.cpp:74) apart from its leading dimension"""
+        K = np.asarray(conf_iou).shape[0]
+        return self.process_batch(*[np.asarray(t)[None, :K] for t in (conf_point, x, y, w, h)], np.asarray(edge)[None], cap=cap)[0]
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().hp_ppn_launch_count(self._h))

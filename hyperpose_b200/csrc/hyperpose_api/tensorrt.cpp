@@ -42,6 +42,7 @@ namespace dnn {
 
     struct tensorrt::cuda_dep {
         hp_engine* engine = nullptr;
+        std::string pack_path; // what save() re-emits
         int c_conf = 0, c_paf = 0, out_h = 0, out_w = 0;
         ~cuda_dep() { hp_engine_destroy(engine); }
     };
@@ -51,6 +52,7 @@ namespace dnn {
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
         m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }
     tensorrt::tensorrt(const onnx& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type, double factor, bool flip_rgb)
@@ -58,6 +60,7 @@ namespace dnn {
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
         m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }
     tensorrt::tensorrt(const tensorrt_serialized& m, cv::Size input_size, int max_batch_size, bool keep_ratio, double factor, bool flip_rgb)
@@ -65,6 +68,7 @@ namespace dnn {
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
         m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }
 
@@ -119,7 +123,18 @@ namespace dnn {
         return collect(m_cuda_dep->engine, batch.size(), m_cuda_dep->c_conf, m_cuda_dep->c_paf, m_cuda_dep->out_h, m_cuda_dep->out_w);
     }
 
-    void tensorrt::save(const std::string) {} // the pack already is the serialised engine
+    // tensorrt.cpp:463-471 serialises the built TensorRT plan.  Here the model pack IS the serialised engine (there
+    // is no build step whose result would be worth caching), so save() re-emits the pack: the saved file is accepted
+    // by tensorrt(tensorrt_serialized{path}, ...) exactly like the plan file in the reference
+    // (examples/gen_serialized_engine.example.cpp:28-46).
+    void tensorrt::save(const std::string path)
+    {
+        std::ifstream src(m_cuda_dep->pack_path, std::ios::binary);
+        std::ofstream dst(path, std::ios::binary | std::ios::trunc);
+        if (!src || !dst) die("save: cannot copy model pack " + m_cuda_dep->pack_path + " -> " + path);
+        dst << src.rdbuf();
+        if (!dst) die("save: write failed for " + path);
+    }
 
     tensorrt::~tensorrt() = default;
 

@@ -169,3 +169,56 @@ def make_pifpaf_fields(seed: int, n_persons, h: int = 49, w: int = 49):
                     paf[b, :, cy, cx] = (rng.uniform(0.85, 0.95), x1 + rng.normal(0, 0.02), y1 + rng.normal(0, 0.02),
                                          x2 + rng.normal(0, 0.02), y2 + rng.normal(0, 0.02), 0.3, 0.3, scale, scale)
     return pif, paf
+
+
+# ---------------------------------------------------------------------------------------------
+# Pose Proposal Network tensors (src/pose_proposal.cpp:14-20): conf_point / conf_iou / x / y / w / h [18,gh,gw] and
+# edge [17,nh,nw,gh,gw]; boxes in network-input pixels
+# ---------------------------------------------------------------------------------------------
+# src/pose_proposal.cpp:24-42
+PPN_PAIRS = [(1, 8), (8, 9), (9, 10), (1, 11), (11, 12), (12, 13), (1, 2), (2, 3), (3, 4), (1, 5), (5, 6), (6, 7),
+             (1, 0), (0, 14), (0, 15), (14, 16), (15, 17)]
+
+
+def make_ppn_tensors(seed: int, n_persons, net_h: int = 384, net_w: int = 384, gh: int = 12, gw: int = 12, nh: int = 9, nw: int = 9,
+                     distractors: int = 12):
+    """(conf_point, conf_iou, x, y, w, h) f32[18,gh,gw] + edge f32[17,nh,nw,gh,gw] for P random skeletons: the joint's cell
+    proposes a box centred on the joint, its 4-neighbours propose weaker overlapping boxes (NMS food), the edge tensor
+    points from the limb's first joint cell to the cell of the second one; `distractors` spurious edges/boxes above threshold."""
+    rng = np.random.default_rng(seed)
+    if isinstance(n_persons, tuple):
+        n_persons = int(rng.integers(n_persons[0], n_persons[1] + 1))
+    K, E = N_PARTS, len(PPN_PAIRS)
+    conf = rng.uniform(0.0, 0.08, (K, gh, gw))
+    xs = rng.uniform(0, net_w, (K, gh, gw)); ys = rng.uniform(0, net_h, (K, gh, gw))
+    ws = rng.uniform(10, 60, (K, gh, gw)); hs = rng.uniform(10, 60, (K, gh, gw))
+    edge = rng.uniform(0.0, 0.04, (E, nh, nw, gh, gw))
+    ch, cw = net_h / gh, net_w / gw
+    skel = random_skeletons(rng, n_persons, net_h, net_w)
+    for person in skel:
+        cells = {}
+        bw = rng.uniform(24, 56)
+        for k, (px, py) in enumerate(person):
+            gx, gy = int(px // cw), int(py // ch)
+            if not (0 <= gx < gw and 0 <= gy < gh):
+                continue
+            cells[k] = (gy, gx)
+            conf[k, gy, gx] = rng.uniform(0.7, 0.95)
+            xs[k, gy, gx], ys[k, gy, gx] = px, py
+            ws[k, gy, gx], hs[k, gy, gx] = bw + rng.normal(0, 1), bw + rng.normal(0, 1)
+            for dy, dx in ((0, 1), (1, 0), (0, -1), (-1, 0)):
+                y2, x2 = gy + dy, gx + dx
+                if 0 <= y2 < gh and 0 <= x2 < gw and conf[k, y2, x2] < 0.1 and rng.random() < 0.7:
+                    conf[k, y2, x2] = rng.uniform(0.15, 0.5)
+                    xs[k, y2, x2], ys[k, y2, x2] = px + rng.normal(0, 3), py + rng.normal(0, 3)
+                    ws[k, y2, x2], hs[k, y2, x2] = bw + rng.normal(0, 2), bw + rng.normal(0, 2)
+        for i, (a, b) in enumerate(PPN_PAIRS):
+            if a in cells and b in cells:
+                dy, dx = cells[b][0] - cells[a][0] + nh // 2, cells[b][1] - cells[a][1] + nw // 2
+                if 0 <= dy < nh and 0 <= dx < nw:
+                    edge[i, dy, dx, cells[a][0], cells[a][1]] = rng.uniform(0.5, 0.9)
+    for _ in range(distractors):
+        edge[rng.integers(E), rng.integers(nh), rng.integers(nw), rng.integers(gh), rng.integers(gw)] = rng.uniform(0.06, 0.4)
+        conf[rng.integers(K), rng.integers(gh), rng.integers(gw)] = rng.uniform(0.11, 0.3)
+    f = lambda a: a.astype(np.float32)
+    return f(conf), f(rng.uniform(0, 1, (K, gh, gw))), f(xs), f(ys), f(ws), f(hs), f(edge)

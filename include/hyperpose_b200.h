@@ -123,6 +123,32 @@ int hp_pifpaf_debug_counts(hp_pifpaf* p, int frame, int* out7);
 int hp_pifpaf_debug_hr(hp_pifpaf* p, int frame, int field, float* out);
 
 /* ------------------------------------------------------------------------------------------
+ * Pose Proposal Network parser -- replaces hyperpose::parser::pose_proposal
+ * (include/hyperpose/operator/parser/proposal_network.hpp:18-80, src/pose_proposal.cpp:44-337).
+ * Tensors per frame: conf_point / x / y / w / h f32[K,gh,gw] (boxes in network-input pixels) and
+ * edge f32[E,nh,nw,gh,gw] (src/pose_proposal.cpp:14-20).  conf_iou is ignored by the reference except for its
+ * leading dimension (:74,:84), which is the K passed here (K >= 18: COCOPAIR_STD indexes key points 0..17).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hp_ppn hp_ppn;
+/* pose_proposal::pose_proposal(net_resolution, point_thresh = 0.10, limb_thresh = 0.05, nms_thresh = 0.3)
+ * (proposal_network.hpp:26) */
+int hp_ppn_create(hp_ppn** out, int net_w, int net_h, float point_thresh, float limb_thresh, float nms_thresh, int device);
+void hp_ppn_destroy(hp_ppn* p);
+/* set_point_thresh / set_limb_thresh / set_nms_thresh (proposal_network.hpp:67-75) */
+int hp_ppn_set_point_thresh(hp_ppn* p, float thresh);
+int hp_ppn_set_limb_thresh(hp_ppn* p, float thresh);
+int hp_ppn_set_nms_thresh(hp_ppn* p, float thresh);
+/* pose_proposal::process (proposal_network.hpp:44-47; src/pose_proposal.cpp:68-337) for N frames, HOST tensors
+ * [N,K,gh,gw] x5 and [N,E,nh,nw,gh,gw]; out[N*cap], n_out[N]. */
+int hp_ppn_process_host(hp_ppn* p, const float* conf_point, const float* x, const float* y, const float* w, const float* h,
+                        const float* edge, int N, int K, int gh, int gw, int E, int nh, int nw, hp_human* out, int cap, int* n_out);
+/* same with DEVICE tensors, asynchronous on `stream` (NULL = the parser's own); results by hp_ppn_fetch */
+int hp_ppn_process_device(hp_ppn* p, const float* d_conf_point, const float* d_x, const float* d_y, const float* d_w, const float* d_h,
+                          const float* d_edge, int N, int K, int gh, int gw, int E, int nh, int nw, void* stream);
+int hp_ppn_fetch(hp_ppn* p, hp_human* out, int cap, int* n_out, int N);
+long long hp_ppn_launch_count(const hp_ppn* p);
+
+/* ------------------------------------------------------------------------------------------
  * DNN engine -- replaces hyperpose::dnn::tensorrt (include/hyperpose/operator/dnn/tensorrt.hpp:33-141,
  * src/tensorrt.cpp:121-471).  The model file is a flat "HPB2PACK" pack (hyperpose_b200/csrc/pack_format.h,
  * written by hyperpose_b200/models.py) instead of .onnx/.uff/.trt (utility/model.hpp:13-32).

@@ -224,3 +224,35 @@ def ref_pifpaf_process(pif: np.ndarray, paf: np.ndarray, net_h: int, net_w: int,
     if n < 0:
         raise RuntimeError(f"ref_pifpaf_process rc={n}")
     return out[:n].copy()
+
+
+_refppn = None
+
+
+def ppn_ref_available() -> bool:
+    if os.path.isdir("/root/reference/src"):
+        build()
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_ppn.so"))
+
+
+def ref_ppn_process(conf_point, conf_iou, x, y, w, h, edge, net_w: int, net_h: int, point_thresh: float = 0.10,
+                    limb_thresh: float = 0.05, nms_thresh: float = 0.3, cap: int = 1024) -> np.ndarray:
+    """The reference's own hyperpose::parser::pose_proposal (src/pose_proposal.cpp compiled verbatim) on one frame."""
+    global _refppn
+    if _refppn is None:
+        if not ppn_ref_available():
+            raise FileNotFoundError("oracle/_ref/libref_ppn.so not built (needs /root/reference)")
+        lib = C.CDLL(os.path.join(HERE, "_ref", "libref_ppn.so"))
+        fp = C.POINTER(C.c_float)
+        lib.ref_ppn_process.restype = C.c_int
+        lib.ref_ppn_process.argtypes = [fp] * 7 + [C.c_int] * 8 + [C.c_float] * 3 + [C.c_void_p, C.c_int]
+        _refppn = lib
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (conf_point, conf_iou, x, y, w, h, edge)]
+    K, gh, gw = arrs[0].shape
+    E, nh, nw = arrs[6].shape[:3]
+    out = np.zeros(cap, HUMAN_REC)
+    n = _refppn.ref_ppn_process(*[_fp(a) for a in arrs], K, gh, gw, E, nh, nw, net_w, net_h, point_thresh, limb_thresh, nms_thresh,
+                                out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"ref_ppn_process rc={n}")
+    return out[:n].copy()

@@ -5,6 +5,7 @@
 // restatements in oracle/paf_oracle.c, which are pinned bit-exactly against Python cv2
 // (tests/test_oracle_cv_pin.py).  TEST INFRASTRUCTURE ONLY.
 #pragma once
+#include <cassert>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -22,6 +23,22 @@ struct Size {
     bool operator==(const Size& o) const { return width == o.width && height == o.height; }
     bool operator!=(const Size& o) const { return !(*this == o); }
 };
+// cv::Rect_<int> as OpenCV 4.4 core/types.hpp defines it (area, and a & b = the intersection, empty -> Rect()):
+// what src/pose_proposal.cpp needs for its box NMS.
+struct Rect {
+    int x = 0, y = 0, width = 0, height = 0;
+    Rect() = default;
+    Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {}
+    int area() const { return width * height; }
+};
+inline Rect operator&(const Rect& a, const Rect& b)
+{
+    const int x1 = a.x > b.x ? a.x : b.x, y1 = a.y > b.y ? a.y : b.y;
+    const int ax2 = a.x + a.width, bx2 = b.x + b.width, ay2 = a.y + a.height, by2 = b.y + b.height;
+    Rect r(x1, y1, (ax2 < bx2 ? ax2 : bx2) - x1, (ay2 < by2 ? ay2 : by2) - y1);
+    if (r.width <= 0 || r.height <= 0) r = Rect();
+    return r;
+}
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{ a, b, c, d } {}

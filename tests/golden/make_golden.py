@@ -47,6 +47,13 @@ PIFPAF_CASES = [("pp_p2", 4, 2, 49, 49, 0.1), ("pp_p5", 5, 5, 49, 49, 0.1), ("pp
                 ("pp_rect", 8, 3, 47, 55, 0.1), ("pp_thr", 9, 4, 49, 49, 0.3), ("pp_small", 10, 2, 25, 33, 0.1)]
 
 
+# (name, seed, persons, net_w, net_h, gh, gw, nh, nw, point_thresh, limb_thresh, nms_thresh, distractors) of the Pose Proposal pin
+PPN_CASES = [("ppn_p1", 20, 1, 384, 384, 12, 12, 9, 9, 0.10, 0.05, 0.3, 12), ("ppn_p4", 21, 4, 384, 384, 12, 12, 9, 9, 0.10, 0.05, 0.3, 12),
+             ("ppn_crowd", 22, (6, 10), 384, 384, 12, 12, 9, 9, 0.10, 0.05, 0.3, 40), ("ppn_empty", 23, 0, 384, 384, 12, 12, 9, 9, 0.10, 0.05, 0.3, 0),
+             ("ppn_rect", 24, 3, 512, 384, 12, 16, 7, 9, 0.10, 0.05, 0.3, 12), ("ppn_thr", 25, 4, 384, 384, 12, 12, 9, 9, 0.30, 0.20, 0.5, 12),
+             ("ppn_dense", 26, 5, 384, 384, 12, 12, 9, 9, 0.05, 0.03, 0.3, 60)]
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -98,8 +105,24 @@ def main():
         pp[name + "_humans"] = oracle.ref_pifpaf_process(pif, paf, (h - 1) * 8 + 1, (w - 1) * 8 + 1, thr)
         pp[name + "_in_sha"] = np.array(sha(pif) + sha(paf))
     np.savez_compressed(os.path.join(HERE, "ref_pifpaf.npz"), **pp)
+    make_ppn()
+
+
+def make_ppn():
+    """goldens of the reference's own src/pose_proposal.cpp (oracle/_ref/libref_ppn.so) on seeded synthetic tensors"""
+    from hyperpose_b200 import synthetic as syn
+    import oracle
+    pn = {}
+    for (name, seed, P, net_w, net_h, gh, gw, nh, nw, pt, lt, nt, nd) in PPN_CASES:
+        t = syn.make_ppn_tensors(seed, P, net_h, net_w, gh, gw, nh, nw, nd)
+        pn[name + "_humans"] = oracle.ref_ppn_process(*t, net_w, net_h, pt, lt, nt)
+        pn[name + "_in_sha"] = np.array("".join(sha(a) for a in t))
+    np.savez_compressed(os.path.join(HERE, "ref_ppn.npz"), **pn)
     print("wrote", os.listdir(HERE))
 
 
 if __name__ == "__main__":
-    main()
+    if "ppn" in sys.argv[1:]:
+        make_ppn()
+    else:
+        main()

@@ -20,7 +20,8 @@ def test_dropin_compiles_against_unchanged_reference_headers():
     syms = subprocess.run(["nm", "-C", "--defined-only", exe], capture_output=True, text=True).stdout
     for want in ["hyperpose::parser::paf::process(", "hyperpose::parser::paf::paf(float, float, cv::Size)",
                  "hyperpose::parser::paf::set_conf_thresh(float)", "hyperpose::dnn::tensorrt::inference(std::vector<cv::Mat",
-                 "hyperpose::dnn::tensorrt::inference(std::vector<float", "hyperpose::dnn::tensorrt::save(", "hyperpose::parser::pifpaf::process("]:
+                 "hyperpose::dnn::tensorrt::inference(std::vector<float", "hyperpose::dnn::tensorrt::save(", "hyperpose::parser::pifpaf::process(",
+                 "hyperpose::parser::pose_proposal::process(", "hyperpose::parser::pose_proposal::set_nms_thresh(float)"]:
         assert want in syms, want
 
 
@@ -31,7 +32,9 @@ def test_cpp_example_runs_operator_api_sequence(tmp_path):
         pytest.skip("example binary not built (needs the reference headers at build time)")
     pack = tmp_path / "tiny.pack"
     pack.write_bytes(models.tiny_test_net(0).to_pack())
-    r = subprocess.run([exe, str(pack), "96", "64", "3"], capture_output=True, text=True, timeout=120)
+    saved = tmp_path / "saved.pack"
+    r = subprocess.run([exe, str(pack), "96", "64", "3", str(saved)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert saved.read_bytes() == pack.read_bytes()      # tensorrt::save re-emits the pack
     assert "conf:[19, 32, 48, ]" in r.stdout and "paf:[38, 32, 48, ]" in r.stdout
     assert "3 images got processed" in r.stdout
