@@ -38,45 +38,71 @@ using namespace hpb;
 //   u8 path : v = (float)((double)u8 * factor) (data.cpp:48); model channel c reads byte (flip ? 2-c : c)
 //   f32 path: input is already scaled NCHW (tensorrt::inference(const std::vector<float>&, size_t))
 // stride 2 (MobileNet / ResNet stems): TF "SAME" padding, pad_before = max((OH-1)*2 + R - H, 0) / 2.
-template <bool U8, int R>
-__global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
-                                                      int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
-                                                      int stride, int OH, int OW, int pad_h, int pad_w, int chunks)
+template <bool U8, int R, int CHUNK>
+__device__ __forceinline__ void im2col_chunk(const void* __restrict__ in, uint4* __restrict__ o, int oswz, int n, int h0, int w0, int H, int W,
+                                             double factor, int flip, const float (&mean)[3])
 {
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)N * OH * OW * chunks;
-    if (gid >= total) return;
-    const int chunk = (int)(gid % chunks);
-    const size_t idx = gid / chunks;
-    const int w0 = (int)(idx % OW) * stride - pad_w;
-    const int h0 = (int)((idx / OW) % OH) * stride - pad_h;
-    const int n = (int)(idx / ((size_t)OW * OH));
-    const float mean[3] = { m0, m1, m2 };
+    // 64 consecutive K entries of one output pixel: k = (r * R + s) * 3 + c, every index a compile-time constant
     constexpr int kmax = R * R * 3;
     __align__(16) __half vals[64];
-    const __half zero = __float2half_rn(0.f);
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
-        const int k = chunk * 64 + j;
-        __half hv = zero;
+        const int k = CHUNK * 64 + j;
+        float v = 0.f;
         if (k < kmax) {
             const int c = k % 3, rs = k / 3, s = rs % R, r = rs / R;
             const int hh = h0 + r, ww = w0 + s;
             if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
                 if (U8) {
                     const uint8_t* px = (const uint8_t*)in + (((size_t)n * H + hh) * W + ww) * 3;
-                    hv = __float2half_rn((float)((double)px[flip ? 2 - c : c] * factor) - mean[c]);
+                    v = (float)((double)px[flip ? 2 - c : c] * factor) - mean[c];
                 } else {
-                    hv = __float2half_rn(((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c]);
+                    v = ((const float*)in)[(((size_t)n * 3 + c) * H + hh) * W + ww] - mean[c];
                 }
             }
         }
-        vals[j] = hv;
+        vals[j] = __float2half_rn(v);
     }
-    uint4* o = (uint4*)(out + (idx * chunks + chunk) * 64);
     const uint4* v4 = (const uint4*)vals;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = v4[i];
+    for (int i = 0; i < 8; ++i) o[i ^ oswz] = v4[i];
+}
+
+// grid = (pixels / 256, chunks): the 64-entry chunk index is uniform per block and resolved at compile time below
+template <bool U8, int R>
+__global__ void __launch_bounds__(256) im2col3_kernel(const void* __restrict__ in, __half* __restrict__ out,
+                                                      int N, int H, int W, double factor, int flip, float m0, float m1, float m2,
+                                                      int stride, int OH, int OW, int pad_h, int pad_w, int chunks)
+{
+    // Each thread builds one 128-byte row.  With one chunk per pixel the block's 256 rows are contiguous in HBM:
+    // they are staged in shared memory (16-byte pieces XOR-swizzled by the row) and written out fully coalesced.
+    __shared__ uint4 stage[256 * 8];
+    const size_t total = (size_t)N * OH * OW;
+    const size_t idx0 = (size_t)blockIdx.x * blockDim.x, idx = idx0 + threadIdx.x;
+    const int chunk = blockIdx.y;
+    constexpr int nchunks = (R * R * 3 + 63) / 64;
+    const bool staged = (nchunks == 1);
+    if (idx < total) {
+        const int w0 = (int)(idx % OW) * stride - pad_w;
+        const int h0 = (int)((idx / OW) % OH) * stride - pad_h;
+        const int n = (int)(idx / ((size_t)OW * OH));
+        const float mean[3] = { m0, m1, m2 };
+        uint4* o = staged ? stage + threadIdx.x * 8 : (uint4*)(out + (idx * chunks + chunk) * 64);
+        const int swz = staged ? (threadIdx.x & 7) : 0;
+        if (nchunks == 1 || chunk == 0) im2col_chunk<U8, R, 0>(in, o, swz, n, h0, w0, H, W, factor, flip, mean);
+        else if (chunk == 1) im2col_chunk<U8, R, (nchunks > 1 ? 1 : 0)>(in, o, swz, n, h0, w0, H, W, factor, flip, mean);
+        else im2col_chunk<U8, R, (nchunks > 2 ? 2 : 0)>(in, o, swz, n, h0, w0, H, W, factor, flip, mean);
+    }
+    if (staged) {
+        __syncthreads();
+        const size_t rows = total - idx0 < 256 ? total - idx0 : 256;
+        uint4* dst = (uint4*)(out + idx0 * 64);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int q = it * 256 + threadIdx.x, row = q >> 3, c = q & 7;
+            if ((size_t)row < rows) dst[q] = stage[row * 8 + (c ^ (row & 7))];
+        }
+    }
 }
 
 // cv::resize(INTER_LINEAR) on CV_8UC3 frames (src/tensorrt.cpp:451), OpenCV's 11-bit fixed-point bilinear:
@@ -429,10 +455,11 @@ struct hp_engine {
     const float* override_paf = nullptr;
     // per-op CUDA-event profiling (bench.py roofline leg)
     bool profiling = false;
-    std::vector<cudaEvent_t> ev;       // n_ops + 1 events
+    static constexpr int EV_DEPTH = 4; // runs in flight: the host never waits for the GPU to read a run's events back
+    std::vector<cudaEvent_t> ev;       // EV_DEPTH sets of n_ops + 1 events
     std::vector<double> op_ms_sum;     // accumulated per op
     long long profiled_runs = 0;
-    bool ev_pending = false;
+    long long ev_head = 0, ev_tail = 0; // event sets recorded / folded in
 };
 
 namespace {
@@ -609,25 +636,38 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     return HP_OK;
 }
 
-void collect_profile(hp_engine* e)
+// folds the oldest recorded event set into the per-op sums; non-blocking mode gives up if that run is still executing
+bool collect_one(hp_engine* e, bool blocking)
 {
-    if (!e->ev_pending) return;
-    cudaEventSynchronize(e->ev.back());
-    for (size_t i = 0; i + 1 < e->ev.size(); ++i) {
+    if (e->ev_tail >= e->ev_head) return false;
+    const size_t n = e->ops.size();
+    cudaEvent_t* set = e->ev.data() + (size_t)(e->ev_tail % hp_engine::EV_DEPTH) * (n + 1);
+    if (!blocking && cudaEventQuery(set[n]) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaEventSynchronize(set[n]);
+    for (size_t i = 0; i < n; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) == cudaSuccess) e->op_ms_sum[i] += ms;
+        if (cudaEventElapsedTime(&ms, set[i], set[i + 1]) == cudaSuccess) e->op_ms_sum[i] += ms;
     }
     e->profiled_runs++;
-    e->ev_pending = false;
+    e->ev_tail++;
+    return true;
+}
+
+void collect_profile(hp_engine* e)
+{
+    while (collect_one(e, true)) {}
 }
 
 int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0, int last = -1)
 {
     if (last < 0) last = (int)e->ops.size() - 1;
     const bool prof = e->profiling && first == 0 && last == (int)e->ops.size() - 1;
+    cudaEvent_t* evset = nullptr;
     if (prof) {
-        collect_profile(e); // folds the previous run's events in (synchronises on its last event only)
-        cudaEventRecord(e->ev[0], st);
+        while (collect_one(e, false)) {}                                            // finished runs, without waiting
+        if (e->ev_head - e->ev_tail >= hp_engine::EV_DEPTH) collect_one(e, true);   // ring full: wait for the oldest
+        evset = e->ev.data() + (size_t)(e->ev_head % hp_engine::EV_DEPTH) * (e->ops.size() + 1);
+        cudaEventRecord(evset[0], st);
     }
     for (int oi = first; oi <= last; ++oi) {
         EngOp& op = e->ops[oi];
@@ -638,8 +678,8 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& ob = e->bufs[po.out_buf];
             const int R = po.R ? (int)po.R : 3;
             const int chunks = ob.channels / 64;
-            const size_t total = (size_t)N * ob.H * ob.W * chunks;
-            const int blocks = (int)((total + 255) / 256);
+            const size_t total = (size_t)N * ob.H * ob.W;
+            const dim3 blocks((unsigned)((total + 255) / 256), (unsigned)chunks);
             const int stride = po.stride ? (int)po.stride : 1;
             const int ph = same_pad_before(e->in_h, R, stride), pw = same_pad_before(e->in_w, R, stride);
 #define HP_IM2COL(U8, RR, SRC, FAC, FLIP) im2col3_kernel<U8, RR><<<blocks, 256, 0, st>>>(SRC, ob.d, N, e->in_h, e->in_w, FAC, FLIP, \
@@ -684,9 +724,9 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
         } else if (po.type == OP_CONV) {
             launch_conv(e, op, N, st, u8_input);
         }
-        if (prof) cudaEventRecord(e->ev[oi + 1], st);
+        if (prof) cudaEventRecord(evset[oi + 1], st);
     }
-    if (prof) e->ev_pending = true;
+    if (prof) e->ev_head++;
     if (e->override_conf && e->override_paf && last == (int)e->ops.size() - 1) {
         const size_t plane = (size_t)e->out_h * e->out_w;
         HP_CUDA_TRY(cudaMemcpyAsync(e->d_conf, e->override_conf, N * e->hdr.conf_channels * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1106,13 +1146,13 @@ int hp_engine_set_profiling(hp_engine* e, int enable)
     if (!e) return HP_ERR_ARG;
     HP_CUDA_TRY(cudaSetDevice(e->device));
     if (enable && e->ev.empty()) {
-        e->ev.resize(e->ops.size() + 1);
+        e->ev.resize((e->ops.size() + 1) * hp_engine::EV_DEPTH);
         for (auto& ev : e->ev) HP_CUDA_TRY(cudaEventCreate(&ev));
     }
     if (enable) {
         e->op_ms_sum.assign(e->ops.size(), 0.0);
         e->profiled_runs = 0;
-        e->ev_pending = false;
+        e->ev_head = e->ev_tail = 0;
     } else {
         collect_profile(e);
     }
