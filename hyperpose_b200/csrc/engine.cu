@@ -216,6 +216,85 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const __half* __restrict
     }
 }
 
+// Depthwise 3x3, stride 1 (every separable block of MobilenetThin-OpenPose except two): column-marching variant.
+// A thread owns one image column x, 4 channels and a run of output rows: it walks DOWN the column, loads the three
+// neighbouring input pixels of each input row once (3 x 8-byte loads, lanes along channels => 256-byte coalesced
+// segments; the x-1 / x+1 neighbours are L1 hits of the adjacent columns' threads) and scatters the row into the three
+// output rows it feeds, so per output there are 3 loads + 36 FMAs and the 36 weights stay in registers for the whole run.
+// Accumulation order per output is tap-row major, tap-column ascending -- the same as dwconv_kernel (bit-identical).
+__global__ void __launch_bounds__(256, 3) dwconv3_col_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out, int out_ld,
+                                                          const float* __restrict__ w /*[9][C]*/, const float* __restrict__ bias,
+                                                          const float* __restrict__ alpha, int N, int H, int W, int C, int rows_per_chunk, int chunks)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = C / 4;
+    const size_t total = (size_t)N * chunks * W * cv;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % cv) * 4;
+    size_t t = idx / cv;
+    const int x = (int)(t % W); t /= W;
+    const int chunk = (int)(t % chunks);
+    const int n = (int)(t / chunks);
+    const int oh0 = chunk * rows_per_chunk, oh1 = min(oh0 + rows_per_chunk, H);
+    if (oh0 >= oh1) return;
+    float4 wt[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wt[k] = __ldg((const float4*)(w + (size_t)k * C + c0));
+    const float4 bs = __ldg((const float4*)(bias + c0)), al = __ldg((const float4*)(alpha + c0));
+    const bool has_l = x > 0, has_r = x + 1 < W;
+    const __half* colp = in + ((size_t)n * H * W + x) * in_ld + c0;
+    __half* outp = out + ((size_t)n * H * W + x) * out_ld + c0;
+    float4 a0 = { 0.f, 0.f, 0.f, 0.f }, a1 = a0, a2 = a0;   // output rows ih-1, ih, ih+1 while input row ih is being read
+#define HP_FMA4(acc, wv, xv) { acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y); acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w); }
+    // one input row: it is tap row 2 of output ih-1 (A, complete afterwards -> stored), tap row 1 of output ih (B), tap row 0 of
+    // output ih+1 (Cc, starts from zero).  Absent neighbours are zeros: fma(0, w, acc) leaves acc unchanged.
+#define HP_DW_STEP(A, B, Cc, IH)                                                                                                   \
+    {                                                                                                                               \
+        uint2 ul = { 0u, 0u }, ur = { 0u, 0u };                                                                                      \
+        const uint2 uc = *(const uint2*)rp;                                                                                          \
+        if (has_l) ul = *(const uint2*)(rp - in_ld);                                                                                 \
+        if (has_r) ur = *(const uint2*)(rp + in_ld);                                                                                 \
+        rp += row_in;                                                                                                                \
+        const float2 l0 = __half22float2(*(const __half2*)&ul.x), l1 = __half22float2(*(const __half2*)&ul.y);                       \
+        const float2 m0 = __half22float2(*(const __half2*)&uc.x), m1 = __half22float2(*(const __half2*)&uc.y);                       \
+        const float2 r0 = __half22float2(*(const __half2*)&ur.x), r1 = __half22float2(*(const __half2*)&ur.y);                       \
+        const float4 vl = { l0.x, l0.y, l1.x, l1.y }, vm = { m0.x, m0.y, m1.x, m1.y }, vr = { r0.x, r0.y, r1.x, r1.y };              \
+        HP_FMA4(A, wt[6], vl); HP_FMA4(A, wt[7], vm); HP_FMA4(A, wt[8], vr);                                                         \
+        HP_FMA4(B, wt[3], vl); HP_FMA4(B, wt[4], vm); HP_FMA4(B, wt[5], vr);                                                         \
+        Cc = make_float4(0.f, 0.f, 0.f, 0.f);                                                                                        \
+        HP_FMA4(Cc, wt[0], vl); HP_FMA4(Cc, wt[1], vm); HP_FMA4(Cc, wt[2], vr);                                                      \
+        if ((IH) - 1 >= oh0) HP_DW_EMIT(A);                                                                                          \
+    }
+#define HP_DW_EMIT(A)                                                                                                              \
+    {                                                                                                                               \
+        float y0 = A.x + bs.x, y1 = A.y + bs.y, y2 = A.z + bs.z, y3 = A.w + bs.w;                                                    \
+        y0 = y0 > 0.f ? y0 : y0 * al.x; y1 = y1 > 0.f ? y1 : y1 * al.y; y2 = y2 > 0.f ? y2 : y2 * al.z; y3 = y3 > 0.f ? y3 : y3 * al.w; \
+        uint2 ov;                                                                                                                    \
+        *(__half2*)&ov.x = __floats2half2_rn(y0, y1);                                                                                \
+        *(__half2*)&ov.y = __floats2half2_rn(y2, y3);                                                                                \
+        *(uint2*)op = ov;                                                                                                            \
+        op += row_out;                                                                                                               \
+    }
+    const size_t row_in = (size_t)W * in_ld, row_out = (size_t)W * out_ld;
+    const int ih_first = max(oh0 - 1, 0), ih_last = min(oh1, H - 1);   // valid input rows feeding this run
+    const __half* rp = colp + (size_t)ih_first * row_in;
+    __half* op = outp + (size_t)oh0 * row_out;
+    int ih = ih_first;
+    for (; ih + 2 <= ih_last; ih += 3) {   // three rows per trip: the accumulators rotate by renaming, not by moves
+        HP_DW_STEP(a0, a1, a2, ih);
+        HP_DW_STEP(a1, a2, a0, ih + 1);
+        HP_DW_STEP(a2, a0, a1, ih + 2);
+    }
+    for (; ih <= ih_last; ++ih) {
+        HP_DW_STEP(a0, a1, a2, ih);
+        a0 = a1; a1 = a2;
+    }
+    if (oh1 - 1 >= ih_last) HP_DW_EMIT(a0);   // bottom image row: its last input row is padding (after the loop a0 holds output row ih_last)
+#undef HP_DW_STEP
+#undef HP_DW_EMIT
+#undef HP_FMA4
+}
+
 // OpenPifPaf heads (hyperpose/Model/pifpaf/model.py:215-281): raw 1x1-conv outputs [N,hc,wc,C] fp16 ->
 //   pixel_shuffle(scale 2) (pifpaf/utils.py:371-379: in-channel ((nc*2+dy)*2+dx) -> out[nc, 2h+dy, 2w+dx]), crop to 2*hc-1,
 //   reshape [fields, comps, ho, wo]; sigmoid on the confidences, softplus on the scales (inference branch, model.py:238-241,270-274);
@@ -704,7 +783,17 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             const float* dw = op.d_dw;
 #define HP_DW(KK, SS) dwconv_kernel<KK, SS><<<blocks, 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels, dw, \
                 dw + (size_t)KK * KK * C, dw + (size_t)KK * KK * C + C, N, ib.H, ib.W, C, ob.H, ob.W, same_pad_before(ib.H, KK, SS), same_pad_before(ib.W, KK, SS))
-            if (K == 3) { if (stride == 2) HP_DW(3, 2); else HP_DW(3, 1); }
+            if (K == 3 && stride == 1 && !getenv("HPB_DW_STRIP")) {
+                // column-marching kernel: enough row chunks to give every SM a few blocks
+                const size_t base = ((size_t)N * ib.W * (C / 4) + 255) / 256;
+                int chunks = (int)((4 * (size_t)e->num_sms + base - 1) / base);
+                chunks = std::max(1, std::min(chunks, std::max(1, ib.H / 4)));
+                const int rows = (ib.H + chunks - 1) / chunks;
+                chunks = (ib.H + rows - 1) / rows;
+                const size_t tot = (size_t)N * chunks * ib.W * (C / 4);
+                dwconv3_col_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels, dw,
+                    dw + (size_t)9 * C, dw + (size_t)9 * C + C, N, ib.H, ib.W, C, rows, chunks);
+            } else if (K == 3) { if (stride == 2) HP_DW(3, 2); else HP_DW(3, 1); }
             else        { if (stride == 2) HP_DW(1, 2); else HP_DW(1, 1); }
 #undef HP_DW
             e->launches++;

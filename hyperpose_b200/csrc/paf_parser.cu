@@ -657,7 +657,10 @@ template <typename T> struct DevBuf {
         p = nullptr;
         n = 0;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        if (e == cudaSuccess) {
+            n = count;
+            e = cudaMemset(p, 0, count * sizeof(T)); // unused record slots travel to the host with the used ones
+        }
         return e;
     }
     void release()

@@ -536,7 +536,9 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
                 __syncwarp();
             }
             if (!got) break;
-            if (ann.kp[cur.end * 3 + 2] > 0.0f) continue;
+            const bool taken = ann.kp[cur.end * 3 + 2] > 0.0f;
+            __syncwarp();   // every lane has read the slot before lane 0 may fill it
+            if (taken) continue;
             if (lane == 0) {
                 ann.kp[cur.end * 3] = cur.x; ann.kp[cur.end * 3 + 1] = cur.y; ann.kp[cur.end * 3 + 2] = cur.v;
                 ann.js[cur.end] = cur.s;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
 
 template <typename T> struct DBuf {
     T* p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t c) { if (c <= n) return cudaSuccess; if (p) cudaFree(p); p = nullptr; n = 0; cudaError_t e = cudaMalloc(&p, c * sizeof(T)); if (e == cudaSuccess) n = c; return e; }
+    cudaError_t ensure(size_t c) { if (c <= n) return cudaSuccess; if (p) cudaFree(p); p = nullptr; n = 0; cudaError_t e = cudaMalloc(&p, c * sizeof(T)); if (e == cudaSuccess) { n = c; e = cudaMemset(p, 0, c * sizeof(T)); } return e; }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
