@@ -437,15 +437,22 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 for (int j = 0; j < 8; ++j) rs[j] = __floats2half2_rn(0.f, 0.f);
                             }
                         }
+                        // bias / PReLU slope of these 16 channels: four 16-byte loads each (the tile origin is a multiple of 64 channels)
+                        float bv[16], av[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            *(float4*)&bv[4 * j] = __ldg((const float4*)(bias + c0) + j);
+                            *(float4*)&av[4 * j] = __ldg((const float4*)(alpha + c0) + j);
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            float a0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
-                            float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
+                            float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
+                            float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
                             float r0 = 0.f, r1 = 0.f;
                             if (kRes && p.res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
                             if (kRes && p.res_mode == 1) { a0 += r0; a1 += r1; }
-                            a0 = a0 > 0.f ? a0 : a0 * __ldg(alpha + c0 + 2 * j);
-                            a1 = a1 > 0.f ? a1 : a1 * __ldg(alpha + c0 + 2 * j + 1);
+                            a0 = a0 > 0.f ? a0 : a0 * av[2 * j];
+                            a1 = a1 > 0.f ? a1 : a1 * av[2 * j + 1];
                             if (kRes && p.res_mode == 2) { a0 += r0; a1 += r1; }
                             const __half2 h2 = __floats2half2_rn(a0, a1);
                             pk[j] = *(const uint32_t*)&h2;
@@ -872,12 +879,18 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
                     ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
                     ptx::tmem_ld_wait();
                     uint32_t pk[8];
+                    float bv[16], av[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        *(float4*)&bv[4 * j] = __ldg((const float4*)(p.bias + c0) + j);
+                        *(float4*)&av[4 * j] = __ldg((const float4*)(p.alpha + c0) + j);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        float a0 = __uint_as_float(v[2 * j]) + __ldg(p.bias + c0 + 2 * j);
-                        float a1 = __uint_as_float(v[2 * j + 1]) + __ldg(p.bias + c0 + 2 * j + 1);
-                        a0 = a0 > 0.f ? a0 : a0 * __ldg(p.alpha + c0 + 2 * j);
-                        a1 = a1 > 0.f ? a1 : a1 * __ldg(p.alpha + c0 + 2 * j + 1);
+                        float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
+                        float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
+                        a0 = a0 > 0.f ? a0 : a0 * av[2 * j];
+                        a1 = a1 > 0.f ? a1 : a1 * av[2 * j + 1];
                         const __half2 h2 = __floats2half2_rn(a0, a1);
                         pk[j] = *(const uint32_t*)&h2;
                     }
