@@ -139,68 +139,85 @@ def _block_diag(w_a: np.ndarray, w_b: np.ndarray) -> np.ndarray:
     return w
 
 
-def openpose_vgg19(seed: int = 0, n_stages: int = 6) -> Graph:
-    """OpenPose-COCO on VGG-19 (BASELINE.json config 3).  Random-init weights (He-normal, seeded).
+def openpose_vgg19(seed: int = 0, n_stages: int = 6, weights=None) -> Graph:
+    """OpenPose-COCO on VGG-19 (BASELINE.json config 3).  `weights`: a hyperpose_b200.weights source
+    (ListWeights of a trained TensorLayer model, or RandomWeights(seed) -- the default: He-normal, seeded).
 
     Both branches of a stage (conf: L2, paf: L1) are executed together: their first layers share the
     input and are merged into one conv (cout 256); later layers run as a 2-group conv; the two 1x1
     output convs are fused into one block-diagonal conv writing [conf | paf] straight into the next
     stage's concat buffer (openpose.py:74: concat([features, conf, paf])).
     """
-    rng = np.random.default_rng(seed)
+    from .weights import RandomWeights
+    ws = weights if weights is not None else RandomWeights(seed)
     g = Graph("openpose_vgg19", 19, 38, 3, mean=tuple(np.array([103.939, 116.779, 123.68]) / 255.0))  # backbones.py:455
     relu = lambda n: np.zeros(n, np.float32)
-    prelu = lambda n: rng.uniform(0.1, 0.4, n).astype(np.float32)
-    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    def plain(name, co, ci, k):                 # single conv -> ([1,co,ci,k,k], bias)
+        w, b = ws.conv(name, co, ci, k)
+        return w[None], b
+
+    def pair(prefix, i, co_conf, co_paf, ci, k, mode):
+        """layer i of the conf and the paf branch as one conv: 'shared' input (concat along cout), 'grouped'
+        (2 groups), 'blockdiag' (different cout per branch, e.g. the 19 / 38-channel outputs); PReLU slopes concatenated"""
+        gain = 1.0 if mode == "blockdiag" else 2.0
+        wc, bc = ws.conv(f"{prefix}.conf.{i}", co_conf, ci, k, gain)
+        wp, bp = ws.conv(f"{prefix}.paf.{i}", co_paf, ci, k, gain)
+        al = np.concatenate([ws.prelu(f"{prefix}.conf.{i}", co_conf), ws.prelu(f"{prefix}.paf.{i}", co_paf)])
+        if mode == "shared":
+            w = np.concatenate([wc, wp], axis=0)[None]
+        elif mode == "grouped":
+            w = np.stack([wc, wp])
+        else:
+            w = _block_diag(wc[None], wp[None])
+        return w, np.concatenate([bc, bp]), al
 
     # ---- VGG-19 front (backbones.py:461-476) ----
     b_col = g.add_buffer(64, 0)
     g.add_im2col(b_col)
     cur = g.add_buffer(64, 0)
-    g.add_conv(b_col, cur, _he(rng, 1, 64, 3, 3, 3), b_(64), relu(64), im2col_input=1, name="conv1_1")
+    g.add_conv(b_col, cur, *plain("conv1_1", 64, 3, 3), relu(64), im2col_input=1, name="conv1_1")
     nxt = g.add_buffer(64, 0)
-    g.add_conv(cur, nxt, _he(rng, 1, 64, 64, 3, 3), b_(64), relu(64), name="conv1_2")
+    g.add_conv(cur, nxt, *plain("conv1_2", 64, 64, 3), relu(64), name="conv1_2")
     cur = g.add_buffer(64, 1); g.add_maxpool(nxt, cur, 64, "maxpool_1")
     for i, (ci, co) in enumerate([(64, 128), (128, 128)]):
-        nxt = g.add_buffer(co, 1); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv2_{i+1}"); cur = nxt
+        nxt = g.add_buffer(co, 1); g.add_conv(cur, nxt, *plain(f"conv2_{i+1}", co, ci, 3), relu(co), name=f"conv2_{i+1}"); cur = nxt
     nxt = g.add_buffer(128, 2); g.add_maxpool(cur, nxt, 128, "maxpool_2"); cur = nxt
     for i, (ci, co) in enumerate([(128, 256), (256, 256), (256, 256), (256, 256)]):
-        nxt = g.add_buffer(co, 2); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv3_{i+1}"); cur = nxt
+        nxt = g.add_buffer(co, 2); g.add_conv(cur, nxt, *plain(f"conv3_{i+1}", co, ci, 3), relu(co), name=f"conv3_{i+1}"); cur = nxt
     nxt = g.add_buffer(256, 3); g.add_maxpool(cur, nxt, 256, "maxpool_3"); cur = nxt
     for i, (ci, co) in enumerate([(256, 512), (512, 512)]):
-        nxt = g.add_buffer(co, 3); g.add_conv(cur, nxt, _he(rng, 1, co, ci, 3, 3), b_(co), relu(co), name=f"conv4_{i+1}"); cur = nxt
+        nxt = g.add_buffer(co, 3); g.add_conv(cur, nxt, *plain(f"conv4_{i+1}", co, ci, 3), relu(co), name=f"conv4_{i+1}"); cur = nxt
     # ---- CPM (openpose.py:36-39) ----
-    nxt = g.add_buffer(256, 3); g.add_conv(cur, nxt, _he(rng, 1, 256, 512, 3, 3), b_(256), relu(256), name="cpm_1"); cur = nxt
+    nxt = g.add_buffer(256, 3); g.add_conv(cur, nxt, *plain("cpm_1", 256, 512, 3), relu(256), name="cpm_1"); cur = nxt
     cat = g.add_buffer(192, 3)   # [features 128 | conf 19 | paf 38 | 7 zero pad]: the refinement stages' input
-    g.add_conv(cur, cat, _he(rng, 1, 128, 256, 3, 3), b_(128), relu(128), name="cpm_2")
+    g.add_conv(cur, cat, *plain("cpm_2", 128, 256, 3), relu(128), name="cpm_2")
     ta = g.add_buffer(256, 3)
     tb = g.add_buffer(256, 3)
     wide = g.add_buffer(1024, 3)
 
-    def out_conv(in_buf, cin_each, last, name):
-        w = _block_diag(_he(rng, 1, 19, cin_each, 1, 1, 1.0), _he(rng, 1, 38, cin_each, 1, 1, 1.0))
+    def out_conv(in_buf, prefix, i, cin_each, last, name):
+        w, b, al = pair(prefix, i, 19, 38, cin_each, 1, "blockdiag")
         if last:
-            g.add_conv(in_buf, 0, w, b_(57), prelu(57), out_mode=OUT_F32_NCHW_SPLIT, split=19, name=name)
+            g.add_conv(in_buf, 0, w, b, al, out_mode=OUT_F32_NCHW_SPLIT, split=19, name=name)
         else:
-            g.add_conv(in_buf, cat, w, b_(57), prelu(57), out_ch_off=128, name=name)
+            g.add_conv(in_buf, cat, w, b, al, out_ch_off=128, name=name)
 
     # ---- init stage (openpose.py:119-154): 3x(3x3,128) + 1x1x512 + 1x1x{19,38}, PReLU after every conv ----
-    w0 = np.concatenate([_he(rng, 1, 128, 128, 3, 3), _he(rng, 1, 128, 128, 3, 3)], axis=1)
-    g.add_conv(cat, ta, w0, b_(256), prelu(256), name="init_1")
-    g.add_conv(ta, tb, _he(rng, 2, 128, 128, 3, 3), b_(256), prelu(256), name="init_2")
-    g.add_conv(tb, ta, _he(rng, 2, 128, 128, 3, 3), b_(256), prelu(256), name="init_3")
-    g.add_conv(ta, wide, _he(rng, 2, 512, 128, 1, 1), b_(1024), prelu(1024), name="init_4")
-    out_conv(wide, 512, n_stages == 1, "init_out")
+    g.add_conv(cat, ta, *pair("init", 1, 128, 128, 128, 3, "shared"), name="init_1")
+    g.add_conv(ta, tb, *pair("init", 2, 128, 128, 128, 3, "grouped"), name="init_2")
+    g.add_conv(tb, ta, *pair("init", 3, 128, 128, 128, 3, "grouped"), name="init_3")
+    g.add_conv(ta, wide, *pair("init", 4, 512, 512, 128, 1, "grouped"), name="init_4")
+    out_conv(wide, "init", 5, 512, n_stages == 1, "init_out")
     # ---- refinement stages (openpose.py:156-199): 5x(7x7,128) + 1x1x128 + 1x1x{19,38} ----
     for s in range(1, n_stages):
-        w0 = np.concatenate([_he(rng, 1, 128, 185, 7, 7), _he(rng, 1, 128, 185, 7, 7)], axis=1)
-        g.add_conv(cat, ta, w0, b_(256), prelu(256), name=f"ref{s}_1")
+        g.add_conv(cat, ta, *pair(f"ref{s}", 1, 128, 128, 185, 7, "shared"), name=f"ref{s}_1")
         src, dst = ta, tb
         for k in range(2, 6):
-            g.add_conv(src, dst, _he(rng, 2, 128, 128, 7, 7), b_(256), prelu(256), name=f"ref{s}_{k}")
+            g.add_conv(src, dst, *pair(f"ref{s}", k, 128, 128, 128, 7, "grouped"), name=f"ref{s}_{k}")
             src, dst = dst, src
-        g.add_conv(src, dst, _he(rng, 2, 128, 128, 1, 1), b_(256), prelu(256), name=f"ref{s}_6")
-        out_conv(dst, 128, s == n_stages - 1, f"ref{s}_out")
+        g.add_conv(src, dst, *pair(f"ref{s}", 6, 128, 128, 128, 1, "grouped"), name=f"ref{s}_6")
+        out_conv(dst, f"ref{s}", 7, 128, s == n_stages - 1, f"ref{s}_out")
     return g
 
 
