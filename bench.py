@@ -451,13 +451,13 @@ def run_ours(args):
             rate, kind = cpu_parse_rate(conf_np, paf_np, 12.0, threads)
             conv_one, conv_threads = cpu_conv_port(WL["graph"])
             conv_one()                                   # warm-up (allocations, oneDNN primitive caches)
-            tc0 = time.time(); n_conv = 0
-            while n_conv < 2 or (time.time() - tc0 < 6.0 and n_conv < 16):
-                conv_one(); n_conv += 1
-            conv_s = (time.time() - tc0) / n_conv
+            tc0 = time.time(); n_cpu_frames = 0
+            while n_cpu_frames < 2 or (time.time() - tc0 < 6.0 and n_cpu_frames < 16):
+                conv_one(); n_cpu_frames += 1
+            conv_s = (time.time() - tc0) / n_cpu_frames
             whole = 1.0 / (conv_s + 1.0 / rate)
             cpu = {"value": whole, "unit": "frames/s", "cores": max(threads, conv_threads), "kind": "port",
-                   "sample": f"conv stage: {n_conv} frames {IN_H}x{IN_W} through a PyTorch fp32 port of the same graph on {conv_threads} threads ({conv_s * 1e3:.0f} ms/frame; the reference's "
+                   "sample": f"conv stage: {n_cpu_frames} frames {IN_H}x{IN_W} through a PyTorch fp32 port of the same graph on {conv_threads} threads ({conv_s * 1e3:.0f} ms/frame; the reference's "
                              f"convs are TensorRT-on-GPU, no CPU implementation exists) + parse stage: 12 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's {BATCH} synthetic "
                              f"{HF}x{WF} crowd frames, {threads} threads of {cores} host cores",
                    "parse_only": {"value": rate, "unit": "frames/s", "cores": threads, "kind": kind}}
