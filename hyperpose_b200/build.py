@@ -22,6 +22,7 @@ SOURCES = [
     ("pifpaf_decoder.cu", EXACT_FLAGS),
     ("ppn_parser.cu", EXACT_FLAGS),
     ("common.cpp", []),
+    ("handoff.cpp", []),
 ]
 
 

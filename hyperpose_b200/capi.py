@@ -157,6 +157,25 @@ class PafParser:
         check(lib().hp_paf_copy_results_device(self._h, d_humans_ptr, d_counts_ptr, N, cap, stream))
 
 
+def handoff_stats() -> dict:
+    """counters of the device-resident engine -> parser hand-off (csrc/handoff.h)"""
+    L = lib()
+    if not getattr(L, "_engine_bound", False):
+        _bind_engine(L)
+        L._engine_bound = True
+    v = [C.c_longlong() for _ in range(4)]
+    check(L.hp_handoff_stats(*[C.byref(x) for x in v]))
+    return dict(zip(("published", "hits", "batch_parses", "misses"), [x.value for x in v]))
+
+
+def handoff_enable(on: bool):
+    L = lib()
+    if not getattr(L, "_engine_bound", False):
+        _bind_engine(L)
+        L._engine_bound = True
+    check(L.hp_handoff_enable(1 if on else 0))
+
+
 # ---------------------------------------------------------------------------------------------
 # DNN engine
 # ---------------------------------------------------------------------------------------------
@@ -165,6 +184,7 @@ EXPORTS += [
     "hp_engine_infer_f32_host", "hp_engine_outputs", "hp_engine_read_outputs_host", "hp_engine_copy_outputs_device", "hp_engine_sync",
     "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
     "hp_pose_run_u8_host", "hp_engine_stage_frame_u8", "hp_engine_infer_staged", "hp_engine_debug_read_frames", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
+    "hp_engine_read_outputs_frames", "hp_engine_head_type", "hp_handoff_enable", "hp_handoff_stats",
 ]
 
 
@@ -193,6 +213,10 @@ def _bind_engine(L):
     L.hp_engine_set_output_override.argtypes = [vp, vp, vp]
     L.hp_engine_set_profiling.argtypes = [vp, C.c_int]
     L.hp_engine_get_profile.argtypes = [vp, vp, vp, vp, C.c_int, ip, C.POINTER(C.c_longlong)]
+    L.hp_engine_read_outputs_frames.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int]
+    L.hp_engine_head_type.argtypes = [vp]
+    L.hp_handoff_enable.argtypes = [C.c_int]
+    L.hp_handoff_stats.argtypes = [C.POINTER(C.c_longlong)] * 4
 
 
 class Engine:
@@ -275,6 +299,24 @@ class Engine:
         paf = np.empty((n, self.c_paf, self.out_h, self.out_w), np.float32)
         check(lib().hp_engine_read_outputs_host(self._h, conf.ctypes.data, paf.ctypes.data, n))
         return conf, paf
+
+    def read_outputs_frames(self, n: int, publish: bool = True):
+        """tensorrt::inference's return value: per image its own host buffers [conf_i, paf_i] (the feature_map_t storage,
+        src/tensorrt.cpp:398-431).  publish=True registers them for the device-resident hand-off (handoff.h)."""
+        if self.head_type == 1:
+            sa, sb = (17, 5, self.out_h, self.out_w), (19, 9, self.out_h, self.out_w)
+        else:
+            sa, sb = (self.c_conf, self.out_h, self.out_w), (self.c_paf, self.out_h, self.out_w)
+        a = [np.empty(sa, np.float32) for _ in range(n)]
+        b = [np.empty(sb, np.float32) for _ in range(n)]
+        pa = (C.c_void_p * n)(*[x.ctypes.data for x in a])
+        pb = (C.c_void_p * n)(*[x.ctypes.data for x in b])
+        check(lib().hp_engine_read_outputs_frames(self._h, pa, pb, n, 1 if publish else 0))
+        return [[a[i], b[i]] for i in range(n)]
+
+    @property
+    def head_type(self) -> int:
+        return int(lib().hp_engine_head_type(self._h))
 
     def device_outputs(self):
         a, b, s = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -18,12 +18,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/hyperpose_b200.h"
 #include "common.h"
 #include "conv_tcgen05.cuh"
+#include "handoff.h"
 #include "pack_format.h"
 
 namespace {
@@ -539,6 +541,10 @@ struct hp_engine {
     std::vector<double> op_ms_sum;     // accumulated per op
     long long profiled_runs = 0;
     long long ev_head = 0, ev_tail = 0; // event sets recorded / folded in
+    // host read-back of the outputs (tensorrt::inference's per-image D2H) + the published device snapshots (handoff.h)
+    float* pin_out = nullptr; size_t pin_out_floats = 0;
+    std::shared_ptr<hpb::handoff::Batch> ho_ring[hpb::handoff::HANDOFF_RING];
+    int ho_pos = 0;
 };
 
 namespace {
@@ -831,6 +837,8 @@ void free_engine(hp_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    hpb::handoff::retire_ring(e->ho_ring);
+    if (e->pin_out) cudaFreeHost(e->pin_out);
     for (auto& b : e->bufs) if (b.d) cudaFree(b.d);
     for (auto& o : e->ops) {
         if (o.plan.d_w) cudaFree(o.plan.d_w);
@@ -1001,6 +1009,9 @@ int hp_engine_info(const hp_engine* e, int* in_w, int* in_h, int* max_batch, int
     return HP_OK;
 }
 
+// 0: conf[c_conf,h,w] / paf[c_paf,h,w] for hyperpose::parser::paf; 1: OpenPifPaf fields pif[17,5,h,w] / paf[19,9,h,w]
+int hp_engine_head_type(const hp_engine* e) { return e ? (int)e->hdr.head_type : HP_ERR_ARG; }
+
 // frames: HOST u8 [N, in_h, in_w, 3] (already network-sized, BGR like cv::Mat).  Asynchronous on the engine stream.
 int hp_engine_infer_u8_host(hp_engine* e, const uint8_t* frames, int N)
 {
@@ -1162,6 +1173,40 @@ int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N)
     if (conf) HP_CUDA_TRY(cudaMemcpyAsync(conf, e->d_conf, N * e->hdr.conf_channels * plane * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     if (paf) HP_CUDA_TRY(cudaMemcpyAsync(paf, e->d_paf, N * e->hdr.paf_channels * plane * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return HP_OK;
+}
+
+// tensorrt::inference's read-back loop (src/tensorrt.cpp:398-431): frame i of the last batch lands in the caller's
+// conf_frames[i] / paf_frames[i] (the storage of the per-image feature_map_t objects).  With publish != 0 a device
+// snapshot of the batch is kept and the host addresses are registered, so that hp_paf_process_host /
+// hp_pifpaf_process_host called later with exactly these buffers parse from the device copy, the whole batch at once
+// (handoff.h).  Results are identical with or without the publication.
+int hp_engine_read_outputs_frames(hp_engine* e, float* const* conf_frames, float* const* paf_frames, int N, int publish)
+{
+    if (!e || !conf_frames || !paf_frames || N <= 0 || N > e->max_batch) { set_error("hp_engine_read_outputs_frames: bad argument"); return HP_ERR_ARG; }
+    for (int i = 0; i < N; ++i)
+        if (!conf_frames[i] || !paf_frames[i]) { set_error("hp_engine_read_outputs_frames: null frame buffer %d", i); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const size_t plane = (size_t)e->out_h * e->out_w;
+    const size_t ea = e->hdr.conf_channels * plane, eb = e->hdr.paf_channels * plane;
+    const size_t need = (size_t)e->max_batch * (ea + eb);
+    if (e->pin_out_floats < need) {
+        if (e->pin_out) cudaFreeHost(e->pin_out);
+        e->pin_out = nullptr; e->pin_out_floats = 0;
+        HP_CUDA_TRY(cudaMallocHost(&e->pin_out, need * sizeof(float)));
+        e->pin_out_floats = need;
+    }
+    float* ha = e->pin_out;
+    float* hb = e->pin_out + (size_t)N * ea;
+    HP_CUDA_TRY(cudaMemcpyAsync(ha, e->d_conf, (size_t)N * ea * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    HP_CUDA_TRY(cudaMemcpyAsync(hb, e->d_paf, (size_t)N * eb * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < N; ++i) {
+        memcpy(conf_frames[i], ha + (size_t)i * ea, ea * sizeof(float));
+        memcpy(paf_frames[i], hb + (size_t)i * eb, eb * sizeof(float));
+    }
+    if (publish && hpb::handoff::enabled())
+        return hpb::handoff::publish(e->ho_ring, &e->ho_pos, e->device, e->stream, e->d_conf, e->d_paf, N, ea, eb, conf_frames, paf_frames, ha, hb);
     return HP_OK;
 }
 

@@ -4,12 +4,15 @@
 // compiled against the UNCHANGED include/hyperpose/operator/dnn/tensorrt.hpp.  All three constructors
 // accept the path of an HPB2PACK model pack (hyperpose_b200/models.py) in place of the .uff/.onnx/.trt file;
 // a file that is not a pack is a fatal error, like an unparsable model in the reference (tensorrt.cpp:141-158).
-// inference() returns, per image, the outputs ordered by name (conf < paf, tensorrt.cpp:405) as host
-// feature_map_t objects with shape [C,H,W], exactly as the reference does.
+// inference() returns, per image, the outputs ordered by name (conf < paf, tensorrt.cpp:405; paf < pif for OpenPifPaf
+// packs) as host feature_map_t objects with shape [C,H,W] ([19,9,h,w] / [17,5,h,w]), exactly as the reference does;
+// the same buffers are published for the device-resident hand-off to the parsers (csrc/handoff.h).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <stdexcept>
 
 #include <hyperpose/operator/dnn/tensorrt.hpp>
@@ -80,18 +83,33 @@ namespace dnn {
     void tensorrt::_batching(std::vector<cv::Mat>&, std::vector<float>&) {} // batching happens on the GPU (im2col3_kernel)
 
     namespace {
+        // tensorrt::inference's read-back (tensorrt.cpp:398-431): one host feature_map_t per image and output, ordered by
+        // tensor name (:405).  PAF networks: "conf" [C,h,w] < "paf" [2L,h,w]; OpenPifPaf networks: "paf" [19,9,h,w] < "pif"
+        // [17,5,h,w] -- the order pifpaf::process(packet[0], packet[1]) relies on (src/pifpaf.cpp:6-7).
+        // The buffers are filled by ONE call that also publishes them for the device-resident hand-off (handoff.h): the
+        // parser.process() calls that follow find the batch on the device and parse it once.
         std::vector<internal_t> collect(hp_engine* e, size_t batch, int cc, int cp, int oh, int ow)
         {
             const size_t plane = (size_t)oh * ow;
-            std::vector<float> conf(batch * cc * plane), paf(batch * cp * plane);
-            if (hp_engine_read_outputs_host(e, conf.data(), paf.data(), (int)batch) != HP_OK) die("hp_engine_read_outputs_host");
+            const bool pifpaf = hp_engine_head_type(e) == 1;
+            std::vector<std::unique_ptr<char[]>> a(batch), b(batch);
+            std::vector<float*> pa(batch), pb(batch);
+            for (size_t j = 0; j < batch; ++j) {
+                a[j].reset(new char[cc * plane * sizeof(float)]);
+                b[j].reset(new char[cp * plane * sizeof(float)]);
+                pa[j] = reinterpret_cast<float*>(a[j].get());
+                pb[j] = reinterpret_cast<float*>(b[j].get());
+            }
+            if (hp_engine_read_outputs_frames(e, pa.data(), pb.data(), (int)batch, 1) != HP_OK) die("hp_engine_read_outputs_frames");
             std::vector<internal_t> ret(batch);
             for (size_t j = 0; j < batch; ++j) {
-                std::unique_ptr<char[]> a(new char[cc * plane * sizeof(float)]), b(new char[cp * plane * sizeof(float)]);
-                std::memcpy(a.get(), conf.data() + j * cc * plane, cc * plane * sizeof(float));
-                std::memcpy(b.get(), paf.data() + j * cp * plane, cp * plane * sizeof(float));
-                ret[j].emplace_back("conf", std::move(a), std::vector<int>{ cc, oh, ow });
-                ret[j].emplace_back("paf", std::move(b), std::vector<int>{ cp, oh, ow });
+                if (pifpaf) { // engine tensor a = pif fields, b = paf fields
+                    ret[j].emplace_back("paf", std::move(b[j]), std::vector<int>{ 19, 9, oh, ow });
+                    ret[j].emplace_back("pif", std::move(a[j]), std::vector<int>{ 17, 5, oh, ow });
+                } else {
+                    ret[j].emplace_back("conf", std::move(a[j]), std::vector<int>{ cc, oh, ow });
+                    ret[j].emplace_back("paf", std::move(b[j]), std::vector<int>{ cp, oh, ow });
+                }
             }
             return ret;
         }

@@ -29,11 +29,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/hyperpose_b200.h"
 #include "common.h"
+#include "handoff.h"
 
 namespace {
 
@@ -871,6 +873,57 @@ int fetch_results(hp_paf* p, hp_human* out, int cap, int* n_out, int N)
     return HP_OK;
 }
 
+// Published-batch path of hp_paf_process_host (handoff.h): `conf` / `paf` are host buffers the engine filled AND published.
+// The first call on a batch parses all of its frames from the device snapshot with this handle's parameters; the
+// other frames (any handle with the same parameters, any thread) are served from the cached records.
+constexpr int HANDOFF_MISS = 1;
+int process_from_handoff(hp_paf* p, const float* conf, const float* paf, int c_conf, int c_paf, int H, int W, hp_human* out, int cap, int* n_out)
+{
+    namespace ho = hpb::handoff;
+    if (H <= 0 || W <= 0 || c_conf <= 0 || c_paf <= 0) return HANDOFF_MISS;
+    const size_t ea = (size_t)c_conf * H * W, eb = (size_t)c_paf * H * W;
+    ho::Hit hit = ho::lookup(conf, paf, ea, eb);
+    if (!hit.batch) return HANDOFF_MISS;
+    ho::Batch& b = *hit.batch;
+    std::lock_guard<std::mutex> lk(b.mu);
+    const int f = hit.frame;
+    if (!b.valid || b.fail_count >= 2 || b.device != p->device || f >= b.N || b.host_a[f] != conf || b.host_b[f] != paf ||
+        b.elems_a != ea || b.elems_b != eb || !ho::fingerprint_matches(b, f)) {
+        ho::count_miss();
+        return HANDOFF_MISS;
+    }
+    if (ensure_geometry(p, b.N, c_conf, c_paf, H, W) != HP_OK) return HANDOFF_MISS; // the host path reports the error
+    const bool cached = b.cache_kind == 1 && b.key_f[0] == p->conf_thresh && b.key_f[1] == p->paf_thresh && b.key_i[0] == p->res_w && b.key_i[1] == p->res_h;
+    if (!cached) {
+        b.cache_kind = 0;
+        HP_CUDA_TRY(cudaStreamWaitEvent(p->stream, b.ready, 0));
+        int rc = launch_pipeline(p, b.d_a, b.d_b, b.N, p->stream);
+        if (rc) return rc;
+        b.humans.resize((size_t)b.N * p->hcap);
+        b.counts.resize(b.N);
+        rc = fetch_results(p, b.humans.data(), p->hcap, b.counts.data(), b.N);
+        if (rc == HP_ERR_CAPACITY) { // the host path grows this handle's capacities; a later frame may try again
+            b.fail_count++;
+            ho::count_miss();
+            return HANDOFF_MISS;
+        }
+        if (rc) return rc;
+        b.cache_kind = 1;
+        b.key_f[0] = p->conf_thresh; b.key_f[1] = p->paf_thresh; b.key_i[0] = p->res_w; b.key_i[1] = p->res_h;
+        b.hcap = p->hcap;
+        ho::count_batch_parse();
+    }
+    const int n = b.counts[f];
+    if (n > cap) {
+        hpb::set_error("hp_paf: frame has %d humans but the caller's capacity is %d", n, cap);
+        return HP_ERR_CAPACITY;
+    }
+    memcpy(out, b.humans.data() + (size_t)f * b.hcap, sizeof(hp_human) * n);
+    *n_out = n;
+    ho::count_hit();
+    return HP_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -996,6 +1049,10 @@ int hp_paf_process_host_batched(hp_paf* p, const float* conf, const float* paf, 
 int hp_paf_process_host(hp_paf* p, const float* conf, const float* paf, int c_conf, int c_paf, int H, int W,
                         hp_human* out, int cap, int* n_out)
 {
+    if (p && conf && paf && out && n_out && cudaSetDevice(p->device) == cudaSuccess) {
+        const int rc = process_from_handoff(p, conf, paf, c_conf, c_paf, H, W, out, cap, n_out);
+        if (rc != HANDOFF_MISS) return rc;
+    }
     return hp_paf_process_host_batched(p, conf, paf, 1, c_conf, c_paf, H, W, out, cap, n_out);
 }
 

@@ -180,6 +180,22 @@ int hp_engine_infer_f32_host(hp_engine* e, const float* nchw, int N);
 int hp_engine_outputs(hp_engine* e, const float** d_conf, const float** d_paf, void** stream);
 /* the reference's per-image D2H of every output (tensorrt.cpp:398-431), as two contiguous host tensors */
 int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N);
+/* The same read-back into N SEPARATE per-image buffers -- the storage of the feature_map_t objects
+ * tensorrt::inference returns (tensorrt.cpp:398-431): conf_frames[i] receives [c_conf,h,w], paf_frames[i] [c_paf,h,w]
+ * (OpenPifPaf packs: pif [17,5,h,w] / paf [19,9,h,w]).  publish != 0 additionally keeps a device snapshot of the
+ * batch and registers the host addresses: hp_paf_process_host / hp_pifpaf_process_host called later with exactly
+ * these buffers (what parser.process(packet[0], packet[1]) does per image, operator_api_batched_images_paf.example.cpp:
+ * 70-74, and what the stream's parse tasks do, stream.hpp:347-373) parse the whole batch ONCE from the device copy and
+ * serve the remaining images from the cached records -- no second trip of the tensors over PCIe, one launch sequence
+ * per batch.  Any mismatch (other address, other shape, changed contents, publication older than 4 batches) takes
+ * the ordinary host path; the results are identical. */
+int hp_engine_read_outputs_frames(hp_engine* e, float* const* conf_frames, float* const* paf_frames, int N, int publish);
+/* 0: conf/paf maps for hyperpose::parser::paf; 1: OpenPifPaf fields (pif, paf) for hyperpose::parser::pifpaf */
+int hp_engine_head_type(const hp_engine* e);
+/* the publication mechanism above: global switch (default on; env HPB_NO_HANDOFF disables) and counters
+ * (batches published, process() calls served from a device snapshot, batched parses run, look-ups that fell back) */
+int hp_handoff_enable(int on);
+int hp_handoff_stats(long long* published, long long* hits, long long* batch_parses, long long* misses);
 /* asynchronous D2D snapshot of the outputs into caller-owned device tensors (software-pipelined callers) */
 int hp_engine_copy_outputs_device(hp_engine* e, float* d_conf, float* d_paf, int N, void* stream);
 int hp_engine_sync(hp_engine* e);

@@ -38,3 +38,26 @@ def test_cpp_example_runs_operator_api_sequence(tmp_path):
     assert saved.read_bytes() == pack.read_bytes()      # tensorrt::save re-emits the pack
     assert "conf:[19, 32, 48, ]" in r.stdout and "paf:[38, 32, 48, ]" in r.stdout
     assert "3 images got processed" in r.stdout
+    # several batches: the parser calls of a batch are served from the device snapshot the engine published
+    # (csrc/handoff.h); with the hand-off disabled the same program prints the same human counts
+    a = subprocess.run([exe, str(pack), "96", "64", "3", "-", "3"], capture_output=True, text=True, timeout=120)
+    b = subprocess.run([exe, str(pack), "96", "64", "3", "-", "3"], capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, HPB_NO_HANDOFF="1"))
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    counts = lambda out: [ln.split("humans = ")[1] for ln in out.splitlines() if "humans = " in ln]
+    assert len(counts(a.stdout)) == 3 and counts(a.stdout) == counts(b.stdout)
+
+
+@pytest.mark.gpu
+def test_cpp_example_pifpaf_sequence(tmp_path):
+    """examples/operator_api_batched_images_pifpaf.example.cpp:48-64: packets come back ordered by name (paf < pif) with
+    rank-4 shapes, which is what pifpaf::process(packet[0], packet[1]) expects (src/pifpaf.cpp:6-7)"""
+    exe = hb.build_cpp_example()
+    if exe is None:
+        pytest.skip("example binary not built (needs the reference headers at build time)")
+    pack = tmp_path / "pifpaf.pack"
+    pack.write_bytes(models.resnet50_pifpaf(0).to_pack())
+    r = subprocess.run([exe, str(pack), "129", "129", "2", "-", "2", "pifpaf"], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "paf:[19, 9, 17, 17, ] pif:[17, 5, 17, 17, ]" in r.stdout
+    assert r.stdout.count("2 images got processed") == 2
