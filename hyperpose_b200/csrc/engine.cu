@@ -479,6 +479,7 @@ struct ConvPlan {
     // fused stem (u8 frames -> first conv, no im2col buffer)
     bool stem = false;
     int stem_R = 3;
+    bool stem3_v2 = false;      // 3x3 stem: conv_stem3_kernel (table-driven gather, two CTAs per SM)
     StemParams sp;
     size_t stem_smem = 0;
     int built_for_N = 0;
@@ -666,10 +667,10 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
     }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
-    // Fused stem: a clear win for the 7x7 stems (ResNet: 0.66 ms instead of 0.64 + 0.2 ms for im2col + conv at cfg4); for the 3x3
-    // stems the 128 gather threads per CTA are latency-bound (0.56 ms vs 0.43 ms measured at cfg3), so those keep the im2col
-    // buffer unless HPB_STEM3 is set.
-    if (im2col && p.tma_store && cout_pad == BN && BN <= 128 && !po.res_mode && (R == 7 || (R == 3 && getenv("HPB_STEM3"))) && R == S && !getenv("HPB_NO_STEM")) {
+    // Fused stem: the first conv reads the u8 frames itself, the im2col buffer is never written (7x7 ResNet stems: conv_stem_kernel<7>,
+    // 0.66 ms instead of 0.64 + 0.2 ms at cfg4; 3x3 VGG / MobileNet stems: conv_stem3_kernel).  HPB_NO_STEM3 keeps the im2col buffer
+    // for 3x3 stems, HPB_STEM3_V1 selects the first 3x3 version (conv_stem_kernel<3>: 0.56 ms vs 0.43 ms for im2col + conv at cfg3).
+    if (im2col && p.tma_store && cout_pad == BN && BN <= 128 && !po.res_mode && (R == 7 || (R == 3 && !getenv("HPB_NO_STEM3"))) && R == S && !getenv("HPB_NO_STEM")) {
         // locate the patch-gather op feeding this conv: its stride / tap size define the stem geometry
         for (auto& o2 : e->ops) {
             if (o2.po.type != OP_IM2COL3 || o2.po.out_buf != po.in_buf) continue;
@@ -681,7 +682,9 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
             sp.stride = stride; sp.pad_h = same_pad_before(e->in_h, R, stride); sp.pad_w = same_pad_before(e->in_w, R, stride);
             sp.factor = e->factor; sp.flip = e->flip_rgb; sp.m0 = e->hdr.mean[0]; sp.m1 = e->hdr.mean[1]; sp.m2 = e->hdr.mean[2];
             sp.BN = BN; sp.cout = cout_g; sp.bias = pl.d_bias; sp.alpha = pl.d_alpha; sp.out_ch_off = (int)po.out_ch_off;
-            pl.stem = true; pl.stem_R = R; pl.stem_smem = conv_stem_smem_bytes(R, BN);
+            pl.stem = true; pl.stem_R = R;
+            pl.stem3_v2 = (R == 3 && !getenv("HPB_STEM3_V1"));
+            pl.stem_smem = pl.stem3_v2 ? conv_stem3_smem_bytes(BN) : conv_stem_smem_bytes(R, BN);
             o2.fused_into_stem = true;
             break;
         }
@@ -698,7 +701,10 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         const int tiles = (int)(((size_t)N * sp.OH * sp.OW + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
         const int per_sm = pl.stem_smem <= 110 * 1024 ? 2 : 1; // two resident CTAs hide the gather latency of the 3x3 stem
         const int grid = std::min(e->num_sms * per_sm, tiles);
-        if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        if (pl.stem3_v2) {
+            if (sp.flip) conv_stem3_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+            else conv_stem3_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        } else if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         else conv_stem_kernel<7><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         e->launches++;
         return HP_OK;
@@ -917,7 +923,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
     if (hdr.head_type == 1) { e->out_h = 2 * e->out_h - 1; e->out_w = 2 * e->out_w - 1; } // pixel-shuffled and cropped
     if (cudaMalloc(&e->d_conf, (size_t)max_batch * hdr.conf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&e->d_paf, (size_t)max_batch * hdr.paf_channels * e->out_h * e->out_w * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&e->d_frames, (size_t)max_batch * in_h * in_w * 3) != cudaSuccess ||
+        cudaMalloc(&e->d_frames, (size_t)max_batch * in_h * in_w * 3 + 16) != cudaSuccess || // + slack: the 3x3 stem reads whole 32-bit words
         cudaMallocHost(&e->pin_frames, (size_t)max_batch * in_h * in_w * 3) != cudaSuccess) {
         set_error("engine: output/frame allocation failed");
         return fail(HP_ERR_CUDA);
@@ -981,8 +987,16 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
         return fail(HP_ERR_CUDA);
     }
-    size_t stem_smem = 0;
-    for (auto& o : e->ops) if (o.plan.stem) stem_smem = std::max(stem_smem, o.plan.stem_smem);
+    size_t stem_smem = 0, stem3_smem = 0;
+    for (auto& o : e->ops) {
+        if (o.plan.stem && o.plan.stem3_v2) stem3_smem = std::max(stem3_smem, o.plan.stem_smem);
+        else if (o.plan.stem) stem_smem = std::max(stem_smem, o.plan.stem_smem);
+    }
+    if (stem3_smem && (cudaFuncSetAttribute(conv_stem3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem3_smem) != cudaSuccess ||
+                       cudaFuncSetAttribute(conv_stem3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem3_smem) != cudaSuccess)) {
+        set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (3x3 stem)", stem3_smem);
+        return fail(HP_ERR_CUDA);
+    }
     if (stem_smem && (cudaFuncSetAttribute(conv_stem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_smem) != cudaSuccess ||
                       cudaFuncSetAttribute(conv_stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (stem)", stem_smem);

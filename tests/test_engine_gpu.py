@@ -42,6 +42,11 @@ def test_tiny_net_every_layer(hw, N):
         got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
         ref = rbufs[bi].cpu().numpy()
         if bi == 0:   # im2col buffer: compare its centre tap (k = 4*3 + c) with the normalised image
+            if not os.environ.get("HPB_NO_STEM3"):
+                # fused 3x3 stem (conv_stem3_kernel): the patches never leave shared memory, this buffer is not written;
+                # buffer 1 (the first conv's output) checks the stem, test_f32_nchw_entry_matches_u8_entry the im2col kernel
+                assert not got.any()
+                continue
             got = got[:, 12:15]
             ref = ref[:, :3]
         # the concat buffer is overwritten by later ops in both executors identically
@@ -264,7 +269,8 @@ def test_full_size_batch_permutation_invariance():
 
 
 def test_fused_3x3_stem_kernel_matches_im2col_path():
-    """conv_stem_kernel<3> (off by default: measured slower than im2col + conv for 3x3 stems) stays correct"""
+    """3x3 stems: conv_stem3_kernel (default; table-driven gather straight from the u8 frames) == the im2col-buffer path
+    (HPB_NO_STEM3) == the first fused version (HPB_STEM3_V1), on an odd-sized input (partial tiles, all four borders)"""
     import subprocess, sys, textwrap
     code = textwrap.dedent('''
         import numpy as np, sys
@@ -278,9 +284,11 @@ def test_fused_3x3_stem_kernel_matches_im2col_path():
     ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     import tempfile
     outs = []
-    for env in ({}, {"HPB_STEM3": "1"}):
+    for env in ({}, {"HPB_NO_STEM3": "1"}, {"HPB_STEM3_V1": "1"}):
         with tempfile.NamedTemporaryFile(suffix=".npy") as f:
             r = subprocess.run([sys.executable, "-c", code, f.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr
             outs.append(np.load(f.name))
-    assert np.allclose(outs[0], outs[1], rtol=0, atol=2e-3 * np.abs(outs[0]).max())
+    # the three paths feed the same fp16 patch values to the same MMA shape: results agree to fp32 summation order
+    assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-4 * np.abs(outs[0]).max())
+    assert np.allclose(outs[0], outs[2], rtol=0, atol=1e-4 * np.abs(outs[0]).max())
