@@ -32,6 +32,7 @@ constexpr int CONV_UMMA_K = 16;     // K of one tcgen05.mma.kind::f16
 constexpr int CONV_MAX_STAGES = 8;
 constexpr int CONV_THREADS = 256;
 constexpr int CONV_A_BYTES = CONV_BLOCK_M * CONV_BLOCK_K * 2; // 16 KiB
+constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
 
 enum ConvOutMode : int {
     OUT_F16_NHWC = 0,       // fp16, out[pixel * ld + ch_off + g * cout_g + n]
@@ -714,6 +715,288 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
+// Halo-box variant for RxS convolutions on large images (the early VGG layers).
+// The im2col-mode kernels above fetch the A operand once PER FILTER TAP: a 3x3 layer pulls every input pixel nine times
+// from L2 into shared memory, and ncu shows those layers pinned at the L2 output limit (lts2xbar ~11 TB/s, xbar->SM
+// 62 B/clk/SM) with the MMA issuer waiting on the full barrier half of the time (profiles/r01_ncu_conv1_2_*).
+// Here a work item is a SPATIAL tile of 16 rows x 8 columns of output pixels (= the 128 UMMA rows).  Per 64-channel
+// chunk ONE tiled-mode TMA load brings the (16+R-1) x (8+S-1) pixel halo box (out-of-image pixels zero-filled by the
+// TMA unit = "SAME" padding) into a 128B-swizzled buffer, and every filter tap (r, s) multiplies straight out of that
+// buffer: its A descriptor is the box address + (r * box_width + s) * 128 B, with a stride-byte-offset of one box row
+// (box_width * 128 B) between the 8-pixel row groups -- the 128B swizzle is a function of the absolute shared-memory
+// address, so a start address that is not 1024-byte aligned reads back exactly what the TMA wrote (verified on
+// hardware: tools/probe_halo.cu, bit-exact for interior, corner and edge tiles).  A traffic drops from R*S x 16 KiB
+// to one 22.5 KiB box per chunk (3x3: 6.4x less); the weights stream through their own ring, one BN x 64 tile per
+// (tap, chunk).  Everything else -- TMEM double buffering, warp roles, bias + PReLU epilogue through swizzled staging
+// tiles -- is as in conv_tcgen05_kernel; the output goes out as a 4-D TMA box {64 ch, 8, 16, 1} that the TMA unit
+// clips at the image border.  Used when the tile grid wastes little of the image (engine.cu: halo_eligible).
+// ---------------------------------------------------------------------------------------------
+constexpr int HALO_TH = 16, HALO_TW = 8;
+constexpr int HALO_MAX_BOXES = 3;
+
+struct HaloParams {
+    int Nb, H, W;
+    int R, S, groups, cin_g;
+    int cout_g, cout_g_pad, BN;
+    int in_ch_off, out_ch_off;
+    int tiles_x, tiles_y;
+    int num_boxes, box_bytes;   // box_bytes: (16+R-1) * (8+S-1) * 128 rounded up to a multiple of 1024
+    int num_b_stages;           // weight ring depth; in resident mode: R * S * chunks tiles, loaded once
+    int b_resident;             // 1: the layer's whole weight matrix (one group, one n-tile) stays in shared memory
+    int tmem_cols;
+    const float* bias; const float* alpha;
+};
+
+template <int KR> // KR > 0: R == S == KR, tap loops unrolled (descriptor offsets become immediates); 0: run-time R, S
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_o, const HaloParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.BN * CONV_BLOCK_K * 2;
+    uint8_t* s_box = smem;                                              // [num_boxes][box_bytes]
+    uint8_t* s_b = s_box + (size_t)p.num_boxes * p.box_bytes;           // [num_b_stages][BN x 128 B]
+    uint8_t* out_stage = s_b + (size_t)p.num_b_stages * b_bytes;        // 2 x 16 KiB (1024-aligned: all sizes are multiples of 1024)
+    uint64_t* a_full = (uint64_t*)(out_stage + 2 * CONV_A_BYTES);       // [HALO_MAX_BOXES]
+    uint64_t* a_empty = a_full + HALO_MAX_BOXES;
+    uint64_t* b_full = a_empty + HALO_MAX_BOXES;                        // [CONV_MAX_STAGES]
+    uint64_t* b_empty = b_full + CONV_MAX_STAGES;
+    uint64_t* tfull_bar = b_empty + CONV_MAX_STAGES;                    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                               // [2]
+    uint64_t* w_bar = tempty_bar + 2;                                   // resident weights landed
+    uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_g = p.cout_g_pad / p.BN;
+    const int nt_total = p.groups * n_tiles_g;
+    const int sp_per_img = p.tiles_x * p.tiles_y;
+    const int total_items = p.Nb * sp_per_img * nt_total;
+    const int chunks = p.cin_g / CONV_BLOCK_K;
+    const int taps = p.R * p.S;
+    const int BW = KR > 0 ? HALO_TW + KR - 1 : HALO_TW + p.S - 1;
+    const int pad_h = p.R / 2, pad_w = p.S / 2;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_x);
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_o);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < p.num_boxes; ++i) {
+            ptx::mbar_init(ptx::smem_u32(a_full + i), 1);
+            ptx::mbar_init(ptx::smem_u32(a_empty + i), 1);
+        }
+        if (!p.b_resident)
+            for (int i = 0; i < p.num_b_stages; ++i) {
+                ptx::mbar_init(ptx::smem_u32(b_full + i), 1);
+                ptx::mbar_init(ptx::smem_u32(b_empty + i), 1);
+            }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4);
+        }
+        ptx::mbar_init(ptx::smem_u32(w_bar), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // item -> (spatial tile, n-tile); n-tiles vary fastest so that neighbouring CTAs share a halo box in L2
+    auto decode = [&](int item, int& n, int& y0, int& x0, int& g, int& n0) {
+        const int nt = item % nt_total, sp = item / nt_total;
+        g = nt / n_tiles_g;
+        n0 = (nt - g * n_tiles_g) * p.BN;
+        n = sp / sp_per_img;
+        const int t = sp - n * sp_per_img;
+        const int ty = t / p.tiles_x;
+        y0 = ty * HALO_TH;
+        x0 = (t - ty * p.tiles_x) * HALO_TW;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer: halo boxes (one per item x chunk) and weight tiles (one per tap) =====================
+        if (ptx::elect_one()) {
+            int box = 0; uint32_t box_phase = 0;       // next box slot to fill
+            int st = 0; uint32_t st_phase = 0;
+            // the box of A-step i+1 is requested before the weight tiles of A-step i, so it is in flight a whole chunk early
+            int nx_item = blockIdx.x, nx_chunk = 0;
+            auto issue_box = [&]() {
+                if (nx_item >= total_items) return;
+                int n, y0, x0, g, n0;
+                decode(nx_item, n, y0, x0, g, n0);
+                ptx::mbar_wait(ptx::smem_u32(a_empty + box), box_phase ^ 1);
+                const uint32_t fb = ptx::smem_u32(a_full + box);
+                ptx::mbar_expect_tx(fb, (uint32_t)((HALO_TH + p.R - 1) * BW * 128));
+                ptx::tma_load_4d(ptx::smem_u32(s_box + (size_t)box * p.box_bytes), &tmap_x, fb,
+                                 p.in_ch_off + g * p.cin_g + nx_chunk * CONV_BLOCK_K, x0 - pad_w, y0 - pad_h, n);
+                if (++box == p.num_boxes) { box = 0; box_phase ^= 1; }
+                if (++nx_chunk == chunks) { nx_chunk = 0; nx_item += gridDim.x; }
+            };
+            if (p.b_resident) { // tile (t, c) of the weight matrix at s_b + (t * chunks + c) * b_bytes, all on one barrier
+                ptx::mbar_expect_tx(ptx::smem_u32(w_bar), (uint32_t)(taps * chunks * b_bytes));
+                for (int t = 0; t < taps; ++t)
+                    for (int c = 0; c < chunks; ++c)
+                        ptx::tma_load_2d(ptx::smem_u32(s_b + (size_t)(t * chunks + c) * b_bytes), &tmap_b, ptx::smem_u32(w_bar), t * p.cin_g + c * CONV_BLOCK_K, 0);
+            }
+            issue_box();
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                int n, y0, x0, g, n0;
+                decode(item, n, y0, x0, g, n0);
+                const int b_row = g * p.cout_g_pad + n0;
+                for (int c = 0; c < chunks; ++c) {
+                    issue_box(); // look-ahead: the next A-step's box
+                    if (p.b_resident) continue;
+                    for (int t = 0; t < taps; ++t) {
+                        ptx::mbar_wait(ptx::smem_u32(b_empty + st), st_phase ^ 1);
+                        const uint32_t fb = ptx::smem_u32(b_full + st);
+                        ptx::mbar_expect_tx(fb, (uint32_t)b_bytes);
+                        ptx::tma_load_2d(ptx::smem_u32(s_b + (size_t)st * b_bytes), &tmap_b, fb, t * p.cin_g + c * CONV_BLOCK_K, b_row);
+                        if (++st == p.num_b_stages) { st = 0; st_phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // This one thread's instruction stream bounds the small-N layers (ncu on conv1_2: ~44 scalar instructions per k-step at
+        // ~10 cycles each against 128 cycles of tensor work), so with KR > 0 the tap loops are unrolled: every descriptor is a
+        // hoisted 64-bit base plus an immediate, two UIADD3.64 + one UTCHMMA per MMA.
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN);
+            const uint64_t a_hi = ((uint64_t)((uint32_t)(BW * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const uint64_t db0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(s_b));
+            const uint64_t b_step = (uint64_t)(b_bytes >> 4);               // one weight tile, in descriptor address units
+            const uint64_t tap_step = b_step * (uint64_t)chunks;            // resident layout: tile (t, c) at (t * chunks + c)
+            int box = 0; uint32_t box_phase = 0;
+            int st = 0; uint32_t st_phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            if (p.b_resident) ptx::mbar_wait(ptx::smem_u32(w_bar), 0);
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                for (int c = 0; c < chunks; ++c) {
+                    ptx::mbar_wait(ptx::smem_u32(a_full + box), box_phase);
+                    ptx::tc_fence_after();
+                    const uint32_t box_addr = ptx::smem_u32(s_box + (size_t)box * p.box_bytes);
+                    // A: rows = the 16 x 8 pixels at box offset (r, s2); K-major, 128B swizzle, row groups one box row apart
+                    const uint64_t da0 = (uint64_t)((box_addr & 0x3ffffu) >> 4) | a_hi;
+                    uint64_t db_res = db0 + b_step * (uint64_t)c;
+                    auto tap = [&](int r, int s2, bool first) {
+                        uint64_t db;
+                        if (p.b_resident) { db = db_res; db_res += tap_step; }
+                        else {
+                            ptx::mbar_wait(ptx::smem_u32(b_full + st), st_phase);
+                            ptx::tc_fence_after();
+                            db = db0 + b_step * (uint64_t)st;
+                        }
+                        const uint64_t da = da0 + (uint64_t)((r * BW + s2) * 8);
+#pragma unroll
+                        for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
+                            ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                        if (!p.b_resident) {
+                            ptx::umma_commit(ptx::smem_u32(b_empty + st));
+                            if (++st == p.num_b_stages) { st = 0; st_phase ^= 1; }
+                        }
+                    };
+                    if (KR > 0) {
+#pragma unroll
+                        for (int r = 0; r < (KR > 0 ? KR : 1); ++r)
+#pragma unroll
+                            for (int s2 = 0; s2 < (KR > 0 ? KR : 1); ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
+                    } else {
+                        for (int r = 0; r < p.R; ++r)
+                            for (int s2 = 0; s2 < p.S; ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
+                    }
+                    ptx::umma_commit(ptx::smem_u32(a_empty + box)); // every tap of this chunk has read the box
+                    if (++box == p.num_boxes) { box = 0; box_phase ^= 1; }
+                }
+                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: TMEM lane j = pixel (j >> 3, j & 7) of the tile =====================
+        const int ew = warp - 4, row = ew * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        int acc = 0; uint32_t acc_phase = 0, stage_ctr = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            int n, y0, x0, g, n0;
+            decode(item, n, y0, x0, g, n0);
+            ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
+            const float* bias = p.bias + g * p.cout_g_pad + n0;
+            const float* alpha = p.alpha + g * p.cout_g_pad + n0;
+            for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
+                if (leader) ptx::bulk_wait_group_read<1>();
+                ptx::named_bar_sync(1, 128);
+                const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = sub * 64 + q * 16;
+                    uint32_t v[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                    ptx::tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 bv = __ldg((const float4*)(bias + c0) + j4);
+                        const float4 av = __ldg((const float4*)(alpha + c0) + j4);
+                        float a0 = __uint_as_float(v[4 * j4]) + bv.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bv.y;
+                        float a2 = __uint_as_float(v[4 * j4 + 2]) + bv.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bv.w;
+                        a0 = a0 > 0.f ? a0 : a0 * av.x; a1 = a1 > 0.f ? a1 : a1 * av.y;
+                        a2 = a2 > 0.f ? a2 : a2 * av.z; a3 = a3 > 0.f ? a3 : a3 * av.w;
+                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                        pk[2 * j4] = *(const uint32_t*)&h01;
+                        pk[2 * j4 + 1] = *(const uint32_t*)&h23;
+                    }
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                }
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(1, 128);
+                if (leader) {
+                    // box {64 ch, 8, 16, 1}: staging row y * 8 + x == TMEM lane; pixels outside the image are clipped by the TMA unit
+                    ptx::tma_store_4d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + g * p.cout_g + n0 + sub * 64, x0, y0, n);
+                    ptx::bulk_commit_group();
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (leader) ptx::bulk_wait_group_read<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+inline int halo_box_bytes(int R, int S) { return ((HALO_TH + R - 1) * (HALO_TW + S - 1) * 128 + 1023) & ~1023; }
+inline size_t conv_halo_smem_bytes(int R, int S, int BN, int boxes, int b_stages)
+{
+    return 1024 + (size_t)boxes * halo_box_bytes(R, S) + (size_t)b_stages * BN * 128 + 2 * CONV_A_BYTES + (2 * HALO_MAX_BOXES + 2 * CONV_MAX_STAGES + 5) * 8 + 16;
+}
+inline int conv_halo_pick_b_stages(int R, int S, int BN, int boxes)
+{
+    const size_t fixed = conv_halo_smem_bytes(R, S, BN, boxes, 0);
+    if (fixed >= CONV_SMEM_LIMIT) return 0;
+    const int st = (int)((CONV_SMEM_LIMIT - fixed) / ((size_t)BN * 128));
+    return st > CONV_MAX_STAGES ? CONV_MAX_STAGES : st;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stem variant: the first convolution of a network (RxR x 3 channels, R in {3,7}, stride 1/2) reading the u8 frames
 // DIRECTLY.  The generic path materialises the im2col patches in HBM (128 B/pixel for 3x3: 494 MB written and read again
 // per cfg3 step); here four producer warps (one thread per pixel of the tile) gather the RxRx3 bytes of their pixel,
@@ -1146,7 +1429,6 @@ inline size_t conv_stem_smem_bytes(int R, int BN)
     return 1024 + (size_t)STEM_STAGES * kch * CONV_A_BYTES + (size_t)kch * BN * 128 + 2 * CONV_A_BYTES + (2 * STEM_STAGES + 5) * 8 + 16;
 }
 
-constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
 constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 6) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
 inline size_t conv_smem_bytes(int BN, int stages, bool tma_store, bool res_tma = false)
 {

@@ -453,6 +453,22 @@ int make_tmap_wgt(CUtensorMap* m, const __half* base, int rows, int K, int BN)
     return HP_OK;
 }
 
+// activations [N,H,W,C] fp16 as a 4-D tiled tensor (C, W, H, N), box {64 ch, box_w, box_h, 1}, 128B swizzle: the halo-box loads
+// and the 16 x 8-pixel output stores of conv_halo_kernel (out-of-tensor elements: zero-filled on load, clipped on store)
+int make_tmap_act_box(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int box_w, int box_h)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
+    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+    cuuint64_t strides[3] = { (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2 };
+    cuuint32_t box[4] = { 64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(box) failed: %d (N=%d H=%d W=%d C=%d box %dx%d)", (int)r, N, H, W, C, box_w, box_h); return HP_ERR_CUDA; }
+    return HP_OK;
+}
+
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 int pick_bn(int cout_g)
@@ -480,6 +496,9 @@ struct ConvPlan {
     bool stem = false;
     int stem_R = 3;
     bool stem3_v2 = false;      // 3x3 stem: conv_stem3_kernel (table-driven gather, two CTAs per SM)
+    // halo-box kernel (conv_halo_kernel): one TMA box per 16 x 8-pixel tile and channel chunk serves every filter tap
+    bool halo = false;
+    HaloParams hp;
     StemParams sp;
     size_t stem_smem = 0;
     int built_for_N = 0;
@@ -666,6 +685,44 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     } else {
         pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
     }
+    // Halo-box kernel for RxS layers whose 16 x 8 tile grid wastes little of the image (the early VGG layers): the A operand comes
+    // from L2 once per chunk instead of once per tap.  HPB_HALO=0 disables it, HPB_HALO=all takes every eligible layer.
+    {
+        const char* hv = getenv("HPB_HALO");
+        const int ty = (ib.H + HALO_TH - 1) / HALO_TH, tx = (ib.W + HALO_TW - 1) / HALO_TW;
+        const double waste = (double)ty * HALO_TH * tx * HALO_TW / ((double)ib.H * ib.W) - 1.0;
+        const bool shape_ok = !im2col && eR == eS && (eR == 3 || eR == 5 || eR == 7) && !po.res_mode && p.tma_store && cout_pad % BN == 0;
+        const bool want = hv ? (strcmp(hv, "all") == 0) : (eR == 3 && waste <= 0.06 && !p.swap_ab);
+        if (shape_ok && want && !(hv && strcmp(hv, "0") == 0)) {
+            const EngBuffer& ob = e->bufs[po.out_buf];
+            HaloParams& h = pl.hp;
+            memset(&h, 0, sizeof(h));
+            h.Nb = e->max_batch; h.H = ib.H; h.W = ib.W; h.R = eR; h.S = eS; h.groups = G; h.cin_g = ecin;
+            h.cout_g = cout_g; h.cout_g_pad = cout_pad; h.BN = BN; h.in_ch_off = (int)po.in_ch_off; h.out_ch_off = (int)po.out_ch_off;
+            h.tiles_x = tx; h.tiles_y = ty;
+            h.num_boxes = BN >= 256 ? 2 : 3;
+            h.box_bytes = halo_box_bytes(eR, eS);
+            h.num_b_stages = conv_halo_pick_b_stages(eR, eS, BN, h.num_boxes);
+            // one group, one n-tile, and the whole weight matrix fits next to the boxes: keep it in shared memory (conv1_2: 72 KiB)
+            const int w_tiles = eR * eS * (ecin / 64);
+            if (G == 1 && cout_pad == BN && !getenv("HPB_HALO_NO_RESIDENT")) {
+                for (int nb = 3; nb >= 2; --nb)
+                    if (conv_halo_smem_bytes(eR, eS, BN, nb, w_tiles) <= CONV_SMEM_LIMIT) { h.num_boxes = nb; h.num_b_stages = w_tiles; h.b_resident = 1; break; }
+            }
+            h.tmem_cols = p.tmem_cols; h.bias = pl.d_bias; h.alpha = pl.d_alpha;
+            if (h.num_b_stages >= 3) {
+                rc = make_tmap_act_box(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, HALO_TW + eS - 1, HALO_TH + eR - 1);
+                if (rc) return rc;
+                rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
+                if (rc) return rc;
+                rc = make_tmap_act_box(&pl.tmap_o, ob.d, e->max_batch, ob.H, ob.W, ob.channels, HALO_TW, HALO_TH);
+                if (rc) return rc;
+                pl.halo = true;
+                p.swap_ab = 0;
+                pl.smem = conv_halo_smem_bytes(eR, eS, BN, h.num_boxes, h.num_b_stages);
+            }
+        }
+    }
     pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
     // Fused stem: the first conv reads the u8 frames itself, the im2col buffer is never written (7x7 ResNet stems: conv_stem_kernel<7>,
     // 0.66 ms instead of 0.64 + 0.2 ms at cfg4; 3x3 VGG / MobileNet stems: conv_stem3_kernel).  HPB_NO_STEM3 keeps the im2col buffer
@@ -706,6 +763,16 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
             else conv_stem3_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         } else if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         else conv_stem_kernel<7><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        e->launches++;
+        return HP_OK;
+    }
+    if (pl.halo) {
+        HaloParams h = pl.hp;
+        h.Nb = N;
+        const long items = (long)N * h.tiles_x * h.tiles_y * h.groups * (h.cout_g_pad / h.BN);
+        const int hgrid = (int)std::min<long>(e->num_sms, items);
+        if (h.R == 3 && h.S == 3) conv_halo_kernel<3><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        else conv_halo_kernel<0><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
         e->launches++;
         return HP_OK;
     }
@@ -985,6 +1052,13 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
                          cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
+        return fail(HP_ERR_CUDA);
+    }
+    size_t halo_smem = 0;
+    for (auto& o : e->ops) if (o.plan.halo) halo_smem = std::max(halo_smem, o.plan.smem);
+    if (halo_smem && (cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess ||
+                      cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess)) {
+        set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (halo)", halo_smem);
         return fail(HP_ERR_CUDA);
     }
     size_t stem_smem = 0, stem3_smem = 0;

@@ -662,6 +662,8 @@ template <typename T> struct DevBuf {
         if (e == cudaSuccess) {
             n = count;
             e = cudaMemset(p, 0, count * sizeof(T)); // unused record slots travel to the host with the used ones
+            // that memset runs on the legacy default stream while the parser works on NON-BLOCKING streams: order them here
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
         }
         return e;
     }

@@ -652,7 +652,11 @@ __global__ void __launch_bounds__(32) pifpaf_grow_kernel(const GrowParams p)
 
 template <typename T> struct DBuf {
     T* p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t c) { if (c <= n) return cudaSuccess; if (p) cudaFree(p); p = nullptr; n = 0; cudaError_t e = cudaMalloc(&p, c * sizeof(T)); if (e == cudaSuccess) { n = c; e = cudaMemset(p, 0, c * sizeof(T)); } return e; }
+    cudaError_t ensure(size_t c) { if (c <= n) return cudaSuccess; if (p) cudaFree(p); p = nullptr; n = 0; cudaError_t e = cudaMalloc(&p, c * sizeof(T)); if (e == cudaSuccess) { n = c; e = cudaMemset(p, 0, c * sizeof(T)); }
+        // the memset runs on the legacy default stream, the parser's work on a NON-BLOCKING stream: without this the zero fill can
+        // land after the first copy / kernel that uses the new buffer
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        return e; }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 

@@ -292,3 +292,37 @@ def test_fused_3x3_stem_kernel_matches_im2col_path():
     # the three paths feed the same fp16 patch values to the same MMA shape: results agree to fp32 summation order
     assert np.allclose(outs[0], outs[1], rtol=0, atol=1e-4 * np.abs(outs[0]).max())
     assert np.allclose(outs[0], outs[2], rtol=0, atol=1e-4 * np.abs(outs[0]).max())
+
+
+def test_halo_box_kernel_matches_im2col_kernels():
+    """conv_halo_kernel (one TMA halo box per 16 x 8-pixel tile serves every filter tap through shifted UMMA descriptors)
+    == the per-tap im2col-mode kernels, on ragged sizes (partial tiles on the right / bottom, all four zero-padded borders,
+    grouped and 7x7 layers with HPB_HALO=all)"""
+    import subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        from hyperpose_b200 import capi, models, synthetic as syn
+        outs = []
+        for (h, w, n) in ((50, 70, 3), (64, 80, 2), (16, 24, 1)):
+            e = capi.Engine(models.tiny_test_net(1).to_pack(), (w, h), max_batch_size=n)
+            e.infer_u8(syn.make_frames_u8(3, n, h, w)); c, p = e.read_outputs(n)
+            outs += [c.ravel(), p.ravel()]
+            e.close()
+        e = capi.Engine(models.openpose_vgg19(0).to_pack(), (104, 72), max_batch_size=2)
+        e.infer_u8(syn.make_frames_u8(5, 2, 72, 104)); c, p = e.read_outputs(2)
+        outs += [c.ravel(), p.ravel()]
+        np.save(sys.argv[1], np.concatenate(outs))
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({"HPB_HALO": "0"}, {"HPB_HALO": "all"}, {}):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr
+            outs.append(np.load(f.name))
+    m = np.abs(outs[0]).max()
+    assert m > 0
+    # same fp16 operands, same fp32 accumulator; only the order of the k-steps differs (chunk-major instead of tap-major)
+    # (through ~40 layers with fp16 activations the re-ordered sums differ by a few fp16 roundings: 8e-4 * max measured)
+    assert np.abs(outs[1] - outs[0]).max() <= 2e-3 * m, np.abs(outs[1] - outs[0]).max() / m
+    assert np.abs(outs[2] - outs[0]).max() <= 2e-3 * m
