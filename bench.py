@@ -484,7 +484,7 @@ def run_ours(args):
                     "api": "hp_pose_run_u8_host (pinned host frames in, human_t records out, synchronous per batch)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "kernel": "conv_tcgen05_kernel", "launches_per_step": n_conv,
+                         "traffic": traffic, "kernel": "conv_tcgen05 family (conv_tcgen05_kernel / _swap_kernel / conv_halo_kernel / conv_stem3_kernel)", "launches_per_step": n_conv,
                          "algorithmic_flops_per_step": algo_flops, "kernel_ms_per_step": conv_ms,
                          "kernel_share_of_step": conv_ms / (ms_total / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"},
             "clocks": clocks,
