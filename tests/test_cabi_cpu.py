@@ -54,3 +54,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".hpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+[\"<].*oracle", src, re.M), f
+
+
+def test_conv_traffic_json_is_the_fold_of_the_committed_launch_list():
+    """bench.py's roofline.traffic comes from profiles/conv_traffic.json; that file must be what tools/summarize_launches.py
+    computes from the committed ncu launch list (no hand-edited numbers)"""
+    import json
+    import subprocess
+    import sys
+    csv_path = os.path.join(ROOT, "profiles", "r01_s2_launches_step.csv")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), csv_path, "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    fold = json.loads(r.stdout[r.stdout.index("{"):])
+    committed = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+    assert fold["conv_launches"] == committed["conv_launches"] == 52
+    assert abs(fold["dram_bytes_per_step"] - committed["dram_bytes_per_step"]) < 1.0
+    assert 0.85 < fold["conv_share_of_step_device_time"] < 0.99
