@@ -718,7 +718,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // Halo-box variant for RxS convolutions on large images (the early VGG layers).
 // The im2col-mode kernels above fetch the A operand once PER FILTER TAP: a 3x3 layer pulls every input pixel nine times
 // from L2 into shared memory, and ncu shows those layers pinned at the L2 output limit (lts2xbar ~11 TB/s, xbar->SM
-// 62 B/clk/SM) with the MMA issuer waiting on the full barrier half of the time (profiles/r01_ncu_conv1_2_*).
+// 62 B/clk/SM) with the MMA issuer waiting on the full barrier half of the time (profiles/r01_s2_ncu_conv1_2_im2col.txt).
 // Here a work item is a SPATIAL tile of 16 rows x 8 columns of output pixels (= the 128 UMMA rows).  Per 64-channel
 // chunk ONE tiled-mode TMA load brings the (16+R-1) x (8+S-1) pixel halo box (out-of-image pixels zero-filled by the
 // TMA unit = "SAME" padding) into a 128B-swizzled buffer, and every filter tap (r, s) multiplies straight out of that
