@@ -84,5 +84,30 @@ def build_cpp_example(ref_root: str = "/root/reference") -> str | None:
     return exe
 
 
+def build_stream_example(ref_root: str = "/root/reference", mock: bool = False) -> str | None:
+    """examples/stream_api_b200.cpp: the reference's STREAM API on the drop-in.  The scheduler is the reference's own --
+    include/hyperpose/stream/stream.hpp instantiated as it is, src/stream.cpp + src/thread_pool.cpp + src/logging.cpp compiled from
+    the reference tree unchanged.  mock=True builds the CPU self-check variant (stand-in engine / parser, no GPU, no library)."""
+    exe = os.path.join(ROOT, "examples", "stream_api_b200_mock" if mock else "stream_api_b200")
+    if not os.path.isdir(os.path.join(ref_root, "include", "hyperpose")):
+        return exe if os.path.exists(exe) else None
+    api = os.path.join(CSRC, "hyperpose_api")
+    ref = [os.path.join(ref_root, "src", f) for f in ("stream.cpp", "thread_pool.cpp", "logging.cpp")]
+    srcs = [os.path.join(ROOT, "examples", "stream_api_b200.cpp")] + ref
+    if not mock:
+        srcs += [os.path.join(api, "paf.cpp"), os.path.join(api, "tensorrt.cpp")]
+    if _newer([s for s in srcs if s.startswith(ROOT)] + ([] if mock else [LIB]) + [os.path.join(CSRC, "shim", "opencv2", "opencv.hpp")], exe):
+        cmd = ["g++", "-std=c++17", "-O2", "-pthread", "-DHP_STREAM_MOCK" if mock else "-DHP_B200_STANDALONE", "-I" + os.path.join(CSRC, "shim"),
+               "-I" + os.path.join(ref_root, "include"), "-I" + os.path.join(ref_root, "src"), "-I" + os.path.join(ROOT, "include")] + srcs
+        if not mock:
+            cmd += ["-L" + PKG, "-lhyperpose_b200", "-Wl,-rpath,$ORIGIN/../hyperpose_b200"]
+        cmd += ["-o", exe]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("stream example failed to compile against the reference's stream sources")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -5,6 +5,7 @@
 // include path.  Only construction / geometry / raw-pixel access is provided: no image processing.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <iostream>
 #include <string>
@@ -76,4 +77,48 @@ private:
     int type_ = 0;
     std::shared_ptr<unsigned char> store_;
 };
+
+// ---- what the reference's stream scheduler touches (include/hyperpose/stream/stream.hpp, src/stream.cpp) ----
+// Declarations + the least behaviour that lets the UNCHANGED scheduler sources compile and run on in-memory frames where OpenCV
+// is absent: resize is the identity for network-sized frames (nearest-neighbour otherwise -- a stand-in, NOT cv::resize; the product's
+// own resize path is hp_engine_stage_frame_u8), the capture yields nothing, the writer counts what it is given.
+enum { CAP_PROP_POS_FRAMES = 1, CAP_PROP_FRAME_WIDTH = 3, CAP_PROP_FRAME_HEIGHT = 4, CAP_PROP_FPS = 5, CAP_PROP_FOURCC = 6, CAP_PROP_FRAME_COUNT = 7 };
+enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_AREA = 3, FILLED = -1 };
+
+inline void resize(const Mat& src, Mat& dst, Size size, double = 0, double = 0, int = INTER_LINEAR)
+{
+    if (src.size() == size) { if (&dst != &src) dst = src; return; }
+    Mat out(size, src.type());
+    const size_t es = src.elemSize();
+    for (int y = 0; y < size.height; ++y) {
+        const int sy = (int)((long long)y * src.rows / size.height);
+        for (int x = 0; x < size.width; ++x) {
+            const int sx = (int)((long long)x * src.cols / size.width);
+            std::memcpy(out.data + ((size_t)y * size.width + x) * es, src.data + ((size_t)sy * src.cols + sx) * es, es);
+        }
+    }
+    dst = out;
+}
+
+class VideoCapture {
+public:
+    VideoCapture() = default;
+    explicit VideoCapture(const std::string&) {}
+    bool isOpened() const { return false; }
+    double get(int) const { return 0.0; }
+    VideoCapture& operator>>(Mat& m) { m = Mat(); return *this; }
+};
+
+class VideoWriter {
+public:
+    VideoWriter() = default;
+    VideoWriter(const std::string&, int, double, Size) {}
+    bool isOpened() const { return true; }
+    VideoWriter& operator<<(const Mat& m) { ++frames_written; last_size = m.size(); return *this; }
+    size_t frames_written = 0;
+    Size last_size;
+};
+
+inline bool imwrite(const std::string&, const Mat&) { return true; }
+inline std::ostream& operator<<(std::ostream& o, const Size& s) { return o << '[' << s.width << " x " << s.height << ']'; }
 } // namespace cv
