@@ -84,9 +84,60 @@ class ListWeights:
 
     @classmethod
     def from_npz(cls, path: str, n_stages: int = 6):
-        """TensorLayer `save_npz` file: one object array under the key 'params'"""
+        """Either TensorLayer weight file of the reference:
+          * `save_weights(format="npz")` / `tl.files.save_npz`: one object array under the key 'params', in all_weights order
+            (hyperpose/Model/train.py:582);
+          * `save_weights(format="npz_dict")` / `tl.files.save_npz_dict`: one entry per weight, keyed by the weight's name
+            `<layer name>/<filters|biases|alpha>:0` (train.py:319, eval.py:109) -> `from_name_dict`."""
         z = np.load(path, allow_pickle=True)
-        return cls(list(z["params"]) if "params" in z.files else [z[k] for k in z.files], n_stages)
+        if "params" in z.files:
+            return cls(list(z["params"]), n_stages)
+        return cls.from_name_dict({k: z[k] for k in z.files}, n_stages)
+
+    @classmethod
+    def from_name_dict(cls, named: dict, n_stages: int = 6):
+        """Name-keyed weights -> the all_weights order.  The VGG layers carry explicit names (`conv1_1` .. `conv4_2`,
+        backbones.py:461-476); every other layer of the model is created without a name (openpose.py:36-39,126-149) and gets
+        TensorLayer's automatic `<class>_<counter>` (`conv2d_7`, `prelu_3`), the counter running in creation order per layer
+        class -- so within a class, ascending counter == creation order, which is all that is needed to line the entries up
+        with `openpose_vgg19_layer_order`.  Shapes are checked entry by entry by the constructor."""
+        import re
+        layers = {}
+        for key, arr in named.items():
+            lname = key.split("/")[0]
+            layers.setdefault(lname, []).append(np.asarray(arr))
+
+        def split(lname):      # (filters, biases) of a conv layer | (alpha,) of a PRelu
+            arrs = layers[lname]
+            four = [a for a in arrs if a.ndim == 4]
+            one = [a for a in arrs if a.ndim != 4]
+            if len(four) == 1 and len(one) == 1:
+                return [four[0], one[0]]
+            if not four and len(one) == 1:
+                return [one[0]]
+            raise ValueError(f"layer {lname}: cannot tell filters / biases / alpha apart ({[a.shape for a in arrs]})")
+
+        def counter(lname):
+            m = re.search(r"_(\d+)$", lname)
+            return int(m.group(1)) if m else 0
+
+        order = openpose_vgg19_layer_order(n_stages)
+        vgg_names = [name for kind, name, *_ in order if kind == "conv" and name.startswith("conv") and "." not in name]
+        unnamed_conv = sorted((n for n in layers if n not in vgg_names and any(a.ndim == 4 for a in layers[n])), key=counter)
+        unnamed_prelu = sorted((n for n in layers if n not in vgg_names and all(a.ndim != 4 for a in layers[n])), key=counter)
+        ci, pi = iter(unnamed_conv), iter(unnamed_prelu)
+        out = []
+        try:
+            for kind, name, *_ in order:
+                if kind == "conv":
+                    out += split(name if name in vgg_names else next(ci))
+                else:
+                    out += split(next(pi))
+        except (StopIteration, KeyError) as e:
+            raise ValueError(f"name-keyed weight file does not hold the layers of OpenPose-VGG19 with {n_stages} stages ({e!r})") from None
+        if next(ci, None) is not None or next(pi, None) is not None:
+            raise ValueError("name-keyed weight file holds more conv / PRelu layers than the model")
+        return cls(out, n_stages)
 
     def conv(self, name, cout, cin, k, gain=2.0):
         w, b = self._conv[name]

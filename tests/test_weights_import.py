@@ -122,3 +122,39 @@ def test_engine_on_imported_weights_matches_two_branch_reference():
     for got, want in ((conf, rc.numpy()), (paf, rp.numpy())):
         assert got.shape == want.shape
         assert float(np.abs(got - want).max()) <= 3e-2 * max(1.0, float(np.abs(want).max()))
+
+
+def test_name_keyed_weight_file_gives_the_same_model(tmp_path):
+    """`save_weights(format="npz_dict")` (hyperpose/Model/train.py:319): entries keyed `<layer>/<filters|biases|alpha>:0`, the
+    stage layers under TensorLayer's automatic `conv2d_<n>` / `prelu_<n>` names; key order in the file is arbitrary"""
+    n_stages = 3
+    arrays = _tl_weight_list(5, n_stages)
+    it = iter(arrays)
+    named, nc, npr = {}, 0, 0
+    for kind, name, co, ci, k in W.openpose_vgg19_layer_order(n_stages):
+        if kind == "conv":
+            if "." in name or name.startswith("cpm"):
+                nc += 1
+                lname = f"conv2d_{nc + 7}"        # counters do not start at 1: other models were built earlier in the process
+            else:
+                lname = name
+            named[f"{lname}/filters:0"] = next(it)
+            named[f"{lname}/biases:0"] = next(it)
+        else:
+            npr += 1
+            named[f"prelu_{npr + 2}/alpha:0"] = next(it)
+    keys = list(named)
+    np.random.default_rng(0).shuffle(keys)
+    path = tmp_path / "newest_model.npz"
+    np.savez(path, **{k: named[k] for k in keys})
+    a = W.ListWeights.from_npz(str(path), n_stages)
+    b = W.ListWeights(arrays, n_stages)
+    for kind, name, co, ci, k in W.openpose_vgg19_layer_order(n_stages):
+        if kind == "conv":
+            assert np.array_equal(a.conv(name, co, ci, k)[0], b.conv(name, co, ci, k)[0]) and np.array_equal(a.conv(name, co, ci, k)[1], b.conv(name, co, ci, k)[1])
+        else:
+            assert np.array_equal(a.prelu(name, co), b.prelu(name, co))
+    # a file with a layer missing is rejected, not silently shifted
+    del named["prelu_4/alpha:0"]
+    with pytest.raises(ValueError):
+        W.ListWeights.from_name_dict(named, n_stages)
