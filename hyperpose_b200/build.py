@@ -23,6 +23,7 @@ SOURCES = [
     ("ppn_parser.cu", EXACT_FLAGS),
     ("common.cpp", []),
     ("handoff.cpp", []),
+    ("pool.cpp", []),
 ]
 
 

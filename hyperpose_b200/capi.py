@@ -300,9 +300,10 @@ class Engine:
         check(lib().hp_engine_read_outputs_host(self._h, conf.ctypes.data, paf.ctypes.data, n))
         return conf, paf
 
-    def read_outputs_frames(self, n: int, publish: bool = True):
+    def read_outputs_frames(self, n: int, publish: bool = False):
         """tensorrt::inference's return value: per image its own host buffers [conf_i, paf_i] (the feature_map_t storage,
-        src/tensorrt.cpp:398-431).  publish=True registers them for the device-resident hand-off (handoff.h)."""
+        src/tensorrt.cpp:398-431).  publish=True (what the C++ drop-in does, where feature_map_t is read-only) registers them
+        for the device-resident hand-off (handoff.h); a look-up compares every byte, so editing the arrays afterwards is safe."""
         if self.head_type == 1:
             sa, sb = (17, 5, self.out_h, self.out_w), (19, 9, self.out_h, self.out_w)
         else:

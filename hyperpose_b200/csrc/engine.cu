@@ -565,6 +565,27 @@ struct hp_engine {
     float* pin_out = nullptr; size_t pin_out_floats = 0;
     std::shared_ptr<hpb::handoff::Batch> ho_ring[hpb::handoff::HANDOFF_RING];
     int ho_pos = 0;
+    // network input of the NEXT run_graph: d_frames, or a slot buffer of the pipelined pose call
+    const uint8_t* cur_frames = nullptr;
+    bool stage_synced = false;     // hp_engine_stage_frame_u8: the previous batch's staging copies have been waited for
+    // pipelined end-to-end call (hp_pose_submit_u8_host / hp_pose_collect): two batches in flight
+    struct PoseSlot {
+        uint8_t* d_frames = nullptr;       // this slot's device input
+        uint8_t* pin_frames = nullptr;     // staging for pageable callers
+        hp_human* pin_humans = nullptr; size_t pin_humans_n = 0;
+        int* pin_counts = nullptr; size_t pin_counts_n = 0;   // [N counts | N flags]
+        cudaEvent_t h2d_done = nullptr, done = nullptr;
+        bool busy = false;
+        int N = 0, hcap = 0;
+        hp_paf* parser = nullptr;
+        cudaGraphExec_t graph = nullptr;   // captured launch sequence (convs + parse + result D2H) of this slot
+        float key_f[2] = { 0, 0 }; int key_i[6] = { 0, 0, 0, 0, 0, 0 }; int key_N = 0; const void* key_parser = nullptr;
+        const void* key_ovr[2] = { nullptr, nullptr };
+    } slots[2];
+    int next_slot = 0;
+    cudaStream_t copy_stream = nullptr;
+    bool graphs_ok = true;
+    long long graph_launches = 0, graph_captures = 0;
 };
 
 namespace {
@@ -755,6 +776,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     if (pl.stem && u8_input) {
         StemParams sp = pl.sp;
         sp.Nb = N;
+        sp.frames = e->cur_frames ? e->cur_frames : e->d_frames;
         const int tiles = (int)(((size_t)N * sp.OH * sp.OW + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
         const int per_sm = pl.stem_smem <= 110 * 1024 ? 2 : 1; // two resident CTAs hide the gather latency of the 3x3 stem
         const int grid = std::min(e->num_sms * per_sm, tiles);
@@ -842,7 +864,8 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             const int ph = same_pad_before(e->in_h, R, stride), pw = same_pad_before(e->in_w, R, stride);
 #define HP_IM2COL(U8, RR, SRC, FAC, FLIP) im2col3_kernel<U8, RR><<<blocks, 256, 0, st>>>(SRC, ob.d, N, e->in_h, e->in_w, FAC, FLIP, \
                 e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2], stride, ob.H, ob.W, ph, pw, chunks)
-            if (u8_input) { if (R == 3) HP_IM2COL(true, 3, e->d_frames, e->factor, e->flip_rgb); else HP_IM2COL(true, 7, e->d_frames, e->factor, e->flip_rgb); }
+            const uint8_t* fr = e->cur_frames ? e->cur_frames : e->d_frames;
+            if (u8_input) { if (R == 3) HP_IM2COL(true, 3, fr, e->factor, e->flip_rgb); else HP_IM2COL(true, 7, fr, e->factor, e->flip_rgb); }
             else          { if (R == 3) HP_IM2COL(false, 3, e->d_input_f32, 1.0, 0); else HP_IM2COL(false, 7, e->d_input_f32, 1.0, 0); }
 #undef HP_IM2COL
             e->launches++;
@@ -931,6 +954,17 @@ void free_engine(hp_engine* e)
     if (e->d_rz_yi) cudaFree(e->d_rz_yi);
     if (e->d_rz_ya) cudaFree(e->d_rz_ya);
     for (auto& ev : e->ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        auto& sl = e->slots[i];
+        if (sl.graph) cudaGraphExecDestroy(sl.graph);
+        if (sl.d_frames) cudaFree(sl.d_frames);
+        if (sl.pin_frames) cudaFreeHost(sl.pin_frames);
+        if (sl.pin_humans) cudaFreeHost(sl.pin_humans);
+        if (sl.pin_counts) cudaFreeHost(sl.pin_counts);
+        if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -955,8 +989,30 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
     PackHeader hdr;
     memcpy(&hdr, pack, sizeof(hdr));
     if (memcmp(hdr.magic, PACK_MAGIC, 8) != 0 || hdr.version != PACK_VERSION) { set_error("hp_engine_create: not an HPB2PACK v%u model pack", PACK_VERSION); return HP_ERR_ARG; }
-    const size_t need = sizeof(PackHeader) + hdr.n_buffers * sizeof(PackBuffer) + hdr.n_ops * sizeof(PackOp) + hdr.blob_floats * sizeof(float);
+    // the file is untrusted: bound the counts before any size arithmetic (no overflow), then check every blob range an op names
+    if (hdr.n_buffers == 0 || hdr.n_buffers > 65536 || hdr.n_ops == 0 || hdr.n_ops > 65536 || hdr.blob_floats > ((uint64_t)1 << 34)) {
+        set_error("hp_engine_create: implausible pack header (%u buffers, %u ops, %llu blob floats)", hdr.n_buffers, hdr.n_ops, (unsigned long long)hdr.blob_floats);
+        return HP_ERR_ARG;
+    }
+    const size_t need = sizeof(PackHeader) + (size_t)hdr.n_buffers * sizeof(PackBuffer) + (size_t)hdr.n_ops * sizeof(PackOp) + (size_t)hdr.blob_floats * sizeof(float);
     if (pack_bytes < need) { set_error("hp_engine_create: truncated pack (%zu < %zu bytes)", pack_bytes, need); return HP_ERR_ARG; }
+    {
+        const PackOp* vops = (const PackOp*)((const uint8_t*)pack + sizeof(PackHeader) + (size_t)hdr.n_buffers * sizeof(PackBuffer));
+        auto in_blob = [&](uint64_t off, uint64_t count) { return off <= hdr.blob_floats && count <= hdr.blob_floats - off; };
+        for (uint32_t i = 0; i < hdr.n_ops; ++i) {
+            PackOp po;
+            memcpy(&po, vops + i, sizeof(po));
+            if (po.type != OP_CONV && po.type != OP_DWCONV) continue;
+            const uint64_t lim = 1u << 16;   // per-dimension bound: keeps the products below 2^64
+            const bool dw = po.type == OP_DWCONV;
+            const uint64_t G = dw ? 1 : po.groups, co = po.cout_g, ci = dw ? 1 : po.cin_g, R = po.R, S = po.S;
+            if (G == 0 || co == 0 || ci == 0 || R == 0 || S == 0 || G > lim || co > lim || ci > lim || R > 15 || S > 15 ||
+                !in_blob(po.w_off, G * co * ci * R * S) || !in_blob(po.b_off, G * co) || !in_blob(po.a_off, G * co)) {
+                set_error("hp_engine_create: op %u names weights outside the pack (groups %u, cout %u, cin %u, %ux%u)", i, po.groups, po.cout_g, po.cin_g, po.R, po.S);
+                return HP_ERR_ARG;
+            }
+        }
+    }
     HP_CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     HP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -1076,7 +1132,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (stem)", stem_smem);
         return fail(HP_ERR_CUDA);
     }
-    HP_CUDA_TRY(cudaDeviceSynchronize());
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_error("hp_engine_create: device error during set-up: %s", cudaGetErrorString(cudaGetLastError())); return fail(HP_ERR_CUDA); }
     *out = e;
     return HP_OK;
 }
@@ -1151,15 +1207,21 @@ int hp_engine_stage_frame_u8(hp_engine* e, int slot, const uint8_t* frame, int s
     HP_CUDA_TRY(cudaSetDevice(e->device));
     const size_t bytes = (size_t)src_h * src_w * 3;
     uint8_t* dst = e->d_frames + (size_t)slot * e->in_h * e->in_w * 3;
-    if (src_h == e->in_h && src_w == e->in_w) { // already network-sized: both resize variants are the identity
+    // Staging memory is one region per batch slot, so the frames of a batch never wait for each other: the stream is
+    // synchronised ONCE per batch (first stage call after a run), not once per frame.
+    if (!e->stage_synced) { HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); e->stage_synced = true; }
+    const size_t slot_bytes = (bytes + 255) & ~(size_t)255;
+    if (e->pin_src_bytes < slot_bytes * e->max_batch) {
         HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
-        if (e->pin_src_bytes < bytes) {
-            if (e->pin_src) cudaFreeHost(e->pin_src);
-            HP_CUDA_TRY(cudaMallocHost(&e->pin_src, bytes));
-            e->pin_src_bytes = bytes;
-        }
-        memcpy(e->pin_src, frame, bytes);
-        HP_CUDA_TRY(cudaMemcpyAsync(dst, e->pin_src, bytes, cudaMemcpyHostToDevice, e->stream));
+        if (e->pin_src) cudaFreeHost(e->pin_src);
+        e->pin_src = nullptr; e->pin_src_bytes = 0;
+        HP_CUDA_TRY(cudaMallocHost(&e->pin_src, slot_bytes * e->max_batch));
+        e->pin_src_bytes = slot_bytes * e->max_batch;
+    }
+    uint8_t* pin = e->pin_src + (e->pin_src_bytes / e->max_batch / 256 * 256) * slot;
+    if (src_h == e->in_h && src_w == e->in_w) { // already network-sized: both resize variants are the identity
+        memcpy(pin, frame, bytes);
+        HP_CUDA_TRY(cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, e->stream));
         return HP_OK;
     }
     if (src_h != e->rz_sh || src_w != e->rz_sw || keep_ratio != e->rz_keep) {
@@ -1189,35 +1251,34 @@ int hp_engine_stage_frame_u8(hp_engine* e, int slot, const uint8_t* frame, int s
         std::vector<int> xi, yi; std::vector<short> xa, ya;
         table(src_w, rw, true, xi, xa);
         table(src_h, rh, false, yi, ya);
-        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));   // earlier frames of this batch may still read the old tables
         if (!e->d_rz_xi) {
             HP_CUDA_TRY(cudaMalloc(&e->d_rz_xi, e->in_w * sizeof(int)));
             HP_CUDA_TRY(cudaMalloc(&e->d_rz_xa, e->in_w * 2 * sizeof(short)));
             HP_CUDA_TRY(cudaMalloc(&e->d_rz_yi, e->in_h * sizeof(int)));
             HP_CUDA_TRY(cudaMalloc(&e->d_rz_ya, e->in_h * 2 * sizeof(short)));
         }
-        HP_CUDA_TRY(cudaMemcpy(e->d_rz_xi, xi.data(), rw * sizeof(int), cudaMemcpyHostToDevice));
-        HP_CUDA_TRY(cudaMemcpy(e->d_rz_xa, xa.data(), rw * 2 * sizeof(short), cudaMemcpyHostToDevice));
-        HP_CUDA_TRY(cudaMemcpy(e->d_rz_yi, yi.data(), rh * sizeof(int), cudaMemcpyHostToDevice));
-        HP_CUDA_TRY(cudaMemcpy(e->d_rz_ya, ya.data(), rh * 2 * sizeof(short), cudaMemcpyHostToDevice));
+        // on the engine's (non-blocking) stream, so that the resize kernels are ordered behind the upload; the vectors are locals
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_rz_xi, xi.data(), rw * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_rz_xa, xa.data(), rw * 2 * sizeof(short), cudaMemcpyHostToDevice, e->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_rz_yi, yi.data(), rh * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(e->d_rz_ya, ya.data(), rh * 2 * sizeof(short), cudaMemcpyHostToDevice, e->stream));
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
         e->rz_sh = src_h; e->rz_sw = src_w; e->rz_keep = keep_ratio; e->rz_rh = rh; e->rz_rw = rw;
         e->rz_area = (src_h == 2 * rh && src_w == 2 * rw) ? 1 : 0;
     }
-    HP_CUDA_TRY(cudaStreamSynchronize(e->stream)); // pin_src / d_src may still feed the previous frame
-    if (e->pin_src_bytes < bytes) {
-        if (e->pin_src) cudaFreeHost(e->pin_src);
-        HP_CUDA_TRY(cudaMallocHost(&e->pin_src, bytes));
-        e->pin_src_bytes = bytes;
-    }
-    if (e->d_src_bytes < bytes) {
+    if (e->d_src_bytes < slot_bytes * e->max_batch) {
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_src) cudaFree(e->d_src);
-        HP_CUDA_TRY(cudaMalloc(&e->d_src, bytes));
-        e->d_src_bytes = bytes;
+        e->d_src = nullptr; e->d_src_bytes = 0;
+        HP_CUDA_TRY(cudaMalloc(&e->d_src, slot_bytes * e->max_batch));
+        e->d_src_bytes = slot_bytes * e->max_batch;
     }
-    memcpy(e->pin_src, frame, bytes);
-    HP_CUDA_TRY(cudaMemcpyAsync(e->d_src, e->pin_src, bytes, cudaMemcpyHostToDevice, e->stream));
+    uint8_t* dsrc = e->d_src + (e->d_src_bytes / e->max_batch / 256 * 256) * slot;
+    memcpy(pin, frame, bytes);
+    HP_CUDA_TRY(cudaMemcpyAsync(dsrc, pin, bytes, cudaMemcpyHostToDevice, e->stream));
     const int total = e->in_h * e->in_w;
-    resize_u8c3_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(e->d_src, src_h, src_w, dst, e->in_h, e->in_w, e->rz_rh, e->rz_rw,
+    resize_u8c3_kernel<<<(total + 255) / 256, 256, 0, e->stream>>>(dsrc, src_h, src_w, dst, e->in_h, e->in_w, e->rz_rh, e->rz_rw,
                                                                  e->d_rz_xi, e->d_rz_xa, e->d_rz_yi, e->d_rz_ya, e->rz_area);
     e->launches++;
     HP_CUDA_TRY(cudaGetLastError());
@@ -1230,6 +1291,7 @@ int hp_engine_infer_staged(hp_engine* e, int N)
     if (!e) return HP_ERR_ARG;
     if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
     HP_CUDA_TRY(cudaSetDevice(e->device));
+    e->stage_synced = false;   // the next batch's first stage call waits for this one's staging copies
     return run_graph(e, N, true, e->stream);
 }
 
@@ -1277,6 +1339,8 @@ int hp_engine_read_outputs_frames(hp_engine* e, float* const* conf_frames, float
     HP_CUDA_TRY(cudaSetDevice(e->device));
     const size_t plane = (size_t)e->out_h * e->out_w;
     const size_t ea = e->hdr.conf_channels * plane, eb = e->hdr.paf_channels * plane;
+    if (publish && hpb::handoff::enabled())   // D2H into the publication's own pinned copy, then into the caller's buffers
+        return hpb::handoff::publish(e->ho_ring, &e->ho_pos, e->device, e->stream, e->d_conf, e->d_paf, N, ea, eb, conf_frames, paf_frames);
     const size_t need = (size_t)e->max_batch * (ea + eb);
     if (e->pin_out_floats < need) {
         if (e->pin_out) cudaFreeHost(e->pin_out);
@@ -1293,8 +1357,6 @@ int hp_engine_read_outputs_frames(hp_engine* e, float* const* conf_frames, float
         memcpy(conf_frames[i], ha + (size_t)i * ea, ea * sizeof(float));
         memcpy(paf_frames[i], hb + (size_t)i * eb, eb * sizeof(float));
     }
-    if (publish && hpb::handoff::enabled())
-        return hpb::handoff::publish(e->ho_ring, &e->ho_pos, e->device, e->stream, e->d_conf, e->d_paf, N, ea, eb, conf_frames, paf_frames, ha, hb);
     return HP_OK;
 }
 
@@ -1399,16 +1461,194 @@ int hp_engine_get_profile(hp_engine* e, double* ms_per_op, int* op_type, double*
     return HP_OK;
 }
 
-// End-to-end pose call: HOST u8 frames -> humans on the host, one stream, tensors never leave the device in between
+// ---------------------------------------------------------------------------------------------------------------------
+// End-to-end pose call: HOST u8 frames -> humans on the host, tensors never leave the device in between
 // (operator API sequence engine.inference(batch) + parser.process(packet) per image,
-//  examples/operator_api_batched_images_paf.example.cpp:64-74).
+//  examples/operator_api_batched_images_paf.example.cpp:64-74), two batches in flight:
+//
+//   hp_pose_submit_u8_host(i+1)  H2D of batch i+1 on the copy stream  | overlaps the convs of batch i
+//   hp_pose_collect(i)           waits for batch i's records (their D2H was enqueued right behind its parse)
+//
+// The per-batch launch sequence (every conv + the four parser kernels + the result D2H, ~65 nodes at cfg3) is captured
+// once per slot into a CUDA graph and replayed with one cudaGraphLaunch; it is re-captured when anything baked into it
+// changes (batch size, parser thresholds / capacities, benchmark override).  HPB_NO_GRAPH=1 launches directly.
+// ---------------------------------------------------------------------------------------------------------------------
+int hp_paf_prepare(hp_paf* p, int N, int c_conf, int c_paf, int H, int W);
+int hp_paf_state(const hp_paf* p, float* thresholds2, int* ints6);
+int hp_paf_copy_results_host_async(hp_paf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream);
+int hp_paf_grow_capacity(hp_paf* p, int flags);
+
+} // extern "C" (helpers below are C++)
+
+namespace {
+
+int pose_enqueue_compute(hp_engine* e, hp_engine::PoseSlot& sl, cudaStream_t st)
+{
+    e->cur_frames = sl.d_frames;
+    int rc = run_graph(e, sl.N, true, st);
+    e->cur_frames = nullptr;
+    if (rc) return rc;
+    rc = hp_paf_process_device(sl.parser, e->d_conf, e->d_paf, sl.N, (int)e->hdr.conf_channels, (int)e->hdr.paf_channels, e->out_h, e->out_w, (void*)st);
+    if (rc) return rc;
+    return hp_paf_copy_results_host_async(sl.parser, sl.pin_humans, sl.pin_counts, sl.N, (void*)st);
+}
+
+int pose_slot_prepare(hp_engine* e, hp_engine::PoseSlot& sl, int idx, hp_paf* parser, int N)
+{
+    const size_t fbytes = (size_t)e->max_batch * e->in_h * e->in_w * 3;
+    if (!e->copy_stream) HP_CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    (void)idx;
+    if (!sl.d_frames) HP_CUDA_TRY(cudaMalloc(&sl.d_frames, fbytes + 16));   // own buffers: the plain entry points keep hp_engine::d_frames
+    if (!sl.h2d_done) HP_CUDA_TRY(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    if (!sl.done) HP_CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    int rc = hp_paf_prepare(parser, N, (int)e->hdr.conf_channels, (int)e->hdr.paf_channels, e->out_h, e->out_w);
+    if (rc) return rc;
+    float kf[2]; int ki[6];
+    hp_paf_state(parser, kf, ki);
+    const size_t need_h = (size_t)e->max_batch * ki[4];
+    if (sl.pin_humans_n < need_h) {
+        if (sl.pin_humans) cudaFreeHost(sl.pin_humans);
+        sl.pin_humans = nullptr; sl.pin_humans_n = 0;
+        HP_CUDA_TRY(cudaMallocHost(&sl.pin_humans, need_h * sizeof(hp_human)));
+        sl.pin_humans_n = need_h;
+        if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }   // the captured D2H targets moved
+    }
+    if (sl.pin_counts_n < (size_t)2 * e->max_batch) {
+        if (sl.pin_counts) cudaFreeHost(sl.pin_counts);
+        sl.pin_counts = nullptr; sl.pin_counts_n = 0;
+        HP_CUDA_TRY(cudaMallocHost(&sl.pin_counts, (size_t)2 * e->max_batch * sizeof(int)));
+        sl.pin_counts_n = (size_t)2 * e->max_batch;
+        if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }
+    }
+    // anything the captured sequence bakes in
+    const bool same = sl.graph && sl.key_N == N && sl.key_parser == (const void*)parser && memcmp(sl.key_f, kf, sizeof(kf)) == 0 && memcmp(sl.key_i, ki, sizeof(ki)) == 0 &&
+                      sl.key_ovr[0] == (const void*)e->override_conf && sl.key_ovr[1] == (const void*)e->override_paf;
+    if (!same && sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }
+    sl.key_N = N; sl.key_parser = parser; memcpy(sl.key_f, kf, sizeof(kf)); memcpy(sl.key_i, ki, sizeof(ki));
+    sl.key_ovr[0] = e->override_conf; sl.key_ovr[1] = e->override_paf;
+    sl.N = N; sl.hcap = ki[4]; sl.parser = parser;
+    return HP_OK;
+}
+
+// enqueue this slot's compute on the engine stream: graph replay when possible, direct launches otherwise
+int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
+{
+    static const bool no_graph = getenv("HPB_NO_GRAPH") != nullptr;
+    if (!no_graph && e->graphs_ok && !e->profiling) {
+        if (!sl.graph) {
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const long long l0 = e->launches;
+                const int rc = pose_enqueue_compute(e, sl, e->stream);
+                const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+                e->launches = l0 - 4;   // capturing launches nothing (the parser counted its four kernels: taken back here)
+                if (rc == HP_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&sl.graph, g, 0) == cudaSuccess) e->graph_captures++;
+                else { sl.graph = nullptr; e->graphs_ok = false; cudaGetLastError(); }
+                if (g) cudaGraphDestroy(g);
+            } else { e->graphs_ok = false; cudaGetLastError(); }
+        }
+        if (sl.graph) {
+            HP_CUDA_TRY(cudaGraphLaunch(sl.graph, e->stream));
+            e->graph_launches++;
+            // the replay runs the same kernels the direct path counts: every engine op + the parser's four
+            int n_k = 4;
+            for (auto& op : e->ops) {
+                const uint32_t t = op.po.type;
+                if (t == OP_IM2COL3 && op.fused_into_stem) continue;
+                n_k += (t == OP_PIFPAF_HEAD) ? 2 : 1;
+            }
+            e->launches += n_k;
+            return HP_OK;
+        }
+    }
+    return pose_enqueue_compute(e, sl, e->stream);
+}
+
+} // namespace
+
+extern "C" {
+
+int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket)
+{
+    if (!e || !parser || !frames || !ticket) { set_error("hp_pose_submit_u8_host: null argument"); return HP_ERR_ARG; }
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    if (e->hdr.head_type != 0) { set_error("hp_pose_submit_u8_host: the model pack has OpenPifPaf heads (use hp_engine_infer_u8_host + hp_pifpaf_process_device)"); return HP_ERR_UNSUPPORTED; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const int idx = e->next_slot;
+    hp_engine::PoseSlot& sl = e->slots[idx];
+    if (sl.busy) { set_error("hp_pose_submit_u8_host: two batches are already in flight -- collect ticket %d first", idx); return HP_ERR_ARG; }
+    int rc = pose_slot_prepare(e, sl, idx, parser, N);
+    if (rc) return rc;
+    const size_t bytes = (size_t)N * e->in_h * e->in_w * 3;
+    cudaPointerAttributes attr;
+    const bool pinned = (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+    if (!pinned) cudaGetLastError();
+    const uint8_t* src = frames;
+    if (!pinned) {   // pageable caller memory: through this slot's pinned staging (free: the slot was collected)
+        if (!sl.pin_frames) HP_CUDA_TRY(cudaMallocHost(&sl.pin_frames, (size_t)e->max_batch * e->in_h * e->in_w * 3));
+        memcpy(sl.pin_frames, frames, bytes);
+        src = sl.pin_frames;
+    }
+    HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+    HP_CUDA_TRY(cudaEventRecord(sl.h2d_done, e->copy_stream));
+    HP_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
+    rc = pose_launch(e, sl);
+    if (rc) return rc;
+    HP_CUDA_TRY(cudaEventRecord(sl.done, e->stream));
+    sl.busy = true;
+    e->next_slot = idx ^ 1;
+    *ticket = idx;
+    return HP_OK;
+}
+
+int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out)
+{
+    if (!e || ticket < 0 || ticket > 1 || !out || !n_out || cap < 0) { set_error("hp_pose_collect: bad argument"); return HP_ERR_ARG; }
+    hp_engine::PoseSlot& sl = e->slots[ticket];
+    if (!sl.busy) { set_error("hp_pose_collect: ticket %d is not in flight", ticket); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    HP_CUDA_TRY(cudaEventSynchronize(sl.done));
+    sl.busy = false;
+    const int N = sl.N;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int flags = 0;
+        for (int f = 0; f < N; ++f) flags |= sl.pin_counts[N + f];
+        if (!flags) break;
+        // the reference is unbounded: grow the parser capacity that overflowed and run this slot's frames again (they are still
+        // in its device buffer), synchronously and outside the graph
+        if (hp_paf_grow_capacity(sl.parser, flags) != HP_OK) { set_error("hp_pose_collect: parser capacity limit reached (flags=%d)", flags); return HP_ERR_CAPACITY; }
+        int rc = pose_slot_prepare(e, sl, ticket, sl.parser, N);
+        if (rc) return rc;
+        rc = pose_enqueue_compute(e, sl, e->stream);
+        if (rc) return rc;
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    for (int f = 0; f < N; ++f) if (sl.pin_counts[N + f]) { set_error("hp_pose_collect: parser capacity exceeded"); return HP_ERR_CAPACITY; }
+    for (int f = 0; f < N; ++f) {
+        const int n = sl.pin_counts[f];
+        if (n > cap) { set_error("hp_pose_collect: frame %d has %d humans but the caller's capacity is %d", f, n, cap); return HP_ERR_CAPACITY; }
+        n_out[f] = n;
+        memcpy(out + (size_t)f * cap, sl.pin_humans + (size_t)f * sl.hcap, sizeof(hp_human) * n);
+    }
+    return HP_OK;
+}
+
+// the synchronous form: one batch in, its humans out
 int hp_pose_run_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, hp_human* out, int cap, int* n_out)
 {
-    int rc = hp_engine_infer_u8_host(e, frames, N);
+    if (e) for (int t = 0; t < 2; ++t) if (e->slots[t].busy) { set_error("hp_pose_run_u8_host: a submitted batch (ticket %d) has not been collected", t); return HP_ERR_ARG; }
+    int ticket = -1;
+    int rc = hp_pose_submit_u8_host(e, parser, frames, N, &ticket);
     if (rc) return rc;
-    rc = hp_paf_process_device(parser, e->d_conf, e->d_paf, N, (int)e->hdr.conf_channels, (int)e->hdr.paf_channels, e->out_h, e->out_w, (void*)e->stream);
-    if (rc) return rc;
-    return hp_paf_fetch(parser, out, cap, n_out, N);
+    return hp_pose_collect(e, ticket, out, cap, n_out);
+}
+
+int hp_pose_stats(const hp_engine* e, long long* graph_captures, long long* graph_launches)
+{
+    if (!e) return HP_ERR_ARG;
+    if (graph_captures) *graph_captures = e->graph_captures;
+    if (graph_launches) *graph_launches = e->graph_launches;
+    return HP_OK;
 }
 
 } // extern "C"

@@ -42,26 +42,17 @@ bool enabled()
 }
 void set_enabled(bool on) { g_enabled.store(on ? 1 : 0); }
 
-void sample(const float* a, size_t elems_a, const float* b, size_t elems_b, Fingerprint* out)
+bool contents_match(const Batch& b, int frame)
 {
-    for (int i = 0; i < FP_SAMPLES; ++i) {
-        out->a[i] = a[(elems_a - 1) * (size_t)i / (FP_SAMPLES - 1)];
-        out->b[i] = b[(elems_b - 1) * (size_t)i / (FP_SAMPLES - 1)];
-    }
-}
-
-bool fingerprint_matches(const Batch& b, int frame)
-{
-    Fingerprint now;
-    sample(b.host_a[frame], b.elems_a, b.host_b[frame], b.elems_b, &now);
+    if (!b.pin) return false;
+    const float* pa = b.pin + (size_t)frame * b.elems_a;
+    const float* pb = b.pin + (size_t)b.N * b.elems_a + (size_t)frame * b.elems_b;
     // bit patterns, not float compares: NaNs must match themselves
-    return std::memcmp(now.a.data(), b.fp[frame].a.data(), sizeof(float) * FP_SAMPLES) == 0
-        && std::memcmp(now.b.data(), b.fp[frame].b.data(), sizeof(float) * FP_SAMPLES) == 0;
+    return std::memcmp(b.host_a[frame], pa, b.elems_a * sizeof(float)) == 0 && std::memcmp(b.host_b[frame], pb, b.elems_b * sizeof(float)) == 0;
 }
 
 int publish(std::shared_ptr<Batch>* ring, int* ring_pos, int device, cudaStream_t st, const float* d_a, const float* d_b, int N,
-            size_t elems_a, size_t elems_b, float* const* host_a, float* const* host_b, const float* host_stage_a,
-            const float* host_stage_b)
+            size_t elems_a, size_t elems_b, float* const* host_a, float* const* host_b)
 {
     std::shared_ptr<Batch>& slot = ring[*ring_pos];
     *ring_pos = (*ring_pos + 1) % HANDOFF_RING;
@@ -86,15 +77,26 @@ int publish(std::shared_ptr<Batch>* ring, int* ring_pos, int device, cudaStream_
         HP_CUDA_TRY(cudaMalloc(&b.d_b, need_b * sizeof(float)));
         b.cap_b = need_b;
     }
+    if (need_a + need_b > b.pin_floats) {
+        if (b.pin) cudaFreeHost(b.pin);
+        b.pin = nullptr; b.pin_floats = 0;
+        HP_CUDA_TRY(cudaMallocHost(&b.pin, (need_a + need_b) * sizeof(float)));
+        b.pin_floats = need_a + need_b;
+    }
     if (!b.ready) HP_CUDA_TRY(cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming));
+    HP_CUDA_TRY(cudaMemcpyAsync(b.pin, d_a, need_a * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(b.pin + need_a, d_b, need_b * sizeof(float), cudaMemcpyDeviceToHost, st));
     HP_CUDA_TRY(cudaMemcpyAsync(b.d_a, d_a, need_a * sizeof(float), cudaMemcpyDeviceToDevice, st));
     HP_CUDA_TRY(cudaMemcpyAsync(b.d_b, d_b, need_b * sizeof(float), cudaMemcpyDeviceToDevice, st));
     HP_CUDA_TRY(cudaEventRecord(b.ready, st));
+    HP_CUDA_TRY(cudaStreamSynchronize(st));
     b.N = N; b.elems_a = elems_a; b.elems_b = elems_b;
     b.host_a.assign(host_a, host_a + N);
     b.host_b.assign(host_b, host_b + N);
-    b.fp.resize(N);
-    for (int i = 0; i < N; ++i) sample(host_stage_a + (size_t)i * elems_a, elems_a, host_stage_b + (size_t)i * elems_b, elems_b, &b.fp[i]);
+    for (int i = 0; i < N; ++i) {   // the caller's per-image buffers (feature_map_t storage) receive the published bytes
+        std::memcpy(host_a[i], b.pin + (size_t)i * elems_a, elems_a * sizeof(float));
+        std::memcpy(host_b[i], b.pin + need_a + (size_t)i * elems_b, elems_b * sizeof(float));
+    }
     b.valid = true;
     {
         std::lock_guard<std::mutex> lg(g_mu);
@@ -115,6 +117,8 @@ void retire_ring(std::shared_ptr<Batch>* ring)
         if (b.d_a) cudaFree(b.d_a);
         if (b.d_b) cudaFree(b.d_b);
         if (b.ready) cudaEventDestroy(b.ready);
+        if (b.pin) cudaFreeHost(b.pin);
+        b.pin = nullptr; b.pin_floats = 0;
         b.d_a = b.d_b = nullptr;
         b.cap_a = b.cap_b = 0;
         b.ready = nullptr;
@@ -133,11 +137,20 @@ Hit lookup(const float* host_a, const float* host_b, size_t elems_a, size_t elem
     if (!sp) { g_map.erase(it); return h; }
     const int f = it->second.second;
     // geometry and the second pointer are immutable while the entry is registered (publish() unregisters under b.mu first);
-    // they are re-checked under b.mu by the caller together with the fingerprint
+    // they are re-checked under b.mu by the caller together with the contents
     if (f >= (int)sp->host_b.size() || sp->host_b[f] != host_b || sp->elems_a != elems_a || sp->elems_b != elems_b) return h;
     h.batch = std::move(sp);
     h.frame = f;
     return h;
+}
+
+std::mutex& registry_mutex() { return g_mu; }
+int device_of_locked(const float* host_a)
+{
+    auto it = g_map.find(host_a);
+    if (it == g_map.end()) return -1;
+    auto sp = it->second.first.lock();
+    return sp ? sp->device : -1;   // Batch::device is written under g_mu-free b.mu, but only while the entry is unregistered
 }
 
 void count_hit() { g_hits.fetch_add(1); }
@@ -159,6 +172,12 @@ int hp_handoff_enable(int on)
 {
     hpb::handoff::set_enabled(on != 0);
     return HP_OK;
+}
+int hp_handoff_device_of(const float* host_conf)
+{
+    if (!host_conf || !hpb::handoff::enabled()) return -1;
+    std::lock_guard<std::mutex> lg(hpb::handoff::registry_mutex());
+    return hpb::handoff::device_of_locked(host_conf);
 }
 int hp_handoff_stats(long long* published, long long* hits, long long* batch_parses, long long* misses)
 {

@@ -875,6 +875,20 @@ int fetch_results(hp_paf* p, hp_human* out, int cap, int* n_out, int N)
     return HP_OK;
 }
 
+// The reference is unbounded (std::vector everywhere): after a run that raised overflow flags, enlarge exactly the capacities
+// that overflowed.  HP_ERR_CAPACITY when a hard limit is reached (4096 peaks per part: the greedy pass' bitmaps).
+int grow_after_overflow(hp_paf* p, int flags)
+{
+    if ((flags & FLAG_PEAK_OVERFLOW) && p->pcap >= MAX_PCAP) return HP_ERR_CAPACITY;
+    if (flags & FLAG_PEAK_OVERFLOW) p->pcap = std::min(p->pcap * 4, MAX_PCAP);
+    if (flags & FLAG_CAND_OVERFLOW) p->ccap *= 4;
+    if (flags & FLAG_HUMAN_OVERFLOW) {
+        if (p->hcap >= 4096 && p->max_refs >= p->assemble_max_refs) return HP_ERR_CAPACITY; // > ~2500 partial humans in one frame
+        hp_paf_set_capacity(p, 0, 0, std::min(p->hcap * 4, 4096));
+    }
+    return HP_OK;
+}
+
 // Published-batch path of hp_paf_process_host (handoff.h): `conf` / `paf` are host buffers the engine filled AND published.
 // The first call on a batch parses all of its frames from the device snapshot with this handle's parameters; the
 // other frames (any handle with the same parameters, any thread) are served from the cached records.
@@ -890,7 +904,7 @@ int process_from_handoff(hp_paf* p, const float* conf, const float* paf, int c_c
     std::lock_guard<std::mutex> lk(b.mu);
     const int f = hit.frame;
     if (!b.valid || b.fail_count >= 2 || b.device != p->device || f >= b.N || b.host_a[f] != conf || b.host_b[f] != paf ||
-        b.elems_a != ea || b.elems_b != eb || !ho::fingerprint_matches(b, f)) {
+        b.elems_a != ea || b.elems_b != eb || !ho::contents_match(b, f)) {
         ho::count_miss();
         return HANDOFF_MISS;
     }
@@ -1037,13 +1051,7 @@ int hp_paf_process_host_batched(hp_paf* p, const float* conf, const float* paf, 
         int flags = 0;
         for (int f = 0; f < N; ++f) flags |= p->pin_counts.p[N + f];
         if (!flags) return rc; // the caller's own `cap` was too small
-        if ((flags & FLAG_PEAK_OVERFLOW) && p->pcap >= MAX_PCAP) return rc;
-        if (flags & FLAG_PEAK_OVERFLOW) p->pcap = std::min(p->pcap * 4, MAX_PCAP);
-        if (flags & FLAG_CAND_OVERFLOW) p->ccap *= 4;
-        if (flags & FLAG_HUMAN_OVERFLOW) {
-            if (p->hcap >= 4096 && p->max_refs >= p->assemble_max_refs) return rc; // > ~2500 partial humans in one frame
-            hp_paf_set_capacity(p, 0, 0, std::min(p->hcap * 4, 4096));
-        }
+        if (grow_after_overflow(p, flags) != HP_OK) return rc;
     }
     return HP_ERR_CAPACITY;
 }
@@ -1056,6 +1064,40 @@ int hp_paf_process_host(hp_paf* p, const float* conf, const float* paf, int c_co
         if (rc != HANDOFF_MISS) return rc;
     }
     return hp_paf_process_host_batched(p, conf, paf, 1, c_conf, c_paf, H, W, out, cap, n_out);
+}
+
+// ---- building blocks of the pipelined end-to-end call (engine.cu: hp_pose_submit_u8_host / hp_pose_collect) ----------------
+// Allocates everything a batch of this geometry needs (nothing is allocated inside a CUDA-graph capture afterwards).
+int hp_paf_prepare(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
+{
+    if (!p) return HP_ERR_ARG;
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    return ensure_geometry(p, N, c_conf, c_paf, H, W);
+}
+// Everything a captured launch sequence bakes in: thresholds, resolution, capacities (a change invalidates the graph).
+int hp_paf_state(const hp_paf* p, float* thresholds2, int* ints6)
+{
+    if (!p) return HP_ERR_ARG;
+    if (thresholds2) { thresholds2[0] = p->conf_thresh; thresholds2[1] = p->paf_thresh; }
+    if (ints6) { ints6[0] = p->res_w; ints6[1] = p->res_h; ints6[2] = p->pcap; ints6[3] = p->ccap; ints6[4] = p->hcap; ints6[5] = p->cap_N; }
+    return HP_OK;
+}
+// Enqueues the D2H of the last batch's records on `stream`: humans[N * hcap] and counts_flags[2N] (counts, then overflow flags)
+// into caller-owned PINNED host memory; no synchronisation.
+int hp_paf_copy_results_host_async(hp_paf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream)
+{
+    if (!p || !pin_humans || !pin_counts_flags || N != p->last_N) { hpb::set_error("hp_paf_copy_results_host_async: bad argument"); return HP_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->last_stream;
+    HP_CUDA_TRY(cudaMemcpyAsync(pin_counts_flags, p->human_cnt(), sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(pin_counts_flags + N, p->flags(), sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(pin_humans, p->humans.p, sizeof(hp_human) * (size_t)N * p->hcap, cudaMemcpyDeviceToHost, st));
+    return HP_OK;
+}
+// After a batch whose flags (OR over its frames) report an overflow: grow those capacities (see grow_after_overflow).
+int hp_paf_grow_capacity(hp_paf* p, int flags)
+{
+    if (!p) return HP_ERR_ARG;
+    return grow_after_overflow(p, flags);
 }
 
 int hp_paf_debug_peaks(hp_paf* p, int frame, hp_peak* out, int cap, int* n_out)

@@ -781,7 +781,7 @@ static int pifpaf_from_handoff(hp_pifpaf* p, const float* pif, const float* paf,
     std::lock_guard<std::mutex> lk(b.mu);
     const int f = hit.frame;
     if (!b.valid || b.fail_count >= 2 || b.device != p->device || f >= b.N || b.host_a[f] != pif || b.host_b[f] != paf ||
-        b.elems_a != ea || b.elems_b != eb || !ho::fingerprint_matches(b, f)) {
+        b.elems_a != ea || b.elems_b != eb || !ho::contents_match(b, f)) {
         ho::count_miss();
         return 1;
     }

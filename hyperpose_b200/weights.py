@@ -76,7 +76,10 @@ class ListWeights:
                     a = next(it)
                     if a.size != co:
                         raise ValueError(f"{name}: expected {co} PRelu slopes, got shape {a.shape}")
-                    self._prelu[name] = a.reshape(co).astype(np.float32)
+                    # TensorLayer 2.2.3 (requirements.txt:6) constrains the slope: PRelu.build creates
+                    # `alpha_var_constrained = tf.nn.sigmoid(alpha_var)` and forward computes relu(x) - sigmoid(alpha) * relu(-x);
+                    # the SAVED array is the raw variable (init ~N(0, 0.05) => slope ~0.5), so the slope the pack needs is sigmoid(alpha).
+                    self._prelu[name] = (1.0 / (1.0 + np.exp(-a.reshape(co).astype(np.float64)))).astype(np.float32)
             except StopIteration:
                 raise ValueError(f"weight list ends before {kind} {name}") from None
         if next(it, None) is not None:
@@ -89,8 +92,11 @@ class ListWeights:
             (hyperpose/Model/train.py:582);
           * `save_weights(format="npz_dict")` / `tl.files.save_npz_dict`: one entry per weight, keyed by the weight's name
             `<layer name>/<filters|biases|alpha>:0` (train.py:319, eval.py:109) -> `from_name_dict`."""
-        z = np.load(path, allow_pickle=True)
+        # npz_dict files need no pickle; only the legacy `params` object array does.  Unpickling executes code from the file:
+        # it is re-opened with allow_pickle=True only for that key, and only a file you trust should be passed here.
+        z = np.load(path, allow_pickle=False)
         if "params" in z.files:
+            z = np.load(path, allow_pickle=True)
             return cls(list(z["params"]), n_stages)
         return cls.from_name_dict({k: z[k] for k in z.files}, n_stages)
 
@@ -104,6 +110,9 @@ class ListWeights:
         import re
         layers = {}
         for key, arr in named.items():
+            # only the three weight kinds of the model; anything else in the file (optimizer slots, counters) is ignored
+            if not key.endswith(("/filters:0", "/biases:0", "/alpha:0")):
+                continue
             lname = key.split("/")[0]
             layers.setdefault(lname, []).append(np.asarray(arr))
 

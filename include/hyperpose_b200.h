@@ -187,8 +187,10 @@ int hp_engine_read_outputs_host(hp_engine* e, float* conf, float* paf, int N);
  * these buffers (what parser.process(packet[0], packet[1]) does per image, operator_api_batched_images_paf.example.cpp:
  * 70-74, and what the stream's parse tasks do, stream.hpp:347-373) parse the whole batch ONCE from the device copy and
  * serve the remaining images from the cached records -- no second trip of the tensors over PCIe, one launch sequence
- * per batch.  Any mismatch (other address, other shape, changed contents, publication older than 4 batches) takes
- * the ordinary host path; the results are identical. */
+ * per batch.  The look-up compares EVERY byte of the two host tensors with the pinned copy the publication keeps: a
+ * buffer edited in place, or freed and re-allocated at the same address, is never served stale results.  Any mismatch
+ * (other address, other shape, any changed byte, publication older than 4 batches) takes the ordinary host path; the
+ * results are identical.  Publishing is opt-in (publish = 0 is a plain read-back). */
 int hp_engine_read_outputs_frames(hp_engine* e, float* const* conf_frames, float* const* paf_frames, int N, int publish);
 /* 0: conf/paf maps for hyperpose::parser::paf; 1: OpenPifPaf fields (pif, paf) for hyperpose::parser::pifpaf */
 int hp_engine_head_type(const hp_engine* e);
@@ -214,8 +216,48 @@ int hp_engine_get_profile(hp_engine* e, double* ms_per_op, int* op_type, double*
 
 /* engine.inference(batch) + parser.process(packet) for every image of the batch
  * (examples/operator_api_batched_images_paf.example.cpp:64-74) as ONE call: host u8 frames in,
- * human_t records out, conf/paf never leave the device. */
+ * human_t records out, conf/paf never leave the device.  Synchronous form of the two calls below; a parser capacity that
+ * overflows is grown and the batch re-run (the reference is unbounded), so HP_ERR_CAPACITY means the CALLER's `cap`. */
 int hp_pose_run_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, hp_human* out, int cap, int* n_out);
+/* The same, two batches in flight: submit enqueues the H2D copy of the frames (own copy stream: it overlaps the convs of
+ * the previously submitted batch), the whole launch sequence (replayed from a CUDA graph captured on first use) and the
+ * D2H of the records, and returns a ticket (0 or 1) at once; collect waits for that batch and hands out its humans.
+ * At most two tickets are outstanding; a third submit without a collect is HP_ERR_ARG.  `frames` may be pageable (it is
+ * copied into pinned staging before submit returns) or page-locked (DMA straight from it: keep it alive until collect). */
+int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket);
+int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out);
+int hp_pose_stats(const hp_engine* e, long long* graph_captures, long long* graph_launches);
+/* building blocks of the above (also usable on their own): pre-allocate for a geometry / read the state a captured launch
+ * sequence bakes in / enqueue the record D2H into PINNED caller memory / grow after an overflow */
+int hp_paf_prepare(hp_paf* p, int N, int c_conf, int c_paf, int H, int W);
+int hp_paf_state(const hp_paf* p, float* thresholds2, int* ints6);
+int hp_paf_copy_results_host_async(hp_paf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream);
+int hp_paf_grow_capacity(hp_paf* p, int flags);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: frames are independent, so they shard across the GPUs of one box with no data-path collective.
+ * One PROCESS, one host thread + engine + parser + stream pair per GPU (weights replicated).  N_total frames are cut into
+ * blocks of max_batch; block k (frames [k*B, (k+1)*B)) runs on GPU k % n -- GPU g gets frames [g*B, (g+1)*B) of every
+ * super-batch of n*B frames -- each GPU pipelines its blocks two deep, and the humans come back in frame order.
+ * The reference has no multi-GPU path at all (one TensorRT context, src/tensorrt.cpp:387-396).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hp_pool hp_pool;
+/* devices: n CUDA ordinals (NULL = 0..n-1); the remaining arguments as hp_engine_create / hp_paf_create */
+int hp_pool_create(hp_pool** out, const int* devices, int n_devices, const void* pack, size_t pack_bytes, int in_w, int in_h,
+                   int max_batch, double factor, int flip_rgb, float conf_thresh, float paf_thresh);
+void hp_pool_destroy(hp_pool* p);
+int hp_pool_size(const hp_pool* p);
+int hp_pool_set_capacity(hp_pool* p, int max_peaks_per_part, int max_candidates_per_limb, int max_humans);
+/* frames: HOST u8 [n_total, in_h, in_w, 3]; out[n_total * cap], n_out[n_total] */
+int hp_pool_run_u8_host(hp_pool* p, const uint8_t* frames, int n_total, hp_human* out, int cap, int* n_out);
+int hp_pool_set_output_override(hp_pool* p, const float* const* d_conf, const float* const* d_paf);
+long long hp_pool_launch_count(const hp_pool* p);
+/* Device of the C++ drop-in classes (hyperpose::dnn::tensorrt has no device argument): env HPB_DEVICE = <ordinal> | "rr"
+ * (engine instances take the GPUs round-robin); unset = 0.  A parser created by the drop-in follows the engine whose
+ * published batch it is first handed (hp_handoff_device_of), else this default. */
+int hp_default_device(void);
+/* device of the published batch that owns this host buffer (engine -> parser hand-off), or -1 */
+int hp_handoff_device_of(const float* host_conf);
 
 #ifdef __cplusplus
 }

@@ -83,9 +83,6 @@ def test_reference_stream_scheduler_builds_over_the_dropin_and_runs_with_a_mock_
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("HPB_RUN_STREAM_EXAMPLE"), reason="first GPU run pending: the round's one attempt hit the reference's "
-                    "std::vector<cv::Mat> input bug (src/stream.cpp:18-30, reproduced on CPU with the mock engine) after which no GPU minutes were left; "
-                    "set HPB_RUN_STREAM_EXAMPLE=1")
 def test_reference_stream_scheduler_runs_on_the_gpu(tmp_path):
     exe = hb.build_stream_example()
     if exe is None:

@@ -5,7 +5,7 @@ The operator API sequence (examples/operator_api_batched_images_paf.example.cpp:
 with every tensor crossing host memory.  The drop-in keeps the interface; these tests pin the behaviour behind it:
   * buffers the engine filled AND published are parsed once per batch from the device snapshot (counters prove it),
     results byte-identical to the oracle and to the ordinary host path;
-  * anything else -- a copy at another address, changed contents, a publication older than 4 batches, the switch
+  * anything else -- a copy at another address, ANY changed byte, a publication older than 4 batches, the switch
     turned off -- takes the host path and gives the same answer."""
 import threading
 
@@ -43,7 +43,7 @@ def test_published_batch_is_parsed_once_on_the_device():
     parser = capi.PafParser()
     eng.infer_u8(frames)
     s0 = capi.handoff_stats()
-    packets = eng.read_outputs_frames(N)                      # tensorrt::inference's return value
+    packets = eng.read_outputs_frames(N, publish=True)                      # tensorrt::inference's return value
     assert _delta(s0)["published"] == 1
     l0 = parser.launch_count
     total = 0
@@ -69,7 +69,7 @@ def test_copies_changed_contents_and_other_parameters():
     eng, frames, conf, paf, keep = _engine_with_synthetic_outputs(N, seed=5)
     parser = capi.PafParser()
     eng.infer_u8(frames)
-    packets = eng.read_outputs_frames(N)
+    packets = eng.read_outputs_frames(N, publish=True)
     # (a) a copy at another address is not a published buffer: ordinary host path, same answer
     s0 = capi.handoff_stats()
     c2, p2 = packets[0][0].copy(), packets[0][1].copy()
@@ -83,19 +83,26 @@ def test_copies_changed_contents_and_other_parameters():
         assert parser.process(*packets[i]).tobytes() == want.tobytes()
     d = _delta(s0)
     assert d["hits"] == N and d["batch_parses"] == 1, d
-    # (c) contents changed behind the API's back (index 0 is one of the fingerprint samples): host path on the new bytes
-    s0 = capi.handoff_stats()
-    packets[2][0][0, 0, 0] += 0.5
-    want = oracle.oracle_process(packets[2][0], packets[2][1], 0.3, 0.1)["humans"]
-    assert parser.process(*packets[2]).tobytes() == want.tobytes()
-    d = _delta(s0)
-    assert d["hits"] == 0 and d["misses"] == 1, d
+    # (c) contents changed behind the API's back -- ONE float somewhere in the middle of either tensor (the look-up compares every
+    #     byte with the published copy, not a sample): host path on the new bytes, never the cached humans of the old ones
+    for which, idx, delta in ((0, (7, 13, 21), 0.5), (1, (29, 5, 40), -0.75)):
+        s0 = capi.handoff_stats()
+        saved = float(packets[2][which][idx])
+        packets[2][which][idx] += delta
+        want = oracle.oracle_process(packets[2][0], packets[2][1], 0.3, 0.1)["humans"]
+        assert parser.process(*packets[2]).tobytes() == want.tobytes()
+        d = _delta(s0)
+        assert d["hits"] == 0 and d["misses"] == 1, d
+        packets[2][which][idx] = saved                          # restored bytes are the published bytes again: served from the cache
+        s0 = capi.handoff_stats()
+        assert parser.process(*packets[2]).tobytes() == oracle.oracle_process(conf[2], paf[2], 0.3, 0.1)["humans"].tobytes()
+        assert _delta(s0)["hits"] == 1
     # (d) switched off: nothing is published, nothing is looked up
     capi.handoff_enable(False)
     try:
         s0 = capi.handoff_stats()
         eng.infer_u8(frames)
-        pk = eng.read_outputs_frames(N)
+        pk = eng.read_outputs_frames(N, publish=True)
         parser.set_conf_thresh(0.05); parser.set_paf_thresh(0.05)
         for i in range(N):
             assert parser.process(*pk[i]).tobytes() == oracle.oracle_process(conf[i], paf[i])["humans"].tobytes()
@@ -113,7 +120,7 @@ def test_old_publications_are_retired_and_engine_teardown_unregisters():
     batches = []
     for _ in range(5):                                        # ring of 4: the first publication is retired by the fifth
         eng.infer_u8(frames)
-        batches.append(eng.read_outputs_frames(N))
+        batches.append(eng.read_outputs_frames(N, publish=True))
     s0 = capi.handoff_stats()
     want = [oracle.oracle_process(conf[i], paf[i])["humans"].tobytes() for i in range(N)]
     for i in range(N):
@@ -135,7 +142,7 @@ def test_stream_style_parser_replicas_on_threads():
     N = 6
     eng, frames, conf, paf, keep = _engine_with_synthetic_outputs(N, seed=11)
     eng.infer_u8(frames)
-    packets = eng.read_outputs_frames(N)
+    packets = eng.read_outputs_frames(N, publish=True)
     replicas = [capi.PafParser() for _ in range(N)]
     got = [None] * N
     s0 = capi.handoff_stats()
@@ -169,7 +176,7 @@ def test_pifpaf_fields_hand_off():
     eng.set_output_override(dp.data_ptr(), da.data_ptr())
     eng.infer_u8(syn.make_frames_u8(1, N, HW, HW))
     s0 = capi.handoff_stats()
-    packets = eng.read_outputs_frames(N)                      # [pif_i [17,5,49,49], paf_i [19,9,49,49]]
+    packets = eng.read_outputs_frames(N, publish=True)                      # [pif_i [17,5,49,49], paf_i [19,9,49,49]]
     dec = capi.PifPafParser(HW, HW, 0.1)
     total = 0
     for i in range(N):

@@ -21,7 +21,7 @@ def _tl_weight_list(seed, n_stages):
             out.append((rng.standard_normal((k, k, ci, co)) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32))   # HWIO
             out.append((rng.standard_normal(co) * 0.05).astype(np.float32))
         else:
-            out.append(rng.uniform(0.05, 0.5, co).astype(np.float32))
+            out.append((rng.standard_normal(co) * 0.5).astype(np.float32))   # raw alpha variable (any sign)
     return out
 
 
@@ -36,7 +36,8 @@ def _reference_forward(arrays, x, n_stages):
         return F.relu(y) if act == "relu" else y
 
     def prelu(x):
-        return F.prelu(x, torch.from_numpy(next(it)))
+        # TensorLayer 2.2.3 PRelu: relu(x) - sigmoid(alpha) * relu(-x) on the RAW saved alpha
+        return F.prelu(x, torch.sigmoid(torch.from_numpy(next(it))))
 
     def pool(x):   # MaxPool2d(2, 2), TF 'SAME': window clipped at the border
         return F.max_pool2d(x, 2, 2, ceil_mode=True)
