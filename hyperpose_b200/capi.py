@@ -185,6 +185,9 @@ EXPORTS += [
     "hp_engine_launch_count", "hp_engine_debug_read_buffer", "hp_engine_debug_write_buffer", "hp_engine_debug_run_ops",
     "hp_pose_run_u8_host", "hp_engine_stage_frame_u8", "hp_engine_infer_staged", "hp_engine_debug_read_frames", "hp_engine_set_output_override", "hp_engine_set_profiling", "hp_engine_get_profile",
     "hp_engine_read_outputs_frames", "hp_engine_head_type", "hp_handoff_enable", "hp_handoff_stats",
+    "hp_pose_submit_u8_host", "hp_pose_collect", "hp_pose_stats", "hp_paf_prepare", "hp_paf_state", "hp_paf_copy_results_host_async",
+    "hp_paf_grow_capacity", "hp_pool_create", "hp_pool_destroy", "hp_pool_size", "hp_pool_set_capacity", "hp_pool_run_u8_host",
+    "hp_pool_set_output_override", "hp_pool_launch_count", "hp_default_device", "hp_handoff_device_of",
 ]
 
 
@@ -217,6 +220,20 @@ def _bind_engine(L):
     L.hp_engine_head_type.argtypes = [vp]
     L.hp_handoff_enable.argtypes = [C.c_int]
     L.hp_handoff_stats.argtypes = [C.POINTER(C.c_longlong)] * 4
+    L.hp_pose_submit_u8_host.argtypes = [vp, vp, vp, C.c_int, ip]
+    L.hp_pose_collect.argtypes = [vp, C.c_int, vp, C.c_int, ip]
+    L.hp_pose_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.hp_pool_create.argtypes = [C.POINTER(vp), ip, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float, C.c_float]
+    L.hp_pool_destroy.argtypes = [vp]
+    L.hp_pool_destroy.restype = None
+    L.hp_pool_size.argtypes = [vp]
+    L.hp_pool_set_capacity.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.hp_pool_run_u8_host.argtypes = [vp, vp, C.c_int, vp, C.c_int, ip]
+    L.hp_pool_set_output_override.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.hp_pool_launch_count.argtypes = [vp]
+    L.hp_pool_launch_count.restype = C.c_longlong
+    L.hp_default_device.restype = C.c_int
+    L.hp_handoff_device_of.argtypes = [vp]
 
 
 class Engine:
@@ -370,6 +387,80 @@ class Engine:
         n = (C.c_int * N)()
         check(lib().hp_pose_run_u8_host(self._h, parser._h, frames.ctypes.data, N, out.ctypes.data, cap, n))
         return [out[i, :n[i]].copy() for i in range(N)]
+
+
+    def submit_pose(self, parser: "PafParser", frames: np.ndarray) -> int:
+        """hp_pose_submit_u8_host: enqueue one batch (H2D on the copy stream, graph replay, record D2H); returns the ticket.
+        `frames` must stay alive until collect_pose when it is page-locked memory (DMA reads it directly)."""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+        t = C.c_int(-1)
+        check(lib().hp_pose_submit_u8_host(self._h, parser._h, frames.ctypes.data, frames.shape[0], C.byref(t)))
+        self._ticket_n = getattr(self, "_ticket_n", {})
+        self._ticket_n[t.value] = frames.shape[0]
+        return t.value
+
+    def collect_pose(self, ticket: int, cap: int = 128):
+        N = self._ticket_n[ticket]
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_pose_collect(self._h, ticket, out.ctypes.data, cap, n))
+        return [out[i, :n[i]].copy() for i in range(N)]
+
+    def pose_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        check(lib().hp_pose_stats(self._h, C.byref(a), C.byref(b)))
+        return {"graph_captures": a.value, "graph_launches": b.value}
+
+
+class Pool:
+    """hp_pool_*: one engine + parser + host thread per GPU inside this process; frames shard in blocks of max_batch
+    (SURVEY 8e), humans come back in frame order."""
+
+    def __init__(self, pack: bytes, input_size, max_batch_size: int, devices=None, factor: float = 1.0 / 255, flip_rgb: bool = True,
+                 conf_thresh: float = 0.05, paf_thresh: float = 0.05):
+        L = lib()
+        if not getattr(L, "_engine_bound", False):
+            _bind_engine(L)
+            L._engine_bound = True
+        n = len(devices) if devices is not None else L.hp_device_count()
+        devs = (C.c_int * n)(*(devices if devices is not None else range(n)))
+        self._h = C.c_void_p()
+        check(L.hp_pool_create(C.byref(self._h), devs, n, pack, len(pack), int(input_size[0]), int(input_size[1]), max_batch_size,
+                               factor, 1 if flip_rgb else 0, conf_thresh, paf_thresh))
+        self.n_gpus, self.in_w, self.in_h, self.max_batch = n, int(input_size[0]), int(input_size[1]), max_batch_size
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.hp_pool_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_capacity(self, peaks_per_part=0, candidates_per_limb=0, humans=0):
+        check(lib().hp_pool_set_capacity(self._h, peaks_per_part, candidates_per_limb, humans))
+
+    def set_output_override(self, d_conf_ptrs, d_paf_ptrs):
+        n = self.n_gpus
+        a = (C.c_void_p * n)(*d_conf_ptrs)
+        b = (C.c_void_p * n)(*d_paf_ptrs)
+        check(lib().hp_pool_set_output_override(self._h, a, b))
+
+    def run(self, frames: np.ndarray, cap: int = 128):
+        """frames u8[N_total, in_h, in_w, 3] (any N_total) -> list of N_total HUMAN_DT arrays, frame order"""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"] and frames.shape[1:] == (self.in_h, self.in_w, 3)
+        N = frames.shape[0]
+        out = np.zeros((N, cap), HUMAN_DT)
+        n = (C.c_int * N)()
+        check(lib().hp_pool_run_u8_host(self._h, frames.ctypes.data, N, out.ctypes.data, cap, n))
+        return [out[i, :n[i]].copy() for i in range(N)]
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().hp_pool_launch_count(self._h))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -58,7 +58,10 @@ namespace parser {
         }
         if (!m_ttl) {
             m_ttl = std::make_unique<ttl_impl>();
-            if (hp_paf_create(&m_ttl->handle, m_conf_thresh, m_paf_thresh, m_resolution_size.width, m_resolution_size.height, 0) != HP_OK)
+            // device: the GPU of the engine whose published batch these tensors belong to (engine -> parser hand-off), else the default
+            int dev = hp_handoff_device_of(conf_map.view<float>());
+            if (dev < 0) dev = hp_default_device();
+            if (hp_paf_create(&m_ttl->handle, m_conf_thresh, m_paf_thresh, m_resolution_size.width, m_resolution_size.height, dev) != HP_OK)
                 die("hp_paf_create");
             m_n_joints = conf_map.shape()[0];
             m_n_connections = paf_map.shape()[0] / 2;

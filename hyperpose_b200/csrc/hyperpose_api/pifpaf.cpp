@@ -24,15 +24,21 @@ std::vector<human_t> pifpaf::process(const feature_map_t& paf, const feature_map
     thread_local float cur_t = -1.f;
     if (!handle || cur_h != m_net_h || cur_w != m_net_w || cur_t != m_keypoint_thresh) {
         if (handle) hp_pifpaf_destroy(handle);
-        if (hp_pifpaf_create(&handle, m_net_h, m_net_w, m_keypoint_thresh, 0) != HP_OK) {
+        int dev = hp_handoff_device_of(pif.view<float>());
+        if (dev < 0) dev = hp_default_device();
+        if (hp_pifpaf_create(&handle, m_net_h, m_net_w, m_keypoint_thresh, dev) != HP_OK) {
             std::cerr << "[HyperPose::ERROR  ] hp_pifpaf_create: " << hp_last_error() << '\n';
             std::exit(-1);
         }
         cur_h = m_net_h; cur_w = m_net_w; cur_t = m_keypoint_thresh;
     }
+    // the reference returns however many poses the decoder finds: grow the output array on HP_ERR_CAPACITY
     std::vector<hp_human> buf(256);
     int n = 0;
-    if (hp_pifpaf_process_host(handle, pif.view<float>(), paf.view<float>(), 1, h, w, buf.data(), (int)buf.size(), &n) != HP_OK) {
+    for (;;) {
+        const int rc = hp_pifpaf_process_host(handle, pif.view<float>(), paf.view<float>(), 1, h, w, buf.data(), (int)buf.size(), &n);
+        if (rc == HP_OK) break;
+        if (rc == HP_ERR_CAPACITY && buf.size() < (1u << 16)) { buf.resize(buf.size() * 4); continue; }
         std::cerr << "[HyperPose::ERROR  ] hp_pifpaf_process_host: " << hp_last_error() << '\n';
         std::exit(-1);
     }

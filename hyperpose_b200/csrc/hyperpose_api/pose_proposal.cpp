@@ -42,7 +42,7 @@ namespace parser {
         thread_local int cur_w = 0, cur_h = 0;
         if (!handle || cur_w != m_net_resolution.width || cur_h != m_net_resolution.height) {
             if (handle) hp_ppn_destroy(handle);
-            if (hp_ppn_create(&handle, m_net_resolution.width, m_net_resolution.height, m_point_thresh, m_limb_thresh, m_nms_thresh, 0) != HP_OK) {
+            if (hp_ppn_create(&handle, m_net_resolution.width, m_net_resolution.height, m_point_thresh, m_limb_thresh, m_nms_thresh, hp_default_device()) != HP_OK) {
                 std::cerr << "[HyperPose::ERROR  ] hp_ppn_create: " << hp_last_error() << '\n';
                 std::exit(-1);
             }

@@ -37,7 +37,8 @@ namespace dnn {
             std::vector<char> blob((size_t)n);
             if (!f.read(blob.data(), n)) die("cannot read model pack " + path);
             hp_engine* e = nullptr;
-            if (hp_engine_create(&e, blob.data(), blob.size(), input_size.width, input_size.height, max_batch, factor, flip_rgb ? 1 : 0, 0) != HP_OK)
+            // the reference API has no device argument: HPB_DEVICE=<ordinal> | rr (round-robin per engine instance), default 0
+            if (hp_engine_create(&e, blob.data(), blob.size(), input_size.width, input_size.height, max_batch, factor, flip_rgb ? 1 : 0, hp_default_device()) != HP_OK)
                 die("hp_engine_create(" + path + ")");
             return e;
         }

@@ -823,9 +823,21 @@ int hp_pifpaf_process_host(hp_pifpaf* p, const float* pif, const float* paf, int
     HP_CUDA_TRY(p->in_paf.ensure(n_paf));
     HP_CUDA_TRY(cudaMemcpyAsync(p->in_pif.p, pif, n_pif * sizeof(float), cudaMemcpyHostToDevice, p->stream));
     HP_CUDA_TRY(cudaMemcpyAsync(p->in_paf.p, paf, n_paf * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-    int rc = hp_pifpaf_process_device(p, p->in_pif.p, p->in_paf.p, N, h, w, p->stream);
-    if (rc) return rc;
-    return hp_pifpaf_fetch(p, out, cap, n_out, N);
+    for (int attempt = 0; attempt < 5; ++attempt) {
+        int rc = hp_pifpaf_process_device(p, p->in_pif.p, p->in_paf.p, N, h, w, p->stream);
+        if (rc) return rc;
+        rc = hp_pifpaf_fetch(p, out, cap, n_out, N);
+        if (rc != HP_ERR_CAPACITY) return rc;
+        // the reference decoder is unbounded (std::vector): grow the internal capacity that overflowed and decode again
+        int fl = 0;
+        for (int f = 0; f < N; ++f) fl |= p->host_c[N + f];
+        if (!(fl & (1 | 2 | 8))) return rc;   // the caller's own `cap`, or the fixed NMS map
+        if (fl & 1) p->seed_cap *= 4;
+        if (fl & 2) p->ann_cap *= 4;
+        if (fl & 8) p->hcap *= 4;
+        if (p->seed_cap > (1 << 20) || p->ann_cap > (1 << 18) || p->hcap > (1 << 16)) return rc;
+    }
+    return HP_ERR_CAPACITY;
 }
 
 long long hp_pifpaf_launch_count(const hp_pifpaf* p) { return p ? p->launches : 0; }

@@ -13,7 +13,7 @@ import pytest
 
 import oracle
 from hyperpose_b200 import capi, models, synthetic as syn
-from tests import torch_ref
+from oracle import torch_backbone as torch_ref
 
 pytestmark = pytest.mark.gpu
 

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from hyperpose_b200 import models, weights as W
-from tests import torch_ref
+from oracle import torch_backbone as torch_ref
 
 
 def _tl_weight_list(seed, n_stages):
