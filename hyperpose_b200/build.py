@@ -110,5 +110,48 @@ def build_stream_example(ref_root: str = "/root/reference", mock: bool = False) 
     return exe
 
 
+REFERENCE_EXAMPLES = ["operator_api_batched_images_paf.example", "operator_api_batched_images_pifpaf.example", "operator_api_batched_images_pose_proposal.example",
+                      "stream_api_video_paf.example", "gen_serialized_engine.example", "cli"]
+
+
+def build_reference_examples(ref_root: str = "/root/reference") -> dict | None:
+    """The reference's OWN example programs, compiled UNMODIFIED from <ref>/examples/*.cpp (+ examples/utils.cpp) against the drop-in:
+    the reference's unchanged headers, its unchanged src/{stream,thread_pool,logging,human,data}.cpp (scheduler, drawing, batching
+    helpers), the B200 classes of hyperpose_api/*.cpp underneath, and the OpenCV / gflags stand-ins of csrc/shim (neither library
+    exists in this image).  Nothing of the reference is copied: every source is compiled where it lies.  Returns {name: binary} in
+    examples/ref_build/ (git-ignored, travels to the GPU box), or the prebuilt set / None where the reference tree is absent."""
+    out_dir = os.path.join(ROOT, "examples", "ref_build")
+    exes = {n: os.path.join(out_dir, n.replace(".example", "")) for n in REFERENCE_EXAMPLES}
+    if not os.path.isdir(os.path.join(ref_root, "include", "hyperpose")):
+        return exes if all(os.path.exists(e) for e in exes.values()) else None
+    os.makedirs(out_dir, exist_ok=True)
+    api = os.path.join(CSRC, "hyperpose_api")
+    shim = os.path.join(CSRC, "shim")
+    inc = ["-I" + shim, "-I" + os.path.join(ref_root, "include"), "-I" + os.path.join(ref_root, "src"), "-I" + os.path.join(ref_root, "examples"),
+           "-I" + os.path.join(ROOT, "include")]
+    common = [os.path.join(ref_root, "src", f) for f in ("stream.cpp", "thread_pool.cpp", "logging.cpp", "human.cpp", "data.cpp")]
+    common += [os.path.join(ref_root, "examples", "utils.cpp")]
+    common += [os.path.join(api, f) for f in ("paf.cpp", "tensorrt.cpp", "pifpaf.cpp", "pose_proposal.cpp")]
+    shim_files = [os.path.join(dp, f) for dp, _, fs in os.walk(shim) for f in fs]
+    objs = []
+    for src in common:
+        o = os.path.join(out_dir, ("ref_" if src.startswith(ref_root) else "b200_") + os.path.basename(src) + ".o")
+        objs.append(o)
+        if _newer([src] + shim_files + [os.path.join(ROOT, "include", "hyperpose_b200.h")], o):
+            r = subprocess.run(["g++", "-std=c++17", "-O2", "-pthread", "-c"] + inc + [src, "-o", o], capture_output=True, text=True)
+            if r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"{src} failed to compile over the shim")
+    for name, exe in exes.items():
+        src = os.path.join(ref_root, "examples", name + ".cpp")
+        if _newer([src, LIB] + objs, exe):
+            cmd = ["g++", "-std=c++17", "-O2", "-pthread"] + inc + [src] + objs + ["-L" + PKG, "-lhyperpose_b200", "-Wl,-rpath,$ORIGIN/../../hyperpose_b200", "-o", exe]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"reference example {name} failed to build unchanged against the drop-in")
+    return exes
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
