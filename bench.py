@@ -165,74 +165,127 @@ def cpu_parse_rate(conf, paf, seconds: float, threads: int):
     return sum(counts) / max(wall, 1e-9), kind
 
 
-def cpu_conv_port(graph_name: str):
-    """conv stage on the host cores: oracle/torch_backbone.py (plain PyTorch fp32, all cores) on ONE synthetic frame.
+def cpu_threads():
+    """every host thread this process may use (cgroup / affinity aware), independent of OMP_NUM_THREADS (torchrun sets it to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_conv_port(graph_name: str, n_frames: int):
+    """conv stage on the host cores: oracle/torch_backbone.py (plain PyTorch fp32) on a batch of `n_frames` synthetic frames with an
+    EXPLICIT thread count (torch.set_num_threads(all host threads): torchrun's OMP_NUM_THREADS=1 does not apply).
     The reference has no CPU implementation of its convs (TensorRT on a GPU, src/tensorrt.cpp:387-396), so this stage
     of the CPU arm is a port, the parse stage is the reference's own code."""
     import torch
     from hyperpose_b200 import models, synthetic as syn
     from oracle import torch_backbone
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
     graph = getattr(models, graph_name)(seed=0)
-    frame = syn.make_frames_u8(2, 1, IN_H, IN_W)
+    frames = syn.make_frames_u8(2, n_frames, IN_H, IN_W)
 
     def run():
         with torch.no_grad():
-            torch_backbone.run_graph(graph, frame, device="cpu")
+            torch_backbone.run_graph(graph, frames, device="cpu")
     return run, torch.get_num_threads()
 
 
+def cpu_parse_batch(conf, paf, n_frames, threads):
+    """the reference's own parser over `n_frames` frames, one replica per thread (what its stream API does, stream.hpp:139,365-373);
+    returns a callable that parses the batch once"""
+    import oracle
+    kind = "reference" if oracle.ref_available() else "port"
+    threads = max(1, min(threads, n_frames))
+    if kind == "reference":
+        reps = [oracle.RefParser() for _ in range(threads)]
+        fns = [lambda i, r=r: r.process(conf[i % conf.shape[0]], paf[i % paf.shape[0]]) for r in reps]
+    else:
+        fns = [lambda i: oracle.oracle_process(conf[i % conf.shape[0]], paf[i % paf.shape[0]]) for _ in range(threads)]
+
+    def run():
+        def work(t):
+            for i in range(t, n_frames, threads):
+                fns[t](i)
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    return run, kind, threads
+
+
+def bench_config(world: int = 1):
+    """the `config` object BOTH arms print (the driver compares them)"""
+    pif = bool(WL.get("pifpaf"))
+    return {"workload": WL["name"],
+            "global_batch": world * BATCH, "input": f"u8 frames {IN_H}x{IN_W}x3, random (default_rng)",
+            "weights": "random-init (He-normal, seed 0) of the reference architecture: " + WL["arch"],
+            "parse_input": f"synthetic {'PIF/PAF fields' if pif else 'crowd tensors'} ({PERSONS[0]}-{PERSONS[1]} persons/frame) copied over the conv outputs after the last conv",
+            "l2": f"{N_INPUT_SETS} distinct input batches rotated ({N_INPUT_SETS * BATCH * IN_H * IN_W * 3 / 1e6:.0f} MB > L2); activations (>1 GB/step) stream through",
+            "parallelism": f"dp{world} (frames shard; NCCL all-gather of keypoint records only)" if world > 1 else "single GPU"}
+
+
 def run_reference(args):
-    """--impl reference: the path on this host's CPU cores, same metric (frames/s, conv + parse).  Each step is a bounded
-    sample of the workload: ONE frame through the conv stage (PyTorch fp32 port on all cores -- the reference's convs are
-    TensorRT-on-GPU and have no CPU implementation) and through the reference's own parser (src/paf.cpp via oracle/_ref)."""
+    """--impl reference: the path on this host's CPU cores, same metric / unit / config as the GPU arm (frames/s through conv + parse
+    on batches of the workload's frames).  Parse stage = the reference's own src/paf.cpp compiled verbatim (oracle/_ref), one replica
+    per thread like its stream API; conv stage = a PyTorch fp32 port of the same graph on ALL host threads (explicit
+    torch.set_num_threads: the reference runs its convs in TensorRT on a GPU and has no CPU implementation of them, so no
+    "reference" conv stage can exist on a CPU).  Each step is a bounded sample: as many frames of the batch as keep the whole
+    --steps/--warmup run within ~3 minutes (the full batch of 16 when the host is fast enough); frames/s does not depend on it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     oracle.build()
     conf, paf = crowd_tensors(1000)
-    cores = os.cpu_count() or 1
-    kind = "reference" if oracle.ref_available() else "port"
-    rp = oracle.RefParser() if kind == "reference" else None
-    conv_one, conv_threads = cpu_conv_port(WL["graph"])
+    cores = cpu_threads()
+    # calibrate: one frame through the conv stage
+    probe, conv_threads = cpu_conv_port(WL["graph"], 1)
+    probe()
+    t0 = time.time(); probe(); t_frame = time.time() - t0
+    budget_s = 170.0
+    n_steps_total = max(args.warmup, 1) + args.steps
+    frames_per_step = int(max(1, min(BATCH, budget_s / n_steps_total / max(t_frame, 1e-3))))
+    conv_run, conv_threads = cpu_conv_port(WL["graph"], frames_per_step)
+    parse_run, kind, parse_threads = cpu_parse_batch(conf, paf, frames_per_step, cores)
     t_conv = t_parse = 0.0
 
-    def step(i, timed):
+    def step(timed):
         nonlocal t_conv, t_parse
         t0 = time.time()
-        conv_one()
+        conv_run()
         t1 = time.time()
-        if kind == "reference":
-            rp.process(conf[i % BATCH], paf[i % BATCH])
-        else:
-            oracle.oracle_process(conf[i % BATCH], paf[i % BATCH])
+        parse_run()
         t2 = time.time()
         if timed:
             t_conv += t1 - t0
             t_parse += t2 - t1
 
-    for i in range(max(args.warmup, 1)):
-        step(i, False)
+    for _ in range(max(args.warmup, 1)):
+        step(False)
     t0 = time.time()
-    for i in range(args.steps):
-        step(i, True)
+    for _ in range(args.steps):
+        step(True)
     dt = time.time() - t0
-    fps = args.steps / dt
-    # the parser alone with every host thread (one replica per thread, stream.hpp:139): reported, not the value
-    threads = min(cores, BATCH)
-    parse_rate, _ = cpu_parse_rate(conf, paf, 3.0, threads)
+    fps = args.steps * frames_per_step / dt
+    # the parser alone with every host thread: the reference's own code on the stage it does run on a CPU
+    parse_rate, _ = cpu_parse_rate(conf, paf, 3.0, min(cores, BATCH))
+    cfg = bench_config(max(1, args.gpus))
     line = {
         "impl": "reference", "metric": METRIC(), "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WL["name"] + " -- CPU arm: one frame per step (bounded sample of the batch)",
-                   "frames_per_step": 1, "persons_per_frame": list(PERSONS),
-                   "conv_stage": f"PyTorch fp32 port of the same graph on {conv_threads} threads (the reference's convs are TensorRT-on-GPU: no CPU implementation exists)",
-                   "parse_stage": "the reference's own src/paf.cpp compiled verbatim (oracle/_ref)" if kind == "reference" else "oracle port of src/paf.cpp"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": conv_threads, "kind": "port",
-                         "sample": f"{args.steps} frames {IN_H}x{IN_W}: conv stage {t_conv / args.steps * 1e3:.0f} ms/frame (torch fp32 port, {conv_threads} threads) + "
-                                   f"parse stage {t_parse / args.steps * 1e3:.1f} ms/frame ({kind} parser, 1 thread) of {cores} host cores",
-                         "parse_only": {"value": parse_rate, "unit": "frames/s", "cores": threads, "kind": kind}},
+        "config": cfg,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": max(conv_threads, parse_threads), "kind": "port",
+                         "sample": f"{frames_per_step} of the batch's {BATCH} frames per step ({args.steps} steps): conv stage {t_conv / args.steps / frames_per_step * 1e3:.0f} ms/frame "
+                                   f"(PyTorch fp32 port of the same graph, torch.set_num_threads({conv_threads}); the reference's convs are TensorRT-on-GPU, no CPU implementation exists) + "
+                                   f"parse stage {t_parse / args.steps / frames_per_step * 1e3:.2f} ms/frame ({kind} parser src/paf.cpp, {parse_threads} replicas on threads) of {cores} usable host threads",
+                         "frames_per_step": frames_per_step, "conv_threads": conv_threads, "parse_threads": parse_threads,
+                         "parse_only": {"value": parse_rate, "unit": "frames/s", "cores": min(cores, BATCH), "kind": kind}},
+        "parse_only": {"value": parse_rate, "unit": "frames/s", "cores": min(cores, BATCH), "kind": kind,
+                       "what": "the reference's own CPU code for the stage it runs on a CPU (src/paf.cpp), same synthetic crowd tensors as the GPU arm's parse stage"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,22 +293,20 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def measure(args, key, dist_ctx, headline=True):
+    """one workload on this rank's GPU; returns (on rank 0) the JSON-line dict.  headline=False: a shorter run for the
+    `extra_configs` entries (no CPU baseline, no parse-batch sweep)."""
     import torch
     import torch.distributed as dist
     from hyperpose_b200 import capi, models, synthetic as syn
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    select_workload(key)
+    rank, local_rank, world, dev = dist_ctx
+    steps = args.steps if headline else max(10, min(args.steps, 20))
+    warmup = args.warmup
 
     graph = getattr(models, WL["graph"])(seed=0)
     pack = graph.to_pack()
-    engine = capi.Engine(pack, (IN_W, IN_H), max_batch_size=BATCH, device=local_rank)
+    engine = capi.Engine(pack, (IN_W, IN_H), max_batch_size=BATCH, device=local_rank, dtype=args.dtype)
     del pack
     PIFPAF = bool(WL.get("pifpaf"))
     HCAP = 128 if PIFPAF else 64
@@ -268,6 +319,7 @@ def run_ours(args):
     # inputs: N_INPUT_SETS distinct batches of frames (device + pinned host), one set of crowd tensors per rank
     rng_seed = 2 + 1000 * rank
     frames_host = [torch.from_numpy(syn.make_frames_u8(rng_seed + i, BATCH, IN_H, IN_W)).pin_memory() for i in range(N_INPUT_SETS)]
+    frames_np = [f.numpy() for f in frames_host]
     frames_dev = [f.to(dev) for f in frames_host]
     if PIFPAF:
         fields = [syn.make_pifpaf_fields(1000 * (rank + 1) + i, PERSONS, HF, WF) for i in range(BATCH)]
@@ -291,15 +343,17 @@ def run_ours(args):
     ev_res = [torch.cuda.Event() for _ in range(2)]
     ev_gat = [torch.cuda.Event() for _ in range(2)]
     gstate = {"n": 0}
+    use_gather = world > 1 and not PIFPAF and not os.environ.get("HPB_NO_GATHER")   # (diagnostic switch; the gather is part of the metric)
+
     def gather_results():
         if PIFPAF:
             return    # config 5 is a single-GPU config: records stay in the decoder's device buffer
         k = gstate["n"] & 1
-        if gstate["n"] >= 2 and world > 1 and not os.environ.get("HPB_NO_GATHER"):
+        if gstate["n"] >= 2 and use_gather:
             st.wait_event(ev_gat[k])              # the gather that last read this buffer has finished
         buf = res_bufs[k]
         parser.copy_results_device(buf.data_ptr(), buf.data_ptr() + hum_bytes, BATCH, HCAP, st.cuda_stream)
-        if world > 1 and not os.environ.get("HPB_NO_GATHER"):   # (diagnostic switch; the gather is part of the metric)
+        if use_gather:
             ev_res[k].record(st)
             sg.wait_event(ev_res[k])
             with torch.cuda.stream(sg):
@@ -308,24 +362,12 @@ def run_ours(args):
         gstate["n"] += 1
 
     def drain_gather():
-        if world > 1 and not PIFPAF and not os.environ.get("HPB_NO_GATHER"):
+        if use_gather:
             for k in range(2):
                 if gstate["n"] > k:
                     st.wait_event(ev_gat[k])
 
-    # Optional (--pipeline; OFF by default: measured SLOWER, 2070 vs 2221 frames/s -- the parser's many small CTAs delay
-    # the start of the next persistent conv kernel's CTAs, whose static tile assignment then runs unbalanced).
-    # Software pipeline of the device-resident path: the PAF parse (+ the keypoint gather) of batch i runs on a second
-    # stream while the convs of batch i+1 run on the first.  The engine's conf/paf outputs are snapshotted (D2D, 14 MB)
-    # on the conv stream so that batch i+1 may overwrite them; events order snapshot <-> parse in both directions.
-    st2 = torch.cuda.Stream(device=dev)
-    snap_conf = torch.empty(BATCH * 19 * HF * WF, dtype=torch.float32, device=dev)
-    snap_paf = torch.empty(BATCH * 38 * HF * WF, dtype=torch.float32, device=dev)
-    ev_ready = torch.cuda.Event()
-    ev_parsed = torch.cuda.Event()
-    state = {"first": True}
-
-    def step_device_serial(i):
+    def step_device(i):
         engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
         if PIFPAF:
             parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, st.cuda_stream)
@@ -333,47 +375,37 @@ def run_ours(args):
             parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
         gather_results()
 
-    def step_device(i):
-        if not args.pipeline:
-            return step_device_serial(i)
-        engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
-        if not state["first"]:
-            st.wait_event(ev_parsed)                  # the previous parse has finished reading the snapshot
-        state["first"] = False
-        engine.copy_outputs_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, st.cuda_stream)
-        ev_ready.record(st)
-        st2.wait_event(ev_ready)
-        parser.process_device(snap_conf.data_ptr(), snap_paf.data_ptr(), BATCH, 19, 38, HF, WF, st2.cuda_stream)
-        parser.copy_results_device(res_bufs[0].data_ptr(), res_bufs[0].data_ptr() + hum_bytes, BATCH, HCAP, st2.cuda_stream)
-        if world > 1:
-            with torch.cuda.stream(st2):
-                dist.all_gather_into_tensor(gath_bufs[0], res_bufs[0])
-        ev_parsed.record(st2)
-
-    def drain_device():
-        if args.pipeline:
-            st.wait_event(ev_parsed)                      # the timed region ends when the last parse/gather has finished
+    # e2e: the public host call, pinned host frames in, human_t records out -- two batches in flight
+    # (hp_pose_submit_u8_host / hp_pose_collect: H2D of batch i+1 under the convs of batch i, CUDA-graph replay)
+    pend = {"t": None}
 
     def step_host(i):
         if PIFPAF:   # engine.inference(batch) + pifpaf.process per image: host frames in, humans out (fields stay on the device)
-            engine.infer_u8(frames_host[i % N_INPUT_SETS].numpy())
+            engine.infer_u8(frames_np[i % N_INPUT_SETS])
             _, _, es = engine.device_outputs()
             parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, es)
             return parser.fetch(BATCH, cap=HCAP)
-        humans = engine.run_pose(parser, frames_host[i % N_INPUT_SETS].numpy(), cap=HCAP)
-        if world > 1:
-            gather_results()
-            sg.synchronize()
+        t = engine.submit_pose(parser, frames_np[i % N_INPUT_SETS])
+        humans = engine.collect_pose(pend["t"], cap=HCAP) if pend["t"] is not None else None
+        pend["t"] = t
         return humans
+
+    def drain_host():
+        if pend["t"] is not None:
+            h = engine.collect_pose(pend["t"], cap=HCAP)
+            pend["t"] = None
+            return h
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
-        for i in range(warmup):
+    def timed(fn, n_steps, n_warm, profile=False):
+        for i in range(n_warm):
             fn(i)
+        if fn is step_host:
+            drain_host()
         barrier()
         l0 = engine.launch_count + parser.launch_count
         if profile:
@@ -381,10 +413,10 @@ def run_ours(args):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(st)
         t0 = time.time()
-        for i in range(steps):
-            fn(warmup + i)
-        if fn is step_device:
-            drain_device()
+        for i in range(n_steps):
+            fn(n_warm + i)
+        if fn is step_host:
+            drain_host()
         drain_gather()                                # the timed region ends when the last keypoint gather has finished
         e1.record(st)
         torch.cuda.synchronize()
@@ -396,7 +428,7 @@ def run_ours(args):
         barrier()
         ms = max(ms_dev, 0.0)
         # host-synchronous paths are bounded by wall clock, device-async ones by the stream events: take the larger
-        ms = max(ms, wall * 1e3) if fn is step_host else ms
+        ms = max(ms, wall * 1e3) if fn is not step_device else ms
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -405,29 +437,78 @@ def run_ours(args):
     # sanity: the device path and the host path agree with each other before anything is timed
     step_device(0)
     torch.cuda.synchronize()
-    state["first"] = True
     ref_h = parser.fetch(BATCH, cap=HCAP)
-    host_h = step_host(0)
+    step_host(0)
+    host_h = drain_host() if not PIFPAF else step_host(0)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(ref_h, host_h)), "device and host paths disagree"
     n_humans = sum(len(h) for h in host_h)
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and headline:
         sampler.start()
-    for i in range(30):                     # (every rank: the steps contain the collective) nvidia-smi needs ~0.3 s to deliver
-        step_device(i)                      # its first sample: keep the GPUs under the same load meanwhile
-    torch.cuda.synchronize()
+    # sustained pre-load: >= 2 s of the same steps before anything is timed, so that the power-cap state of the timed
+    # region is the steady one (every rank: the steps contain the collective); nvidia-smi also needs ~0.3 s for its first sample
+    t_pre = time.time()
+    n_pre = 0
+    pre_target = 2.0 if headline else 0.5
+    while True:
+        for i in range(10):
+            step_device(n_pre + i)
+        n_pre += 10
+        torch.cuda.synchronize()
+        flag = torch.tensor([1.0 if time.time() - t_pre < pre_target else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() == 0.0 or n_pre >= 2000:
+            break
     sampler.lines.clear()                   # keep only samples taken under load
-    ms_total, launches = timed(step_device, args.steps, args.warmup, profile=True)
-    clocks = sampler.stop() if rank == 0 else None
+    # pass A: the timed K steps, per-op profiling OFF -> value
+    ms_total, launches = timed(step_device, steps, warmup)
+    clocks = sampler.stop() if rank == 0 and headline else None
+    # pass B: the same K steps with per-op CUDA events on the launching stream -> kernel time for the roofline
+    ms_prof, _ = timed(step_device, steps, warmup, profile=True)
     prof_ms, prof_ty, prof_fl, prof_runs = engine.get_profile()
-    ms_e2e, _ = timed(step_host, max(3, args.steps // 2), max(3, args.warmup))
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, steps)
+    ms_e2e, _ = timed(step_host, e2e_steps, max(3, warmup))
+    # the synchronous form of the same public call (one batch in flight), for the record
+    sync_steps = max(3, steps // 2)
+    if PIFPAF:
+        ms_sync = None
+    else:
+        def step_sync(i):
+            return engine.run_pose(parser, frames_np[i % N_INPUT_SETS], cap=HCAP)
+        ms_sync, _ = timed(step_sync, sync_steps, 3)
+        ms_sync = max(ms_sync, 1e-6)
 
-    frames_total = world * BATCH * args.steps
+    frames_total = world * BATCH * steps
     value = frames_total / (ms_total / 1e3)
     e2e_value = world * BATCH * e2e_steps / (ms_e2e / 1e3)
 
+    # parser alone on device-resident tensors at several batch sizes (launch-bound at small batches: SURVEY 8d)
+    parse_sweep = None
+    if headline and not PIFPAF and rank == 0:
+        parse_sweep = []
+        for nb in (16, 64, 128):
+            reps = nb // BATCH if nb >= BATCH else 1
+            cbig = d_conf.repeat(reps, 1, 1, 1)[:nb].contiguous(); pbig = d_paf.repeat(reps, 1, 1, 1)[:nb].contiguous()
+            p2 = capi.PafParser(0.05, 0.05, device=local_rank)
+            p2.set_capacity(peaks_per_part=128, candidates_per_limb=2048, humans=HCAP)
+            for _ in range(3):
+                p2.process_device(cbig.data_ptr(), pbig.data_ptr(), nb, 19, 38, HF, WF, st.cuda_stream)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            reps_t = 20
+            e0.record(st)
+            for _ in range(reps_t):
+                p2.process_device(cbig.data_ptr(), pbig.data_ptr(), nb, 19, 38, HF, WF, st.cuda_stream)
+            e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps_t
+            parse_sweep.append({"frames": nb, "ms": ms, "frames_per_s": nb / (ms / 1e3)})
+            p2.close()
+            del cbig, pbig
+
+    line = None
     if rank == 0:
         peaks, peak_src = load_peaks()
         conv_ms = float(prof_ms[prof_ty == models.OP_CONV].sum())
@@ -435,79 +516,136 @@ def run_ours(args):
         n_conv = int((prof_ty == models.OP_CONV).sum())
         algo_flops = ALGO_FLOPS_PER_FRAME * BATCH
         achieved = algo_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-        traffic = None
+        if args.dtype == "tf32":
+            peak = float(peaks.get("tf32_tflops_sustained", 0.5 * float(peaks.get("bf16_tflops_sustained", 1400.0))))
+            peak_note = (f"{peak_src} tf32_tflops_sustained" if "tf32_tflops_sustained" in peaks else
+                         f"half of the {peak_src} bf16_tflops_sustained (kind::tf32 issues K=8 per instruction against K=16 for f16/bf16: the tensor pipe's TF32 rate is half its 16-bit rate)")
+        else:
+            peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+            peak_note = f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"
+        traffic, traffic_source = None, None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
-        if os.path.exists(tpath) and args.workload == "cfg3":      # the ncu capture is of the headline workload only
+        if os.path.exists(tpath) and key == "cfg3" and args.dtype == "f16":      # the ncu capture is of the headline workload only
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_step")
+                traffic_source = tj.get("source", "ncu capture committed under profiles/ (not measured in this run)")
             except Exception:
                 traffic = None
-        # bounded CPU baseline (rank 0, N=1 only): ~12 s of the reference parser on the host cores
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline and not PIFPAF:
-            cores = os.cpu_count() or 1
+        h2d = BATCH * IN_H * IN_W * 3
+        d2h = BATCH * HCAP * rec_bytes + BATCH * 8
+        cfg = bench_config(world)
+        line = {
+            "metric": METRIC(), "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": ("tf32 operands (fp32 activations in HBM), f32 accumulate (conv); f32/f64 (parse)" if args.dtype == "tf32"
+                      else "f16 operands, f32 accumulate (conv); f32/f64 (parse)"), "data": "synthetic",
+            "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": ("hp_engine_infer_u8_host + hp_pifpaf_process_device + hp_pifpaf_fetch (synchronous per batch)" if PIFPAF else
+                            "hp_pose_submit_u8_host / hp_pose_collect (pinned host frames in, human_t records out, two batches in flight, CUDA-graph replay)"),
+                    "synchronous_call": (None if ms_sync is None else {"value": world * BATCH * sync_steps / (ms_sync / 1e3), "api": "hp_pose_run_u8_host (one batch in flight)"}),
+                    "graphs": engine.pose_stats()},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "traffic_source": traffic_source,
+                         "kernel": "conv_tcgen05 family (conv_tcgen05_kernel / _swap_kernel / conv_halo_kernel / conv_stem3_kernel)", "launches_per_step": n_conv,
+                         "algorithmic_flops_per_step": algo_flops, "kernel_ms_per_step": conv_ms,
+                         "kernel_share_of_step": conv_ms / (ms_prof / steps), "peak_source": peak_note,
+                         "timing": f"per-op CUDA events on the launching stream over a second pass of the same {steps} steps ({ms_prof / steps:.3f} ms/step with the events; `value` is timed without them)"},
+            "clocks": clocks,
+            "sustained_preload": {"steps": n_pre, "seconds": pre_target},
+        }
+        # SURVEY 8d: backbone-only and parser-only rates of the same run (per GPU), and the parser against its HBM bound
+        step_ms = ms_prof / steps
+        parse_ms = max(step_ms - conv_ms - other_ms, 1e-6)
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # SURVEY 8d: (19+38)*Hf*Wf*4 B per frame for conf/PAF; (17*5+19*9)*h*w*4 B for the PIF/PAF fields
+        frame_bytes = ((17 * 5 + 19 * 9) if PIFPAF else 57) * HF * WF * 4
+        parse_bytes = BATCH * frame_bytes
+        line["breakdown"] = {"backbone_ms_per_step": conv_ms + other_ms, "backbone_frames_per_s": BATCH / ((conv_ms + other_ms) / 1e3),
+                             "parse_ms_per_step": parse_ms, "parse_frames_per_s": BATCH / (parse_ms / 1e3),
+                             "parse_hbm_frac": (parse_bytes / (parse_ms / 1e3) / 1e9 / hbm) if parse_bytes else None,
+                             "parse_algorithmic_bytes_per_step": parse_bytes,
+                             "note": "parse = step minus the engine's per-op events (parser kernels + result copy); its HBM bound counts only the network-output tensors read once"}
+        if parse_sweep:
+            for e in parse_sweep:
+                e["hbm_frac"] = e["frames"] * frame_bytes / (e["ms"] / 1e3) / 1e9 / hbm
+            line["breakdown"]["parse_alone_by_batch"] = parse_sweep
+        layers = [{"op": i, "name": graph.ops[i].name, "type": int(prof_ty[i]), "ms": float(prof_ms[i]),
+                   "tflops": (float(prof_fl[i]) * BATCH / (prof_ms[i] / 1e3) / 1e12 if prof_ms[i] > 0 and prof_fl[i] > 0 else None)}
+                  for i in range(len(prof_ms))]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_layers_{key}_{args.dtype}_n{world}.json"), "w") as f:
+            json.dump({"ms_per_step": ms_total / steps, "conv_ms": conv_ms, "other_engine_ms": other_ms, "profiled_runs": prof_runs, "layers": layers}, f, indent=1)
+        # bounded CPU baseline (rank 0, N=1, headline only): the reference parser on the host cores + the conv port
+        if world == 1 and headline and not args.no_cpu_baseline and not PIFPAF:
+            cores = cpu_threads()
             threads = min(cores, BATCH)
-            rate, kind = cpu_parse_rate(conf_np, paf_np, 12.0, threads)
-            conv_one, conv_threads = cpu_conv_port(WL["graph"])
+            rate, kind = cpu_parse_rate(conf_np, paf_np, 10.0, threads)
+            conv_one, conv_threads = cpu_conv_port(WL["graph"], 1)
             conv_one()                                   # warm-up (allocations, oneDNN primitive caches)
             tc0 = time.time(); n_cpu_frames = 0
             while n_cpu_frames < 2 or (time.time() - tc0 < 6.0 and n_cpu_frames < 16):
                 conv_one(); n_cpu_frames += 1
             conv_s = (time.time() - tc0) / n_cpu_frames
             whole = 1.0 / (conv_s + 1.0 / rate)
-            cpu = {"value": whole, "unit": "frames/s", "cores": max(threads, conv_threads), "kind": "port",
-                   "sample": f"conv stage: {n_cpu_frames} frames {IN_H}x{IN_W} through a PyTorch fp32 port of the same graph on {conv_threads} threads ({conv_s * 1e3:.0f} ms/frame; the reference's "
-                             f"convs are TensorRT-on-GPU, no CPU implementation exists) + parse stage: 12 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's {BATCH} synthetic "
-                             f"{HF}x{WF} crowd frames, {threads} threads of {cores} host cores",
+            line["cpu_baseline"] = {"value": whole, "unit": "frames/s", "cores": max(threads, conv_threads), "kind": "port",
+                   "sample": f"conv stage: {n_cpu_frames} frames {IN_H}x{IN_W} through a PyTorch fp32 port of the same graph, torch.set_num_threads({conv_threads}) ({conv_s * 1e3:.0f} ms/frame; the reference's "
+                             f"convs are TensorRT-on-GPU, no CPU implementation exists) + parse stage: 10 s of the reference CPU parser (src/paf.cpp via oracle/_ref) on the step's {BATCH} synthetic "
+                             f"{HF}x{WF} crowd frames, {threads} threads of {cores} usable host threads",
                    "parse_only": {"value": rate, "unit": "frames/s", "cores": threads, "kind": kind}}
-        layers = [{"op": i, "name": graph.ops[i].name, "type": int(prof_ty[i]), "ms": float(prof_ms[i]),
-                   "tflops": (float(prof_fl[i]) * BATCH / (prof_ms[i] / 1e3) / 1e12 if prof_ms[i] > 0 and prof_fl[i] > 0 else None)}
-                  for i in range(len(prof_ms))]
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"bench_layers_n{world}.json"), "w") as f:
-            json.dump({"ms_per_step": ms_total / args.steps, "conv_ms": conv_ms, "other_engine_ms": other_ms, "profiled_runs": prof_runs, "layers": layers}, f, indent=1)
-        h2d = BATCH * IN_H * IN_W * 3
-        d2h = BATCH * HCAP * rec_bytes + BATCH * 8
-        line = {
-            "metric": METRIC(), "value": value, "unit": "frames/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands, f32 accumulate (conv); f32/f64 (parse)", "data": "synthetic",
-            "config": {"workload": WL["name"],
-                       "global_batch": world * BATCH, "input": f"u8 frames {IN_H}x{IN_W}x3, random (default_rng)",
-                       "weights": "random-init (He-normal, seed 0) of the reference architecture: " + WL["arch"],
-                       "parse_input": f"synthetic {'PIF/PAF fields' if PIFPAF else 'crowd tensors'} ({PERSONS[0]}-{PERSONS[1]} persons/frame, {n_humans} humans/batch) copied over the conv outputs after the last conv",
-                       "l2": f"{N_INPUT_SETS} distinct input batches rotated ({N_INPUT_SETS * BATCH * IN_H * IN_W * 3 / 1e6:.0f} MB > L2); activations (>1 GB/step) stream through",
-                       "parallelism": f"dp{world} (frames shard; NCCL all-gather of keypoint records only)" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "hp_pose_run_u8_host (pinned host frames in, human_t records out, synchronous per batch)"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "kernel": "conv_tcgen05 family (conv_tcgen05_kernel / _swap_kernel / conv_halo_kernel / conv_stem3_kernel)", "launches_per_step": n_conv,
-                         "algorithmic_flops_per_step": algo_flops, "kernel_ms_per_step": conv_ms,
-                         "kernel_share_of_step": conv_ms / (ms_total / args.steps), "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)"},
-            "clocks": clocks,
-        }
-        # SURVEY 8d: backbone-only and parser-only rates of the same run (per GPU), and the parser against its HBM bound
-        step_ms = ms_total / args.steps
-        parse_ms = max(step_ms - conv_ms - other_ms, 1e-6)
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        # SURVEY 8d: (19+38)*Hf*Wf*4 B per frame for conf/PAF; (17*5+19*9)*h*w*4 B for the PIF/PAF fields
-        parse_bytes = BATCH * ((17 * 5 + 19 * 9) if PIFPAF else 57) * HF * WF * 4
-        line["breakdown"] = {"backbone_ms_per_step": conv_ms + other_ms, "backbone_frames_per_s": BATCH / ((conv_ms + other_ms) / 1e3),
-                             "parse_ms_per_step": parse_ms, "parse_frames_per_s": BATCH / (parse_ms / 1e3),
-                             "parse_hbm_frac": (parse_bytes / (parse_ms / 1e3) / 1e9 / hbm) if parse_bytes else None,
-                             "parse_algorithmic_bytes_per_step": parse_bytes,
-                             "note": "parse = step minus the engine's per-op events (parser kernels + result copy); its HBM bound counts only the network-output tensors read once"}
-        if cpu:
-            line["cpu_baseline"] = cpu
+            gpu_parse = max(parse_sweep, key=lambda e: e["frames_per_s"]) if parse_sweep else None
+            line["parse_only"] = {"gpu": {"value": BATCH / (parse_ms / 1e3), "unit": "frames/s", "what": f"parse stage inside the step, batch {BATCH}"},
+                                  "gpu_best_batch": gpu_parse,
+                                  "cpu_reference": {"value": rate, "unit": "frames/s", "cores": threads, "kind": kind, "what": "the reference's own src/paf.cpp, one replica per thread"},
+                                  "ratio_in_step": BATCH / (parse_ms / 1e3) / rate}
+        line["humans_per_batch"] = n_humans
+    engine.close()
+    parser.close()
+    del frames_dev, frames_host, d_conf, d_paf
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = (rank, local_rank, world, dev)
+    line = measure(args, args.workload, ctx, headline=True)
+    # the other single-GPU BASELINE configs in the same run (N=1 only): one entry each under `extra_configs`
+    if world == 1 and args.workload == "cfg3" and args.dtype == "f16" and not args.no_extra:
+        extra = []
+        for key in ("cfg2", "cfg4", "cfg5"):
+            try:
+                e = measure(args, key, ctx, headline=False)
+                extra.append({k: e[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline", "breakdown", "gpu_launches")})
+            except Exception as ex:      # an extra config must never cost the headline line
+                extra.append({"workload": key, "error": repr(ex)})
+        line["extra_configs"] = extra
+        if not args.no_tf32_line:
+            try:
+                a2 = argparse.Namespace(**vars(args)); a2.dtype = "tf32"
+                e = measure(a2, "cfg3", ctx, headline=False)
+                line["tf32"] = {k: e[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "dtype", "e2e", "roofline", "gpu_launches")}
+            except Exception as ex:
+                line["tf32"] = {"error": repr(ex)}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    engine.close()
-    parser.close()
 
 
 def main():
@@ -517,7 +655,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", action="store_true", help="two-stream software pipeline (parse of batch i overlaps convs of batch i+1)")
+    ap.add_argument("--dtype", default="f16", choices=["f16", "tf32"], help="conv arithmetic: f16 = data_type::kHALF, tf32 = data_type::kFLOAT of the reference API (tensorrt.hpp:14-22)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs entries (cfg2 / cfg4 / cfg5) of the default run")
+    ap.add_argument("--no-tf32-line", action="store_true", help="skip the tf32 entry of the default run")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline cfg3)")
     args = ap.parse_args()
     select_workload(args.workload)

@@ -188,12 +188,15 @@ EXPORTS += [
     "hp_pose_submit_u8_host", "hp_pose_collect", "hp_pose_stats", "hp_paf_prepare", "hp_paf_state", "hp_paf_copy_results_host_async",
     "hp_paf_grow_capacity", "hp_pool_create", "hp_pool_destroy", "hp_pool_size", "hp_pool_set_capacity", "hp_pool_run_u8_host",
     "hp_pool_set_output_override", "hp_pool_launch_count", "hp_default_device", "hp_handoff_device_of",
+    "hp_engine_create_ex", "hp_engine_dtype",
 ]
 
 
 def _bind_engine(L):
     vp, ip = C.c_void_p, C.POINTER(C.c_int)
     L.hp_engine_create.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+    L.hp_engine_create_ex.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+    L.hp_engine_dtype.argtypes = [vp]
     L.hp_engine_destroy.argtypes = [vp]
     L.hp_engine_destroy.restype = None
     L.hp_engine_info.argtypes = [vp, ip, ip, ip, ip, ip, ip, ip, C.POINTER(C.c_double)]
@@ -241,15 +244,17 @@ class Engine:
     Engine(model_pack, input_size=(w, h), max_batch_size, factor=1/255, flip_rgb=True); inference(frames)."""
 
     def __init__(self, pack: bytes, input_size, max_batch_size: int = 8, factor: float = 1.0 / 255, flip_rgb: bool = True,
-                 device: int = 0):
+                 device: int = 0, dtype: str = "f16"):
+        """dtype: "f16" (= data_type::kHALF) or "tf32" (= data_type::kFLOAT of the reference ctor, tensorrt.hpp:14-22)"""
         L = lib()
         if not getattr(L, "_engine_bound", False):
             _bind_engine(L)
             L._engine_bound = True
         self._h = C.c_void_p()
         self._pack = pack
-        check(L.hp_engine_create(C.byref(self._h), pack, len(pack), int(input_size[0]), int(input_size[1]), max_batch_size,
-                                 factor, 1 if flip_rgb else 0, device))
+        self.dtype = dtype
+        check(L.hp_engine_create_ex(C.byref(self._h), pack, len(pack), int(input_size[0]), int(input_size[1]), max_batch_size,
+                                    factor, 1 if flip_rgb else 0, device, {"f16": 0, "tf32": 1}[dtype]))
         v = [C.c_int() for _ in range(7)]
         fl = C.c_double()
         check(L.hp_engine_info(self._h, *[C.byref(x) for x in v], C.byref(fl)))

@@ -529,6 +529,7 @@ struct EngBuffer {
 
 struct hp_engine {
     int device = 0;
+    int dtype = 0;   // HP_DTYPE_F16 | HP_DTYPE_TF32
     int in_h = 0, in_w = 0, max_batch = 0;
     double factor = 1.0 / 255;
     int flip_rgb = 1;
@@ -976,6 +977,16 @@ extern "C" {
 int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
                      double factor, int flip_rgb, int device)
 {
+    return hp_engine_create_ex(out, pack, pack_bytes, in_w, in_h, max_batch, factor, flip_rgb, device, HP_DTYPE_F16);
+}
+
+int hp_engine_dtype(const hp_engine* e) { return e ? e->dtype : HP_ERR_ARG; }
+
+int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
+                        double factor, int flip_rgb, int device, int dtype)
+{
+    if (dtype != HP_DTYPE_F16 && dtype != HP_DTYPE_TF32) { set_error("hp_engine_create_ex: unknown dtype %d", dtype); return HP_ERR_ARG; }
+    if (dtype == HP_DTYPE_TF32) { set_error("hp_engine_create_ex: the tf32 path is not built in this library"); return HP_ERR_UNSUPPORTED; }
     if (!out || !pack) { set_error("hp_engine_create: null argument"); return HP_ERR_ARG; }
     *out = nullptr;
     int ndev = 0;
@@ -1019,7 +1030,7 @@ int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int i
     if (prop.major != 10) { set_error("hp_engine_create: device is sm_%d%d; this engine is tcgen05/TMA code for sm_100a only", prop.major, prop.minor); return HP_ERR_UNSUPPORTED; }
 
     hp_engine* e = new hp_engine();
-    e->device = device; e->in_h = in_h; e->in_w = in_w; e->max_batch = max_batch;
+    e->device = device; e->dtype = dtype; e->in_h = in_h; e->in_w = in_w; e->max_batch = max_batch;
     e->factor = factor; e->flip_rgb = flip_rgb; e->hdr = hdr; e->num_sms = prop.multiProcessorCount;
     const uint8_t* ptr = (const uint8_t*)pack + sizeof(PackHeader);
     const PackBuffer* pb = (const PackBuffer*)ptr;

@@ -159,6 +159,15 @@ typedef struct hp_engine hp_engine;
  * (tensorrt.hpp:44-74).  pack/pack_bytes: model pack image in host memory. */
 int hp_engine_create(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
                      double factor, int flip_rgb, int device);
+/* The same with the arithmetic the reference's `data_type` ctor argument selects (tensorrt.hpp:14-22,48,61):
+ *   HP_DTYPE_F16  (= data_type::kHALF):  fp16 operands and activations, fp32 accumulation -- what hp_engine_create builds;
+ *   HP_DTYPE_TF32 (= data_type::kFLOAT, the reference default): fp32 activations in HBM, tcgen05.mma.kind::tf32 (fp32 operands
+ *                 read with a 10-bit mantissa by the tensor core, fp32 accumulation) -- TensorRT's own FP32 mode on tensor-core GPUs. */
+#define HP_DTYPE_F16 0
+#define HP_DTYPE_TF32 1
+int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, int in_w, int in_h, int max_batch,
+                        double factor, int flip_rgb, int device, int dtype);
+int hp_engine_dtype(const hp_engine* e);
 void hp_engine_destroy(hp_engine* e);
 /* max_batch_size() / input_size() (tensorrt.hpp:81-85) + output geometry; any pointer may be NULL */
 int hp_engine_info(const hp_engine* e, int* in_w, int* in_h, int* max_batch, int* c_conf, int* c_paf, int* out_h, int* out_w,
