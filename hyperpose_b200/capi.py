@@ -359,12 +359,12 @@ class Engine:
     def debug_read_buffer(self, buf: int, n: int) -> np.ndarray:
         H, W, Cc = C.c_int(), C.c_int(), C.c_int()
         check(lib().hp_engine_debug_read_buffer(self._h, buf, None, n, C.byref(H), C.byref(W), C.byref(Cc)))
-        out = np.empty((n, H.value, W.value, Cc.value), np.float16)
+        out = np.empty((n, H.value, W.value, Cc.value), np.float32 if self.dtype == "tf32" else np.float16)
         check(lib().hp_engine_debug_read_buffer(self._h, buf, out.ctypes.data, n, C.byref(H), C.byref(W), C.byref(Cc)))
         return out
 
     def debug_write_buffer(self, buf: int, arr: np.ndarray):
-        arr = np.ascontiguousarray(arr, np.float16)
+        arr = np.ascontiguousarray(arr, np.float32 if self.dtype == "tf32" else np.float16)
         check(lib().hp_engine_debug_write_buffer(self._h, buf, arr.ctypes.data, arr.shape[0]))
 
     def debug_run_ops(self, first: int, last: int, n: int):

@@ -25,6 +25,7 @@
 #include "../../include/hyperpose_b200.h"
 #include "common.h"
 #include "conv_tcgen05.cuh"
+#include "conv_tf32.cuh"
 #include "handoff.h"
 #include "pack_format.h"
 
@@ -302,7 +303,8 @@ __global__ void __launch_bounds__(256, 3) dwconv3_col_kernel(const __half* __res
 //   reshape [fields, comps, ho, wo]; sigmoid on the confidences, softplus on the scales (inference branch, model.py:238-241,270-274);
 //   regressed vectors are offsets from the cell, the C++ decoder wants absolute cell coordinates (postprocessor.cpp:326-328):
 //   the index grid is added here (what the exported OpenPifPaf graph does).
-__global__ void __launch_bounds__(256) pifpaf_head_kernel(const __half* __restrict__ raw, int raw_ld, float* __restrict__ out, int N, int hc, int wc,
+template <typename T>
+__global__ void __launch_bounds__(256) pifpaf_head_kernel(const T* __restrict__ raw, int raw_ld, float* __restrict__ out, int N, int hc, int wc,
                                                           int fields, int comps, int ho, int wo, int is_paf)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(256) pifpaf_head_kernel(const __half* __restri
     const int n = (int)(t / fields);
     const int nc = k * comps + comp;
     const int ch = (nc * 2 + (y & 1)) * 2 + (x & 1);
-    float v = __half2float(raw[(((size_t)n * hc + (y >> 1)) * wc + (x >> 1)) * raw_ld + ch]);
+    float v = (float)raw[(((size_t)n * hc + (y >> 1)) * wc + (x >> 1)) * raw_ld + ch];
     const bool is_conf = comp == 0;
     const bool is_scale = is_paf ? (comp == 7 || comp == 8) : (comp == 4);
     const bool is_x = is_paf ? (comp == 1 || comp == 3) : (comp == 1);
@@ -403,8 +405,9 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 // activations [N,H,W,C] fp16 in im2col mode: 128 consecutive output pixels x 64 channels per load; the bounding box
 // [-pad, dim - pad) holds one base position per output pixel, filter taps are the im2col offsets of the copy instruction
 // (semantics verified on hardware with tools/probe_im2col.cu)
-int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int R, int S, int pixels_per_load = CONV_BLOCK_M)
+int make_tmap_act_im2col(CUtensorMap* m, const void* base, int N, int H, int W, int C, int R, int S, int pixels_per_load = CONV_BLOCK_M, bool f32 = false)
 {
+    const int es = f32 ? 4 : 2;
     static PFN_encodeIm2col enc = nullptr;
     if (!enc) {
         void* p = nullptr;
@@ -414,40 +417,40 @@ int make_tmap_act_im2col(CUtensorMap* m, const __half* base, int N, int H, int W
     }
     if (!enc) { set_error("cuTensorMapEncodeIm2col entry point not available"); return HP_ERR_CUDA; }
     cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
-    cuuint64_t strides[3] = { (cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2 };
+    cuuint64_t strides[3] = { (cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es };
     const int pad_w = S / 2, pad_h = R / 2;
     int lower[2] = { -pad_w, -pad_h };
     int upper[2] = { pad_w - (S - 1), pad_h - (R - 1) };
     cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, lower, upper, 64, (cuuint32_t)pixels_per_load, estr,
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, lower, upper, f32 ? 32 : 64, (cuuint32_t)pixels_per_load, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed: %d (N=%d H=%d W=%d C=%d R=%d S=%d)", (int)r, N, H, W, C, R, S); return HP_ERR_CUDA; }
     return HP_OK;
 }
 // output [N*H*W, C] fp16 as a 2-D tensor: dims (C, pixels), box (64, 128), 128B swizzle (TMA store clips at the last pixel)
-int make_tmap_out(CUtensorMap* m, const __half* base, size_t pixels, int C, int rows = CONV_BLOCK_M)
+int make_tmap_out(CUtensorMap* m, const void* base, size_t pixels, int C, int rows = CONV_BLOCK_M, bool f32 = false)
 {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
     cuuint64_t dims[2] = { (cuuint64_t)C, (cuuint64_t)pixels };
-    cuuint64_t strides[1] = { (cuuint64_t)C * 2 };
-    cuuint32_t box[2] = { 64, (cuuint32_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)C * (f32 ? 4 : 2) };
+    cuuint32_t box[2] = { f32 ? 32u : 64u, (cuuint32_t)rows };
     cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(output) failed: %d (pixels=%zu C=%d)", (int)r, pixels, C); return HP_ERR_CUDA; }
     return HP_OK;
 }
 // weights [rows, K] fp16 K-major: dims (K, rows), box (64, BN)
-int make_tmap_wgt(CUtensorMap* m, const __half* base, int rows, int K, int BN)
+int make_tmap_wgt(CUtensorMap* m, const void* base, int rows, int K, int BN, bool f32 = false)
 {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
     cuuint64_t dims[2] = { (cuuint64_t)K, (cuuint64_t)rows };
-    cuuint64_t strides[1] = { (cuuint64_t)K * 2 };
-    cuuint32_t box[2] = { 64, (cuuint32_t)BN };
+    cuuint64_t strides[1] = { (cuuint64_t)K * (f32 ? 4 : 2) };
+    cuuint32_t box[2] = { f32 ? 32u : 64u, (cuuint32_t)BN };
     cuuint32_t estr[2] = { 1, 1 };
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d (rows=%d K=%d BN=%d)", (int)r, rows, K, BN); return HP_ERR_CUDA; }
     return HP_OK;
@@ -488,6 +491,8 @@ struct ConvPlan {
     ConvParams prm;
     CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2, tmap_r;
     __half* d_w = nullptr;
+    float* d_w32 = nullptr;      // tf32 plan: fp32 K-major weights, rounded to TF32
+    bool tf32 = false;
     float* d_bias = nullptr;
     float* d_alpha = nullptr;
     int grid = 0;
@@ -591,8 +596,116 @@ struct hp_engine {
 
 namespace {
 
+// round-to-nearest (ties away from zero in magnitude) onto the TF32 grid: 8-bit exponent, 10-bit mantissa
+inline float tf32_round(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+// data_type::kFLOAT plan: fp32 activations, conv_tf32_kernel (conv_tf32.cuh); one generic kernel for every layer
+int build_conv_plan_tf32(hp_engine* e, EngOp& op, const float* blob)
+{
+    const PackOp& po = op.po;
+    ConvPlan& pl = op.plan;
+    pl.tf32 = true;
+    const EngBuffer& ib = e->bufs[po.in_buf];
+    const int G = (int)po.groups, R = (int)po.R, S = (int)po.S, cin_g = (int)po.cin_g, cout_g = (int)po.cout_g;
+    const bool im2col = po.im2col_input != 0;
+    if (im2col && (G != 1 || R * S * cin_g > ib.channels)) { set_error("engine: bad im2col conv"); return HP_ERR_ARG; }
+    if (!im2col && G > 1 && cin_g % 32 != 0) { set_error("engine(tf32): grouped conv needs cin_g %% 32 == 0 (got %d)", cin_g); return HP_ERR_UNSUPPORTED; }
+    const int eR = im2col ? 1 : R, eS = im2col ? 1 : S;
+    const int ecin = im2col ? round_up(R * S * cin_g, 32) : round_up(cin_g, 32);
+    if ((int)po.in_ch_off + G * ecin > ib.channels && !(G == 1 && (int)po.in_ch_off + ecin <= round_up(ib.channels, 32) && false)) {
+        // a 32-channel chunk may not run past the buffer: the engine pads conv inputs to 64 channels, so this only trips on a bad pack
+        set_error("engine(tf32): conv reads channels [%d,%d) of a %d-channel buffer", po.in_ch_off, po.in_ch_off + G * ecin, ib.channels);
+        return HP_ERR_ARG;
+    }
+    const int BN = (im2col && cout_g <= 128) ? round_up(cout_g, 64) : pick_bn(cout_g);
+    const int cout_pad = round_up(cout_g, BN);
+    const int K = eR * eS * ecin;
+    std::vector<float> w((size_t)G * cout_pad * K, 0.f), bias((size_t)G * cout_pad, 0.f), alpha((size_t)G * cout_pad, 0.f);
+    const float* Wt = blob + po.w_off;
+    for (int g = 0; g < G; ++g)
+        for (int o = 0; o < cout_g; ++o) {
+            bias[(size_t)g * cout_pad + o] = blob[po.b_off + (size_t)g * cout_g + o];
+            alpha[(size_t)g * cout_pad + o] = blob[po.a_off + (size_t)g * cout_g + o];
+            for (int c = 0; c < cin_g; ++c)
+                for (int r = 0; r < R; ++r)
+                    for (int s2 = 0; s2 < S; ++s2) {
+                        const float v = Wt[((((size_t)g * cout_g + o) * cin_g + c) * R + r) * S + s2];
+                        const size_t k = im2col ? (size_t)((r * S + s2) * cin_g + c) : ((size_t)(r * S + s2) * ecin + c);
+                        w[((size_t)g * cout_pad + o) * K + k] = tf32_round(v);
+                    }
+        }
+    HP_CUDA_TRY(cudaMalloc(&pl.d_w32, w.size() * sizeof(float)));
+    HP_CUDA_TRY(cudaMalloc(&pl.d_bias, bias.size() * sizeof(float)));
+    HP_CUDA_TRY(cudaMalloc(&pl.d_alpha, alpha.size() * sizeof(float)));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_w32, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    HP_CUDA_TRY(cudaMemcpy(pl.d_alpha, alpha.data(), alpha.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    ConvParams& p = pl.prm;
+    memset(&p, 0, sizeof(p));
+    p.Nb = e->max_batch; p.H = ib.H; p.W = ib.W;
+    p.R = eR; p.S = eS; p.groups = G; p.cin_g = ecin;
+    p.cout_g = cout_g; p.cout_g_pad = cout_pad; p.BN = BN;
+    p.m_tiles = (int)(((size_t)e->max_batch * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
+    p.in_ch_off = (int)po.in_ch_off;
+    p.tma_store = (po.out_mode == OUT_F16_NHWC && BN % 32 == 0 && (G == 1 || cout_g % 32 == 0)) ? 1 : 0;
+    int tc = 32;
+    while (tc < 2 * BN) tc *= 2;
+    p.tmem_cols = tc;
+    p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.out_mode = (int)po.out_mode;
+    if (po.out_mode == OUT_F32_NCHW_SPLIT) {
+        p.out = e->d_conf; p.out2 = e->d_paf; p.split = (int)po.split;
+        if ((int)po.split != (int)e->hdr.conf_channels || cout_g - (int)po.split != (int)e->hdr.paf_channels || G != 1) {
+            set_error("engine: output conv must produce conf(%u)+paf(%u) channels", e->hdr.conf_channels, e->hdr.paf_channels);
+            return HP_ERR_ARG;
+        }
+    } else {
+        const EngBuffer& ob = e->bufs[po.out_buf];
+        if (ob.H != ib.H || ob.W != ib.W || (int)po.out_ch_off + G * cout_g > ob.channels) { set_error("engine: conv output buffer mismatch"); return HP_ERR_ARG; }
+        p.out = ob.d; p.out_ld = ob.channels; p.out_ch_off = (int)po.out_ch_off;
+        if ((int)po.out_ch_off + (G - 1) * cout_g + cout_pad > ob.channels || po.out_ch_off % 4) p.tma_store = 0;
+    }
+    if (po.res_mode) {
+        if (po.out_mode != OUT_F16_NHWC || po.res_buf >= e->bufs.size()) { set_error("engine: bad residual"); return HP_ERR_ARG; }
+        const EngBuffer& rb = e->bufs[po.res_buf];
+        if (rb.H != ib.H || rb.W != ib.W || (int)po.res_ch_off + G * cout_g > rb.channels || po.res_ch_off % 8 || cout_g % 16) { set_error("engine: residual buffer mismatch"); return HP_ERR_ARG; }
+        p.res = (const __half*)rb.d; p.res_ld = rb.channels; p.res_ch_off = (int)po.res_ch_off; p.res_mode = (int)po.res_mode;
+    }
+    const bool res_tma = p.tma_store && po.res_mode;
+    p.num_stages = conv_pick_stages(BN, p.tma_store != 0, res_tma);
+    int rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS, CONV_BLOCK_M, true);
+    if (rc) return rc;
+    rc = make_tmap_wgt(&pl.tmap_b, pl.d_w32, G * cout_pad, K, BN, true);
+    if (rc) return rc;
+    memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
+    memset(&pl.tmap_r, 0, sizeof(pl.tmap_r));
+    memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
+    if (p.tma_store) {
+        const EngBuffer& ob = e->bufs[po.out_buf];
+        rc = make_tmap_out(&pl.tmap_o, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels, CONV_BLOCK_M, true);
+        if (rc) return rc;
+    }
+    if (res_tma) {
+        const EngBuffer& rb = e->bufs[po.res_buf];
+        rc = make_tmap_out(&pl.tmap_r, rb.d, (size_t)e->max_batch * rb.H * rb.W, rb.channels, CONV_BLOCK_M, true);
+        if (rc) return rc;
+    }
+    pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, res_tma);
+    pl.flops_per_frame = 2.0 * ib.H * ib.W * (double)G * cout_g * cin_g * R * S;
+    return HP_OK;
+}
+
 int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
 {
+    if (e->dtype == HP_DTYPE_TF32) return build_conv_plan_tf32(e, op, blob);
     const PackOp& po = op.po;
     ConvPlan& pl = op.plan;
     const EngBuffer& ib = e->bufs[po.in_buf];
@@ -774,6 +887,17 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
 int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
 {
     ConvPlan& pl = op.plan;
+    if (pl.tf32) {
+        ConvParams p = pl.prm;
+        p.Nb = N;
+        p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
+        const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
+        const int grid = std::min(e->num_sms, n_tiles);
+        if (p.res_mode) conv_tf32_kernel<true><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+        else conv_tf32_kernel<false><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+        e->launches++;
+        return HP_OK;
+    }
     if (pl.stem && u8_input) {
         StemParams sp = pl.sp;
         sp.Nb = N;
@@ -839,6 +963,49 @@ void collect_profile(hp_engine* e)
     while (collect_one(e, true)) {}
 }
 
+// every non-conv op of the graph on fp32 activation buffers (data_type::kFLOAT engine)
+void run_helper_op_tf32(hp_engine* e, EngOp& op, int N, bool u8_input, cudaStream_t st)
+{
+    const PackOp& po = op.po;
+    if (po.type == OP_IM2COL3) {
+        EngBuffer& ob = e->bufs[po.out_buf];
+        const int R = po.R ? (int)po.R : 3, stride = po.stride ? (int)po.stride : 1;
+        const int ph = same_pad_before(e->in_h, R, stride), pw = same_pad_before(e->in_w, R, stride);
+        const size_t total = (size_t)N * ob.H * ob.W * (ob.channels / 4);
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        const uint8_t* fr = e->cur_frames ? e->cur_frames : e->d_frames;
+        if (u8_input) im2col_f32_kernel<true><<<blocks, 256, 0, st>>>(fr, (float*)ob.d, N, e->in_h, e->in_w, e->factor, e->flip_rgb, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
+                                                                     R, stride, ob.H, ob.W, ph, pw, ob.channels);
+        else im2col_f32_kernel<false><<<blocks, 256, 0, st>>>(e->d_input_f32, (float*)ob.d, N, e->in_h, e->in_w, 1.0, 0, e->hdr.mean[0], e->hdr.mean[1], e->hdr.mean[2],
+                                                              R, stride, ob.H, ob.W, ph, pw, ob.channels);
+        e->launches++;
+    } else if (po.type == OP_PIFPAF_HEAD) {
+        EngBuffer& a = e->bufs[po.in_buf];
+        EngBuffer& b = e->bufs[po.res_buf];
+        const size_t t1 = (size_t)N * 17 * 5 * e->out_h * e->out_w, t2 = (size_t)N * 19 * 9 * e->out_h * e->out_w;
+        pifpaf_head_kernel<float><<<(int)((t1 + 255) / 256), 256, 0, st>>>((const float*)a.d, a.channels, e->d_conf, N, a.H, a.W, 17, 5, e->out_h, e->out_w, 0);
+        pifpaf_head_kernel<float><<<(int)((t2 + 255) / 256), 256, 0, st>>>((const float*)b.d, b.channels, e->d_paf, N, b.H, b.W, 19, 9, e->out_h, e->out_w, 1);
+        e->launches += 2;
+    } else if (po.type == OP_DWCONV) {
+        EngBuffer& ib = e->bufs[po.in_buf];
+        EngBuffer& ob = e->bufs[po.out_buf];
+        const int C = (int)po.cout_g, K = (int)po.R, stride = po.stride ? (int)po.stride : 1;
+        const size_t total = (size_t)N * ob.H * ob.W * (C / 4);
+        const float* dw = op.d_dw;
+        dwconv_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)ib.d + po.in_ch_off, ib.channels, (float*)ob.d + po.out_ch_off, ob.channels, dw,
+            dw + (size_t)K * K * C, dw + (size_t)K * K * C + C, N, ib.H, ib.W, C, ob.H, ob.W, K, stride, same_pad_before(ib.H, K, stride), same_pad_before(ib.W, K, stride));
+        e->launches++;
+    } else if (po.type == OP_MAXPOOL2) {
+        EngBuffer& ib = e->bufs[po.in_buf];
+        EngBuffer& ob = e->bufs[po.out_buf];
+        const int C = (int)po.cout_g, K = po.R ? (int)po.R : 2;
+        const size_t total = (size_t)N * ob.H * ob.W * (C / 4);
+        maxpool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)ib.d + po.in_ch_off, (float*)ob.d + po.out_ch_off, N, ib.H, ib.W, ib.channels, C, ob.channels,
+                                                                           ob.H, ob.W, K, same_pad_before(ib.H, K, 2), same_pad_before(ib.W, K, 2));
+        e->launches++;
+    }
+}
+
 int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0, int last = -1)
 {
     if (last < 0) last = (int)e->ops.size() - 1;
@@ -853,7 +1020,9 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
     for (int oi = first; oi <= last; ++oi) {
         EngOp& op = e->ops[oi];
         const PackOp& po = op.po;
-        if (po.type == OP_IM2COL3 && op.fused_into_stem && u8_input) {
+        if (e->dtype == HP_DTYPE_TF32 && po.type != OP_CONV) {
+            run_helper_op_tf32(e, op, N, u8_input, st);
+        } else if (po.type == OP_IM2COL3 && op.fused_into_stem && u8_input) {
             // the consumer is conv_stem_kernel: patches are built in shared memory, nothing to do here
         } else if (po.type == OP_IM2COL3) {
             EngBuffer& ob = e->bufs[po.out_buf];
@@ -874,8 +1043,8 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& a = e->bufs[po.in_buf];
             EngBuffer& b = e->bufs[po.res_buf];
             const size_t t1 = (size_t)N * 17 * 5 * e->out_h * e->out_w, t2 = (size_t)N * 19 * 9 * e->out_h * e->out_w;
-            pifpaf_head_kernel<<<(int)((t1 + 255) / 256), 256, 0, st>>>(a.d, a.channels, e->d_conf, N, a.H, a.W, 17, 5, e->out_h, e->out_w, 0);
-            pifpaf_head_kernel<<<(int)((t2 + 255) / 256), 256, 0, st>>>(b.d, b.channels, e->d_paf, N, b.H, b.W, 19, 9, e->out_h, e->out_w, 1);
+            pifpaf_head_kernel<__half><<<(int)((t1 + 255) / 256), 256, 0, st>>>(a.d, a.channels, e->d_conf, N, a.H, a.W, 17, 5, e->out_h, e->out_w, 0);
+            pifpaf_head_kernel<__half><<<(int)((t2 + 255) / 256), 256, 0, st>>>(b.d, b.channels, e->d_paf, N, b.H, b.W, 19, 9, e->out_h, e->out_w, 1);
             e->launches += 2;
         } else if (po.type == OP_DWCONV) {
             EngBuffer& ib = e->bufs[po.in_buf];
@@ -939,6 +1108,7 @@ void free_engine(hp_engine* e)
     for (auto& b : e->bufs) if (b.d) cudaFree(b.d);
     for (auto& o : e->ops) {
         if (o.plan.d_w) cudaFree(o.plan.d_w);
+        if (o.plan.d_w32) cudaFree(o.plan.d_w32);
         if (o.plan.d_bias) cudaFree(o.plan.d_bias);
         if (o.plan.d_alpha) cudaFree(o.plan.d_alpha);
         if (o.d_dw) cudaFree(o.d_dw);
@@ -986,7 +1156,7 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
                         double factor, int flip_rgb, int device, int dtype)
 {
     if (dtype != HP_DTYPE_F16 && dtype != HP_DTYPE_TF32) { set_error("hp_engine_create_ex: unknown dtype %d", dtype); return HP_ERR_ARG; }
-    if (dtype == HP_DTYPE_TF32) { set_error("hp_engine_create_ex: the tf32 path is not built in this library"); return HP_ERR_UNSUPPORTED; }
+
     if (!out || !pack) { set_error("hp_engine_create: null argument"); return HP_ERR_ARG; }
     *out = nullptr;
     int ndev = 0;
@@ -1048,7 +1218,7 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
         b.H = in_h; b.W = in_w;
         for (int d = 0; d < b.down; ++d) { b.H = (b.H + 1) / 2; b.W = (b.W + 1) / 2; }
         if (b.channels % 8) { set_error("engine: buffer %u has %d channels (need a multiple of 8)", i, b.channels); return fail(HP_ERR_ARG); }
-        const size_t bytes = (size_t)max_batch * b.H * b.W * b.channels * sizeof(__half);
+        const size_t bytes = (size_t)max_batch * b.H * b.W * b.channels * (dtype == HP_DTYPE_TF32 ? sizeof(float) : sizeof(__half));
         if (cudaMalloc(&b.d, bytes) != cudaSuccess) { set_error("engine: cudaMalloc(%zu) failed", bytes); return fail(HP_ERR_CUDA); }
         cudaMemset(b.d, 0, bytes); // padding channels must read as zero
     }
@@ -1115,6 +1285,13 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
             return fail(HP_ERR_UNSUPPORTED);
         }
     }
+    if (max_smem > 0 && dtype == HP_DTYPE_TF32) {
+        if (cudaFuncSetAttribute(conv_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
+            set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (tf32)", max_smem);
+            return fail(HP_ERR_CUDA);
+        }
+    } else
     if (max_smem > 0 && (cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
@@ -1402,7 +1579,8 @@ int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int
     if (W) *W = b.W;
     if (C) *C = b.channels;
     HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
-    if (out_f16) HP_CUDA_TRY(cudaMemcpy(out_f16, b.d, (size_t)N * b.H * b.W * b.channels * sizeof(__half), cudaMemcpyDeviceToHost));
+    const size_t es = e->dtype == HP_DTYPE_TF32 ? sizeof(float) : sizeof(__half);   // element type follows the engine's dtype
+    if (out_f16) HP_CUDA_TRY(cudaMemcpy(out_f16, b.d, (size_t)N * b.H * b.W * b.channels * es, cudaMemcpyDeviceToHost));
     return HP_OK;
 }
 
@@ -1412,7 +1590,8 @@ int hp_engine_debug_write_buffer(hp_engine* e, int buf, const void* in_f16, int 
     HP_CUDA_TRY(cudaSetDevice(e->device));
     const EngBuffer& b = e->bufs[buf];
     HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
-    HP_CUDA_TRY(cudaMemcpy(b.d, in_f16, (size_t)N * b.H * b.W * b.channels * sizeof(__half), cudaMemcpyHostToDevice));
+    const size_t es = e->dtype == HP_DTYPE_TF32 ? sizeof(float) : sizeof(__half);
+    HP_CUDA_TRY(cudaMemcpy(b.d, in_f16, (size_t)N * b.H * b.W * b.channels * es, cudaMemcpyHostToDevice));
     return HP_OK;
 }
 
@@ -1480,7 +1659,7 @@ int hp_engine_get_profile(hp_engine* e, double* ms_per_op, int* op_type, double*
 //   hp_pose_submit_u8_host(i+1)  H2D of batch i+1 on the copy stream  | overlaps the convs of batch i
 //   hp_pose_collect(i)           waits for batch i's records (their D2H was enqueued right behind its parse)
 //
-// The per-batch launch sequence (every conv + the four parser kernels + the result D2H, ~65 nodes at cfg3) is captured
+// The per-batch launch sequence (every conv + the two parser kernels + the result D2H, ~60 nodes at cfg3) is captured
 // once per slot into a CUDA graph and replayed with one cudaGraphLaunch; it is re-captured when anything baked into it
 // changes (batch size, parser thresholds / capacities, benchmark override).  HPB_NO_GRAPH=1 launches directly.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1552,7 +1731,7 @@ int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
                 const long long l0 = e->launches;
                 const int rc = pose_enqueue_compute(e, sl, e->stream);
                 const cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-                e->launches = l0 - 4;   // capturing launches nothing (the parser counted its four kernels: taken back here)
+                e->launches = l0 - 2;   // capturing launches nothing (the parser counted its two kernels: taken back here)
                 if (rc == HP_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&sl.graph, g, 0) == cudaSuccess) e->graph_captures++;
                 else { sl.graph = nullptr; e->graphs_ok = false; cudaGetLastError(); }
                 if (g) cudaGraphDestroy(g);
@@ -1561,8 +1740,8 @@ int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
         if (sl.graph) {
             HP_CUDA_TRY(cudaGraphLaunch(sl.graph, e->stream));
             e->graph_launches++;
-            // the replay runs the same kernels the direct path counts: every engine op + the parser's four
-            int n_k = 4;
+            // the replay runs the same kernels the direct path counts: every engine op + the parser's two
+            int n_k = 2;
             for (auto& op : e->ops) {
                 const uint32_t t = op.po.type;
                 if (t == OP_IM2COL3 && op.fused_into_stem) continue;

@@ -28,7 +28,17 @@ namespace dnn {
             std::cerr << "[HyperPose::ERROR  ] " << what << ": " << hp_last_error() << '\n';
             std::exit(1);
         }
-        hp_engine* load_engine(const std::string& path, cv::Size input_size, int max_batch, double factor, bool flip_rgb)
+        // data_type of the reference ctor (tensorrt.hpp:14-22,48,61): kFLOAT (the default every example uses) selects the tcgen05
+        // kind::tf32 engine (fp32 tensors, TF32 multiplies -- TensorRT's own FP32 convolution math on tensor-core GPUs), kHALF the
+        // f16 engine.  A serialized engine carries no precision argument in the reference API (its plan was built with one): the pack
+        // runs as kHALF unless HPB_DTYPE=tf32 says otherwise.
+        int dtype_of(const data_type& t) { return t.val == data_type::kHALF ? HP_DTYPE_F16 : HP_DTYPE_TF32; }
+        int serialized_dtype()
+        {
+            const char* v = std::getenv("HPB_DTYPE");
+            return (v && std::string(v) == "tf32") ? HP_DTYPE_TF32 : HP_DTYPE_F16;
+        }
+        hp_engine* load_engine(const std::string& path, cv::Size input_size, int max_batch, double factor, bool flip_rgb, int dtype)
         {
             std::ifstream f(path, std::ios::binary | std::ios::ate);
             if (!f) die("cannot open model pack " + path);
@@ -38,7 +48,7 @@ namespace dnn {
             if (!f.read(blob.data(), n)) die("cannot read model pack " + path);
             hp_engine* e = nullptr;
             // the reference API has no device argument: HPB_DEVICE=<ordinal> | rr (round-robin per engine instance), default 0
-            if (hp_engine_create(&e, blob.data(), blob.size(), input_size.width, input_size.height, max_batch, factor, flip_rgb ? 1 : 0, hp_default_device()) != HP_OK)
+            if (hp_engine_create_ex(&e, blob.data(), blob.size(), input_size.width, input_size.height, max_batch, factor, flip_rgb ? 1 : 0, hp_default_device(), dtype) != HP_OK)
                 die("hp_engine_create(" + path + ")");
             return e;
         }
@@ -51,19 +61,19 @@ namespace dnn {
         ~cuda_dep() { hp_engine_destroy(engine); }
     };
 
-    tensorrt::tensorrt(const uff& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type, double factor, bool flip_rgb)
+    tensorrt::tensorrt(const uff& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type dtype, double factor, bool flip_rgb)
         : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
-        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb, dtype_of(dtype));
         m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }
-    tensorrt::tensorrt(const onnx& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type, double factor, bool flip_rgb)
+    tensorrt::tensorrt(const onnx& m, cv::Size input_size, int max_batch_size, bool keep_ratio, data_type dtype, double factor, bool flip_rgb)
         : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
-        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb, dtype_of(dtype));
         m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }
@@ -71,7 +81,7 @@ namespace dnn {
         : m_inp_size(input_size), m_max_batch_size(max_batch_size), m_keep_ratio(keep_ratio), m_factor(factor), m_flip_rgb(flip_rgb)
         , m_cuda_dep(std::make_unique<cuda_dep>())
     {
-        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb);
+        m_cuda_dep->engine = load_engine(m.model_path, input_size, max_batch_size, factor, flip_rgb, serialized_dtype());
         m_cuda_dep->pack_path = m.model_path;
         _create_binding_buffers();
     }

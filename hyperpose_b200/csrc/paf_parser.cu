@@ -2,18 +2,17 @@
 //
 // Replaces the reference's CPU parser hyperpose::parser::paf
 //   src/paf.cpp:57-375, src/post_process.hpp:26-205, src/coco.hpp:6-52
-// with four batched CUDA kernels (grid covers every frame of the batch):
+// with two batched CUDA kernels (grid covers every frame of the batch):
 //
 //   K1 paf_peaks_kernel    resize_area (post_process.hpp:26-52) + smooth (:54-69) + 3x3 max-pool NMS
 //                          (:71-102) + peak scan (:175-192), fused per smem tile.  The 4x up-sampled maps
 //                          are never written to HBM.  Tiles whose source values cannot reach conf_thresh
 //                          are skipped (provably peak-free, see tile_can_skip()).
-//   K2 paf_order_kernel    restores the reference's channel-major / row-major peak order and ids.
-//   K3 paf_limb_kernel     get_connection_candidates + get_connections (paf.cpp:93-144, 234-272): 10 lanes
-//                          per peak pair sample the PAF line integral (up-sampling recomputed on the fly from
-//                          the 1/8-resolution field staged in shared memory), ballot/shuffle reductions,
-//                          then score-ordered greedy matching.
-//   K4 paf_assemble_kernel get_humans (paf.cpp:146-232) + conversion (:359-372): one warp per frame.
+//   K2 paf_limbs_kernel    one CTA per (limb, frame): restores the reference's channel-major / row-major peak order and ids,
+//                          get_connection_candidates + get_connections (paf.cpp:93-144, 234-272: 10 lanes per peak pair sample
+//                          the PAF line integral -- up-sampling recomputed on the fly from the 1/8-resolution field staged in
+//                          shared memory -- ballot/shuffle reductions, score-ordered greedy matching), and, in the last CTA of a
+//                          frame to finish, get_humans (paf.cpp:146-232) + conversion (:359-372).
 //
 // Arithmetic contract (bit-exactness with oracle/paf_oracle.c): every fp32 operation on the result path
 // is spelled with an explicit round-to-nearest intrinsic (__fmul_rn/__fadd_rn/__fmaf_rn/__fdiv_rn) in
@@ -78,7 +77,12 @@ __host__ __device__ inline int refl101(int p, int len)
 // ---------------------------------------------------------------------------------------------
 // K1: fused up-sample + Gaussian + NMS + peak emission
 // ---------------------------------------------------------------------------------------------
-constexpr int K1_THREADS = 256;
+// The kernel is ISSUE-bound (ncu, round 1: ~9.3k warp instructions per tile, 9504 tiles per 16-frame batch = 99 us), so this
+// version is organised around instruction count: the horizontal lerp of the up-sampling is computed once per SOURCE row (the
+// default resolution stretches rows 7x: ~9 source rows feed 48 tile rows), both filter passes produce 16 outputs per thread
+// from one 32-value register window (1 shared load per 8.5 FMAs), every pass is exactly one round of the 192-thread CTA, and
+// the source bounds of a tile come from host tables instead of shared-memory atomics.
+constexpr int K1_THREADS = 192;
 constexpr int TH = 30, TW = 62;          // interior tile of the up-map handled by one CTA
 constexpr int HALO = 9;                  // 8 (17-tap blur) + 1 (3x3 NMS)
 constexpr int UT_H = TH + 2 * HALO;      // 48 rows of up-sampled values (virtual = reflected coordinates)
@@ -88,16 +92,20 @@ constexpr int RT_W = TW + 2;             // 64 row-pass output columns (interior
 constexpr int RT_LD = RT_W + 1;          // 65
 constexpr int CT_H = TH + 2;             // 32 column-pass output rows
 constexpr int SRC_MAX_H = UT_H + 1, SRC_MAX_W = UT_W + 1; // scale >= 1 => at most one source px per up px (+1)
-constexpr int RUN = 8;                   // outputs per thread per pass (sliding window of RUN+16 inputs)
+constexpr int RUN = 16;                  // outputs per thread per pass (sliding window of RUN+16 inputs)
+constexpr int HL_ROWS = 16;              // source rows per tile for which the horizontal lerp is cached (more: direct path)
+static_assert(UT_H * (RT_W / RUN) == K1_THREADS, "row pass: one work item per thread");
+static_assert(RT_W * (CT_H / RUN) <= K1_THREADS && CT_H % RUN == 0, "column pass: one work item per thread");
 
 struct PeakParams {
     const float* conf; // [N, c_conf, H, W]
     int c_conf, H, W, UH, UW;
     const int* xi; const float* xf; // [UW] area-upscale table
     const int* yi; const float* yf; // [UH]
+    const int* tile_bounds;         // [tiles_y][2] source row lo/hi, then [tiles_x][2] source col lo/hi (host: tile_source_bounds)
     float thresh;
     float skip_below; // tiles whose source max is <= this cannot contain a peak; -inf disables skipping
-    int tiles_x;
+    int tiles_x, tiles_y;
     int pcap;            // capacity per (frame, part)
     int* peak_cnt;       // [N,18]
     int* raw_key;        // [N,18,pcap]  y*UW + x
@@ -112,9 +120,9 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     __shared__ float sU[UT_H * UT_LD];
     __shared__ float sA[(SRC_MAX_H * SRC_MAX_W > UT_H * RT_LD) ? SRC_MAX_H * SRC_MAX_W : UT_H * RT_LD];
     __shared__ float sS[CT_H * RT_LD];
+    __shared__ float sHl[HL_ROWS * UT_LD];   // horizontal lerp of the tile's source rows
     __shared__ int sXi[UT_W], sYi[UT_H];
     __shared__ float sXf[UT_W], sYf[UT_H];
-    __shared__ int sBounds[4]; // src row lo/hi, col lo/hi
     __shared__ float sMax[K1_THREADS / 32];
     __shared__ int sSkip;
 
@@ -125,29 +133,9 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     const int H = p.H, W = p.W, UH = p.UH, UW = p.UW;
     const float* src = p.conf + ((size_t)frame * p.c_conf + part) * H * W;
 
-    if (tid < 4) sBounds[tid] = (tid & 1) ? -1 : 0x7fffffff;
-    __syncthreads();
-    // stage the coefficient tables of the (reflected) rows / columns this tile needs
-    for (int i = tid; i < UT_W + UT_H; i += K1_THREADS) {
-        if (i < UT_W) {
-            const int rx = refl101(x0 - HALO + i, UW);
-            const int s = __ldg(p.xi + rx);
-            sXi[i] = s;
-            sXf[i] = __ldg(p.xf + rx);
-            atomicMin(&sBounds[2], s);
-            atomicMax(&sBounds[3], min(s + 1, W - 1));
-        } else {
-            const int j = i - UT_W;
-            const int ry = refl101(y0 - HALO + j, UH);
-            const int s = __ldg(p.yi + ry);
-            sYi[j] = s;
-            sYf[j] = __ldg(p.yf + ry);
-            atomicMin(&sBounds[0], s);
-            atomicMax(&sBounds[1], min(s + 1, H - 1));
-        }
-    }
-    __syncthreads();
-    const int sr0 = sBounds[0], sr1 = sBounds[1], sc0 = sBounds[2], sc1 = sBounds[3];
+    // source rows / columns this tile's (reflected) rows and columns touch: precomputed on the host
+    const int sr0 = __ldg(p.tile_bounds + 2 * ty), sr1 = __ldg(p.tile_bounds + 2 * ty + 1);
+    const int sc0 = __ldg(p.tile_bounds + 2 * p.tiles_y + 2 * tx), sc1 = __ldg(p.tile_bounds + 2 * p.tiles_y + 2 * tx + 1);
     const int sh = sr1 - sr0 + 1, sw = sc1 - sc0 + 1; // <= SRC_MAX_H x SRC_MAX_W because UH >= H, UW >= W
     float* sSrc = sA;
     float lmax = -INFINITY;
@@ -161,6 +149,19 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     if ((tid & 31) == 0) sMax[tid >> 5] = lmax;
+    // the coefficient tables of the (reflected) rows / columns this tile needs
+    for (int i = tid; i < UT_W + UT_H; i += K1_THREADS) {
+        if (i < UT_W) {
+            const int rx = refl101(x0 - HALO + i, UW);
+            sXi[i] = __ldg(p.xi + rx);
+            sXf[i] = __ldg(p.xf + rx);
+        } else {
+            const int j = i - UT_W;
+            const int ry = refl101(y0 - HALO + j, UH);
+            sYi[j] = __ldg(p.yi + ry);
+            sYf[j] = __ldg(p.yf + ry);
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         float m = sMax[0];
@@ -174,26 +175,44 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     if (sSkip) return;
 
     // ---- up-sample into virtual (reflected) coordinates: sU[vy][vx] = up(refl(y0-9+vy), refl(x0-9+vx))
-    //      HResizeLinear then VResizeLinear, products rounded separately (oracle orc_resize_area_up)
-    for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
-        const int vy = i / UT_W, vx = i - vy * UT_W;
-        const int sx0 = sXi[vx], sx1 = min(sx0 + 1, W - 1);
-        const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
-        const float a1 = sXf[vx], a0 = __fsub_rn(1.f, a1);
-        const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
-        const float* r0 = sSrc + (sy0 - sr0) * sw - sc0;
-        const float* r1 = sSrc + (sy1 - sr0) * sw - sc0;
-        const float h0 = __fadd_rn(__fmul_rn(r0[sx0], a0), __fmul_rn(r0[sx1], a1));
-        const float h1 = __fadd_rn(__fmul_rn(r1[sx0], a0), __fmul_rn(r1[sx1], a1));
-        sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    //      HResizeLinear then VResizeLinear, products rounded separately (oracle orc_resize_area_up).
+    //      The horizontal pass depends on the SOURCE row only: computed once per source row when few rows feed the tile.
+    if (sh <= HL_ROWS) {
+        for (int i = tid; i < sh * UT_W; i += K1_THREADS) {
+            const int r = i / UT_W, vx = i - r * UT_W;
+            const int sx0 = sXi[vx], sx1 = min(sx0 + 1, W - 1);
+            const float a1 = sXf[vx], a0 = __fsub_rn(1.f, a1);
+            const float* row = sSrc + r * sw - sc0;
+            sHl[r * UT_LD + vx] = __fadd_rn(__fmul_rn(row[sx0], a0), __fmul_rn(row[sx1], a1));
+        }
+        __syncthreads();
+        for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
+            const int vy = i / UT_W, vx = i - vy * UT_W;
+            const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
+            const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
+            sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(sHl[(sy0 - sr0) * UT_LD + vx], b0), __fmul_rn(sHl[(sy1 - sr0) * UT_LD + vx], b1));
+        }
+    } else {
+        for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
+            const int vy = i / UT_W, vx = i - vy * UT_W;
+            const int sx0 = sXi[vx], sx1 = min(sx0 + 1, W - 1);
+            const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
+            const float a1 = sXf[vx], a0 = __fsub_rn(1.f, a1);
+            const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
+            const float* r0 = sSrc + (sy0 - sr0) * sw - sc0;
+            const float* r1 = sSrc + (sy1 - sr0) * sw - sc0;
+            const float h0 = __fadd_rn(__fmul_rn(r0[sx0], a0), __fmul_rn(r0[sx1], a1));
+            const float h1 = __fadd_rn(__fmul_rn(r1[sx0], a0), __fmul_rn(r1[sx1], a1));
+            sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        }
     }
     __syncthreads(); // sSrc is dead from here; sA becomes sTmp
 
     // ---- row pass: sTmp[vy][c], c = 0..63 <-> real column j = x0 - 1 + c; taps left->right.
-    //      work item = (row, run of 8 columns); adjacent threads take adjacent rows (odd strides).
+    //      work item = (row, run of 16 columns), one per thread; adjacent threads take adjacent rows (odd strides).
     float* sTmp = sA;
-    for (int it = tid; it < UT_H * (RT_W / RUN); it += K1_THREADS) {
-        const int vy = it % UT_H, run = it / UT_H;
+    {
+        const int vy = tid % UT_H, run = tid / UT_H;
         const int c0 = run * RUN;
         const float* in = sU + vy * UT_LD + c0; // window input k for output c is in[c - c0 + k] (vx = c + k)
         float w[RUN + 16];
@@ -225,8 +244,8 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     __syncthreads();
 
     // ---- column pass (symmetric): sS[r][c], r = 0..31 <-> real row i = y0 - 1 + r (virtual row r + 8).
-    //      one work item per thread: column c = tid % 64, run of 8 rows r0 = (tid / 64) * 8.
-    {
+    //      one work item per thread: column c = tid % 64, run of 16 rows r0 = (tid / 64) * 16.
+    if (tid < RT_W * (CT_H / RUN)) {
         const int c = tid % RT_W, r0 = (tid / RT_W) * RUN;
         const int j = x0 - 1 + c;
         const bool col_ok = (j >= 0 && j < UW);
@@ -276,52 +295,25 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: per (frame, part) rank-sort by scan position -> all_peaks in reference order, ids = index
-// ---------------------------------------------------------------------------------------------
-struct OrderParams {
-    int pcap, UW;
-    const int* peak_cnt;    // [N,18]
-    const int* raw_key;
-    const float* raw_score;
-    int* part_base;         // [N,19]
-    int* px; int* py; float* pscore; // [N, 18*pcap]
-};
-
-__global__ void __launch_bounds__(128) paf_order_kernel(const OrderParams p)
-{
-    extern __shared__ int sKey[];
-    const int part = blockIdx.x, frame = blockIdx.y;
-    const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
-    const int n = min(cnt[part], p.pcap);
-    int base = 0;
-    for (int q = 0; q < part; ++q) base += min(cnt[q], p.pcap);
-    if (part == 0 && threadIdx.x == 0) {
-        int b = 0;
-        for (int q = 0; q < HP_N_PARTS; ++q) {
-            p.part_base[frame * (HP_N_PARTS + 1) + q] = b;
-            b += min(cnt[q], p.pcap);
-        }
-        p.part_base[frame * (HP_N_PARTS + 1) + HP_N_PARTS] = b;
-    }
-    const size_t raw = ((size_t)frame * HP_N_PARTS + part) * p.pcap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sKey[i] = p.raw_key[raw + i];
-    __syncthreads();
-    const size_t out = (size_t)frame * HP_N_PARTS * p.pcap + base;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int k = sKey[i];
-        int rank = 0;
-        for (int q = 0; q < n; ++q) rank += (sKey[q] < k); // keys are unique pixel positions
-        p.px[out + rank] = k % p.UW;
-        p.py[out + rank] = k / p.UW;
-        p.pscore[out + rank] = p.raw_score[raw + i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3: limb scoring + greedy matching, one CTA per (limb, frame)
+// K2: everything after the peak scan, one CTA per (limb, frame):
+//   (a) peak ordering   -- the CTA restores the reference's channel-major / row-major peak order (ids = index) for the two
+//                          parts of its limb: rank-sort by scan position.  A part belongs to several limbs; every CTA that
+//                          needs it writes the SAME ordered records to the same place (idempotent), so no CTA waits for another.
+//   (b) limb scoring    -- get_connection_candidates (paf.cpp:93-144): 10 lanes per peak pair, ballot / shuffle reductions
+//   (c) matching        -- std::sort by score + greedy one-to-one (paf.cpp:234-272), candidates kept in shared memory
+//   (d) assembly        -- get_humans + filter + conversion (paf.cpp:146-232, 359-372) by the LAST CTA of the frame to finish
+//                          (threadfence + per-frame arrival counter): the strictly ordered merge runs on one warp out of
+//                          shared memory (connections, peak scores and the partial humans, stored part-major so that the
+//                          32-wide "touch" test is bank-conflict free), the per-part loops of a merge on 18 lanes.
+// Round 1 ran (a), (b+c) and (d) as three launches with one warp per frame for (d): 6 + 39 + 141 us per 16 frames, most of
+// it the latency chain of global loads inside (d)'s sequential loop.
 // ---------------------------------------------------------------------------------------------
 constexpr int K3_THREADS = 128;
-constexpr int MAX_PCAP = 4096; // bitmap size for the greedy pass
+constexpr int MAX_PCAP = 4096;   // bitmap size for the greedy pass
+constexpr int SM_CAND = 512;     // candidates per limb kept in shared memory (more: global scratch)
+constexpr int SM_KEYS = 512;     // raw peak keys per part staged for the rank sort
+constexpr int SM_CONN = 1024;    // connections per frame staged for the assembly
+constexpr int SM_PSC = 2048;     // peak scores per frame staged for the assembly
 
 struct LimbParams {
     const float* paf; // [N, c_paf, H, W]
@@ -329,12 +321,19 @@ struct LimbParams {
     const int* xi; const float* xf; const int* yi; const float* yf;
     float paf_thresh;
     int feat_height; // m_feature_size.height == W of the feature map (paf.cpp:329,354)
-    int pcap, ccap;
-    const int* part_base; const int* px; const int* py; const float* pscore;
+    int pcap, ccap, hcap, max_refs;
+    const int* peak_cnt;             // [N,18]
+    const int* raw_key;              // [N,18,pcap]  y*UW + x
+    const float* raw_score;          // [N,18,pcap]
+    int* part_base;                  // [N,19]
+    int* px; int* py; float* pscore; // [N, 18*pcap] ordered peaks
     unsigned long long* cand;        // [N,19,ccap]
     unsigned long long* cand_sorted; // [N,19,ccap]
     hp_connection* conn;             // [N,19,pcap]
     int* conn_cnt;                   // [N,19]
+    int* frame_done;                 // [N] arrival counter of the frame's limb CTAs
+    hp_human* humans;                // [N,hcap]
+    int* human_cnt;                  // [N]
     int* flags;
     int stage_bytes; // dynamic smem available for staging the two PAF channels (0 = never stage)
 };
@@ -360,230 +359,288 @@ __device__ __forceinline__ unsigned long long make_key(float score, int ia, int 
     return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)(0xffffffffu - (((unsigned)ia << 16) | (unsigned)ib));
 }
 
-__global__ void __launch_bounds__(K3_THREADS) paf_limb_kernel(const LimbParams p)
+__device__ __forceinline__ hp_connection ld_conn_cg(const hp_connection* c)
 {
-    extern __shared__ float sPaf[];
-    __shared__ int sNcand;
+    hp_connection r;
+    r.cid1 = __ldcg(&c->cid1); r.cid2 = __ldcg(&c->cid2); r.score = __ldcg(&c->score);
+    return r;
+}
+
+__global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams p)
+{
+    extern __shared__ __align__(16) unsigned char sDyn[];   // phase (b): the two PAF channels; phase (d): the assembly state
+    __shared__ int sNcand, sLast;
+    __shared__ int sBase[HP_N_PARTS + 1];
     __shared__ unsigned sUsedA[MAX_PCAP / 32], sUsedB[MAX_PCAP / 32];
+    __shared__ unsigned long long sCand[SM_CAND], sSorted[SM_CAND];
+    __shared__ int sKeys[SM_KEYS];
 
     const int limb = blockIdx.x, frame = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pa = c_pairs[limb][0], pb = c_pairs[limb][1];
-    const int* pbase = p.part_base + frame * (HP_N_PARTS + 1);
-    const int base_a = pbase[pa], na = pbase[pa + 1] - base_a;
-    const int base_b = pbase[pb], nb = pbase[pb + 1] - base_b;
+    const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
+    if (tid == 0) {
+        int bsum = 0;
+        for (int q = 0; q < HP_N_PARTS; ++q) { sBase[q] = bsum; bsum += min(cnt[q], p.pcap); }
+        sBase[HP_N_PARTS] = bsum;
+        sNcand = 0;
+    }
+    __syncthreads();
+    if (limb == 0 && tid <= HP_N_PARTS) p.part_base[frame * (HP_N_PARTS + 1) + tid] = sBase[tid];
+    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
+    int* px = p.px + peak_off;
+    int* py = p.py + peak_off;
+    float* pscore = p.pscore + peak_off;
+
+    // ---- (a) order the peaks of this limb's two parts (post_process.hpp:175-192: ids follow the scan order)
+    for (int which = 0; which < 2; ++which) {
+        const int part = which ? pb : pa;
+        const int n = sBase[part + 1] - sBase[part];
+        const size_t raw = ((size_t)frame * HP_N_PARTS + part) * p.pcap;
+        const int* keys = p.raw_key + raw;
+        const bool staged = n <= SM_KEYS;
+        __syncthreads();   // sKeys of the previous part is dead
+        if (staged) {
+            for (int i = tid; i < n; i += K3_THREADS) sKeys[i] = keys[i];
+            __syncthreads();
+        }
+        const int out = sBase[part];
+        for (int i = tid; i < n; i += K3_THREADS) {
+            const int k = staged ? sKeys[i] : keys[i];
+            int rank = 0;
+            if (staged) { for (int q = 0; q < n; ++q) rank += (sKeys[q] < k); }   // keys are unique pixel positions
+            else        { for (int q = 0; q < n; ++q) rank += (keys[q] < k); }
+            px[out + rank] = k % p.UW;
+            py[out + rank] = k / p.UW;
+            pscore[out + rank] = p.raw_score[raw + i];
+        }
+    }
+    __syncthreads();   // this CTA's own global writes are visible to all of its threads from here on
+
+    const int base_a = sBase[pa], na = sBase[pa + 1] - base_a;
+    const int base_b = sBase[pb], nb = sBase[pb + 1] - base_b;
     int* conn_cnt = p.conn_cnt + frame * HP_N_PAIRS + limb;
+    const int H = p.H, W = p.W;
     if (na == 0 || nb == 0) {
         if (tid == 0) *conn_cnt = 0;
-        return;
-    }
-    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
-    const int* px = p.px + peak_off;
-    const int* py = p.py + peak_off;
-    const int H = p.H, W = p.W;
-    const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
-    const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
-    const int npairs = na * nb;
-
-    if (tid == 0) sNcand = 0;
-    // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
-    if (npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
-        for (int i = tid; i < H * W; i += K3_THREADS) {
-            sPaf[i] = __ldg(P1 + i);
-            sPaf[H * W + i] = __ldg(P2 + i);
-        }
-        P1 = sPaf;
-        P2 = sPaf + H * W;
-    }
-    __syncthreads();
-
-    unsigned long long* cand = p.cand + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
-    unsigned long long* sorted = p.cand_sorted + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
-
-    // ---- get_connection_candidates: 3 peak pairs per warp pass, 10 lanes (= 10 samples) per pair
-    const int grp = lane / STEP_PAF, smp = lane - grp * STEP_PAF;
-    const unsigned gmask = (grp < 3) ? (0x3ffu << (grp * STEP_PAF)) : 0u;
-    constexpr int NW = K3_THREADS / 32;
-    for (int pb0 = warp * 3; pb0 < npairs; pb0 += NW * 3) { // warp-uniform trip count
-        const int pidx = pb0 + grp;
-        const bool active = (grp < 3) && (pidx < npairs);
-        int ia = 0, ib = 0;
-        float score = 0.f, norm = 1.f;
-        bool valid = false;
-        if (active) {
-            ia = pidx / nb;
-            ib = pidx - ia * nb;
-            const int ax = px[base_a + ia], ay = py[base_a + ia];
-            const int bx = px[base_b + ib], by = py[base_b + ib];
-            const int dx = bx - ax, dy = by - ay;
-            norm = (float)sqrt((double)(dx * dx + dy * dy)); // paf.cpp:104
-            valid = !((double)norm < 1e-12);                   // paf.cpp:105
-            if (valid) {
-                const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
-                const float stepx = __fdiv_rn((float)dx, (float)STEP_PAF); // paf.cpp:77-78
-                const float stepy = __fdiv_rn((float)dy, (float)STEP_PAF);
-                const float fx = __fadd_rn((float)ax, __fmul_rn((float)smp, stepx));
-                const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
-                const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
-                const int ly = (int)((double)fy + 0.5);
-                const float vpx = up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
-                const float vpy = up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
-                score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
+    } else {
+        const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
+        const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
+        const int npairs = na * nb;
+        // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
+        if (npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
+            float* sPaf = reinterpret_cast<float*>(sDyn);
+            for (int i = tid; i < H * W; i += K3_THREADS) {
+                sPaf[i] = __ldg(P1 + i);
+                sPaf[H * W + i] = __ldg(P2 + i);
             }
+            P1 = sPaf;
+            P2 = sPaf + H * W;
         }
-        const unsigned ball = __ballot_sync(0xffffffffu, valid && score > p.paf_thresh);
-        const int criterion1 = __popc(ball & gmask);
-        float sum = 0.f; // sequential i = 0..9 accumulation order of paf.cpp:121-127
+        __syncthreads();
+
+        unsigned long long* cand = p.cand + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+        unsigned long long* sorted = p.cand_sorted + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+
+        // ---- (b) get_connection_candidates: 3 peak pairs per warp pass, 10 lanes (= 10 samples) per pair
+        const int grp = lane / STEP_PAF, smp = lane - grp * STEP_PAF;
+        const unsigned gmask = (grp < 3) ? (0x3ffu << (grp * STEP_PAF)) : 0u;
+        constexpr int NW = K3_THREADS / 32;
+        for (int pb0 = warp * 3; pb0 < npairs; pb0 += NW * 3) { // warp-uniform trip count
+            const int pidx = pb0 + grp;
+            const bool active = (grp < 3) && (pidx < npairs);
+            int ia = 0, ib = 0;
+            float score = 0.f, norm = 1.f;
+            bool valid = false;
+            if (active) {
+                ia = pidx / nb;
+                ib = pidx - ia * nb;
+                const int ax = px[base_a + ia], ay = py[base_a + ia];
+                const int bx = px[base_b + ib], by = py[base_b + ib];
+                const int dx = bx - ax, dy = by - ay;
+                norm = (float)sqrt((double)(dx * dx + dy * dy)); // paf.cpp:104
+                valid = !((double)norm < 1e-12);                   // paf.cpp:105
+                if (valid) {
+                    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
+                    const float stepx = __fdiv_rn((float)dx, (float)STEP_PAF); // paf.cpp:77-78
+                    const float stepy = __fdiv_rn((float)dy, (float)STEP_PAF);
+                    const float fx = __fadd_rn((float)ax, __fmul_rn((float)smp, stepx));
+                    const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
+                    const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
+                    const int ly = (int)((double)fy + 0.5);
+                    const float vpx = up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                    const float vpy = up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                    score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, valid && score > p.paf_thresh);
+            const int criterion1 = __popc(ball & gmask);
+            float sum = 0.f; // sequential i = 0..9 accumulation order of paf.cpp:121-127
 #pragma unroll
-        for (int i = 0; i < STEP_PAF; ++i) {
-            const int srcl = min(grp * STEP_PAF + i, 31);
-            sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, score, srcl));
-        }
-        if (valid && smp == 0) {
-            double pen = 0.5 * (double)p.feat_height / (double)norm - 1.0; // paf.cpp:129
-            if (pen > 0.0) pen = 0.0;
-            const float criterion2 = (float)((double)__fdiv_rn(sum, (float)STEP_PAF) + pen);
-            if (criterion1 > THRESH_VECTOR_CNT1 && criterion2 > 0.f) {
-                const int slot = atomicAdd(&sNcand, 1);
-                if (slot < p.ccap) cand[slot] = make_key(criterion2, ia, ib);
+            for (int i = 0; i < STEP_PAF; ++i) {
+                const int srcl = min(grp * STEP_PAF + i, 31);
+                sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, score, srcl));
+            }
+            if (valid && smp == 0) {
+                double pen = 0.5 * (double)p.feat_height / (double)norm - 1.0; // paf.cpp:129
+                if (pen > 0.0) pen = 0.0;
+                const float criterion2 = (float)((double)__fdiv_rn(sum, (float)STEP_PAF) + pen);
+                if (criterion1 > THRESH_VECTOR_CNT1 && criterion2 > 0.f) {
+                    const int slot = atomicAdd(&sNcand, 1);
+                    const unsigned long long key = make_key(criterion2, ia, ib);
+                    if (slot < SM_CAND) sCand[slot] = key;
+                    else if (slot < p.ccap) cand[slot] = key;
+                }
             }
         }
-    }
-    __syncthreads();
-    int ncand = sNcand;
-    if (ncand > p.ccap) {
-        if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
-        ncand = p.ccap;
-    }
-    __threadfence_block();
-
-    // ---- std::sort by score desc (paf.cpp:249-250): rank sort on unique keys
-    for (int i = tid; i < ncand; i += K3_THREADS) {
-        const unsigned long long k = cand[i];
-        int rank = 0;
-        for (int q = 0; q < ncand; ++q) rank += (cand[q] > k);
-        sorted[rank] = k;
-    }
-    for (int i = tid; i < MAX_PCAP / 32; i += K3_THREADS) { sUsedA[i] = 0u; sUsedB[i] = 0u; }
-    __syncthreads();
-    __threadfence_block();
-
-    // ---- greedy one-to-one selection in score order (paf.cpp:252-270)
-    if (tid == 0) {
-        hp_connection* conn = p.conn + ((size_t)frame * HP_N_PAIRS + limb) * p.pcap;
-        const int max_conn = min(na, nb);
-        int nconn = 0;
-        for (int i = 0; i < ncand && nconn < max_conn; ++i) {
-            const unsigned long long k = sorted[i];
-            const unsigned inv = 0xffffffffu - (unsigned)(k & 0xffffffffu);
-            const int ia = (int)(inv >> 16), ib = (int)(inv & 0xffffu);
-            if ((sUsedA[ia >> 5] >> (ia & 31)) & 1u) continue;
-            if ((sUsedB[ib >> 5] >> (ib & 31)) & 1u) continue;
-            sUsedA[ia >> 5] |= 1u << (ia & 31);
-            sUsedB[ib >> 5] |= 1u << (ib & 31);
-            hp_connection c;
-            c.cid1 = base_a + ia; // peak ids == index in the ordered all_peaks list
-            c.cid2 = base_b + ib;
-            c.score = __uint_as_float((unsigned)(k >> 32));
-            conn[nconn++] = c;
+        __syncthreads();
+        int ncand = sNcand;
+        if (ncand > p.ccap) {
+            if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
+            ncand = p.ccap;
         }
-        *conn_cnt = nconn;
+        // the common case keeps the whole list in shared memory; a longer one moves to the global scratch arrays
+        const bool in_smem = ncand <= SM_CAND;
+        if (!in_smem) {
+            for (int i = tid; i < SM_CAND; i += K3_THREADS) cand[i] = sCand[i];
+            __threadfence_block();
+            __syncthreads();
+        }
+        const unsigned long long* cin = in_smem ? sCand : cand;
+        unsigned long long* cout = in_smem ? sSorted : sorted;
+
+        // ---- (c) std::sort by score desc (paf.cpp:249-250): rank sort on unique keys
+        for (int i = tid; i < ncand; i += K3_THREADS) {
+            const unsigned long long k = cin[i];
+            int rank = 0;
+            for (int q = 0; q < ncand; ++q) rank += (cin[q] > k);
+            cout[rank] = k;
+        }
+        for (int i = tid; i < MAX_PCAP / 32; i += K3_THREADS) { sUsedA[i] = 0u; sUsedB[i] = 0u; }
+        __threadfence_block();
+        __syncthreads();
+
+        // greedy one-to-one selection in score order (paf.cpp:252-270)
+        if (tid == 0) {
+            hp_connection* conn = p.conn + ((size_t)frame * HP_N_PAIRS + limb) * p.pcap;
+            const int max_conn = min(na, nb);
+            int nconn = 0;
+            for (int i = 0; i < ncand && nconn < max_conn; ++i) {
+                const unsigned long long k = cout[i];
+                const unsigned inv = 0xffffffffu - (unsigned)(k & 0xffffffffu);
+                const int ia = (int)(inv >> 16), ib = (int)(inv & 0xffffu);
+                if ((sUsedA[ia >> 5] >> (ia & 31)) & 1u) continue;
+                if ((sUsedB[ib >> 5] >> (ib & 31)) & 1u) continue;
+                sUsedA[ia >> 5] |= 1u << (ia & 31);
+                sUsedB[ib >> 5] |= 1u << (ib & 31);
+                hp_connection c;
+                c.cid1 = base_a + ia; // peak ids == index in the ordered all_peaks list
+                c.cid2 = base_b + ib;
+                c.score = __uint_as_float((unsigned)(k >> 32));
+                conn[nconn++] = c;
+            }
+            *conn_cnt = nconn;
+        }
     }
-}
 
-// ---------------------------------------------------------------------------------------------
-// K4: get_humans + filter + conversion; one warp per frame
-// ---------------------------------------------------------------------------------------------
-struct AssembleParams {
-    int pcap, hcap, UW, UH;
-    const int* part_base; const int* px; const int* py; const float* pscore;
-    const hp_connection* conn; const int* conn_cnt;
-    hp_human* humans;  // [N,hcap]
-    int* human_cnt;    // [N]
-    int* flags;
-    int max_refs;      // smem capacity for partial humans
-};
+    // ---- (d) the last CTA of the frame to arrive assembles the humans
+    __threadfence();   // ordered peaks, connections and counts of this CTA: visible device-wide before the arrival is counted
+    __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(p.frame_done + frame, 1) == HP_N_PAIRS - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
 
-struct HumanRef { // paf.cpp:19-37 (id == position in the vector, kept implicit)
-    int parts[HP_N_PARTS];
-    float score;
-    int n_parts;
-};
+    const int n_peaks = sBase[HP_N_PARTS];
+    const int MAXR = p.max_refs;
+    int* rParts = reinterpret_cast<int*>(sDyn);                       // [18][MAXR] part-major: lane h reads parts[q][h] conflict-free
+    float* rScore = reinterpret_cast<float*>(rParts + HP_N_PARTS * MAXR);
+    int* rNparts = reinterpret_cast<int*>(rScore + MAXR);
+    hp_connection* sConn = reinterpret_cast<hp_connection*>(rNparts + MAXR);   // [SM_CONN]
+    float* sPsc = reinterpret_cast<float*>(sConn + SM_CONN);                   // [SM_PSC]
+    int* sCnt = reinterpret_cast<int*>(sUsedA);                                // [20] connection offsets (bitmaps are dead)
+    const volatile int* ccnt = p.conn_cnt + frame * HP_N_PAIRS;
+    if (tid == 0) {
+        int t = 0;
+        for (int q = 0; q < HP_N_PAIRS; ++q) { sCnt[q] = t; t += ccnt[q]; }
+        sCnt[HP_N_PAIRS] = t;
+    }
+    __syncthreads();
+    const int n_conn = sCnt[HP_N_PAIRS];
+    const bool conn_staged = n_conn <= SM_CONN, psc_staged = n_peaks <= SM_PSC;
+    const hp_connection* gconn = p.conn + (size_t)frame * HP_N_PAIRS * p.pcap;
+    if (conn_staged)
+        for (int q = 0; q < HP_N_PAIRS; ++q)
+            for (int i = tid; i < sCnt[q + 1] - sCnt[q]; i += K3_THREADS) sConn[sCnt[q] + i] = ld_conn_cg(gconn + (size_t)q * p.pcap + i);
+    if (psc_staged)
+        for (int i = tid; i < n_peaks; i += K3_THREADS) sPsc[i] = __ldcg(pscore + i);   // other CTAs wrote these: read past L1
+    __syncthreads();
+    if (warp != 0) return;
+    const float* psc = psc_staged ? sPsc : pscore;   // (unstaged: > 2048 peaks in one frame; plain loads are fine for values no earlier read of this SM cached)
 
-__global__ void __launch_bounds__(32) paf_assemble_kernel(const AssembleParams p)
-{
-    extern __shared__ HumanRef sRef[];
-    const int frame = blockIdx.x, lane = threadIdx.x;
-    const int* pbase = p.part_base + frame * (HP_N_PARTS + 1);
-    const int n_peaks = pbase[HP_N_PARTS];
-    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
-    const float* pscore = p.pscore + peak_off;
-    const int* px = p.px + peak_off;
-    const int* py = p.py + peak_off;
     int nh = 0;
-
     for (int pair_id = 0; pair_id < HP_N_PAIRS; ++pair_id) {
         const int part1 = c_pairs[pair_id][0], part2 = c_pairs[pair_id][1];
-        const int ncn = p.conn_cnt[frame * HP_N_PAIRS + pair_id];
-        const hp_connection* conns = p.conn + ((size_t)frame * HP_N_PAIRS + pair_id) * p.pcap;
+        const int ncn = sCnt[pair_id + 1] - sCnt[pair_id];
+        const hp_connection* conns = conn_staged ? sConn + sCnt[pair_id] : gconn + (size_t)pair_id * p.pcap;
         for (int ci = 0; ci < ncn; ++ci) {
-            const hp_connection cn = conns[ci];
+            const hp_connection cn = conn_staged ? conns[ci] : ld_conn_cg(conns + ci);
             // touches (paf.cpp:33-36) evaluated for 32 humans at a time; first two hits in vector order
             int t0 = -1, t1 = -1, nt = 0;
             for (int hb = 0; hb < nh && nt < 2; hb += 32) {
                 const int h = hb + lane;
-                const bool touch = (h < nh) && (sRef[h].parts[part1] == cn.cid1 || sRef[h].parts[part2] == cn.cid2);
-                unsigned b = __ballot_sync(0xffffffffu, touch);
-                while (b && nt < 2) {
-                    const int l = __ffs(b) - 1;
+                const bool touch = (h < nh) && (rParts[part1 * MAXR + h] == cn.cid1 || rParts[part2 * MAXR + h] == cn.cid2);
+                unsigned bal = __ballot_sync(0xffffffffu, touch);
+                while (bal && nt < 2) {
+                    const int l = __ffs(bal) - 1;
                     if (nt == 0) t0 = hb + l; else t1 = hb + l;
                     ++nt;
-                    b &= b - 1;
+                    bal &= bal - 1;
                 }
             }
-            int delta = 0;
-            if (lane == 0) {
-                if (nt == 1) { // paf.cpp:172-178
-                    HumanRef& h1 = sRef[t0];
-                    if (h1.parts[part2] != cn.cid2) {
-                        h1.parts[part2] = cn.cid2;
-                        ++h1.n_parts;
-                        h1.score = __fadd_rn(h1.score, __fadd_rn(pscore[cn.cid2], cn.score));
+            // every branch below is warp-uniform (nt, t0, t1, nh are the same on all lanes)
+            if (nt == 1) { // paf.cpp:172-178
+                if (lane == 0 && rParts[part2 * MAXR + t0] != cn.cid2) {
+                    rParts[part2 * MAXR + t0] = cn.cid2;
+                    rNparts[t0] += 1;
+                    rScore[t0] = __fadd_rn(rScore[t0], __fadd_rn(psc[cn.cid2], cn.score));
+                }
+            } else if (nt >= 2) { // paf.cpp:179-210
+                int va = 0, vb = 0;
+                if (lane < HP_N_PARTS) { va = rParts[lane * MAXR + t0]; vb = rParts[lane * MAXR + t1]; }
+                const bool shared_part = __ballot_sync(0xffffffffu, lane < HP_N_PARTS && va > 0 && vb > 0) != 0u; // `id > 0` quirk (paf.cpp:185)
+                if (!shared_part) {
+                    if (lane < HP_N_PARTS) rParts[lane * MAXR + t0] = va + vb + 1; // paf.cpp:193
+                    if (lane == 0) {
+                        rNparts[t0] += rNparts[t1];
+                        rScore[t0] = __fadd_rn(__fadd_rn(rScore[t0], rScore[t1]), cn.score);
                     }
-                } else if (nt >= 2) { // paf.cpp:179-210
-                    HumanRef& h1 = sRef[t0];
-                    const HumanRef& h2 = sRef[t1];
-                    int membership = 0;
-                    for (int i = 0; i < HP_N_PARTS; ++i)
-                        if (h1.parts[i] > 0 && h2.parts[i] > 0) membership = 2; // `id > 0` quirk (paf.cpp:185)
-                    if (membership == 0) {
-                        for (int i = 0; i < HP_N_PARTS; ++i) h1.parts[i] += h2.parts[i] + 1; // paf.cpp:193
-                        h1.n_parts += h2.n_parts;
-                        h1.score = __fadd_rn(h1.score, h2.score);
-                        h1.score = __fadd_rn(h1.score, cn.score);
-                        for (int h = t1; h + 1 < nh; ++h) sRef[h] = sRef[h + 1]; // vector::erase (paf.cpp:201-205)
-                        delta = -1;
-                    } else {
-                        h1.parts[part2] = cn.cid2;
-                        h1.n_parts += 1;
-                        h1.score = __fadd_rn(h1.score, __fadd_rn(pscore[cn.cid2], cn.score));
+                    __syncwarp();
+                    // vector::erase (paf.cpp:201-205): lanes 0..17 shift one part column each, 18 the scores, 19 the counts
+                    for (int h = t1; h + 1 < nh; ++h) {
+                        if (lane < HP_N_PARTS) rParts[lane * MAXR + h] = rParts[lane * MAXR + h + 1];
+                        else if (lane == HP_N_PARTS) rScore[h] = rScore[h + 1];
+                        else if (lane == HP_N_PARTS + 1) rNparts[h] = rNparts[h + 1];
                     }
-                } else if (pair_id <= 16) { // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
-                    if (nh < p.max_refs) {
-                        HumanRef& h = sRef[nh];
-                        for (int i = 0; i < HP_N_PARTS; ++i) h.parts[i] = -1;
-                        h.parts[part1] = cn.cid1;
-                        h.parts[part2] = cn.cid2;
-                        h.n_parts = 2;
-                        h.score = __fadd_rn(__fadd_rn(pscore[cn.cid1], pscore[cn.cid2]), cn.score);
-                        delta = 1;
-                    } else {
-                        atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
+                    nh -= 1;
+                } else if (lane == 0) {
+                    rParts[part2 * MAXR + t0] = cn.cid2;
+                    rNparts[t0] += 1;
+                    rScore[t0] = __fadd_rn(rScore[t0], __fadd_rn(psc[cn.cid2], cn.score));
+                }
+            } else if (pair_id <= 16) { // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
+                if (nh < MAXR) {
+                    if (lane < HP_N_PARTS) rParts[lane * MAXR + nh] = (lane == part1) ? cn.cid1 : (lane == part2) ? cn.cid2 : -1;
+                    if (lane == 0) {
+                        rNparts[nh] = 2;
+                        rScore[nh] = __fadd_rn(__fadd_rn(psc[cn.cid1], psc[cn.cid2]), cn.score);
                     }
+                    nh += 1;
+                } else if (lane == 0) {
+                    atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
                 }
             }
             __syncwarp();
-            nh += __shfl_sync(0xffffffffu, delta, 0);
         }
     }
 
@@ -592,28 +649,24 @@ __global__ void __launch_bounds__(32) paf_assemble_kernel(const AssembleParams p
     for (int hb = 0; hb < nh; hb += 32) {
         const int h = hb + lane;
         bool keep = false;
-        if (h < nh) {
-            const HumanRef& r = sRef[h];
-            keep = !(r.n_parts < THRESH_PART_CNT || __fdiv_rn(r.score, (float)r.n_parts) < 0.4f);
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, keep);
-        const int idx = no + __popc(b & ((1u << lane) - 1u));
+        if (h < nh) keep = !(rNparts[h] < THRESH_PART_CNT || __fdiv_rn(rScore[h], (float)rNparts[h]) < 0.4f);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int idx = no + __popc(bal & ((1u << lane) - 1u));
         if (keep) {
             if (idx < p.hcap) {
-                const HumanRef& r = sRef[h];
                 hp_human* o = p.humans + (size_t)frame * p.hcap + idx;
-                o->score = r.score;
+                o->score = rScore[h];
                 for (int i = 0; i < HP_N_PARTS; ++i) {
-                    const int id = r.parts[i];
+                    const int id = rParts[i * MAXR + h];
                     hp_body_part bp;
                     bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
                     // ids fabricated by the `+=` merge quirk would be an out-of-bounds read (UB) in the
                     // reference; like the oracle, such parts are reported absent.
                     if (id != -1 && id >= 0 && id < n_peaks) {
                         bp.has_value = 1;
-                        bp.score = pscore[id];
-                        bp.x = __fdiv_rn((float)px[id], (float)p.UW);
-                        bp.y = __fdiv_rn((float)py[id], (float)p.UH);
+                        bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
+                        bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
+                        bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
                     }
                     o->parts[i] = bp;
                 }
@@ -621,9 +674,15 @@ __global__ void __launch_bounds__(32) paf_assemble_kernel(const AssembleParams p
                 atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
             }
         }
-        no += __popc(b);
+        no += __popc(bal);
     }
     if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
+}
+
+// bytes of dynamic shared memory the assembly phase of paf_limbs_kernel needs for `max_refs` partial humans
+constexpr size_t assemble_smem_bytes(int max_refs)
+{
+    return (size_t)max_refs * (HP_N_PARTS + 2) * 4 + (size_t)SM_CONN * sizeof(hp_connection) + (size_t)SM_PSC * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -646,6 +705,23 @@ void area_up_table(int src, int dst, std::vector<int>& idx, std::vector<float>& 
         if (s >= src - 1) { f = 0.f; s = src - 1; }
         idx[d] = s;
         frac[d] = f;
+    }
+}
+
+// Source rows (or columns) the tile starting at up-map position t0 reads: the tile's window [t0 - 9, t0 + extent + 9) in
+// reflected coordinates (BORDER_REFLECT_101), each position touching source index idx[.] and idx[.] + 1 (clamped).
+void tile_source_bounds(const std::vector<int>& idx, int src_len, int up_len, int tile, int window, std::vector<int>& out)
+{
+    const int tiles = (up_len + tile - 1) / tile;
+    for (int t = 0; t < tiles; ++t) {
+        int lo = 0x7fffffff, hi = -1;
+        for (int k = 0; k < window; ++k) {
+            const int s = idx[refl101(t * tile - HALO + k, up_len)];
+            lo = std::min(lo, s);
+            hi = std::max(hi, std::min(s + 1, src_len - 1));
+        }
+        out.push_back(lo);
+        out.push_back(hi);
     }
 }
 
@@ -710,9 +786,9 @@ struct hp_paf {
     int N = 0, c_conf = 0, c_paf = 0, H = 0, W = 0, UH = 0, UW = 0;
     int cap_pcap = 0, cap_ccap = 0, cap_hcap = 0, cap_N = 0;
 
-    DevBuf<int> xi, yi;
+    DevBuf<int> xi, yi, tile_bounds;
     DevBuf<float> xf, yf;
-    DevBuf<int> counters; // [N*18 peak_cnt | N*19 conn_cnt | N human_cnt | N flags]
+    DevBuf<int> counters; // [N*18 peak_cnt | N*19 conn_cnt | N human_cnt | N flags | N frame_done]
     DevBuf<int> raw_key, part_base, px, py;
     DevBuf<float> raw_score, pscore;
     DevBuf<unsigned long long> cand, cand_sorted;
@@ -724,13 +800,15 @@ struct hp_paf {
     PinnedBuf<int> pin_counts; // [N human_cnt | N flags]
     int last_N = 0;
     cudaStream_t last_stream = nullptr;
-    int limb_stage_bytes = 0;
-    int assemble_max_refs = 560; // 560 * 80 B < 48 KB (no opt-in needed); raised at create when the device allows
+    int limb_dyn_bytes = 0;       // dynamic shared memory paf_limbs_kernel may use (opted in at create)
+    int assemble_max_refs = 256;  // partial humans that fit next to the staged connections / scores
 
     int* peak_cnt() { return counters.p; }
     int* conn_cnt() { return counters.p + (size_t)cap_N * HP_N_PARTS; }
     int* human_cnt() { return counters.p + (size_t)cap_N * (HP_N_PARTS + HP_N_PAIRS); }
     int* flags() { return counters.p + (size_t)cap_N * (HP_N_PARTS + HP_N_PAIRS + 1); }
+    int* frame_done() { return counters.p + (size_t)cap_N * (HP_N_PARTS + HP_N_PAIRS + 2); }
+    static constexpr int COUNTERS_PER_FRAME = HP_N_PARTS + HP_N_PAIRS + 3;
 };
 
 namespace {
@@ -757,19 +835,25 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
     if (p->pcap > MAX_PCAP) p->pcap = MAX_PCAP;
     const bool geo_changed = (H != p->H || W != p->W || UH != p->UH || UW != p->UW);
     if (geo_changed) {
-        std::vector<int> idx;
+        std::vector<int> idx_x, idx_y;
         std::vector<float> fr;
-        area_up_table(W, UW, idx, fr);
+        area_up_table(W, UW, idx_x, fr);
         HP_CUDA_TRY(p->xi.ensure(UW));
         HP_CUDA_TRY(p->xf.ensure(UW));
-        HP_CUDA_TRY(cudaMemcpyAsync(p->xi.p, idx.data(), UW * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->xi.p, idx_x.data(), UW * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         HP_CUDA_TRY(cudaMemcpyAsync(p->xf.p, fr.data(), UW * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-        HP_CUDA_TRY(cudaStreamSynchronize(p->stream)); // idx/fr are stack vectors
-        area_up_table(H, UH, idx, fr);
+        HP_CUDA_TRY(cudaStreamSynchronize(p->stream)); // the vectors are locals
+        area_up_table(H, UH, idx_y, fr);
         HP_CUDA_TRY(p->yi.ensure(UH));
         HP_CUDA_TRY(p->yf.ensure(UH));
-        HP_CUDA_TRY(cudaMemcpyAsync(p->yi.p, idx.data(), UH * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->yi.p, idx_y.data(), UH * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         HP_CUDA_TRY(cudaMemcpyAsync(p->yf.p, fr.data(), UH * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        // per tile row / tile column: the source rows / columns its halo window reads (K1 stages exactly that rectangle)
+        std::vector<int> tb;
+        tile_source_bounds(idx_y, H, UH, TH, UT_H, tb);
+        tile_source_bounds(idx_x, W, UW, TW, UT_W, tb);
+        HP_CUDA_TRY(p->tile_bounds.ensure(tb.size()));
+        HP_CUDA_TRY(cudaMemcpyAsync(p->tile_bounds.p, tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         HP_CUDA_TRY(cudaStreamSynchronize(p->stream));
     }
     p->H = H; p->W = W; p->UH = UH; p->UW = UW; p->c_conf = c_conf; p->c_paf = c_paf;
@@ -777,7 +861,7 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
         const int cN = std::max(N, p->cap_N);
         p->cap_N = cN;
         p->cap_pcap = p->pcap; p->cap_ccap = p->ccap; p->cap_hcap = p->hcap;
-        HP_CUDA_TRY(p->counters.ensure((size_t)cN * (HP_N_PARTS + HP_N_PAIRS + 2)));
+        HP_CUDA_TRY(p->counters.ensure((size_t)cN * hp_paf::COUNTERS_PER_FRAME));
         HP_CUDA_TRY(p->raw_key.ensure((size_t)cN * HP_N_PARTS * p->pcap));
         HP_CUDA_TRY(p->raw_score.ensure((size_t)cN * HP_N_PARTS * p->pcap));
         HP_CUDA_TRY(p->part_base.ensure((size_t)cN * (HP_N_PARTS + 1)));
@@ -798,7 +882,7 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
 int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, cudaStream_t st)
 {
     const int UH = p->UH, UW = p->UW;
-    HP_CUDA_TRY(cudaMemsetAsync(p->counters.p, 0, (size_t)p->cap_N * (HP_N_PARTS + HP_N_PAIRS + 2) * sizeof(int), st));
+    HP_CUDA_TRY(cudaMemsetAsync(p->counters.p, 0, (size_t)p->cap_N * hp_paf::COUNTERS_PER_FRAME * sizeof(int), st));
 
     PeakParams k1;
     k1.conf = d_conf; k1.c_conf = p->c_conf; k1.H = p->H; k1.W = p->W; k1.UH = UH; k1.UW = UW;
@@ -806,40 +890,32 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k1.thresh = p->conf_thresh;
     k1.skip_below = (p->conf_thresh > 0.f) ? p->conf_thresh * (1.f - 1e-5f) : -INFINITY;
     k1.tiles_x = (UW + TW - 1) / TW;
+    k1.tiles_y = (UH + TH - 1) / TH;
+    k1.tile_bounds = p->tile_bounds.p;
     k1.pcap = p->pcap;
     k1.peak_cnt = p->peak_cnt(); k1.raw_key = p->raw_key.p; k1.raw_score = p->raw_score.p; k1.flags = p->flags();
     k1.n8 = UW & ~7;
     k1.n4 = (UW - k1.n8 >= 4) ? k1.n8 + 4 : k1.n8;
-    const int tiles_y = (UH + TH - 1) / TH;
-    dim3 g1(k1.tiles_x * tiles_y, HP_N_PARTS, N);
+    dim3 g1(k1.tiles_x * k1.tiles_y, HP_N_PARTS, N);
     paf_peaks_kernel<<<g1, K1_THREADS, 0, st>>>(k1);
-
-    OrderParams k2;
-    k2.pcap = p->pcap; k2.UW = UW; k2.peak_cnt = p->peak_cnt(); k2.raw_key = p->raw_key.p; k2.raw_score = p->raw_score.p;
-    k2.part_base = p->part_base.p; k2.px = p->px.p; k2.py = p->py.p; k2.pscore = p->pscore.p;
-    paf_order_kernel<<<dim3(HP_N_PARTS, N), 128, p->pcap * sizeof(int), st>>>(k2);
 
     LimbParams k3;
     k3.paf = d_paf; k3.c_paf = p->c_paf; k3.H = p->H; k3.W = p->W; k3.UH = UH; k3.UW = UW;
     k3.xi = p->xi.p; k3.xf = p->xf.p; k3.yi = p->yi.p; k3.yf = p->yf.p;
     k3.paf_thresh = p->paf_thresh;
     k3.feat_height = p->W; // m_feature_size = cv::Size(fw, fh) with fh = W (paf.cpp:329); .height -> get_connections (:354)
-    k3.pcap = p->pcap; k3.ccap = p->ccap;
+    k3.pcap = p->pcap; k3.ccap = p->ccap; k3.hcap = p->hcap; k3.max_refs = p->max_refs;
+    k3.peak_cnt = p->peak_cnt(); k3.raw_key = p->raw_key.p; k3.raw_score = p->raw_score.p;
     k3.part_base = p->part_base.p; k3.px = p->px.p; k3.py = p->py.p; k3.pscore = p->pscore.p;
     k3.cand = p->cand.p; k3.cand_sorted = p->cand_sorted.p; k3.conn = p->conn.p; k3.conn_cnt = p->conn_cnt();
+    k3.frame_done = p->frame_done(); k3.humans = p->humans.p; k3.human_cnt = p->human_cnt();
     k3.flags = p->flags();
     const int want = 2 * p->H * p->W * (int)sizeof(float);
-    k3.stage_bytes = (want <= p->limb_stage_bytes) ? want : 0;
-    paf_limb_kernel<<<dim3(HP_N_PAIRS, N), K3_THREADS, k3.stage_bytes, st>>>(k3);
-
-    AssembleParams k4;
-    k4.pcap = p->pcap; k4.hcap = p->hcap; k4.UW = UW; k4.UH = UH;
-    k4.part_base = p->part_base.p; k4.px = p->px.p; k4.py = p->py.p; k4.pscore = p->pscore.p;
-    k4.conn = p->conn.p; k4.conn_cnt = p->conn_cnt();
-    k4.humans = p->humans.p; k4.human_cnt = p->human_cnt(); k4.flags = p->flags(); k4.max_refs = p->max_refs;
-    paf_assemble_kernel<<<N, 32, p->max_refs * sizeof(HumanRef), st>>>(k4);
+    k3.stage_bytes = (want <= p->limb_dyn_bytes) ? want : 0;
+    const size_t dyn = std::max((size_t)k3.stage_bytes, assemble_smem_bytes(p->max_refs));
+    paf_limbs_kernel<<<dim3(HP_N_PAIRS, N), K3_THREADS, dyn, st>>>(k3);
     HP_CUDA_TRY(cudaGetLastError());
-    p->launches += 4;
+    p->launches += 2;
     p->last_N = N;
     p->last_stream = st;
     return HP_OK;
@@ -964,20 +1040,24 @@ int hp_paf_create(hp_paf** out, float conf_thresh, float paf_thresh, int res_w, 
     p->res_h = res_h;
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete p; hpb::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return HP_ERR_CUDA; }
-    // opt in to a large dynamic shared-memory carve-out for staging the two PAF channels of a limb
+    // opt in to the large dynamic shared-memory carve-out of paf_limbs_kernel: the two PAF channels of a limb in phase (b),
+    // the partial humans + connections + peak scores of a frame in phase (d)
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    int stage = max_optin - 4096;
-    if (stage > 160 * 1024) stage = 160 * 1024;
-    if (stage > 0 && cudaFuncSetAttribute(paf_limb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage) == cudaSuccess)
-        p->limb_stage_bytes = stage;
-    else
+    cudaFuncAttributes fa;
+    size_t static_smem = 16 * 1024;
+    if (cudaFuncGetAttributes(&fa, paf_limbs_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes;
+    else cudaGetLastError();
+    int dyn = max_optin - (int)static_smem - 1024;
+    if (dyn > 200 * 1024) dyn = 200 * 1024;
+    if (dyn > 48 * 1024 - (int)static_smem && cudaFuncSetAttribute(paf_limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) == cudaSuccess)
+        p->limb_dyn_bytes = dyn;
+    else {
         cudaGetLastError();
-    int refs_bytes = std::min(max_optin - 2048, 200 * 1024);
-    if (refs_bytes > 48 * 1024 && cudaFuncSetAttribute(paf_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, refs_bytes) == cudaSuccess)
-        p->assemble_max_refs = refs_bytes / (int)sizeof(HumanRef);
-    else
-        cudaGetLastError();
+        p->limb_dyn_bytes = 48 * 1024 - (int)static_smem;
+    }
+    p->assemble_max_refs = (int)((p->limb_dyn_bytes - (SM_CONN * sizeof(hp_connection) + SM_PSC * 4)) / ((HP_N_PARTS + 2) * 4));
+    if (p->max_refs > p->assemble_max_refs) p->max_refs = p->assemble_max_refs;
     *out = p;
     return HP_OK;
 }
@@ -987,7 +1067,7 @@ void hp_paf_destroy(hp_paf* p)
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
-    p->xi.release(); p->yi.release(); p->xf.release(); p->yf.release(); p->counters.release();
+    p->xi.release(); p->yi.release(); p->xf.release(); p->yf.release(); p->tile_bounds.release(); p->counters.release();
     p->raw_key.release(); p->part_base.release(); p->px.release(); p->py.release();
     p->raw_score.release(); p->pscore.release(); p->cand.release(); p->cand_sorted.release();
     p->conn.release(); p->humans.release(); p->in_conf.release(); p->in_paf.release();

@@ -211,7 +211,8 @@ int hp_handoff_stats(long long* published, long long* hits, long long* batch_par
 int hp_engine_copy_outputs_device(hp_engine* e, float* d_conf, float* d_paf, int N, void* stream);
 int hp_engine_sync(hp_engine* e);
 long long hp_engine_launch_count(const hp_engine* e);
-/* test hooks: read / write an activation buffer (fp16 NHWC), run a sub-range [first,last] of the op list */
+/* test hooks: read / write an activation buffer (NHWC; fp16 elements on an HP_DTYPE_F16 engine, fp32 on HP_DTYPE_TF32),
+ * run a sub-range [first,last] of the op list */
 int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int* H, int* W, int* C);
 int hp_engine_debug_write_buffer(hp_engine* e, int buf, const void* in_f16, int N);
 int hp_engine_debug_run_ops(hp_engine* e, int first_op, int last_op, int N);

@@ -119,7 +119,7 @@ def test_device_resident_hand_off():
     got = parser.fetch(4)
     for i in range(4):
         _cmp_frame(got[i], oracle.oracle_process(conf[i], paf[i]), f"dev frame {i}")
-    assert parser.launch_count >= 4
+    assert parser.launch_count >= 2
     parser.close()
 
 
