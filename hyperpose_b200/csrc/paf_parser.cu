@@ -112,8 +112,13 @@ struct PeakParams {
     float* raw_score;    // [N,18,pcap]
     int* flags;          // [N]
     int n8, n4;          // column classes of the separable filter (see oracle/paf_oracle.c)
+    const float* up;     // kFromUp: resized maps [N, c_conf, UH, UW] written by resize_area_generic_kernel
 };
 
+// kFromUp = false: the default, fused path (resolution >= feature map on both axes: 2-tap area-mode up-sampling recomputed per tile).
+// kFromUp = true : resolutions that SHRINK an axis (true INTER_AREA averaging, or the mixed regime): the resized maps were
+//                  materialised by resize_area_generic_kernel and the tile is loaded from them (reflected coordinates).
+template <bool kFromUp>
 __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams p)
 {
     // sSrc (dead after the up-sample) and sTmp (row-pass output) share storage.
@@ -133,6 +138,28 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     const int H = p.H, W = p.W, UH = p.UH, UW = p.UW;
     const float* src = p.conf + ((size_t)frame * p.c_conf + part) * H * W;
 
+    if (kFromUp) {
+        const float* up = p.up + ((size_t)frame * p.c_conf + part) * UH * UW;
+        float lmax = -INFINITY;
+        for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
+            const int vy = i / UT_W, vx = i - vy * UT_W;
+            const float v = __ldg(up + (size_t)refl101(y0 - HALO + vy, UH) * UW + refl101(x0 - HALO + vx, UW));
+            sU[vy * UT_LD + vx] = v;
+            lmax = fmaxf(lmax, v);
+            if (v != v) lmax = INFINITY;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((tid & 31) == 0) sMax[tid >> 5] = lmax;
+        __syncthreads();
+        if (tid == 0) {
+            float m = sMax[0];
+            for (int i = 1; i < K1_THREADS / 32; ++i) m = fmaxf(m, sMax[i]);
+            sSkip = (m <= p.skip_below) ? 1 : 0;   // smoothed <= max of the window (1 + 3e-6): same bound as below
+        }
+        __syncthreads();
+        if (sSkip) return;
+    } else {
     // source rows / columns this tile's (reflected) rows and columns touch: precomputed on the host
     const int sr0 = __ldg(p.tile_bounds + 2 * ty), sr1 = __ldg(p.tile_bounds + 2 * ty + 1);
     const int sc0 = __ldg(p.tile_bounds + 2 * p.tiles_y + 2 * tx), sc1 = __ldg(p.tile_bounds + 2 * p.tiles_y + 2 * tx + 1);
@@ -207,6 +234,7 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
         }
     }
     __syncthreads(); // sSrc is dead from here; sA becomes sTmp
+    }
 
     // ---- row pass: sTmp[vy][c], c = 0..63 <-> real column j = x0 - 1 + c; taps left->right.
     //      work item = (row, run of 16 columns), one per thread; adjacent threads take adjacent rows (odd strides).
@@ -295,6 +323,75 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K0 (only for resolutions that shrink an axis): cv::resize(INTER_AREA) of every channel into HBM, one thread per destination
+// value, the reference's arithmetic in the reference's order (oracle/paf_oracle.c orc_resize_area, pinned to cv2):
+//   mode 0  2-tap area-mode lerp on both axes (mixed regime: one axis grows);
+//   mode 1  integer factors: block sum in row-major order, four at a time (sum += ((s0+s1)+s2)+s3), times (float)(1/area);
+//           the 2 x 2 case is ((a+b)+(c+d)) * 0.25 for dx < (dw & ~3) (OpenCV's SIMD kernel) and the scalar order on the tail;
+//   mode 2  fractional: DecimateAlpha tables -- buf = sum_k S[sx_k] * alpha_k per source row, dst = beta_0 buf_0 + beta_1 buf_1 + ...
+// ---------------------------------------------------------------------------------------------
+struct ResizeParams {
+    const float* src; float* dst;   // [N*C, H, W] -> [N*C, UH, UW]
+    int planes, H, W, UH, UW;
+    int mode, isx, isy;
+    const int* xi; const float* xf; const int* yi; const float* yf;           // mode 0
+    const int* xofs; const int* xsi; const float* xal;                          // mode 2: entries [xofs[dx], xofs[dx+1])
+    const int* yofs; const int* ysi; const float* yal;
+};
+
+__global__ void __launch_bounds__(256) resize_area_generic_kernel(const ResizeParams p)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)p.planes * p.UH * p.UW;
+    if (idx >= total) return;
+    const int dx = (int)(idx % p.UW);
+    const int dy = (int)((idx / p.UW) % p.UH);
+    const int pl = (int)(idx / ((size_t)p.UW * p.UH));
+    const float* S = p.src + (size_t)pl * p.H * p.W;
+    const int W = p.W;
+    float out;
+    if (p.mode == 0) {
+        const int x0 = __ldg(p.xi + dx), x1 = min(x0 + 1, W - 1);
+        const int y0 = __ldg(p.yi + dy), y1 = min(y0 + 1, p.H - 1);
+        const float a1 = __ldg(p.xf + dx), a0 = __fsub_rn(1.f, a1);
+        const float b1 = __ldg(p.yf + dy), b0 = __fsub_rn(1.f, b1);
+        const float h0 = __fadd_rn(__fmul_rn(S[y0 * W + x0], a0), __fmul_rn(S[y0 * W + x1], a1));
+        const float h1 = __fadd_rn(__fmul_rn(S[y1 * W + x0], a0), __fmul_rn(S[y1 * W + x1], a1));
+        out = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+    } else if (p.mode == 1) {
+        const int isx = p.isx, isy = p.isy, area = isx * isy;
+        const float* B = S + (size_t)dy * isy * W + (size_t)dx * isx;
+        if (isx == 2 && isy == 2 && dx < (p.UW & ~3)) {
+            out = __fmul_rn(__fadd_rn(__fadd_rn(B[0], B[1]), __fadd_rn(B[W], B[W + 1])), 0.25f);
+        } else {
+            float sum = 0.f;
+            int k = 0;
+            for (; k <= area - 4; k += 4) {
+                float g = __fadd_rn(B[(k / isx) * W + k % isx], B[((k + 1) / isx) * W + (k + 1) % isx]);
+                g = __fadd_rn(g, B[((k + 2) / isx) * W + (k + 2) % isx]);
+                g = __fadd_rn(g, B[((k + 3) / isx) * W + (k + 3) % isx]);
+                sum = __fadd_rn(sum, g);
+            }
+            for (; k < area; ++k) sum = __fadd_rn(sum, B[(k / isx) * W + k % isx]);
+            out = __fmul_rn(sum, __fdiv_rn(1.f, (float)area));
+        }
+    } else {
+        const int xb = __ldg(p.xofs + dx), xe = __ldg(p.xofs + dx + 1);
+        const int yb = __ldg(p.yofs + dy), ye = __ldg(p.yofs + dy + 1);
+        float sum = 0.f;
+        for (int j = yb; j < ye; ++j) {
+            const float* R = S + (size_t)__ldg(p.ysi + j) * W;
+            float buf = 0.f;
+            for (int k = xb; k < xe; ++k) buf = __fadd_rn(buf, __fmul_rn(R[__ldg(p.xsi + k)], __ldg(p.xal + k)));
+            const float t = __fmul_rn(__ldg(p.yal + j), buf);
+            sum = (j == yb) ? t : __fadd_rn(sum, t);
+        }
+        out = sum;
+    }
+    p.dst[idx] = out;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: everything after the peak scan, one CTA per (limb, frame):
 //   (a) peak ordering   -- the CTA restores the reference's channel-major / row-major peak order (ids = index) for the two
 //                          parts of its limb: rank-sort by scan position.  A part belongs to several limbs; every CTA that
@@ -336,6 +433,7 @@ struct LimbParams {
     int* human_cnt;                  // [N]
     int* flags;
     int stage_bytes; // dynamic smem available for staging the two PAF channels (0 = never stage)
+    const float* up_paf; // resolutions that shrink an axis: resized PAF maps [N, c_paf, UH, UW] (resize_area_generic_kernel); else null
 };
 
 // up-sampled PAF value at up-map pixel (lx, ly), recomputed from the low-resolution field
@@ -427,8 +525,13 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
         const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
         const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
         const int npairs = na * nb;
+        const float* U1 = nullptr; const float* U2 = nullptr;   // materialised up-maps of the two channels (shrinking resolutions)
+        if (p.up_paf) {
+            U1 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * p.UH * p.UW;
+            U2 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * p.UH * p.UW;
+        }
         // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
-        if (npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
+        if (!p.up_paf && npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
             float* sPaf = reinterpret_cast<float*>(sDyn);
             for (int i = tid; i < H * W; i += K3_THREADS) {
                 sPaf[i] = __ldg(P1 + i);
@@ -468,8 +571,8 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
                     const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
                     const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
                     const int ly = (int)((double)fy + 0.5);
-                    const float vpx = up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
-                    const float vpy = up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                    const float vpx = U1 ? __ldg(U1 + (size_t)ly * p.UW + lx) : up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                    const float vpy = U2 ? __ldg(U2 + (size_t)ly * p.UW + lx) : up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
                     score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
                 }
             }
@@ -708,6 +811,23 @@ void area_up_table(int src, int dst, std::vector<int>& idx, std::vector<float>& 
     }
 }
 
+// OpenCV computeResizeAreaTab (resize.cpp), grouped by destination index: entries [ofs[d], ofs[d+1]) = (source index, weight)
+void decimate_table(int ssize, int dsize, double scale, std::vector<int>& ofs, std::vector<int>& si, std::vector<float>& al)
+{
+    ofs.assign(1, 0); si.clear(); al.clear();
+    for (int dx = 0; dx < dsize; ++dx) {
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        const double cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1);
+        sx1 = std::min(sx1, sx2);
+        if (sx1 - fsx1 > 1e-3) { si.push_back(sx1 - 1); al.push_back((float)((sx1 - fsx1) / cell)); }
+        for (int sx = sx1; sx < sx2; ++sx) { si.push_back(sx); al.push_back((float)(1.0 / cell)); }
+        if (fsx2 - sx2 > 1e-3) { si.push_back(sx2); al.push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell)); }
+        ofs.push_back((int)si.size());
+    }
+}
+
 // Source rows (or columns) the tile starting at up-map position t0 reads: the tile's window [t0 - 9, t0 + extent + 9) in
 // reflected coordinates (BORDER_REFLECT_101), each position touching source index idx[.] and idx[.] + 1 (clamped).
 void tile_source_bounds(const std::vector<int>& idx, int src_len, int up_len, int tile, int window, std::vector<int>& out)
@@ -788,6 +908,11 @@ struct hp_paf {
 
     DevBuf<int> xi, yi, tile_bounds;
     DevBuf<float> xf, yf;
+    // resolutions that shrink an axis (cv::resize INTER_AREA beyond pure up-scaling): materialised maps + the resize description
+    bool generic = false;
+    int rz_mode = 0, rz_isx = 1, rz_isy = 1;
+    DevBuf<int> rz_xofs, rz_xsi, rz_yofs, rz_ysi;
+    DevBuf<float> rz_xal, rz_yal, up_conf, up_paf;
     DevBuf<int> counters; // [N*18 peak_cnt | N*19 conn_cnt | N human_cnt | N flags | N frame_done]
     DevBuf<int> raw_key, part_base, px, py;
     DevBuf<float> raw_score, pscore;
@@ -827,14 +952,34 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
         p->res_h = W * 4;
     }
     const int UW = p->res_w, UH = p->res_h;
-    if (UW < W || UH < H) {
-        hpb::set_error("hp_paf: resolution %dx%d smaller than the feature map %dx%d is not supported "
-                       "(true INTER_AREA down-scaling is not on the reference's default path)", UW, UH, W, H);
-        return HP_ERR_UNSUPPORTED;
-    }
     if (p->pcap > MAX_PCAP) p->pcap = MAX_PCAP;
     const bool geo_changed = (H != p->H || W != p->W || UH != p->UH || UW != p->UW);
     if (geo_changed) {
+        // cv::resize's dispatch (resize.cpp): true area averaging when BOTH axes shrink or keep, else 2-tap area-mode interpolation
+        p->generic = (UW < W || UH < H);
+        const double scale_x = 1.0 / ((double)UW / (double)W), scale_y = 1.0 / ((double)UH / (double)H);
+        p->rz_mode = 0;
+        if (p->generic && scale_x >= 1.0 && scale_y >= 1.0) {
+            const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
+            if (fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16) {
+                p->rz_mode = 1; p->rz_isx = isx; p->rz_isy = isy;
+            } else {
+                p->rz_mode = 2;
+                std::vector<int> ofs, si; std::vector<float> al;
+                decimate_table(W, UW, scale_x, ofs, si, al);
+                HP_CUDA_TRY(p->rz_xofs.ensure(ofs.size())); HP_CUDA_TRY(p->rz_xsi.ensure(si.size())); HP_CUDA_TRY(p->rz_xal.ensure(al.size()));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_xofs.p, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_xsi.p, si.data(), si.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_xal.p, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaStreamSynchronize(p->stream));
+                decimate_table(H, UH, scale_y, ofs, si, al);
+                HP_CUDA_TRY(p->rz_yofs.ensure(ofs.size())); HP_CUDA_TRY(p->rz_ysi.ensure(si.size())); HP_CUDA_TRY(p->rz_yal.ensure(al.size()));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_yofs.p, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_ysi.p, si.data(), si.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaMemcpyAsync(p->rz_yal.p, al.data(), al.size() * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+                HP_CUDA_TRY(cudaStreamSynchronize(p->stream));
+            }
+        }
         std::vector<int> idx_x, idx_y;
         std::vector<float> fr;
         area_up_table(W, UW, idx_x, fr);
@@ -850,8 +995,12 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
         HP_CUDA_TRY(cudaMemcpyAsync(p->yf.p, fr.data(), UH * sizeof(float), cudaMemcpyHostToDevice, p->stream));
         // per tile row / tile column: the source rows / columns its halo window reads (K1 stages exactly that rectangle)
         std::vector<int> tb;
-        tile_source_bounds(idx_y, H, UH, TH, UT_H, tb);
-        tile_source_bounds(idx_x, W, UW, TW, UT_W, tb);
+        if (!p->generic) {
+            tile_source_bounds(idx_y, H, UH, TH, UT_H, tb);
+            tile_source_bounds(idx_x, W, UW, TW, UT_W, tb);
+        } else {
+            tb.assign(4, 0);
+        }
         HP_CUDA_TRY(p->tile_bounds.ensure(tb.size()));
         HP_CUDA_TRY(cudaMemcpyAsync(p->tile_bounds.p, tb.data(), tb.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         HP_CUDA_TRY(cudaStreamSynchronize(p->stream));
@@ -875,6 +1024,10 @@ int ensure_geometry(hp_paf* p, int N, int c_conf, int c_paf, int H, int W)
         HP_CUDA_TRY(p->pin_humans.ensure((size_t)cN * p->hcap));
         HP_CUDA_TRY(p->pin_counts.ensure((size_t)cN * 2));
     }
+    if (p->generic) {
+        HP_CUDA_TRY(p->up_conf.ensure((size_t)std::max(N, p->cap_N) * c_conf * UH * UW));
+        HP_CUDA_TRY(p->up_paf.ensure((size_t)std::max(N, p->cap_N) * c_paf * UH * UW));
+    }
     p->N = N;
     return HP_OK;
 }
@@ -897,7 +1050,22 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k1.n8 = UW & ~7;
     k1.n4 = (UW - k1.n8 >= 4) ? k1.n8 + 4 : k1.n8;
     dim3 g1(k1.tiles_x * k1.tiles_y, HP_N_PARTS, N);
-    paf_peaks_kernel<<<g1, K1_THREADS, 0, st>>>(k1);
+    k1.up = nullptr;
+    if (p->generic) {   // resolutions that shrink an axis: materialise cv::resize(INTER_AREA) of every channel, then run from the maps
+        ResizeParams rz;
+        rz.H = p->H; rz.W = p->W; rz.UH = UH; rz.UW = UW; rz.mode = p->rz_mode; rz.isx = p->rz_isx; rz.isy = p->rz_isy;
+        rz.xi = p->xi.p; rz.xf = p->xf.p; rz.yi = p->yi.p; rz.yf = p->yf.p;
+        rz.xofs = p->rz_xofs.p; rz.xsi = p->rz_xsi.p; rz.xal = p->rz_xal.p; rz.yofs = p->rz_yofs.p; rz.ysi = p->rz_ysi.p; rz.yal = p->rz_yal.p;
+        rz.src = d_conf; rz.dst = p->up_conf.p; rz.planes = N * p->c_conf;
+        resize_area_generic_kernel<<<(unsigned)(((size_t)rz.planes * UH * UW + 255) / 256), 256, 0, st>>>(rz);
+        rz.src = d_paf; rz.dst = p->up_paf.p; rz.planes = N * p->c_paf;
+        resize_area_generic_kernel<<<(unsigned)(((size_t)rz.planes * UH * UW + 255) / 256), 256, 0, st>>>(rz);
+        p->launches += 2;
+        k1.up = p->up_conf.p;
+        paf_peaks_kernel<true><<<g1, K1_THREADS, 0, st>>>(k1);
+    } else {
+        paf_peaks_kernel<false><<<g1, K1_THREADS, 0, st>>>(k1);
+    }
 
     LimbParams k3;
     k3.paf = d_paf; k3.c_paf = p->c_paf; k3.H = p->H; k3.W = p->W; k3.UH = UH; k3.UW = UW;
@@ -910,6 +1078,7 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k3.cand = p->cand.p; k3.cand_sorted = p->cand_sorted.p; k3.conn = p->conn.p; k3.conn_cnt = p->conn_cnt();
     k3.frame_done = p->frame_done(); k3.humans = p->humans.p; k3.human_cnt = p->human_cnt();
     k3.flags = p->flags();
+    k3.up_paf = p->generic ? p->up_paf.p : nullptr;
     const int want = 2 * p->H * p->W * (int)sizeof(float);
     k3.stage_bytes = (want <= p->limb_dyn_bytes) ? want : 0;
     const size_t dyn = std::max((size_t)k3.stage_bytes, assemble_smem_bytes(p->max_refs));
@@ -1068,6 +1237,7 @@ void hp_paf_destroy(hp_paf* p)
     cudaSetDevice(p->device);
     if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
     p->xi.release(); p->yi.release(); p->xf.release(); p->yf.release(); p->tile_bounds.release(); p->counters.release();
+    p->rz_xofs.release(); p->rz_xsi.release(); p->rz_yofs.release(); p->rz_ysi.release(); p->rz_xal.release(); p->rz_yal.release(); p->up_conf.release(); p->up_paf.release();
     p->raw_key.release(); p->part_base.release(); p->px.release(); p->py.release();
     p->raw_score.release(); p->pscore.release(); p->cand.release(); p->cand_sorted.release();
     p->conn.release(); p->humans.release(); p->in_conf.release(); p->in_paf.release();

@@ -64,8 +64,9 @@ def load_oracle():
                                         C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                         C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                         C.c_void_p, C.c_int, C.POINTER(C.c_int)]
-        lib.orc_resize_area_up.restype = C.c_int
-        lib.orc_resize_area_up.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
+        for fn in (lib.orc_resize_area_up, lib.orc_resize_area):
+            fn.restype = C.c_int
+            fn.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, C.c_int]
         lib.orc_gaussian17.restype = None
         lib.orc_gaussian17.argtypes = [fp, fp, C.c_int, C.c_int]
         lib.orc_gauss17_kernel.restype = fp
@@ -89,6 +90,16 @@ def resize_area_up(img: np.ndarray, dh: int, dw: int) -> np.ndarray:
     rc = load_oracle().orc_resize_area_up(_fp(img), img.shape[0], img.shape[1], _fp(out), dh, dw)
     if rc:
         raise ValueError(f"orc_resize_area_up rc={rc}")
+    return out
+
+
+def resize_area(img: np.ndarray, dh: int, dw: int) -> np.ndarray:
+    """cv::resize(INTER_AREA) on one fp32 plane, any sizes (true area averaging when both axes shrink)"""
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.empty((dh, dw), np.float32)
+    rc = load_oracle().orc_resize_area(_fp(img), img.shape[0], img.shape[1], _fp(out), dh, dw)
+    if rc:
+        raise ValueError(f"orc_resize_area rc={rc}")
     return out
 
 

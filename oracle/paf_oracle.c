@@ -63,9 +63,42 @@ void orc_area_up_tab(int src, int dst, int32_t* idx, float* frac)
     }
 }
 
-int orc_resize_area_up(const float* src, int sh, int sw, float* dst, int dh, int dw)
+/* cv::resize(..., INTER_AREA) on one CV_32FC1 plane, every size combination (OpenCV resize.cpp, cv::resize dispatch):
+ *   scale = src/dst per axis (computed as 1 / (dst/src) in double, like OpenCV);
+ *   * BOTH axes shrink or keep (scale_x >= 1 && scale_y >= 1): true area averaging --
+ *       integer factors ("is_area_fast"): resizeAreaFast_: sum of the iscale_y x iscale_x block (row-major, the scalar loop
+ *         unrolled by four: sum += ((s0 + s1) + s2) + s3), times (float)(1 / area); the 2 x 2 case runs the SIMD kernel
+ *         ((a + b) + (c + d)) * 0.25f on dx < (dw & ~3) and the scalar loop on the tail;
+ *       otherwise resizeArea_ with computeResizeAreaTab (DecimateAlpha): buf[dx] = sum_k S[sx_k] * alpha_k per source row,
+ *         dst = beta_0 * buf_0 + beta_1 * buf_1 + ... in table order, all float, products and sums rounded separately;
+ *   * any axis grows (scale < 1): the 2-tap "area_mode" interpolation on BOTH axes with orc_area_up_tab's index / fraction
+ *     formula (for the shrinking axis the same formula simply skips source pixels).
+ * Pinned bit-exactly against Python cv2 4.13 for all four regimes (tests/golden/cv_pin_area.npz). */
+typedef struct { int di, si; float alpha; } orc_dec;
+
+static int decimate_tab(int ssize, int dsize, double scale, orc_dec* tab)
 {
-    if (dh < sh || dw < sw || sh <= 0 || sw <= 0) return -3;
+    int k = 0;
+    for (int dx = 0; dx < dsize; ++dx) {
+        double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        double cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        if (sx2 > ssize - 1) sx2 = ssize - 1;
+        if (sx1 > sx2) sx1 = sx2;
+        if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+        for (int sx = sx1; sx < sx2; ++sx) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+        if (fsx2 - sx2 > 1e-3) {
+            double a = fsx2 - sx2;
+            if (a > 1.0) a = 1.0;
+            if (a > cell) a = cell;
+            tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(a / cell);
+        }
+    }
+    return k;
+}
+
+static int resize_lerp2(const float* src, int sh, int sw, float* dst, int dh, int dw)
+{
     int32_t* xi = (int32_t*)malloc(sizeof(int32_t) * dw);
     int32_t* yi = (int32_t*)malloc(sizeof(int32_t) * dh);
     float* xf = (float*)malloc(sizeof(float) * dw);
@@ -93,6 +126,71 @@ int orc_resize_area_up(const float* src, int sh, int sw, float* dst, int dh, int
     }
     free(xi); free(yi); free(xf); free(yf); free(row0); free(row1);
     return 0;
+}
+
+int orc_resize_area(const float* src, int sh, int sw, float* dst, int dh, int dw)
+{
+    if (sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0) return -3;
+    const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);
+    if (!(scale_x >= 1.0 && scale_y >= 1.0)) return resize_lerp2(src, sh, sw, dst, dh, dw);
+    const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
+    if (fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16) {
+        const int area = isx * isy;
+        const float scale = 1.f / (float)area;
+        for (int dy = 0; dy < dh; ++dy)
+            for (int dx = 0; dx < dw; ++dx) {
+                const float* S = src + (size_t)dy * isy * sw + (size_t)dx * isx;
+                if (isx == 2 && isy == 2 && dx < (dw & ~3)) { /* ResizeAreaFastVec_SIMD_32f */
+                    const float top = S[0] + S[1], bot = S[sw] + S[sw + 1];
+                    dst[dy * dw + dx] = (top + bot) * 0.25f;
+                    continue;
+                }
+                float sum = 0.f;
+                int k = 0;
+                for (; k <= area - 4; k += 4) { /* CV_ENABLE_UNROLLED */
+                    float g = S[(k / isx) * sw + k % isx] + S[((k + 1) / isx) * sw + (k + 1) % isx];
+                    g = g + S[((k + 2) / isx) * sw + (k + 2) % isx];
+                    g = g + S[((k + 3) / isx) * sw + (k + 3) % isx];
+                    sum = sum + g;
+                }
+                for (; k < area; ++k) sum = sum + S[(k / isx) * sw + k % isx];
+                dst[dy * dw + dx] = sum * scale;
+            }
+        return 0;
+    }
+    orc_dec* xtab = (orc_dec*)malloc(sizeof(orc_dec) * ((size_t)sw * 2 + 2 * dw + 4));
+    orc_dec* ytab = (orc_dec*)malloc(sizeof(orc_dec) * ((size_t)sh * 2 + 2 * dh + 4));
+    const int nx = decimate_tab(sw, dw, scale_x, xtab), ny = decimate_tab(sh, dh, scale_y, ytab);
+    float* buf = (float*)malloc(sizeof(float) * dw);
+    float* sum = (float*)malloc(sizeof(float) * dw);
+    int prev_dy = -1;
+    for (int j = 0; j < ny; ++j) {
+        const float beta = ytab[j].alpha;
+        const int dy = ytab[j].di;
+        const float* S = src + (size_t)ytab[j].si * sw;
+        for (int dx = 0; dx < dw; ++dx) buf[dx] = 0.f;
+        for (int k = 0; k < nx; ++k) {
+            const float t = S[xtab[k].si] * xtab[k].alpha;
+            buf[xtab[k].di] = buf[xtab[k].di] + t;
+        }
+        if (dy != prev_dy) {
+            if (prev_dy >= 0) for (int dx = 0; dx < dw; ++dx) dst[prev_dy * dw + dx] = sum[dx];
+            for (int dx = 0; dx < dw; ++dx) sum[dx] = beta * buf[dx];
+            prev_dy = dy;
+        } else {
+            for (int dx = 0; dx < dw; ++dx) { const float t = beta * buf[dx]; sum[dx] = sum[dx] + t; }
+        }
+    }
+    if (prev_dy >= 0) for (int dx = 0; dx < dw; ++dx) dst[prev_dy * dw + dx] = sum[dx];
+    free(xtab); free(ytab); free(buf); free(sum);
+    return 0;
+}
+
+/* the up-scaling regime only (kept for the callers that state it): dst >= src on both axes */
+int orc_resize_area_up(const float* src, int sh, int sw, float* dst, int dh, int dw)
+{
+    if (dh < sh || dw < sw || sh <= 0 || sw <= 0) return -3;
+    return resize_lerp2(src, sh, sw, dst, dh, dw);
 }
 
 /* cv::borderInterpolate(BORDER_REFLECT_101) */
@@ -185,7 +283,6 @@ int orc_paf_process(const float* conf, const float* paf, int c_conf, int c_paf, 
     const int fw = H, fh = W;
     if (res_w == -1 || res_h == -1) { res_w = fw * 4; res_h = fh * 4; }
     const int UW = res_w, UH = res_h; /* up-maps are [C, UH, UW] (paf.cpp:326-327) */
-    if (UW < W || UH < H) return -3;
     const int feat_height = fh; /* m_feature_size = cv::Size(fw, fh); .height passed on (paf.cpp:329,354) */
 
     const size_t plane = (size_t)UH * UW;
@@ -197,8 +294,8 @@ int orc_paf_process(const float* conf, const float* paf, int c_conf, int c_paf, 
     /* resize_area (post_process.hpp:26-52). NOTE: when dims are equal the reference
      * returns without copying (post_process.hpp:31-32), leaving uninitialised buffers;
      * here equal dims degenerate to an exact copy (fx = 0), the evident intent. */
-    for (int k = 0; k < c_conf; ++k) orc_resize_area_up(conf + (size_t)k * H * W, H, W, up_conf + k * plane, UH, UW);
-    for (int k = 0; k < c_paf; ++k) orc_resize_area_up(paf + (size_t)k * H * W, H, W, up_paf + k * plane, UH, UW);
+    for (int k = 0; k < c_conf; ++k) orc_resize_area(conf + (size_t)k * H * W, H, W, up_conf + k * plane, UH, UW);
+    for (int k = 0; k < c_paf; ++k) orc_resize_area(paf + (size_t)k * H * W, H, W, up_paf + k * plane, UH, UW);
 
     /* find_peak_coords (post_process.hpp:147-195): smooth all channels, pool, scan. */
     for (int k = 0; k < c_conf; ++k) {

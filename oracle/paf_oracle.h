@@ -34,6 +34,8 @@ typedef struct { int32_t cid1, cid2; float score; } orc_conn;             /* paf
 
 /* cv::resize(INTER_AREA) for dst >= src in both axes (post_process.hpp:50). */
 int orc_resize_area_up(const float* src, int sh, int sw, float* dst, int dh, int dw);
+/* cv::resize(INTER_AREA), any source / destination size: true area averaging when both axes shrink, else the 2-tap area-mode lerp. */
+int orc_resize_area(const float* src, int sh, int sw, float* dst, int dh, int dw);
 /* coefficient table of the same (exposed for the GPU tests). */
 void orc_area_up_tab(int src, int dst, int32_t* idx, float* frac);
 /* cv::GaussianBlur(17x17, sigma=3, REFLECT_101) (post_process.hpp:66-67). */

@@ -62,7 +62,7 @@ private:
 inline void resize(const Mat& src, Mat& dst, Size dsize, double = 0, double = 0, int interpolation = INTER_LINEAR)
 {
     if (interpolation != INTER_AREA || src.type() != 5 || dst.size() != dsize
-        || orc_resize_area_up(reinterpret_cast<const float*>(src.data), src.rows, src.cols,
+        || orc_resize_area(reinterpret_cast<const float*>(src.data), src.rows, src.cols,
                reinterpret_cast<float*>(dst.data), dsize.height, dsize.width)
             != 0)
         std::abort();

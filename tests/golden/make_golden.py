@@ -54,6 +54,50 @@ PPN_CASES = [("ppn_p1", 20, 1, 384, 384, 12, 12, 9, 9, 0.10, 0.05, 0.3, 12), ("p
              ("ppn_dense", 26, 5, 384, 384, 12, 12, 9, 9, 0.05, 0.03, 0.3, 60)]
 
 
+# (src_h, src_w, dst_h, dst_w) of the INTER_AREA pin for the regimes beyond pure up-scaling (A5): mixed (one axis shrinks: 2-tap
+# area-mode lerp on both), integer factors (resizeAreaFast_, incl. the 2x2 SIMD kernel and its scalar tail), fractional (DecimateAlpha)
+AREA_CASES = [(46, 82, 100, 60), (46, 82, 30, 200), (46, 200, 800, 184), (46, 82, 23, 41), (48, 84, 16, 28), (48, 84, 12, 21), (46, 82, 46, 41),
+              (46, 82, 23, 82), (40, 84, 20, 41), (46, 82, 30, 50), (46, 82, 45, 81), (46, 82, 20, 82), (54, 46, 13, 17), (46, 82, 46, 50), (46, 82, 11, 19)]
+
+# parser cases whose up-map shrinks an axis: (name, seed, persons, hf, wf, res_w, res_h, conf_thresh, paf_thresh)
+AREA_FRAME_CASES = [
+    # default resolution (width 4*Hf, height 4*Wf) = (120, 520): width 120 < Wf = 130 -> mixed regime.  (Much wider maps, e.g. 24x120,
+    # stretch rows ~20x: the plateaus give limb candidates with EXACTLY equal scores and the reference's unstable std::sort
+    # (paf.cpp:246) then picks among them arbitrarily -- the region test_oracle_matches_live_reference_sweep documents.)
+    ("wide_default", 11, 3, 30, 130, -1, -1, 0.05, 0.05),
+    ("user_mixed", 12, 3, 46, 54, 40, 300, 0.05, 0.05),      # x shrinks, y grows
+    ("user_half", 13, 3, 46, 54, 27, 23, 0.05, 0.05),        # exact 2x2 reduction (SIMD kernel + tail)
+    ("user_third", 14, 2, 48, 54, 18, 16, 0.05, 0.05),       # 3x3 integer reduction
+    ("user_frac", 15, 3, 46, 54, 41, 33, 0.05, 0.05),        # fractional reduction on both axes
+    ("user_keep_x", 16, 3, 46, 54, 54, 30, 0.05, 0.05),      # one axis kept (scale 1), the other shrinks: area regime
+]
+
+
+def make_area():
+    """tests/golden/cv_pin_area.npz (real cv2) + ref_humans_area.npz (the reference's own paf.cpp over the pinned resize)"""
+    import cv2
+    import oracle
+    from hyperpose_b200 import synthetic as syn
+    oracle.build()
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for i, (sh, sw, dh, dw) in enumerate(AREA_CASES):
+        img = np.random.default_rng(300 + i).random((sh, sw), dtype=np.float32)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+        out[f"area{i}_sha"] = np.array(sha(ref))
+        if ref.size <= 4096:
+            out[f"area{i}_out"] = ref
+    np.savez_compressed(os.path.join(HERE, "cv_pin_area.npz"), **out)
+    ref = {}
+    for (name, seed, P, hf, wf, rw, rh, ct, pt) in AREA_FRAME_CASES:
+        conf, paf = syn.make_frame_tensors(seed, P, hf, wf)
+        rp = oracle.RefParser(ct, pt, rw, rh)
+        ref[name + "_humans"] = rp.process(conf, paf)
+        ref[name + "_in_sha"] = np.array(sha(conf) + sha(paf))
+        rp.close()
+    np.savez_compressed(os.path.join(HERE, "ref_humans_area.npz"), **ref)
+    print({k: len(v) for k, v in ref.items() if k.endswith("_humans")})
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -120,6 +164,10 @@ def make_ppn():
     np.savez_compressed(os.path.join(HERE, "ref_ppn.npz"), **pn)
     print("wrote", os.listdir(HERE))
 
+
+if __name__ == "__main__" and "area" in sys.argv[1:]:
+    make_area()
+    sys.exit(0)
 
 if __name__ == "__main__":
     if "ppn" in sys.argv[1:]:

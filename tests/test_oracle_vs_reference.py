@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from hyperpose_b200 import synthetic as syn
-from tests.golden.make_golden import FRAME_CASES, sha
+from tests.golden.make_golden import AREA_FRAME_CASES, FRAME_CASES, sha
 
 
 @pytest.fixture(scope="module")
@@ -26,6 +26,22 @@ def test_oracle_matches_reference_golden(ref_humans, case):
     want = ref_humans[name + "_humans"]
     assert len(got) == len(want)
     assert got.tobytes() == want.tobytes()      # byte-identical human_t records, same order
+
+
+@pytest.mark.parametrize("case", AREA_FRAME_CASES, ids=[c[0] for c in AREA_FRAME_CASES])
+def test_oracle_matches_reference_golden_on_shrinking_resolutions(golden_dir, case):
+    """A5 beyond pure up-scaling: resolutions that shrink an axis (mixed 2-tap regime, integer and fractional area averaging).
+    Goldens = the reference's own src/paf.cpp over the cv2-pinned resize (tests/golden/make_golden.py area)."""
+    ref = np.load(os.path.join(golden_dir, "ref_humans_area.npz"))
+    name, seed, P, hf, wf, rw, rh, ct, pt = case
+    conf, paf = syn.make_frame_tensors(seed, P, hf, wf)
+    assert sha(conf) + sha(paf) == str(ref[name + "_in_sha"]), "synthetic generator drifted from the goldens"
+    o = oracle.oracle_process(conf, paf, ct, pt, rw, rh)
+    assert o["humans"].tobytes() == ref[name + "_humans"].tobytes()
+    if oracle.ref_available():
+        rp = oracle.RefParser(ct, pt, rw, rh)
+        assert rp.process(conf, paf).tobytes() == o["humans"].tobytes()
+        rp.close()
 
 
 def test_goldens_are_not_vacuous(ref_humans):
@@ -83,8 +99,8 @@ def test_oracle_matches_live_reference_sweep(seed):
         candidates with an unstable std::sort -- the greedy assignment then depends on the sort's tie order (the
         restatement freezes score desc, idx1, idx2; seen on seeds 114 / 117 with noise 0: peaks identical, two
         limbs assigned differently among equal-score candidates);
-      * feature maps wider than 4:1: the default resolution (width 4*H) then DOWN-scales an axis = true INTER_AREA
-        averaging in OpenCV, which neither the shimmed reference nor the product implements (HP_ERR_UNSUPPORTED)."""
+      * feature maps wider than 4:1 (the default resolution then shrinks an axis) are covered separately by
+        test_oracle_matches_reference_golden_on_shrinking_resolutions."""
     rng = np.random.default_rng(seed)
     hf = int(rng.integers(9, 50))
     wf = int(rng.integers(9, min(90, 4 * hf) + 1))

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from hyperpose_b200 import capi, synthetic as syn
-from tests.golden.make_golden import FRAME_CASES
+from tests.golden.make_golden import AREA_FRAME_CASES, FRAME_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -132,13 +132,41 @@ def test_bad_rank_is_rejected():
     parser.close()
 
 
-def test_downscaling_resolution_is_rejected_not_approximated():
-    # default resolution of a 9x70 map is 36 wide (< 70): true INTER_AREA down-scaling is not implemented
-    parser = capi.PafParser()
-    with pytest.raises(capi.HyperposeError) as e:
-        parser.process(np.zeros((19, 9, 70), np.float32), np.zeros((38, 9, 70), np.float32))
-    assert e.value.status == capi.HP_ERR_UNSUPPORTED
+@pytest.mark.parametrize("case", AREA_FRAME_CASES, ids=[c[0] for c in AREA_FRAME_CASES])
+def test_resolutions_that_shrink_an_axis(case, golden_dir):
+    """A5 beyond pure up-scaling (src/post_process.hpp:27-52 works for ANY resolution): mixed regime (2-tap lerp), integer-factor and
+    fractional area averaging -- peaks, connections and humans bit-exact against the oracle (pinned to cv2) and against what the
+    reference's own src/paf.cpp produced (committed golden)"""
+    name, seed, P, hf, wf, rw, rh, ct, pt = case
+    conf, paf = syn.make_frame_tensors(seed, P, hf, wf)
+    orc = oracle.oracle_process(conf, paf, ct, pt, rw, rh)
+    parser = capi.PafParser(ct, pt, (rw, rh))
+    got = parser.process(conf, paf)
+    _check_debug(parser, 0, orc, name)
+    _cmp_frame(got, orc, name)
+    want = np.load(os.path.join(golden_dir, "ref_humans_area.npz"))[name + "_humans"]
+    assert got.tobytes() == want.tobytes()
+    # batched, mixed with itself: same answer per frame
+    N = 3
+    b = parser.process_batch(np.repeat(conf[None], N, 0), np.repeat(paf[None], N, 0))
+    assert all(x.tobytes() == got.tobytes() for x in b)
     parser.close()
+
+
+def test_shrinking_resolution_noise_field_vs_oracle():
+    """structureless input through the down-scaling path: hundreds of peaks, no golden needed -- oracle parity on peaks and connections"""
+    rng = np.random.default_rng(5)
+    conf = rng.random((19, 40, 84), dtype=np.float32) * 0.3
+    paf = (rng.random((38, 40, 84), dtype=np.float32) - 0.5)
+    for res in ((42, 20), (41, 20), (50, 31), (30, 100)):       # 2x2 (SIMD + even width), 2x2 with a scalar tail, fractional, mixed
+        parser = capi.PafParser(0.12, 0.05, res)
+        parser.set_capacity(peaks_per_part=1024, candidates_per_limb=1 << 15, humans=256)
+        got = parser.process(conf, paf, cap=256)
+        orc = oracle.oracle_process(conf, paf, 0.12, 0.05, res[0], res[1], peak_cap=1 << 16, conn_cap=1 << 13)
+        assert len(orc["peaks"]) > 30, res
+        pk = parser.debug_peaks(0)
+        assert np.array_equal(pk["x"], orc["peaks"]["x"]) and np.array_equal(pk["y"], orc["peaks"]["y"]) and pk["score"].tobytes() == orc["peaks"]["score"].tobytes(), res
+        parser.close()
 
 
 def test_full_size_property_permutation_invariance():

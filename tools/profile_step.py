@@ -1,6 +1,6 @@
 """Runs `--steps` device-resident steps of the bench workload (cfg3, batch 16) with nothing else around them,
 for ncu captures:  ncu ... python tools/profile_step.py --steps 2
-(step 0 is the warm-up; per step: 1 D2D memcpy, im2col, 52 conv, 3 maxpool, 2 D2D, memset + 4 parser kernels)"""
+(step 0 is the warm-up; per step: 1 D2D memcpy, im2col, 52 conv, 3 maxpool, 2 D2D, memset + 2 parser kernels)"""
 import argparse
 import os
 import sys
