@@ -13,8 +13,9 @@ keypoint records to rank 0).  Because random weights give structureless heat-map
 crowd tensors are copied over the backbone's outputs after the last conv (hp_engine_set_output_override,
 SURVEY 8d) -- all conv work is still executed; this is stated in config.parse_input.
 
-  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather)
-  e2e   : the public host call hp_pose_run_u8_host -- pinned host frames H2D, human_t records D2H, every step
+  value : device-resident inputs (u8 frames already in HBM), results left on the device (rank 0 after gather);
+          hp_pose_submit_u8_device / hp_pose_collect (CUDA-graph replay, two batches in flight)
+  e2e   : the public host call hp_pose_submit_u8_host / hp_pose_collect -- pinned host frames H2D, human_t records D2H, every step
   roofline : the conv kernel (dominant): algorithmic FLOPs / CUDA-event time of the conv launches, measured in
              the timed region on the launching stream, vs the measured cuBLAS bf16 peak
   cpu_baseline : the reference's CPU parser timed on this host (parse stage only: the reference never runs
@@ -332,7 +333,8 @@ def measure(args, key, dist_ctx, headline=True):
     engine.set_output_override(d_conf.data_ptr(), d_paf.data_ptr())
     out_conf_ptr, out_paf_ptr, _ = engine.device_outputs()
 
-    st = torch.cuda.Stream(device=dev)
+    # everything is enqueued on the ENGINE's own stream (events, timing, result copies): wrap it for torch
+    st = torch.cuda.ExternalStream(engine.device_outputs()[2], device=dev)
     rec_bytes = capi.HUMAN_DT.itemsize
     # keypoint records + per-frame counts of one batch in ONE buffer (a single NCCL all-gather per step), double-buffered so
     # that the gather of batch i runs on a side stream while batch i+1 is computed
@@ -367,13 +369,32 @@ def measure(args, key, dist_ctx, headline=True):
                 if gstate["n"] > k:
                     st.wait_event(ev_gat[k])
 
+    # value: frames already resident in HBM, results left on the device (rank 0 after the gather).  The launch sequence of a
+    # batch is replayed from the CUDA graph hp_pose_submit_u8_device captured (two batches in flight: the host collects batch
+    # i-1 while batch i runs); --no-graph (and the OpenPifPaf workload) launches every kernel on the stream instead.
+    use_graph = not PIFPAF and not args.no_graph
+    dpend = {"t": None}
+
     def step_device(i):
+        if use_graph:
+            t = engine.submit_pose_device(parser, frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH)
+            gather_results()
+            if dpend["t"] is not None:
+                engine.collect_pose(dpend["t"], cap=HCAP)
+            dpend["t"] = t
+            return
         engine.infer_u8_device(frames_dev[i % N_INPUT_SETS].data_ptr(), BATCH, st.cuda_stream)
         if PIFPAF:
             parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, st.cuda_stream)
         else:
             parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, 19, 38, HF, WF, st.cuda_stream)
         gather_results()
+
+    def drain_device():
+        if dpend["t"] is not None:
+            h = engine.collect_pose(dpend["t"], cap=HCAP)
+            dpend["t"] = None
+            return h
 
     # e2e: the public host call, pinned host frames in, human_t records out -- two batches in flight
     # (hp_pose_submit_u8_host / hp_pose_collect: H2D of batch i+1 under the convs of batch i, CUDA-graph replay)
@@ -406,6 +427,8 @@ def measure(args, key, dist_ctx, headline=True):
             fn(i)
         if fn is step_host:
             drain_host()
+        if fn is step_device:
+            drain_device()
         barrier()
         l0 = engine.launch_count + parser.launch_count
         if profile:
@@ -417,6 +440,8 @@ def measure(args, key, dist_ctx, headline=True):
             fn(n_warm + i)
         if fn is step_host:
             drain_host()
+        if fn is step_device:
+            drain_device()
         drain_gather()                                # the timed region ends when the last keypoint gather has finished
         e1.record(st)
         torch.cuda.synchronize()
@@ -436,8 +461,10 @@ def measure(args, key, dist_ctx, headline=True):
 
     # sanity: the device path and the host path agree with each other before anything is timed
     step_device(0)
+    ref_h = drain_device()
     torch.cuda.synchronize()
-    ref_h = parser.fetch(BATCH, cap=HCAP)
+    if ref_h is None:
+        ref_h = parser.fetch(BATCH, cap=HCAP)
     step_host(0)
     host_h = drain_host() if not PIFPAF else step_host(0)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(ref_h, host_h)), "device and host paths disagree"
@@ -455,6 +482,7 @@ def measure(args, key, dist_ctx, headline=True):
         for i in range(10):
             step_device(n_pre + i)
         n_pre += 10
+        drain_device()
         torch.cuda.synchronize()
         flag = torch.tensor([1.0 if time.time() - t_pre < pre_target else 0.0], device=dev)
         if world > 1:
@@ -656,6 +684,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="f16", choices=["f16", "tf32"], help="conv arithmetic: f16 = data_type::kHALF, tf32 = data_type::kFLOAT of the reference API (tensorrt.hpp:14-22)")
+    ap.add_argument("--no-graph", action="store_true", help="device-resident steps launch every kernel on the stream instead of replaying the captured CUDA graph")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs entries (cfg2 / cfg4 / cfg5) of the default run")
     ap.add_argument("--no-tf32-line", action="store_true", help="skip the tf32 entry of the default run")
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS), help="BASELINE.json config (default: the headline cfg3)")

@@ -188,7 +188,7 @@ EXPORTS += [
     "hp_pose_submit_u8_host", "hp_pose_collect", "hp_pose_stats", "hp_paf_prepare", "hp_paf_state", "hp_paf_copy_results_host_async",
     "hp_paf_grow_capacity", "hp_pool_create", "hp_pool_destroy", "hp_pool_size", "hp_pool_set_capacity", "hp_pool_run_u8_host",
     "hp_pool_set_output_override", "hp_pool_launch_count", "hp_default_device", "hp_handoff_device_of",
-    "hp_engine_create_ex", "hp_engine_dtype",
+    "hp_engine_create_ex", "hp_engine_dtype", "hp_pose_submit_u8_device",
 ]
 
 
@@ -224,6 +224,7 @@ def _bind_engine(L):
     L.hp_handoff_enable.argtypes = [C.c_int]
     L.hp_handoff_stats.argtypes = [C.POINTER(C.c_longlong)] * 4
     L.hp_pose_submit_u8_host.argtypes = [vp, vp, vp, C.c_int, ip]
+    L.hp_pose_submit_u8_device.argtypes = [vp, vp, vp, C.c_int, ip]
     L.hp_pose_collect.argtypes = [vp, C.c_int, vp, C.c_int, ip]
     L.hp_pose_stats.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     L.hp_pool_create.argtypes = [C.POINTER(vp), ip, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_float, C.c_float]
@@ -402,6 +403,14 @@ class Engine:
         check(lib().hp_pose_submit_u8_host(self._h, parser._h, frames.ctypes.data, frames.shape[0], C.byref(t)))
         self._ticket_n = getattr(self, "_ticket_n", {})
         self._ticket_n[t.value] = frames.shape[0]
+        return t.value
+
+    def submit_pose_device(self, parser: "PafParser", d_frames_ptr: int, n: int) -> int:
+        """hp_pose_submit_u8_device: the frames are already in device memory"""
+        t = C.c_int(-1)
+        check(lib().hp_pose_submit_u8_device(self._h, parser._h, d_frames_ptr, n, C.byref(t)))
+        self._ticket_n = getattr(self, "_ticket_n", {})
+        self._ticket_n[t.value] = n
         return t.value
 
     def collect_pose(self, ticket: int, cap: int = 128):

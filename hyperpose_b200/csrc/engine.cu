@@ -1758,30 +1758,34 @@ int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
 
 extern "C" {
 
-int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket)
+static int pose_submit(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket, bool device_src)
 {
-    if (!e || !parser || !frames || !ticket) { set_error("hp_pose_submit_u8_host: null argument"); return HP_ERR_ARG; }
+    if (!e || !parser || !frames || !ticket) { set_error("hp_pose_submit: null argument"); return HP_ERR_ARG; }
     if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
-    if (e->hdr.head_type != 0) { set_error("hp_pose_submit_u8_host: the model pack has OpenPifPaf heads (use hp_engine_infer_u8_host + hp_pifpaf_process_device)"); return HP_ERR_UNSUPPORTED; }
+    if (e->hdr.head_type != 0) { set_error("hp_pose_submit: the model pack has OpenPifPaf heads (use hp_engine_infer_u8_host + hp_pifpaf_process_device)"); return HP_ERR_UNSUPPORTED; }
     HP_CUDA_TRY(cudaSetDevice(e->device));
     const int idx = e->next_slot;
     hp_engine::PoseSlot& sl = e->slots[idx];
-    if (sl.busy) { set_error("hp_pose_submit_u8_host: two batches are already in flight -- collect ticket %d first", idx); return HP_ERR_ARG; }
+    if (sl.busy) { set_error("hp_pose_submit: two batches are already in flight -- collect ticket %d first", idx); return HP_ERR_ARG; }
     int rc = pose_slot_prepare(e, sl, idx, parser, N);
     if (rc) return rc;
     const size_t bytes = (size_t)N * e->in_h * e->in_w * 3;
-    cudaPointerAttributes attr;
-    const bool pinned = (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost);
-    if (!pinned) cudaGetLastError();
-    const uint8_t* src = frames;
-    if (!pinned) {   // pageable caller memory: through this slot's pinned staging (free: the slot was collected)
-        if (!sl.pin_frames) HP_CUDA_TRY(cudaMallocHost(&sl.pin_frames, (size_t)e->max_batch * e->in_h * e->in_w * 3));
-        memcpy(sl.pin_frames, frames, bytes);
-        src = sl.pin_frames;
+    if (device_src) {   // frames already in HBM: a D2D copy into the slot (the captured graph reads the slot's buffer), on the compute stream
+        HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, frames, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    } else {
+        cudaPointerAttributes attr;
+        const bool pinned = (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+        if (!pinned) cudaGetLastError();
+        const uint8_t* src = frames;
+        if (!pinned) {   // pageable caller memory: through this slot's pinned staging (free: the slot was collected)
+            if (!sl.pin_frames) HP_CUDA_TRY(cudaMallocHost(&sl.pin_frames, (size_t)e->max_batch * e->in_h * e->in_w * 3));
+            memcpy(sl.pin_frames, frames, bytes);
+            src = sl.pin_frames;
+        }
+        HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        HP_CUDA_TRY(cudaEventRecord(sl.h2d_done, e->copy_stream));
+        HP_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
     }
-    HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
-    HP_CUDA_TRY(cudaEventRecord(sl.h2d_done, e->copy_stream));
-    HP_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
     rc = pose_launch(e, sl);
     if (rc) return rc;
     HP_CUDA_TRY(cudaEventRecord(sl.done, e->stream));
@@ -1789,6 +1793,17 @@ int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, 
     e->next_slot = idx ^ 1;
     *ticket = idx;
     return HP_OK;
+}
+
+int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket)
+{
+    return pose_submit(e, parser, frames, N, ticket, false);
+}
+
+// the same with the frames already resident in device memory (what a decoder / capture pipeline on the GPU hands over)
+int hp_pose_submit_u8_device(hp_engine* e, hp_paf* parser, const uint8_t* d_frames, int N, int* ticket)
+{
+    return pose_submit(e, parser, d_frames, N, ticket, true);
 }
 
 int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out)

@@ -235,6 +235,7 @@ int hp_pose_run_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int
  * At most two tickets are outstanding; a third submit without a collect is HP_ERR_ARG.  `frames` may be pageable (it is
  * copied into pinned staging before submit returns) or page-locked (DMA straight from it: keep it alive until collect). */
 int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket);
+int hp_pose_submit_u8_device(hp_engine* e, hp_paf* parser, const uint8_t* d_frames, int N, int* ticket);   /* frames already in HBM */
 int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out);
 int hp_pose_stats(const hp_engine* e, long long* graph_captures, long long* graph_launches);
 /* building blocks of the above (also usable on their own): pre-allocate for a geometry / read the state a captured launch
