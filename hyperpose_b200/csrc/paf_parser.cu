@@ -82,6 +82,9 @@ __host__ __device__ inline int refl101(int p, int len)
 // default resolution stretches rows 7x: ~9 source rows feed 48 tile rows), both filter passes produce 16 outputs per thread
 // from one 32-value register window (1 shared load per 8.5 FMAs), every pass is exactly one round of the 192-thread CTA, and
 // the source bounds of a tile come from host tables instead of shared-memory atomics.
+// Both filter passes run on the packed fp32 pipe of sm_100 (FFMA2 / FADD2 / FMUL2 via __ffma2_rn & co: two IEEE fp32 operations
+// per instruction, each lane rounded exactly like the scalar instruction): the row pass pairs two ROWS (the up-sampled tile is
+// stored as float2 {row 2r, row 2r+1}), the column pass pairs two COLUMNS (the row-pass output is row-major with an even stride).
 constexpr int K1_THREADS = 192;
 constexpr int TH = 30, TW = 62;          // interior tile of the up-map handled by one CTA
 constexpr int HALO = 9;                  // 8 (17-tap blur) + 1 (3x3 NMS)
@@ -89,13 +92,16 @@ constexpr int UT_H = TH + 2 * HALO;      // 48 rows of up-sampled values (virtua
 constexpr int UT_W = TW + 2 * HALO;      // 80 cols
 constexpr int UT_LD = UT_W + 1;          // 81: odd stride -> row-parallel accesses are conflict-free
 constexpr int RT_W = TW + 2;             // 64 row-pass output columns (interior + 1 each side)
-constexpr int RT_LD = RT_W + 1;          // 65
+constexpr int RT_LD = RT_W + 2;          // 66: even, so that a column pair is one aligned 8-byte shared-memory access
 constexpr int CT_H = TH + 2;             // 32 column-pass output rows
 constexpr int SRC_MAX_H = UT_H + 1, SRC_MAX_W = UT_W + 1; // scale >= 1 => at most one source px per up px (+1)
-constexpr int RUN = 16;                  // outputs per thread per pass (sliding window of RUN+16 inputs)
+constexpr int RUN = 8;                   // outputs per thread per pass and lane of the pair (sliding window of RUN+16 inputs)
 constexpr int HL_ROWS = 16;              // source rows per tile for which the horizontal lerp is cached (more: direct path)
-static_assert(UT_H * (RT_W / RUN) == K1_THREADS, "row pass: one work item per thread");
-static_assert(RT_W * (CT_H / RUN) <= K1_THREADS && CT_H % RUN == 0, "column pass: one work item per thread");
+static_assert(UT_H % 2 == 0 && (UT_H / 2) * (RT_W / RUN) == K1_THREADS, "row pass: one (row pair, run) per thread");
+static_assert(RT_W % 2 == 0 && (RT_W / 2) * (CT_H / RUN) <= K1_THREADS && CT_H % RUN == 0, "column pass: one (column pair, run) per thread");
+
+// up-sampled tile, rows paired: element (vy, vx) of the 48 x 80 tile
+__device__ __forceinline__ float& tile_u(float2* sU2, int vy, int vx) { return reinterpret_cast<float*>(sU2 + (vy >> 1) * UT_LD + vx)[vy & 1]; }
 
 struct PeakParams {
     const float* conf; // [N, c_conf, H, W]
@@ -122,9 +128,9 @@ template <bool kFromUp>
 __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams p)
 {
     // sSrc (dead after the up-sample) and sTmp (row-pass output) share storage.
-    __shared__ float sU[UT_H * UT_LD];
-    __shared__ float sA[(SRC_MAX_H * SRC_MAX_W > UT_H * RT_LD) ? SRC_MAX_H * SRC_MAX_W : UT_H * RT_LD];
-    __shared__ float sS[CT_H * RT_LD];
+    __shared__ float2 sU2[(UT_H / 2) * UT_LD];   // {row 2r, row 2r+1} per column
+    __shared__ __align__(8) float sA[(SRC_MAX_H * SRC_MAX_W > UT_H * RT_LD) ? SRC_MAX_H * SRC_MAX_W : UT_H * RT_LD];
+    __shared__ __align__(8) float sS[CT_H * RT_LD];
     __shared__ float sHl[HL_ROWS * UT_LD];   // horizontal lerp of the tile's source rows
     __shared__ int sXi[UT_W], sYi[UT_H];
     __shared__ float sXf[UT_W], sYf[UT_H];
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
         for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
             const int vy = i / UT_W, vx = i - vy * UT_W;
             const float v = __ldg(up + (size_t)refl101(y0 - HALO + vy, UH) * UW + refl101(x0 - HALO + vx, UW));
-            sU[vy * UT_LD + vx] = v;
+            tile_u(sU2, vy, vx) = v;
             lmax = fmaxf(lmax, v);
             if (v != v) lmax = INFINITY;
         }
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
             const int vy = i / UT_W, vx = i - vy * UT_W;
             const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
             const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
-            sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(sHl[(sy0 - sr0) * UT_LD + vx], b0), __fmul_rn(sHl[(sy1 - sr0) * UT_LD + vx], b1));
+            tile_u(sU2, vy, vx) = __fadd_rn(__fmul_rn(sHl[(sy0 - sr0) * UT_LD + vx], b0), __fmul_rn(sHl[(sy1 - sr0) * UT_LD + vx], b1));
         }
     } else {
         for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
@@ -230,68 +236,81 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
             const float* r1 = sSrc + (sy1 - sr0) * sw - sc0;
             const float h0 = __fadd_rn(__fmul_rn(r0[sx0], a0), __fmul_rn(r0[sx1], a1));
             const float h1 = __fadd_rn(__fmul_rn(r1[sx0], a0), __fmul_rn(r1[sx1], a1));
-            sU[vy * UT_LD + vx] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+            tile_u(sU2, vy, vx) = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
         }
     }
     __syncthreads(); // sSrc is dead from here; sA becomes sTmp
     }
 
     // ---- row pass: sTmp[vy][c], c = 0..63 <-> real column j = x0 - 1 + c; taps left->right.
-    //      work item = (row, run of 16 columns), one per thread; adjacent threads take adjacent rows (odd strides).
+    //      work item = (row PAIR, run of 8 columns), one per thread: every packed instruction serves rows 2rp and 2rp+1.
     float* sTmp = sA;
     {
-        const int vy = tid % UT_H, run = tid / UT_H;
+        const int rp = tid % (UT_H / 2), run = tid / (UT_H / 2);
         const int c0 = run * RUN;
-        const float* in = sU + vy * UT_LD + c0; // window input k for output c is in[c - c0 + k] (vx = c + k)
-        float w[RUN + 16];
+        const float2* in = sU2 + rp * UT_LD + c0; // window input k for output c is in[c - c0 + k] (vx = c + k)
+        float2 w[RUN + 16];
 #pragma unroll
         for (int k = 0; k < RUN + 16; ++k) w[k] = in[k];
         const int jlast = x0 - 1 + c0 + RUN - 1;
-        float acc[RUN];
+        float2 acc[RUN];
         if (jlast < p.n4) {
+            const float2 g0 = make_float2(c_g17[0], c_g17[0]);
 #pragma unroll
-            for (int o = 0; o < RUN; ++o) acc[o] = __fmul_rn(c_g17[0], w[o]);
+            for (int o = 0; o < RUN; ++o) acc[o] = __fmul2_rn(g0, w[o]);
 #pragma unroll
-            for (int t = 1; t < 17; ++t)
+            for (int t = 1; t < 17; ++t) {
+                const float2 g = make_float2(c_g17[t], c_g17[t]);
 #pragma unroll
-                for (int o = 0; o < RUN; ++o) acc[o] = __fmaf_rn(c_g17[t], w[o + t], acc[o]);
+                for (int o = 0; o < RUN; ++o) acc[o] = __ffma2_rn(g, w[o + t], acc[o]);
+            }
         } else {
 #pragma unroll
             for (int o = 0; o < RUN; ++o) {
                 const bool fma = (x0 - 1 + c0 + o) < p.n4;
-                float s = __fmul_rn(c_g17[0], w[o]);
+                float2 s2 = __fmul2_rn(make_float2(c_g17[0], c_g17[0]), w[o]);
 #pragma unroll
-                for (int t = 1; t < 17; ++t)
-                    s = fma ? __fmaf_rn(c_g17[t], w[o + t], s) : __fadd_rn(s, __fmul_rn(c_g17[t], w[o + t]));
-                acc[o] = s;
+                for (int t = 1; t < 17; ++t) {
+                    const float2 g = make_float2(c_g17[t], c_g17[t]);
+                    s2 = fma ? __ffma2_rn(g, w[o + t], s2) : __fadd2_rn(s2, __fmul2_rn(g, w[o + t]));
+                }
+                acc[o] = s2;
             }
         }
 #pragma unroll
-        for (int o = 0; o < RUN; ++o) sTmp[vy * RT_LD + c0 + o] = acc[o];
+        for (int o = 0; o < RUN; ++o) {
+            sTmp[(2 * rp) * RT_LD + c0 + o] = acc[o].x;
+            sTmp[(2 * rp + 1) * RT_LD + c0 + o] = acc[o].y;
+        }
     }
     __syncthreads();
 
     // ---- column pass (symmetric): sS[r][c], r = 0..31 <-> real row i = y0 - 1 + r (virtual row r + 8).
-    //      one work item per thread: column c = tid % 64, run of 16 rows r0 = (tid / 64) * 16.
-    if (tid < RT_W * (CT_H / RUN)) {
-        const int c = tid % RT_W, r0 = (tid / RT_W) * RUN;
-        const int j = x0 - 1 + c;
-        const bool col_ok = (j >= 0 && j < UW);
-        const bool fma = j < p.n8;
-        float w[RUN + 16];
+    //      work item = (column PAIR c, c+1; run of 8 rows); the two columns can fall into different column classes of the
+    //      reference's SIMD filter (FMA below n8, mul + add from n8 on): then both chains are computed and each lane keeps its own.
+    if (tid < (RT_W / 2) * (CT_H / RUN)) {
+        const int c = (tid % (RT_W / 2)) * 2, r0 = (tid / (RT_W / 2)) * RUN;
+        const int j0 = x0 - 1 + c, j1 = j0 + 1;
+        const bool fma0 = j0 < p.n8, fma1 = j1 < p.n8;
+        float2 w[RUN + 16];
 #pragma unroll
-        for (int k = 0; k < RUN + 16; ++k) w[k] = sTmp[(r0 + k) * RT_LD + c];
+        for (int k = 0; k < RUN + 16; ++k) w[k] = *reinterpret_cast<const float2*>(sTmp + (r0 + k) * RT_LD + c);
+        const float2 g8 = make_float2(c_g17[8], c_g17[8]);
 #pragma unroll
         for (int o = 0; o < RUN; ++o) {
-            float s = __fmul_rn(c_g17[8], w[o + 8]);
+            float2 sf = __fmul2_rn(g8, w[o + 8]), sn = sf;
 #pragma unroll
             for (int t = 1; t <= 8; ++t) {
-                const float a = __fadd_rn(w[o + 8 + t], w[o + 8 - t]);
-                s = fma ? __fmaf_rn(c_g17[8 + t], a, s) : __fadd_rn(s, __fmul_rn(c_g17[8 + t], a));
+                const float2 a = __fadd2_rn(w[o + 8 + t], w[o + 8 - t]);
+                const float2 g = make_float2(c_g17[8 + t], c_g17[8 + t]);
+                if (fma0 || fma1) sf = __ffma2_rn(g, a, sf);
+                if (!fma0 || !fma1) sn = __fadd2_rn(sn, __fmul2_rn(g, a));
             }
+            const float v0 = fma0 ? sf.x : sn.x, v1 = fma1 ? sf.y : sn.y;
             const int i = y0 - 1 + r0 + o;
-            const bool ok = col_ok && i >= 0 && i < UH;
-            sS[(r0 + o) * RT_LD + c] = ok ? s : -INFINITY; // out-of-image neighbours never win the max
+            const bool row_ok = i >= 0 && i < UH;
+            sS[(r0 + o) * RT_LD + c] = (row_ok && j0 >= 0 && j0 < UW) ? v0 : -INFINITY; // out-of-image neighbours never win the max
+            sS[(r0 + o) * RT_LD + c + 1] = (row_ok && j1 >= 0 && j1 < UW) ? v1 : -INFINITY;
         }
     }
     __syncthreads();
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
             if (slot < p.pcap) {
                 const size_t o = ((size_t)frame * HP_N_PARTS + part) * p.pcap + slot;
                 p.raw_key[o] = i * UW + j;
-                p.raw_score[o] = sU[(r + HALO) * UT_LD + (c + HALO)]; // score = UNsmoothed up-map value
+                p.raw_score[o] = tile_u(sU2, r + HALO, c + HALO); // score = UNsmoothed up-map value
             } else {
                 atomicOr(p.flags + frame, FLAG_PEAK_OVERFLOW);
             }
@@ -455,6 +474,88 @@ __device__ __forceinline__ float up_sample(const float* P, int W, int H, int lx,
 __device__ __forceinline__ unsigned long long make_key(float score, int ia, int ib)
 {
     return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)(0xffffffffu - (((unsigned)ia << 16) | (unsigned)ib));
+}
+
+// ---- get_humans with the partial humans in REGISTERS: lane h owns human h (<= 32 alive at any time, the common case) ----------
+// One warp walking a strictly ordered list is latency-bound: with the state in shared memory every connection costs a chain of
+// ~7 dependent shared-memory accesses (~500 cycles measured, 100 us per 16-frame batch).  Here the "touch" test is two register
+// compares + one ballot, an attach is a predicated register update on one lane, and only a merge of two humans (rare) moves data
+// between lanes (18 shuffles).  The pair loop is unrolled through a template so that parts[part1] / parts[part2] are fixed registers.
+struct RegHuman {
+    int parts[HP_N_PARTS];
+    float score;
+    int np;
+};
+
+template <int PAIR, int P1, int P2>
+__device__ __forceinline__ bool assemble_pair_regs(RegHuman& me, int& nh, const int lane, const hp_connection* __restrict__ conns, const float2* __restrict__ cps, const int ncn)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    for (int ci = 0; ci < ncn; ++ci) {
+        const hp_connection cn = conns[ci];
+        const float2 ps = cps[ci];                   // peak scores of (cid1, cid2), looked up when the list was staged
+        const bool touch = lane < nh && (me.parts[P1] == cn.cid1 || me.parts[P2] == cn.cid2);   // paf.cpp:33-36
+        const unsigned bal = __ballot_sync(FULL, touch);
+        if (bal == 0u) {
+            if (PAIR <= 16) {                        // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
+                if (nh >= 32) return false;          // a 33rd partial human: the caller falls back to the shared-memory path
+                if (lane == nh) {
+#pragma unroll
+                    for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] = -1;
+                    me.parts[P1] = cn.cid1;
+                    me.parts[P2] = cn.cid2;
+                    me.np = 2;
+                    me.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
+                }
+                nh += 1;
+            }
+            continue;
+        }
+        const int t0 = __ffs(bal) - 1;
+        const unsigned rest = bal & (bal - 1u);
+        if (rest == 0u) {                            // one touching human: paf.cpp:172-178
+            if (lane == t0 && me.parts[P2] != cn.cid2) {
+                me.parts[P2] = cn.cid2;
+                me.np += 1;
+                me.score = __fadd_rn(me.score, __fadd_rn(ps.y, cn.score));
+            }
+            continue;
+        }
+        const int t1 = __ffs(rest) - 1;              // first two in vector order: paf.cpp:179-210
+        int other[HP_N_PARTS];
+        bool shared_part = false;
+#pragma unroll
+        for (int i = 0; i < HP_N_PARTS; ++i) {
+            other[i] = __shfl_sync(FULL, me.parts[i], t1);
+            shared_part |= (me.parts[i] > 0 && other[i] > 0);   // `id > 0` quirk (paf.cpp:185); meaningful on lane t0
+        }
+        shared_part = __shfl_sync(FULL, (int)shared_part, t0) != 0;
+        if (!shared_part) {
+            const int np1 = __shfl_sync(FULL, me.np, t1);
+            const float sc1 = __shfl_sync(FULL, me.score, t1);
+            if (lane == t0) {
+#pragma unroll
+                for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] += other[i] + 1;   // paf.cpp:193
+                me.np += np1;
+                me.score = __fadd_rn(__fadd_rn(me.score, sc1), cn.score);
+            }
+            // vector::erase of human t1 (paf.cpp:201-205): every later human moves down one lane
+#pragma unroll
+            for (int i = 0; i < HP_N_PARTS; ++i) {
+                const int v = __shfl_down_sync(FULL, me.parts[i], 1);
+                if (lane >= t1) me.parts[i] = v;
+            }
+            const float vs = __shfl_down_sync(FULL, me.score, 1);
+            const int vn = __shfl_down_sync(FULL, me.np, 1);
+            if (lane >= t1) { me.score = vs; me.np = vn; }
+            nh -= 1;
+        } else if (lane == t0) {
+            me.parts[P2] = cn.cid2;
+            me.np += 1;
+            me.score = __fadd_rn(me.score, __fadd_rn(ps.y, cn.score));
+        }
+    }
+    return true;
 }
 
 __device__ __forceinline__ hp_connection ld_conn_cg(const hp_connection* c)
@@ -661,6 +762,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     int* rNparts = reinterpret_cast<int*>(rScore + MAXR);
     hp_connection* sConn = reinterpret_cast<hp_connection*>(rNparts + MAXR);   // [SM_CONN]
     float* sPsc = reinterpret_cast<float*>(sConn + SM_CONN);                   // [SM_PSC]
+    float2* sConnPs = reinterpret_cast<float2*>(sPsc + SM_PSC);                // [SM_CONN] peak scores of (cid1, cid2)
     int* sCnt = reinterpret_cast<int*>(sUsedA);                                // [20] connection offsets (bitmaps are dead)
     const volatile int* ccnt = p.conn_cnt + frame * HP_N_PAIRS;
     if (tid == 0) {
@@ -674,12 +776,60 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     const hp_connection* gconn = p.conn + (size_t)frame * HP_N_PAIRS * p.pcap;
     if (conn_staged)
         for (int q = 0; q < HP_N_PAIRS; ++q)
-            for (int i = tid; i < sCnt[q + 1] - sCnt[q]; i += K3_THREADS) sConn[sCnt[q] + i] = ld_conn_cg(gconn + (size_t)q * p.pcap + i);
+            for (int i = tid; i < sCnt[q + 1] - sCnt[q]; i += K3_THREADS) {
+                const hp_connection c = ld_conn_cg(gconn + (size_t)q * p.pcap + i);
+                sConn[sCnt[q] + i] = c;
+                sConnPs[sCnt[q] + i] = make_float2(__ldcg(pscore + c.cid1), __ldcg(pscore + c.cid2));
+            }
     if (psc_staged)
         for (int i = tid; i < n_peaks; i += K3_THREADS) sPsc[i] = __ldcg(pscore + i);   // other CTAs wrote these: read past L1
     __syncthreads();
     if (warp != 0) return;
     const float* psc = psc_staged ? sPsc : pscore;   // (unstaged: > 2048 peaks in one frame; plain loads are fine for values no earlier read of this SM cached)
+
+    if (conn_staged) {   // fast path: partial humans in registers, one per lane
+        RegHuman me;
+#pragma unroll
+        for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] = -1;
+        me.score = 0.f; me.np = 0;
+        int nhr = 0;
+        bool ok = true;
+#define HP_PAIR(ID, A, B) if (ok) ok = assemble_pair_regs<ID, A, B>(me, nhr, lane, sConn + sCnt[ID], sConnPs + sCnt[ID], sCnt[ID + 1] - sCnt[ID]);
+        // COCOPAIRS (src/coco.hpp:32-52) == c_pairs above
+        HP_PAIR(0, 1, 2) HP_PAIR(1, 1, 5) HP_PAIR(2, 2, 3) HP_PAIR(3, 3, 4) HP_PAIR(4, 5, 6) HP_PAIR(5, 6, 7) HP_PAIR(6, 1, 8)
+        HP_PAIR(7, 8, 9) HP_PAIR(8, 9, 10) HP_PAIR(9, 1, 11) HP_PAIR(10, 11, 12) HP_PAIR(11, 12, 13) HP_PAIR(12, 1, 0)
+        HP_PAIR(13, 0, 14) HP_PAIR(14, 14, 16) HP_PAIR(15, 0, 15) HP_PAIR(16, 15, 17) HP_PAIR(17, 2, 16) HP_PAIR(18, 5, 17)
+#undef HP_PAIR
+        if (ok) {
+            // filter (paf.cpp:226-230) + conversion (paf.cpp:359-372): lane h writes human h
+            const bool keep = lane < nhr && !(me.np < THRESH_PART_CNT || __fdiv_rn(me.score, (float)me.np) < 0.4f);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int idx = __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
+                if (idx < p.hcap) {
+                    hp_human* o = p.humans + (size_t)frame * p.hcap + idx;
+                    o->score = me.score;
+#pragma unroll
+                    for (int i = 0; i < HP_N_PARTS; ++i) {
+                        const int id = me.parts[i];
+                        hp_body_part bp;
+                        bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
+                        if (id >= 0 && id < n_peaks) {   // ids fabricated by the `+=` merge quirk are reported absent (see below)
+                            bp.has_value = 1;
+                            bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
+                            bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
+                            bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
+                        }
+                        o->parts[i] = bp;
+                    }
+                } else {
+                    atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
+                }
+            }
+            if (lane == 0) p.human_cnt[frame] = min(__popc(bal), p.hcap);
+            return;
+        }
+    }
 
     int nh = 0;
     for (int pair_id = 0; pair_id < HP_N_PAIRS; ++pair_id) {
@@ -785,7 +935,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
 // bytes of dynamic shared memory the assembly phase of paf_limbs_kernel needs for `max_refs` partial humans
 constexpr size_t assemble_smem_bytes(int max_refs)
 {
-    return (size_t)max_refs * (HP_N_PARTS + 2) * 4 + (size_t)SM_CONN * sizeof(hp_connection) + (size_t)SM_PSC * 4;
+    return (size_t)max_refs * (HP_N_PARTS + 2) * 4 + (size_t)SM_CONN * sizeof(hp_connection) + (size_t)SM_PSC * 4 + (size_t)SM_CONN * sizeof(float2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -857,9 +1007,16 @@ template <typename T> struct DevBuf {
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
         if (e == cudaSuccess) {
             n = count;
-            e = cudaMemset(p, 0, count * sizeof(T)); // unused record slots travel to the host with the used ones
-            // that memset runs on the legacy default stream while the parser works on NON-BLOCKING streams: order them here
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            // unused record slots travel to the host with the used ones: zero them.  On a private non-blocking stream + a stream
+            // (not device) synchronise: another host thread of the process may be capturing a CUDA graph on this device (pool
+            // workers), during which neither the legacy stream nor cudaDeviceSynchronize may be touched.
+            static thread_local cudaStream_t zs = nullptr;
+            static thread_local int zs_dev = -1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!zs || zs_dev != dev) { if (cudaStreamCreateWithFlags(&zs, cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError(); zs_dev = dev; }
+            e = cudaMemsetAsync(p, 0, count * sizeof(T), zs);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(zs);
         }
         return e;
     }
@@ -1225,7 +1382,7 @@ int hp_paf_create(hp_paf** out, float conf_thresh, float paf_thresh, int res_w, 
         cudaGetLastError();
         p->limb_dyn_bytes = 48 * 1024 - (int)static_smem;
     }
-    p->assemble_max_refs = (int)((p->limb_dyn_bytes - (SM_CONN * sizeof(hp_connection) + SM_PSC * 4)) / ((HP_N_PARTS + 2) * 4));
+    p->assemble_max_refs = (int)((p->limb_dyn_bytes - (SM_CONN * sizeof(hp_connection) + SM_PSC * 4 + SM_CONN * sizeof(float2))) / ((HP_N_PARTS + 2) * 4));
     if (p->max_refs > p->assemble_max_refs) p->max_refs = p->assemble_max_refs;
     *out = p;
     return HP_OK;
