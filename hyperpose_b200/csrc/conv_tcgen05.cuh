@@ -140,6 +140,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variants (thread-block clusters): the tile lands at the SAME shared-memory offset in every CTA of cta_mask and
+// completes bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of cta_mask once the previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3)
 {
     asm volatile(
@@ -550,9 +574,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // the epilogue transposes through the swizzled staging tiles (one 2-byte shared store per value) and issues
 // TMA stores of rows [0,128) and [128,NPX) (second tensor map with an NPX-128 row box).
 // ---------------------------------------------------------------------------------------------
+// kMC (weight multicast): launched as clusters of TWO CTAs that walk the same (group, channel block) over two neighbouring pixel
+// units in lockstep.  The 16 KiB weight tile of a k-step is the same for both, so each CTA loads HALF of it (64 rows) and
+// multicasts that half into both CTAs' stage; per CTA and k-step the L2 -> SM traffic drops from 16 + NPX/8 KiB to 8 + NPX/8 KiB
+// (42.6 -> 34.6 KiB at NPX = 208) -- and that port, not the tensor pipe, is what bounds these layers (profiles/r01_s2_layer_bounds.md).
+// A stage may be refilled only when BOTH CTAs' MMAs have released it: the empty barriers count two arrivals, and every
+// tcgen05.commit arrives on the barrier of both CTAs.  tmap_bh = the weight map with a 64-row box.
+template <bool kMC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2, const ConvParams p)
+                         const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
+                         const __grid_constant__ CUtensorMap tmap_bh, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -572,20 +604,31 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int units = (total_px + npx - 1) / npx;
     const int c_tiles = p.cout_g_pad / 128;                  // 128-channel blocks per group
     const int gc = p.groups * c_tiles;
-    const int total_tiles = units * gc;
     const int chunks = p.cin_g / CONV_BLOCK_K;
     const int ksteps = p.R * p.S * chunks;
+    // work list.  plain: tile = (unit, sub) with sub fastest, CTA b takes tiles b, b + grid, ...
+    //            kMC  : item = (unit PAIR, sub) with sub fastest, cluster c takes items c, c + clusters, ...; CTA rank r of the
+    //                   cluster works on unit 2 * pair + r (a unit past the end computes on TMA zero-fill and stores nothing)
+    const uint32_t crank = kMC ? ptx::cluster_ctarank() : 0u;
+    const int my_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int my_step = kMC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int total_items = kMC ? ((units + 1) / 2) * gc : units * gc;
+    auto decode = [&](int item, int& unit, int& sub) {
+        sub = item % gc;
+        unit = kMC ? 2 * (item / gc) + (int)crank : item / gc;
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         ptx::prefetch_tmap(&tmap_o);
         ptx::prefetch_tmap(&tmap_o2);
+        if (kMC) ptx::prefetch_tmap(&tmap_bh);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < p.num_stages; ++i) {
             ptx::mbar_init(ptx::smem_u32(full_bar + i), 1);
-            ptx::mbar_init(ptx::smem_u32(empty_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(empty_bar + i), kMC ? 2 : 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
@@ -596,6 +639,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512u);
     ptx::tc_fence_before();
     __syncthreads();
+    if (kMC) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast into them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -604,8 +648,9 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             int stage = 0;
             uint32_t phase = 0;
             const int pad_h = p.R / 2, pad_w = p.S / 2;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int sub = tile % gc, unit = tile / gc;
+            for (int item = my_first; item < total_items; item += my_step) {
+                int unit, sub;
+                decode(item, unit, sub);
                 const int g = sub / c_tiles, ct = sub - g * c_tiles;
                 // pixels past the last image are zero-filled by the TMA unit and never stored
                 const PixelPos q0 = unflatten(p, unit * npx);
@@ -619,7 +664,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             const uint32_t fb = ptx::smem_u32(full_bar + stage);
                             const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                             ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                            ptx::tma_load_2d(sw, &tmap_b, fb, kcol, b_row);
+                            if (kMC) ptx::tma_load_2d_mc(sw + crank * (W_BYTES / 2), &tmap_bh, fb, kcol, b_row + (int)crank * 64, (uint16_t)3);
+                            else ptx::tma_load_2d(sw, &tmap_b, fb, kcol, b_row);
                             ptx::tma_load_im2col_4d(sw + W_BYTES, &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K, q0.w - pad_w, q0.h - pad_h, q0.n, s, r);
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         }
@@ -632,7 +678,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = my_first; item < total_items; item += my_step) {
                 ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
@@ -645,7 +691,8 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
                         ptx::umma_f16(d_tmem, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(ptx::smem_u32(empty_bar + stage));
+                    if (kMC) ptx::umma_commit_mc(ptx::smem_u32(empty_bar + stage), (uint16_t)3);   // frees the slot in BOTH CTAs' view
+                    else ptx::umma_commit(ptx::smem_u32(empty_bar + stage));
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
@@ -661,8 +708,9 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int chunk = (ch & 63) >> 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int sub = tile % gc, unit = tile / gc;
+        for (int item = my_first; item < total_items; item += my_step) {
+            int unit, sub;
+            decode(item, unit, sub);
             const int g = sub / c_tiles, ct = sub - g * c_tiles;
             const float bias = __ldg(p.bias + g * p.cout_g_pad + ct * 128 + ch);
             const float alpha = __ldg(p.alpha + g * p.cout_g_pad + ct * 128 + ch);
@@ -708,6 +756,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (kMC) ptx::cluster_sync();   // nobody leaves while the peer may still multicast into this CTA or arrive on its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 512u);

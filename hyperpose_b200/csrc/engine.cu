@@ -489,7 +489,7 @@ int pick_bn(int cout_g)
 
 struct ConvPlan {
     ConvParams prm;
-    CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2, tmap_r;
+    CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2, tmap_r, tmap_bh;
     __half* d_w = nullptr;
     float* d_w32 = nullptr;      // tf32 plan: fp32 K-major weights, rounded to TF32
     bool tf32 = false;
@@ -573,6 +573,8 @@ struct hp_engine {
     int ho_pos = 0;
     // network input of the NEXT run_graph: d_frames, or a slot buffer of the pipelined pose call
     const uint8_t* cur_frames = nullptr;
+    bool swap_multicast = false;   // conv_tcgen05_swap_kernel<true>: clusters of two CTAs multicast the weight tiles (HPB_SWAP_MC)
+    int max_swap_clusters = 0;
     bool stage_synced = false;     // hp_engine_stage_frame_u8: the previous batch's staging copies have been waited for
     // pipelined end-to-end call (hp_pose_submit_u8_host / hp_pose_collect): two batches in flight
     struct PoseSlot {
@@ -802,6 +804,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     }
     // swapped-operand kernel: output channels in blocks of 128, enough k-steps to amortise the transposing epilogue
     memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
+    memset(&pl.tmap_bh, 0, sizeof(pl.tmap_bh));
     // (restricted to one 128-channel block per group: with several blocks every block would re-fetch the same pixels
     //  through L2, which the 2x larger L2->SM traffic does not pay for on the merged 256-channel layers)
     p.swap_ab = (p.tma_store && !po.res_mode && cout_pad == 128 && cout_g == cout_pad && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
@@ -813,6 +816,8 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS, p.npx);
         if (rc) return rc;
         rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, 128);
+        if (rc) return rc;
+        rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, 64);   // half tiles of the weight-multicast variant
         if (rc) return rc;
         rc = make_tmap_out(&pl.tmap_o2, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels, p.npx > 128 ? p.npx - 128 : 128);
         if (rc) return rc;
@@ -928,8 +933,22 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
     if (p.swap_ab) {
         const long total_px = (long)N * p.H * p.W;
-        const int n_tiles = (int)((total_px + p.npx - 1) / p.npx) * p.groups * (p.cout_g_pad / 128);
-        conv_tcgen05_swap_kernel<<<std::min(e->num_sms, n_tiles), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, p);
+        const int units = (int)((total_px + p.npx - 1) / p.npx), gc = p.groups * (p.cout_g_pad / 128);
+        if (e->swap_multicast) {
+            // clusters of two CTAs share every weight tile (each loads half, multicast): see conv_tcgen05_swap_kernel<true>
+            const int items = ((units + 1) / 2) * gc;
+            const int clusters = std::max(1, std::min(e->max_swap_clusters, items));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            HP_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tcgen05_swap_kernel<true>, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p));
+        } else {
+            conv_tcgen05_swap_kernel<false><<<std::min(e->num_sms, units * gc), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p);
+        }
         e->launches++;
         return HP_OK;
     }
@@ -1294,7 +1313,8 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
     } else
     if (max_smem > 0 && (cudaFuncSetAttribute(conv_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
                          cudaFuncSetAttribute(conv_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
-                         cudaFuncSetAttribute(conv_tcgen05_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
+                         cudaFuncSetAttribute(conv_tcgen05_swap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+                         cudaFuncSetAttribute(conv_tcgen05_swap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory", max_smem);
         return fail(HP_ERR_CUDA);
     }
@@ -1319,6 +1339,26 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
                       cudaFuncSetAttribute(conv_stem_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (stem)", stem_smem);
         return fail(HP_ERR_CUDA);
+    }
+    // weight-multicast clusters for the swapped-operand layers: how many 2-CTA clusters of this footprint can be resident at once
+    {
+        const char* mc = getenv("HPB_SWAP_MC");
+        size_t swap_smem = 0;
+        for (auto& o : e->ops) if (o.po.type == OP_CONV && !o.plan.tf32 && o.plan.prm.swap_ab) swap_smem = std::max(swap_smem, o.plan.smem);
+        if (swap_smem && dtype == HP_DTYPE_F16 && !(mc && strcmp(mc, "0") == 0)) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(2 * (e->num_sms / 2)); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = swap_smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, conv_tcgen05_swap_kernel<true>, &cfg) == cudaSuccess && nc >= e->num_sms / 2 - 4) {
+                e->max_swap_clusters = std::min(nc, e->num_sms / 2);
+                e->swap_multicast = mc != nullptr;   // opt-in (HPB_SWAP_MC=1) until it is the measured default
+            } else cudaGetLastError();
+        }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { set_error("hp_engine_create: device error during set-up: %s", cudaGetErrorString(cudaGetLastError())); return fail(HP_ERR_CUDA); }
     *out = e;

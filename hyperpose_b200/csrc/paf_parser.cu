@@ -97,6 +97,7 @@ constexpr int CT_H = TH + 2;             // 32 column-pass output rows
 constexpr int SRC_MAX_H = UT_H + 1, SRC_MAX_W = UT_W + 1; // scale >= 1 => at most one source px per up px (+1)
 constexpr int RUN = 8;                   // outputs per thread per pass and lane of the pair (sliding window of RUN+16 inputs)
 constexpr int HL_ROWS = 16;              // source rows per tile for which the horizontal lerp is cached (more: direct path)
+static_assert(UT_H % 4 == 0 && 2 * UT_W <= K1_THREADS, "up-sampling: one (tile column, half of the row pairs) per thread");
 static_assert(UT_H % 2 == 0 && (UT_H / 2) * (RT_W / RUN) == K1_THREADS, "row pass: one (row pair, run) per thread");
 static_assert(RT_W % 2 == 0 && (RT_W / 2) * (CT_H / RUN) <= K1_THREADS && CT_H % RUN == 0, "column pass: one (column pair, run) per thread");
 
@@ -219,11 +220,25 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
             sHl[r * UT_LD + vx] = __fadd_rn(__fmul_rn(row[sx0], a0), __fmul_rn(row[sx1], a1));
         }
         __syncthreads();
-        for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
-            const int vy = i / UT_W, vx = i - vy * UT_W;
-            const int sy0 = sYi[vy], sy1 = min(sy0 + 1, H - 1);
-            const float b1 = sYf[vy], b0 = __fsub_rn(1.f, b1);
-            tile_u(sU2, vy, vx) = __fadd_rn(__fmul_rn(sHl[(sy0 - sr0) * UT_LD + vx], b0), __fmul_rn(sHl[(sy1 - sr0) * UT_LD + vx], b1));
+        // vertical pass: a thread owns one tile column and walks down half of the row pairs; one packed 8-byte store per pair
+        if (tid < 2 * UT_W) {
+            const int vx = tid % UT_W, rp0 = (tid / UT_W) * (UT_H / 4);
+            const float* col = sHl + vx;
+#pragma unroll 4
+            for (int rp = rp0; rp < rp0 + UT_H / 4; ++rp) {
+                float2 o;
+                {
+                    const int sy0 = sYi[2 * rp], sy1 = min(sy0 + 1, H - 1);
+                    const float b1 = sYf[2 * rp], b0 = __fsub_rn(1.f, b1);
+                    o.x = __fadd_rn(__fmul_rn(col[(sy0 - sr0) * UT_LD], b0), __fmul_rn(col[(sy1 - sr0) * UT_LD], b1));
+                }
+                {
+                    const int sy0 = sYi[2 * rp + 1], sy1 = min(sy0 + 1, H - 1);
+                    const float b1 = sYf[2 * rp + 1], b0 = __fsub_rn(1.f, b1);
+                    o.y = __fadd_rn(__fmul_rn(col[(sy0 - sr0) * UT_LD], b0), __fmul_rn(col[(sy1 - sr0) * UT_LD], b1));
+                }
+                sU2[rp * UT_LD + vx] = o;
+            }
         }
     } else {
         for (int i = tid; i < UT_H * UT_W; i += K1_THREADS) {
@@ -476,83 +491,88 @@ __device__ __forceinline__ unsigned long long make_key(float score, int ia, int 
     return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned)(0xffffffffu - (((unsigned)ia << 16) | (unsigned)ib));
 }
 
-// ---- get_humans with the partial humans in REGISTERS: lane h owns human h (<= 32 alive at any time, the common case) ----------
+// ---- get_humans with the partial humans in REGISTERS: lane l owns humans l and l + 32 (up to 64 ever created per frame) ------
 // One warp walking a strictly ordered list is latency-bound: with the state in shared memory every connection costs a chain of
-// ~7 dependent shared-memory accesses (~500 cycles measured, 100 us per 16-frame batch).  Here the "touch" test is two register
-// compares + one ballot, an attach is a predicated register update on one lane, and only a merge of two humans (rare) moves data
-// between lanes (18 shuffles).  The pair loop is unrolled through a template so that parts[part1] / parts[part2] are fixed registers.
+// ~7 dependent shared-memory accesses (~500 cycles measured, >100 us per 16-frame crowd batch).  Here the "touch" test is register
+// compares + two ballots, an attach is a predicated register update on one lane, and only a merge of two humans moves data between
+// lanes (18 shuffles).  Humans are never moved: the reference's vector::erase + renumbering (paf.cpp:201-205) only matters through
+// the ORDER of the survivors (first two touching humans; output order), and a slot index that is never reused keeps exactly that
+// order -- a merged-away human is just marked dead.  The pair loop is unrolled through a template so that parts[part1] / parts[part2]
+// are fixed registers.  More than 64 humans created in one frame: the caller falls back to the shared-memory path.
 struct RegHuman {
     int parts[HP_N_PARTS];
     float score;
-    int np;
+    int np;      // n_parts; < 0: dead (merged into another human) or never created
 };
 
 template <int PAIR, int P1, int P2>
-__device__ __forceinline__ bool assemble_pair_regs(RegHuman& me, int& nh, const int lane, const hp_connection* __restrict__ conns, const float2* __restrict__ cps, const int ncn)
+__device__ __forceinline__ bool assemble_pair_regs(RegHuman& ha, RegHuman& hb, int& n_created, const int lane, const hp_connection* __restrict__ conns,
+                                                   const float2* __restrict__ cps, const int ncn)
 {
     constexpr unsigned FULL = 0xffffffffu;
     for (int ci = 0; ci < ncn; ++ci) {
         const hp_connection cn = conns[ci];
         const float2 ps = cps[ci];                   // peak scores of (cid1, cid2), looked up when the list was staged
-        const bool touch = lane < nh && (me.parts[P1] == cn.cid1 || me.parts[P2] == cn.cid2);   // paf.cpp:33-36
-        const unsigned bal = __ballot_sync(FULL, touch);
-        if (bal == 0u) {
+        // paf.cpp:33-36 on every live human; slots 0..31 live in set A, 32..63 in set B
+        const unsigned ba = __ballot_sync(FULL, ha.np >= 0 && (ha.parts[P1] == cn.cid1 || ha.parts[P2] == cn.cid2));
+        const unsigned bb = __ballot_sync(FULL, hb.np >= 0 && (hb.parts[P1] == cn.cid1 || hb.parts[P2] == cn.cid2));
+        if ((ba | bb) == 0u) {
             if (PAIR <= 16) {                        // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
-                if (nh >= 32) return false;          // a 33rd partial human: the caller falls back to the shared-memory path
-                if (lane == nh) {
+                if (n_created >= 64) return false;   // the caller falls back to the shared-memory path
+                RegHuman& h = (n_created < 32) ? ha : hb;
+                if (lane == (n_created & 31)) {
 #pragma unroll
-                    for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] = -1;
-                    me.parts[P1] = cn.cid1;
-                    me.parts[P2] = cn.cid2;
-                    me.np = 2;
-                    me.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
+                    for (int i = 0; i < HP_N_PARTS; ++i) h.parts[i] = -1;
+                    h.parts[P1] = cn.cid1;
+                    h.parts[P2] = cn.cid2;
+                    h.np = 2;
+                    h.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
                 }
-                nh += 1;
+                n_created += 1;
             }
             continue;
         }
-        const int t0 = __ffs(bal) - 1;
-        const unsigned rest = bal & (bal - 1u);
-        if (rest == 0u) {                            // one touching human: paf.cpp:172-178
-            if (lane == t0 && me.parts[P2] != cn.cid2) {
-                me.parts[P2] = cn.cid2;
-                me.np += 1;
-                me.score = __fadd_rn(me.score, __fadd_rn(ps.y, cn.score));
+        // first and second touching human in vector (= slot) order
+        const int t0 = ba ? __ffs(ba) - 1 : 32 + __ffs(bb) - 1;
+        const unsigned ra = ba & (ba - 1u);
+        const unsigned rb = ba ? bb : (bb & (bb - 1u));
+        const bool t0a = t0 < 32;
+        if ((ra | rb) == 0u) {                       // one touching human: paf.cpp:172-178
+            RegHuman& h = t0a ? ha : hb;
+            if (lane == (t0 & 31) && h.parts[P2] != cn.cid2) {
+                h.parts[P2] = cn.cid2;
+                h.np += 1;
+                h.score = __fadd_rn(h.score, __fadd_rn(ps.y, cn.score));
             }
             continue;
         }
-        const int t1 = __ffs(rest) - 1;              // first two in vector order: paf.cpp:179-210
+        const int t1 = ra ? __ffs(ra) - 1 : 32 + __ffs(rb) - 1;   // paf.cpp:179-210
+        const bool t1a = t1 < 32;
         int other[HP_N_PARTS];
         bool shared_part = false;
 #pragma unroll
         for (int i = 0; i < HP_N_PARTS; ++i) {
-            other[i] = __shfl_sync(FULL, me.parts[i], t1);
-            shared_part |= (me.parts[i] > 0 && other[i] > 0);   // `id > 0` quirk (paf.cpp:185); meaningful on lane t0
+            other[i] = __shfl_sync(FULL, t1a ? ha.parts[i] : hb.parts[i], t1 & 31);
+            const int mine = t0a ? ha.parts[i] : hb.parts[i];
+            shared_part |= (mine > 0 && other[i] > 0);             // `id > 0` quirk (paf.cpp:185); meaningful on lane t0
         }
-        shared_part = __shfl_sync(FULL, (int)shared_part, t0) != 0;
+        shared_part = __shfl_sync(FULL, (int)shared_part, t0 & 31) != 0;
+        RegHuman& h0 = t0a ? ha : hb;
         if (!shared_part) {
-            const int np1 = __shfl_sync(FULL, me.np, t1);
-            const float sc1 = __shfl_sync(FULL, me.score, t1);
-            if (lane == t0) {
+            const int np1 = __shfl_sync(FULL, t1a ? ha.np : hb.np, t1 & 31);
+            const float sc1 = __shfl_sync(FULL, t1a ? ha.score : hb.score, t1 & 31);
+            if (lane == (t0 & 31)) {
 #pragma unroll
-                for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] += other[i] + 1;   // paf.cpp:193
-                me.np += np1;
-                me.score = __fadd_rn(__fadd_rn(me.score, sc1), cn.score);
+                for (int i = 0; i < HP_N_PARTS; ++i) h0.parts[i] += other[i] + 1;   // paf.cpp:193
+                h0.np += np1;
+                h0.score = __fadd_rn(__fadd_rn(h0.score, sc1), cn.score);
             }
-            // vector::erase of human t1 (paf.cpp:201-205): every later human moves down one lane
-#pragma unroll
-            for (int i = 0; i < HP_N_PARTS; ++i) {
-                const int v = __shfl_down_sync(FULL, me.parts[i], 1);
-                if (lane >= t1) me.parts[i] = v;
-            }
-            const float vs = __shfl_down_sync(FULL, me.score, 1);
-            const int vn = __shfl_down_sync(FULL, me.np, 1);
-            if (lane >= t1) { me.score = vs; me.np = vn; }
-            nh -= 1;
-        } else if (lane == t0) {
-            me.parts[P2] = cn.cid2;
-            me.np += 1;
-            me.score = __fadd_rn(me.score, __fadd_rn(ps.y, cn.score));
+            RegHuman& h1 = t1a ? ha : hb;
+            if (lane == (t1 & 31)) h1.np = -1;       // vector::erase (paf.cpp:201-205): the slot dies, nobody moves
+        } else if (lane == (t0 & 31)) {
+            h0.parts[P2] = cn.cid2;
+            h0.np += 1;
+            h0.score = __fadd_rn(h0.score, __fadd_rn(ps.y, cn.score));
         }
     }
     return true;
@@ -787,46 +807,52 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     if (warp != 0) return;
     const float* psc = psc_staged ? sPsc : pscore;   // (unstaged: > 2048 peaks in one frame; plain loads are fine for values no earlier read of this SM cached)
 
-    if (conn_staged) {   // fast path: partial humans in registers, one per lane
-        RegHuman me;
+    if (conn_staged) {   // fast path: partial humans in registers, two per lane
+        RegHuman ha, hb;
 #pragma unroll
-        for (int i = 0; i < HP_N_PARTS; ++i) me.parts[i] = -1;
-        me.score = 0.f; me.np = 0;
-        int nhr = 0;
+        for (int i = 0; i < HP_N_PARTS; ++i) { ha.parts[i] = -1; hb.parts[i] = -1; }
+        ha.score = 0.f; hb.score = 0.f; ha.np = -1; hb.np = -1;
+        int n_created = 0;
         bool ok = true;
-#define HP_PAIR(ID, A, B) if (ok) ok = assemble_pair_regs<ID, A, B>(me, nhr, lane, sConn + sCnt[ID], sConnPs + sCnt[ID], sCnt[ID + 1] - sCnt[ID]);
+#define HP_PAIR(ID, A, B) if (ok) ok = assemble_pair_regs<ID, A, B>(ha, hb, n_created, lane, sConn + sCnt[ID], sConnPs + sCnt[ID], sCnt[ID + 1] - sCnt[ID]);
         // COCOPAIRS (src/coco.hpp:32-52) == c_pairs above
         HP_PAIR(0, 1, 2) HP_PAIR(1, 1, 5) HP_PAIR(2, 2, 3) HP_PAIR(3, 3, 4) HP_PAIR(4, 5, 6) HP_PAIR(5, 6, 7) HP_PAIR(6, 1, 8)
         HP_PAIR(7, 8, 9) HP_PAIR(8, 9, 10) HP_PAIR(9, 1, 11) HP_PAIR(10, 11, 12) HP_PAIR(11, 12, 13) HP_PAIR(12, 1, 0)
         HP_PAIR(13, 0, 14) HP_PAIR(14, 14, 16) HP_PAIR(15, 0, 15) HP_PAIR(16, 15, 17) HP_PAIR(17, 2, 16) HP_PAIR(18, 5, 17)
 #undef HP_PAIR
         if (ok) {
-            // filter (paf.cpp:226-230) + conversion (paf.cpp:359-372): lane h writes human h
-            const bool keep = lane < nhr && !(me.np < THRESH_PART_CNT || __fdiv_rn(me.score, (float)me.np) < 0.4f);
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            const int idx = __popc(bal & ((1u << lane) - 1u));
-            if (keep) {
-                if (idx < p.hcap) {
-                    hp_human* o = p.humans + (size_t)frame * p.hcap + idx;
-                    o->score = me.score;
+            // filter (paf.cpp:226-230) + conversion (paf.cpp:359-372) in slot order: set A first, then set B
+            int no = 0;
 #pragma unroll
-                    for (int i = 0; i < HP_N_PARTS; ++i) {
-                        const int id = me.parts[i];
-                        hp_body_part bp;
-                        bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
-                        if (id >= 0 && id < n_peaks) {   // ids fabricated by the `+=` merge quirk are reported absent (see below)
-                            bp.has_value = 1;
-                            bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
-                            bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
-                            bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
+            for (int set = 0; set < 2; ++set) {
+                const RegHuman& me = set ? hb : ha;
+                const bool keep = me.np >= 0 && !(me.np < THRESH_PART_CNT || __fdiv_rn(me.score, (float)me.np) < 0.4f);
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                const int idx = no + __popc(bal & ((1u << lane) - 1u));
+                if (keep) {
+                    if (idx < p.hcap) {
+                        hp_human* o = p.humans + (size_t)frame * p.hcap + idx;
+                        o->score = me.score;
+#pragma unroll
+                        for (int i = 0; i < HP_N_PARTS; ++i) {
+                            const int id = me.parts[i];
+                            hp_body_part bp;
+                            bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
+                            if (id >= 0 && id < n_peaks) {   // ids fabricated by the `+=` merge quirk are reported absent (see below)
+                                bp.has_value = 1;
+                                bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
+                                bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
+                                bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
+                            }
+                            o->parts[i] = bp;
                         }
-                        o->parts[i] = bp;
+                    } else {
+                        atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
                     }
-                } else {
-                    atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW);
                 }
+                no += __popc(bal);
             }
-            if (lane == 0) p.human_cnt[frame] = min(__popc(bal), p.hcap);
+            if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
             return;
         }
     }

@@ -326,3 +326,30 @@ def test_halo_box_kernel_matches_im2col_kernels():
     # (through ~40 layers with fp16 activations the re-ordered sums differ by a few fp16 roundings: 8e-4 * max measured)
     assert np.abs(outs[1] - outs[0]).max() <= 2e-3 * m, np.abs(outs[1] - outs[0]).max() / m
     assert np.abs(outs[2] - outs[0]).max() <= 2e-3 * m
+
+
+def test_weight_multicast_swap_kernel_is_bit_identical():
+    """conv_tcgen05_swap_kernel<true> (HPB_SWAP_MC=1: clusters of two CTAs, each loads half of every weight tile and multicasts it
+    to both) feeds the same operands to the same MMAs in the same order as the plain variant: outputs are bit-identical -- small
+    (odd unit counts: a cluster whose second CTA runs past the end) and at the full cfg3 size"""
+    import subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, sys
+        sys.path.insert(0, %r)
+        from hyperpose_b200 import capi, models, synthetic as syn
+        outs = []
+        for (h, w, n, st) in ((72, 104, 2, 2), (56, 88, 3, 3), (368, 656, 3, 6)):
+            e = capi.Engine(models.openpose_vgg19(0, n_stages=st).to_pack(), (w, h), max_batch_size=n)
+            e.infer_u8(syn.make_frames_u8(5, n, h, w)); c, p = e.read_outputs(n)
+            outs += [c.ravel(), p.ravel()]
+            e.close()
+        np.save(sys.argv[1], np.concatenate(outs))
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({"HPB_SWAP_MC": "0"}, {"HPB_SWAP_MC": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(f.name))
+    assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
+    assert np.array_equal(outs[0], outs[1])
