@@ -29,7 +29,7 @@ EXPORTS = [
     "hp_last_error", "hp_device_count", "hp_version",
     "hp_paf_create", "hp_paf_destroy", "hp_paf_set_conf_thresh", "hp_paf_set_paf_thresh", "hp_paf_set_capacity",
     "hp_paf_process_host", "hp_paf_process_host_batched", "hp_paf_process_device", "hp_paf_fetch",
-    "hp_paf_debug_peaks", "hp_paf_debug_connections", "hp_paf_launch_count", "hp_paf_copy_results_device",
+    "hp_paf_debug_peaks", "hp_paf_debug_connections", "hp_paf_launch_count", "hp_paf_copy_results_device", "hp_paf_debug_timing",
 ]
 
 
@@ -152,6 +152,13 @@ class PafParser:
     @property
     def launch_count(self) -> int:
         return int(lib().hp_paf_launch_count(self._h))
+
+    def debug_timing(self, N: int):
+        """HPB_PAF_TIMING=1: (cta[N,19,4] ns stamps: start, ordered, candidates, matched; asm[N,2]: assembly start, end)"""
+        out = np.zeros(N * (N_PAIRS * 4 + 2), np.uint64)
+        lib().hp_paf_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        check(lib().hp_paf_debug_timing(self._h, out.ctypes.data, N))
+        return out[:N * N_PAIRS * 4].reshape(N, N_PAIRS, 4), out[N * N_PAIRS * 4:].reshape(N, 2)
 
     def copy_results_device(self, d_humans_ptr: int, d_counts_ptr: int, N: int, cap: int, stream: int = 0):
         check(lib().hp_paf_copy_results_device(self._h, d_humans_ptr, d_counts_ptr, N, cap, stream))

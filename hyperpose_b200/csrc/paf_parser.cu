@@ -468,7 +468,15 @@ struct LimbParams {
     int* flags;
     int stage_bytes; // dynamic smem available for staging the two PAF channels (0 = never stage)
     const float* up_paf; // resolutions that shrink an axis: resized PAF maps [N, c_paf, UH, UW] (resize_area_generic_kernel); else null
+    unsigned long long* dbg_t; // optional phase timestamps (%globaltimer, ns): [N][19][4] per CTA (start, ordered, candidates, matched) + [N][2] assembly (start, end); null = off
 };
+
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // up-sampled PAF value at up-map pixel (lx, ly), recomputed from the low-resolution field
 // exactly as orc_resize_area_up does (horizontal lerp on two source rows, then vertical).
@@ -510,23 +518,35 @@ __device__ __forceinline__ bool assemble_pair_regs(RegHuman& ha, RegHuman& hb, i
                                                    const float2* __restrict__ cps, const int ncn)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    if (ncn == 0) return true;
+    // the list does not depend on the state: the next record is fetched before the dependent chain of the current one
+    hp_connection cn_next = conns[0];
+    float2 ps_next = cps[0];
     for (int ci = 0; ci < ncn; ++ci) {
-        const hp_connection cn = conns[ci];
-        const float2 ps = cps[ci];                   // peak scores of (cid1, cid2), looked up when the list was staged
-        // paf.cpp:33-36 on every live human; slots 0..31 live in set A, 32..63 in set B
+        const hp_connection cn = cn_next;
+        const float2 ps = ps_next;                   // peak scores of (cid1, cid2), looked up when the list was staged
+        if (ci + 1 < ncn) { cn_next = conns[ci + 1]; ps_next = cps[ci + 1]; }
+        // paf.cpp:33-36 on every live human; slots 0..31 live in set A, 32..63 in set B (tested only once it is populated)
         const unsigned ba = __ballot_sync(FULL, ha.np >= 0 && (ha.parts[P1] == cn.cid1 || ha.parts[P2] == cn.cid2));
-        const unsigned bb = __ballot_sync(FULL, hb.np >= 0 && (hb.parts[P1] == cn.cid1 || hb.parts[P2] == cn.cid2));
+        unsigned bb = 0u;
+        if (n_created > 32) bb = __ballot_sync(FULL, hb.np >= 0 && (hb.parts[P1] == cn.cid1 || hb.parts[P2] == cn.cid2));
         if ((ba | bb) == 0u) {
             if (PAIR <= 16) {                        // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
                 if (n_created >= 64) return false;   // the caller falls back to the shared-memory path
-                RegHuman& h = (n_created < 32) ? ha : hb;
-                if (lane == (n_created & 31)) {
+                if (n_created < 32) {
+                    if (lane == n_created) {
 #pragma unroll
-                    for (int i = 0; i < HP_N_PARTS; ++i) h.parts[i] = -1;
-                    h.parts[P1] = cn.cid1;
-                    h.parts[P2] = cn.cid2;
-                    h.np = 2;
-                    h.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
+                        for (int i = 0; i < HP_N_PARTS; ++i) ha.parts[i] = -1;
+                        ha.parts[P1] = cn.cid1; ha.parts[P2] = cn.cid2;
+                        ha.np = 2;
+                        ha.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
+                    }
+                } else if (lane == n_created - 32) {
+#pragma unroll
+                    for (int i = 0; i < HP_N_PARTS; ++i) hb.parts[i] = -1;
+                    hb.parts[P1] = cn.cid1; hb.parts[P2] = cn.cid2;
+                    hb.np = 2;
+                    hb.score = __fadd_rn(__fadd_rn(ps.x, ps.y), cn.score);
                 }
                 n_created += 1;
             }
@@ -538,11 +558,16 @@ __device__ __forceinline__ bool assemble_pair_regs(RegHuman& ha, RegHuman& hb, i
         const unsigned rb = ba ? bb : (bb & (bb - 1u));
         const bool t0a = t0 < 32;
         if ((ra | rb) == 0u) {                       // one touching human: paf.cpp:172-178
-            RegHuman& h = t0a ? ha : hb;
-            if (lane == (t0 & 31) && h.parts[P2] != cn.cid2) {
-                h.parts[P2] = cn.cid2;
-                h.np += 1;
-                h.score = __fadd_rn(h.score, __fadd_rn(ps.y, cn.score));
+            if (t0a) {
+                if (lane == t0 && ha.parts[P2] != cn.cid2) {
+                    ha.parts[P2] = cn.cid2;
+                    ha.np += 1;
+                    ha.score = __fadd_rn(ha.score, __fadd_rn(ps.y, cn.score));
+                }
+            } else if (lane == t0 - 32 && hb.parts[P2] != cn.cid2) {
+                hb.parts[P2] = cn.cid2;
+                hb.np += 1;
+                hb.score = __fadd_rn(hb.score, __fadd_rn(ps.y, cn.score));
             }
             continue;
         }
@@ -589,6 +614,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
 {
     extern __shared__ __align__(16) unsigned char sDyn[];   // phase (b): the two PAF channels; phase (d): the assembly state
     __shared__ int sNcand, sLast;
+    __shared__ __align__(8) unsigned long long sBulkBar;
     __shared__ int sBase[HP_N_PARTS + 1];
     __shared__ unsigned sUsedA[MAX_PCAP / 32], sUsedB[MAX_PCAP / 32];
     __shared__ unsigned long long sCand[SM_CAND], sSorted[SM_CAND];
@@ -598,6 +624,8 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pa = c_pairs[limb][0], pb = c_pairs[limb][1];
     const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
+    unsigned long long* dbg = p.dbg_t ? p.dbg_t + ((size_t)frame * HP_N_PAIRS + limb) * 4 : nullptr;
+    if (dbg && tid == 0) dbg[0] = gtimer();
     if (tid == 0) {
         int bsum = 0;
         for (int q = 0; q < HP_N_PARTS; ++q) { sBase[q] = bsum; bsum += min(cnt[q], p.pcap); }
@@ -635,6 +663,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
         }
     }
     __syncthreads();   // this CTA's own global writes are visible to all of its threads from here on
+    if (dbg && tid == 0) dbg[1] = gtimer();
 
     const int base_a = sBase[pa], na = sBase[pa + 1] - base_a;
     const int base_b = sBase[pb], nb = sBase[pb + 1] - base_b;
@@ -654,9 +683,29 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
         // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
         if (!p.up_paf && npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
             float* sPaf = reinterpret_cast<float*>(sDyn);
-            for (int i = tid; i < H * W; i += K3_THREADS) {
-                sPaf[i] = __ldg(P1 + i);
-                sPaf[H * W + i] = __ldg(P2 + i);
+            const unsigned plane_bytes = (unsigned)(H * W * sizeof(float));
+            if ((plane_bytes & 15u) == 0u && ((size_t)P1 & 15) == 0 && ((size_t)P2 & 15) == 0) {
+                // two bulk async copies (TMA, 1-D) issued by one thread instead of ~60 dependent load / store rounds per thread
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBulkBar);
+                if (tid == 0) {
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * plane_bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf)), "l"(P1), "r"(plane_bytes), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf + H * W)), "l"(P2), "r"(plane_bytes), "r"(bar) : "memory");
+                }
+                __syncthreads();   // the barrier is initialised before anybody polls it
+                unsigned done;
+                do {
+                    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+                } while (!done);
+            } else {
+                for (int i = tid; i < H * W; i += K3_THREADS) {
+                    sPaf[i] = __ldg(P1 + i);
+                    sPaf[H * W + i] = __ldg(P2 + i);
+                }
             }
             P1 = sPaf;
             P2 = sPaf + H * W;
@@ -718,6 +767,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
             }
         }
         __syncthreads();
+        if (dbg && tid == 0) dbg[2] = gtimer();
         int ncand = sNcand;
         if (ncand > p.ccap) {
             if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
@@ -768,12 +818,15 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     }
 
     // ---- (d) the last CTA of the frame to arrive assembles the humans
+    if (dbg && tid == 0) dbg[3] = gtimer();
     __threadfence();   // ordered peaks, connections and counts of this CTA: visible device-wide before the arrival is counted
     __syncthreads();
     if (tid == 0) sLast = (atomicAdd(p.frame_done + frame, 1) == HP_N_PAIRS - 1) ? 1 : 0;
     __syncthreads();
     if (!sLast) return;
     __threadfence();
+    unsigned long long* dbg_a = p.dbg_t ? p.dbg_t + (size_t)gridDim.y * HP_N_PAIRS * 4 + (size_t)frame * 2 : nullptr;
+    if (dbg_a && tid == 0) dbg_a[0] = gtimer();
 
     const int n_peaks = sBase[HP_N_PARTS];
     const int MAXR = p.max_refs;
@@ -784,11 +837,15 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
     float* sPsc = reinterpret_cast<float*>(sConn + SM_CONN);                   // [SM_PSC]
     float2* sConnPs = reinterpret_cast<float2*>(sPsc + SM_PSC);                // [SM_CONN] peak scores of (cid1, cid2)
     int* sCnt = reinterpret_cast<int*>(sUsedA);                                // [20] connection offsets (bitmaps are dead)
-    const volatile int* ccnt = p.conn_cnt + frame * HP_N_PAIRS;
-    if (tid == 0) {
-        int t = 0;
-        for (int q = 0; q < HP_N_PAIRS; ++q) { sCnt[q] = t; t += ccnt[q]; }
-        sCnt[HP_N_PAIRS] = t;
+    if (tid < 32) {   // connection counts of the 19 limbs (other CTAs wrote them: read past L1), exclusive prefix by shuffles
+        const int c = tid < HP_N_PAIRS ? __ldcg(p.conn_cnt + frame * HP_N_PAIRS + tid) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        if (tid <= HP_N_PAIRS) sCnt[tid] = incl - c;   // sCnt[19] = total (lane 19 holds c = 0)
     }
     __syncthreads();
     const int n_conn = sCnt[HP_N_PAIRS];
@@ -853,6 +910,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
                 no += __popc(bal);
             }
             if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
+            if (dbg_a && lane == 0) dbg_a[1] = gtimer();
             return;
         }
     }
@@ -956,6 +1014,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
         no += __popc(bal);
     }
     if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
+    if (dbg_a && lane == 0) dbg_a[1] = gtimer() | 1ull;   // odd: the shared-memory path ran
 }
 
 // bytes of dynamic shared memory the assembly phase of paf_limbs_kernel needs for `max_refs` partial humans
@@ -1096,6 +1155,7 @@ struct hp_paf {
     int rz_mode = 0, rz_isx = 1, rz_isy = 1;
     DevBuf<int> rz_xofs, rz_xsi, rz_yofs, rz_ysi;
     DevBuf<float> rz_xal, rz_yal, up_conf, up_paf;
+    DevBuf<unsigned long long> dbg_t;   // HPB_PAF_TIMING=1: phase timestamps of the last batch (hp_paf_debug_timing)
     DevBuf<int> counters; // [N*18 peak_cnt | N*19 conn_cnt | N human_cnt | N flags | N frame_done]
     DevBuf<int> raw_key, part_base, px, py;
     DevBuf<float> raw_score, pscore;
@@ -1262,6 +1322,11 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k3.frame_done = p->frame_done(); k3.humans = p->humans.p; k3.human_cnt = p->human_cnt();
     k3.flags = p->flags();
     k3.up_paf = p->generic ? p->up_paf.p : nullptr;
+    k3.dbg_t = nullptr;
+    if (getenv("HPB_PAF_TIMING")) {
+        HP_CUDA_TRY(p->dbg_t.ensure((size_t)p->cap_N * (HP_N_PAIRS * 4 + 2)));
+        k3.dbg_t = p->dbg_t.p;
+    }
     const int want = 2 * p->H * p->W * (int)sizeof(float);
     k3.stage_bytes = (want <= p->limb_dyn_bytes) ? want : 0;
     const size_t dyn = std::max((size_t)k3.stage_bytes, assemble_smem_bytes(p->max_refs));
@@ -1420,7 +1485,7 @@ void hp_paf_destroy(hp_paf* p)
     cudaSetDevice(p->device);
     if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
     p->xi.release(); p->yi.release(); p->xf.release(); p->yf.release(); p->tile_bounds.release(); p->counters.release();
-    p->rz_xofs.release(); p->rz_xsi.release(); p->rz_yofs.release(); p->rz_ysi.release(); p->rz_xal.release(); p->rz_yal.release(); p->up_conf.release(); p->up_paf.release();
+    p->dbg_t.release(); p->rz_xofs.release(); p->rz_xsi.release(); p->rz_yofs.release(); p->rz_ysi.release(); p->rz_xal.release(); p->rz_yal.release(); p->up_conf.release(); p->up_paf.release();
     p->raw_key.release(); p->part_base.release(); p->px.release(); p->py.release();
     p->raw_score.release(); p->pscore.release(); p->cand.release(); p->cand_sorted.release();
     p->conn.release(); p->humans.release(); p->in_conf.release(); p->in_paf.release();
@@ -1576,6 +1641,16 @@ int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* o
 }
 
 long long hp_paf_launch_count(const hp_paf* p) { return p ? p->launches : 0; }
+
+// diagnostics (HPB_PAF_TIMING=1): %globaltimer stamps of the last batch's paf_limbs_kernel, N * (19 * 4 + 2) values
+int hp_paf_debug_timing(hp_paf* p, unsigned long long* out, int N)
+{
+    if (!p || !out || N != p->last_N || !p->dbg_t.p) { hpb::set_error("hp_paf_debug_timing: no timing data (set HPB_PAF_TIMING=1)"); return HP_ERR_ARG; }
+    HP_CUDA_TRY(cudaSetDevice(p->device));
+    HP_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
+    HP_CUDA_TRY(cudaMemcpy(out, p->dbg_t.p, (size_t)N * (HP_N_PAIRS * 4 + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return HP_OK;
+}
 
 int hp_paf_copy_results_device(hp_paf* p, hp_human* d_humans, int* d_counts, int N, int cap, void* stream)
 {

@@ -100,6 +100,8 @@ int hp_paf_debug_peaks(hp_paf* p, int frame, hp_peak* out, int cap, int* n_out);
 int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* out, int cap, int* n_out);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long hp_paf_launch_count(const hp_paf* p);
+/* diagnostics: with HPB_PAF_TIMING=1 in the environment the limb kernel stamps its phases (%globaltimer, ns); N * (19 * 4 + 2) values */
+int hp_paf_debug_timing(hp_paf* p, unsigned long long* out, int N);
 /* multi-GPU gather leg: copies the last batch's records (padded to `cap` >= the parser's human capacity per
  * frame) and counts into caller-owned DEVICE buffers, asynchronously on `stream` (NULL = the batch's stream),
  * so they can be handed to NCCL without a host round trip. */
