@@ -167,22 +167,75 @@ def cpu_parse_rate(conf, paf, seconds: float, threads: int):
 
 
 def cpu_threads():
-    """every host thread this process may use (cgroup / affinity aware), independent of OMP_NUM_THREADS (torchrun sets it to 1)"""
+    """every host thread this process may use (affinity mask AND cgroup CPU quota), independent of OMP_NUM_THREADS (torchrun
+    sets it to 1)"""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:    # cgroup v2 quota: "<quota> <period>" or "max <period>"
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_conv_threads():
+    """thread count for the conv stage of the CPU arm: one per PHYSICAL core the process may use.  (An OpenMP team wider than
+    the cores it can actually run on collapses at every barrier: measured on a 128-thread host, 128 threads -> 26 s per frame
+    against 0.9 s with 64.)"""
+    n = cpu_threads()
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = max(1, min(n, phys))
+    except Exception:
+        n = max(1, n // 2) if n >= 16 else n
+    return n
+
+
+_CONV_THREADS = {}
+
+
+def calibrate_conv_threads(graph_name: str):
+    """picks the conv-stage thread count by measurement: the graph on ONE quarter-area frame with the physical-core count and with
+    half of it (SMT siblings / cgroup quotas make "all threads" the slow choice on some hosts); cached per graph."""
+    if graph_name in _CONV_THREADS:
+        return _CONV_THREADS[graph_name]
+    import torch
+    from hyperpose_b200 import models, synthetic as syn
+    from oracle import torch_backbone
+    n = cpu_conv_threads()
+    cands = sorted({n, max(1, n // 2)}, reverse=True)
+    best, best_t = cands[-1], None
+    if len(cands) > 1:
+        graph = getattr(models, graph_name)(seed=0)
+        probe = syn.make_frames_u8(3, 1, (IN_H // 16) * 8, (IN_W // 16) * 8)
+        for c in cands:
+            torch.set_num_threads(c)
+            with torch.no_grad():
+                torch_backbone.run_graph(graph, probe, device="cpu")     # warm-up (primitive caches)
+                t0 = time.time()
+                torch_backbone.run_graph(graph, probe, device="cpu")
+                dt = time.time() - t0
+            if best_t is None or dt < best_t:
+                best, best_t = c, dt
+    _CONV_THREADS[graph_name] = best
+    return best
 
 
 def cpu_conv_port(graph_name: str, n_frames: int):
     """conv stage on the host cores: oracle/torch_backbone.py (plain PyTorch fp32) on a batch of `n_frames` synthetic frames with an
-    EXPLICIT thread count (torch.set_num_threads(all host threads): torchrun's OMP_NUM_THREADS=1 does not apply).
+    EXPLICIT, measured thread count (torch.set_num_threads: torchrun's OMP_NUM_THREADS=1 does not apply; calibrate_conv_threads).
     The reference has no CPU implementation of its convs (TensorRT on a GPU, src/tensorrt.cpp:387-396), so this stage
     of the CPU arm is a port, the parse stage is the reference's own code."""
     import torch
     from hyperpose_b200 import models, synthetic as syn
     from oracle import torch_backbone
-    threads = cpu_threads()
+    threads = calibrate_conv_threads(graph_name)
     torch.set_num_threads(threads)
     graph = getattr(models, graph_name)(seed=0)
     frames = syn.make_frames_u8(2, n_frames, IN_H, IN_W)
