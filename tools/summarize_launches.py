@@ -41,6 +41,7 @@ conv = [b for k, b in by.items() if k.startswith("conv_")]
 out = {"dram_bytes_per_step": sum(b["rd"] + b["wr"] for b in conv), "dram_read_bytes": sum(b["rd"] for b in conv),
        "dram_write_bytes": sum(b["wr"] for b in conv), "conv_launches": sum(b["launches"] for b in conv),
        "conv_share_of_step_device_time": sum(b["us"] for b in conv) / tot,
+       "source": "ncu capture " + os.path.basename(path) + " committed under profiles/ (not measured in the bench run itself)",
        "note": "sum over the conv launches (conv_tcgen05 / swap / halo / stem kernels) of one warm cfg3 step (batch 16): ncu --metrics "
                "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over tools/profile_step.py (" + os.path.basename(path) + ")"}
 print(json.dumps(out, indent=1))
