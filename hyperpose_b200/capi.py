@@ -154,11 +154,12 @@ class PafParser:
         return int(lib().hp_paf_launch_count(self._h))
 
     def debug_timing(self, N: int):
-        """HPB_PAF_TIMING=1: (cta[N,19,4] ns stamps: start, ordered, candidates, matched; asm[N,2]: assembly start, end)"""
-        out = np.zeros(N * (N_PAIRS * 4 + 2), np.uint64)
+        """HPB_PAF_TIMING=1: (cta[N,19,4] ns stamps: start, ordered, candidates, matched; asm[N,6]: assembly start, end | path in the low
+        two bits, then -- component-parallel path only -- staged, labelled, grouped, lanes done)"""
+        out = np.zeros(N * (N_PAIRS * 4 + 6), np.uint64)
         lib().hp_paf_debug_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         check(lib().hp_paf_debug_timing(self._h, out.ctypes.data, N))
-        return out[:N * N_PAIRS * 4].reshape(N, N_PAIRS, 4), out[N * N_PAIRS * 4:].reshape(N, 2)
+        return out[:N * N_PAIRS * 4].reshape(N, N_PAIRS, 4), out[N * N_PAIRS * 4:].reshape(N, 6)
 
     def copy_results_device(self, d_humans_ptr: int, d_counts_ptr: int, N: int, cap: int, stream: int = 0):
         check(lib().hp_paf_copy_results_device(self._h, d_humans_ptr, d_counts_ptr, N, cap, stream))

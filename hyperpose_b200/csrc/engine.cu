@@ -586,11 +586,15 @@ struct hp_engine {
         bool busy = false;
         int N = 0, hcap = 0;
         hp_paf* parser = nullptr;
+        hp_pifpaf* decoder = nullptr;      // OpenPifPaf packs: the slot's batch is decoded on the decoder's stream
+        cudaEvent_t conv_done = nullptr;   // (pifpaf) the engine's kernels of this slot have finished: the decoder may start
         cudaGraphExec_t graph = nullptr;   // captured launch sequence (convs + parse + result D2H) of this slot
         float key_f[2] = { 0, 0 }; int key_i[6] = { 0, 0, 0, 0, 0, 0 }; int key_N = 0; const void* key_parser = nullptr;
         const void* key_ovr[2] = { nullptr, nullptr };
     } slots[2];
     int next_slot = 0;
+    int reserve_sms = 0;                   // SMs the persistent conv kernels leave to a decoder running underneath them (pipelined pifpaf call)
+    cudaEvent_t heads_wait = nullptr;      // run_graph: the head op waits for this event (the previous batch's fields have been consumed)
     cudaStream_t copy_stream = nullptr;
     bool graphs_ok = true;
     long long graph_launches = 0, graph_captures = 0;
@@ -897,7 +901,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         p.Nb = N;
         p.m_tiles = (int)(((size_t)N * p.H * p.W + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
         const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
-        const int grid = std::min(e->num_sms, n_tiles);
+        const int grid = std::min(e->num_sms - e->reserve_sms, n_tiles);
         if (p.res_mode) conv_tf32_kernel<true><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
         else conv_tf32_kernel<false><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
         e->launches++;
@@ -909,7 +913,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         sp.frames = e->cur_frames ? e->cur_frames : e->d_frames;
         const int tiles = (int)(((size_t)N * sp.OH * sp.OW + CONV_BLOCK_M - 1) / CONV_BLOCK_M);
         const int per_sm = pl.stem_smem <= 110 * 1024 ? 2 : 1; // two resident CTAs hide the gather latency of the 3x3 stem
-        const int grid = std::min(e->num_sms * per_sm, tiles);
+        const int grid = std::min((e->num_sms - e->reserve_sms) * per_sm, tiles);
         if (pl.stem3_v2) {
             if (sp.flip) conv_stem3_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
             else conv_stem3_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
@@ -922,7 +926,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         HaloParams h = pl.hp;
         h.Nb = N;
         const long items = (long)N * h.tiles_x * h.tiles_y * h.groups * (h.cout_g_pad / h.BN);
-        const int hgrid = (int)std::min<long>(e->num_sms, items);
+        const int hgrid = (int)std::min<long>(e->num_sms - e->reserve_sms, items);
         if (h.R == 3 && h.S == 3) conv_halo_kernel<3><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
         else conv_halo_kernel<0><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
         e->launches++;
@@ -947,13 +951,13 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
             cfg.attrs = at; cfg.numAttrs = 1;
             HP_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tcgen05_swap_kernel<true>, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p));
         } else {
-            conv_tcgen05_swap_kernel<false><<<std::min(e->num_sms, units * gc), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p);
+            conv_tcgen05_swap_kernel<false><<<std::min(e->num_sms - e->reserve_sms, units * gc), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p);
         }
         e->launches++;
         return HP_OK;
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
-    const int grid = std::min(e->num_sms, n_tiles);
+    const int grid = std::min(e->num_sms - e->reserve_sms, n_tiles);
     if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     else conv_tcgen05_kernel<false><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
@@ -1059,6 +1063,7 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
 #undef HP_IM2COL
             e->launches++;
         } else if (po.type == OP_PIFPAF_HEAD) {
+            if (e->heads_wait) cudaStreamWaitEvent(st, e->heads_wait, 0);   // the previous batch's decoder has read the field tensors
             EngBuffer& a = e->bufs[po.in_buf];
             EngBuffer& b = e->bufs[po.res_buf];
             const size_t t1 = (size_t)N * 17 * 5 * e->out_h * e->out_w, t2 = (size_t)N * 19 * 9 * e->out_h * e->out_w;
@@ -1153,6 +1158,7 @@ void free_engine(hp_engine* e)
         if (sl.pin_counts) cudaFreeHost(sl.pin_counts);
         if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.conv_done) cudaEventDestroy(sl.conv_done);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1707,6 +1713,10 @@ int hp_paf_prepare(hp_paf* p, int N, int c_conf, int c_paf, int H, int W);
 int hp_paf_state(const hp_paf* p, float* thresholds2, int* ints6);
 int hp_paf_copy_results_host_async(hp_paf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream);
 int hp_paf_grow_capacity(hp_paf* p, int flags);
+int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_paf, int N, int h, int w, void* stream);
+int hp_pifpaf_pipeline_info(hp_pifpaf* p, void** stream, void** inputs_free_event, int* hcap);
+int hp_pifpaf_copy_results_host_async(hp_pifpaf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream);
+int hp_pifpaf_grow_capacity(hp_pifpaf* p, int flags);
 
 } // extern "C" (helpers below are C++)
 
@@ -1756,7 +1766,7 @@ int pose_slot_prepare(hp_engine* e, hp_engine::PoseSlot& sl, int idx, hp_paf* pa
     if (!same && sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }
     sl.key_N = N; sl.key_parser = parser; memcpy(sl.key_f, kf, sizeof(kf)); memcpy(sl.key_i, ki, sizeof(ki));
     sl.key_ovr[0] = e->override_conf; sl.key_ovr[1] = e->override_paf;
-    sl.N = N; sl.hcap = ki[4]; sl.parser = parser;
+    sl.N = N; sl.hcap = ki[4]; sl.parser = parser; sl.decoder = nullptr;
     return HP_OK;
 }
 
@@ -1797,6 +1807,99 @@ int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
 } // namespace
 
 extern "C" {
+
+// ---- OpenPifPaf packs: engine on its stream, decoder on the decoder's stream, two batches in flight ----
+static int pifpaf_slot_prepare(hp_engine* e, hp_engine::PoseSlot& sl, hp_pifpaf* dec, int N)
+{
+    const size_t fbytes = (size_t)e->max_batch * e->in_h * e->in_w * 3;
+    if (!e->copy_stream) HP_CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    if (!sl.d_frames) HP_CUDA_TRY(cudaMalloc(&sl.d_frames, fbytes + 16));
+    if (!sl.h2d_done) HP_CUDA_TRY(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    if (!sl.done) HP_CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    if (!sl.conv_done) HP_CUDA_TRY(cudaEventCreateWithFlags(&sl.conv_done, cudaEventDisableTiming));
+    if (sl.graph) { cudaGraphExecDestroy(sl.graph); sl.graph = nullptr; }   // (a PAF-parser graph of an earlier use of this slot)
+    int hcap = 0;
+    hp_pifpaf_pipeline_info(dec, nullptr, nullptr, &hcap);
+    const size_t need_h = (size_t)e->max_batch * hcap;
+    if (sl.pin_humans_n < need_h) {
+        if (sl.pin_humans) cudaFreeHost(sl.pin_humans);
+        sl.pin_humans = nullptr; sl.pin_humans_n = 0;
+        HP_CUDA_TRY(cudaMallocHost(&sl.pin_humans, need_h * sizeof(hp_human)));
+        sl.pin_humans_n = need_h;
+    }
+    if (sl.pin_counts_n < (size_t)2 * e->max_batch) {
+        if (sl.pin_counts) cudaFreeHost(sl.pin_counts);
+        sl.pin_counts = nullptr; sl.pin_counts_n = 0;
+        HP_CUDA_TRY(cudaMallocHost(&sl.pin_counts, (size_t)2 * e->max_batch * sizeof(int)));
+        sl.pin_counts_n = (size_t)2 * e->max_batch;
+    }
+    sl.N = N; sl.hcap = hcap; sl.parser = nullptr; sl.decoder = dec;
+    return HP_OK;
+}
+
+// engine kernels of the slot on the engine stream, then the decoder + the record D2H on the decoder's stream
+static int pifpaf_enqueue(hp_engine* e, hp_engine::PoseSlot& sl)
+{
+    void* dst = nullptr; void* free_ev = nullptr;
+    hp_pifpaf_pipeline_info(sl.decoder, &dst, &free_ev, nullptr);
+    cudaStream_t dec_stream = (cudaStream_t)dst;
+    e->cur_frames = sl.d_frames;
+    e->heads_wait = (cudaEvent_t)free_ev;    // NULL before the decoder's first batch
+    int rc = run_graph(e, sl.N, true, e->stream);
+    e->cur_frames = nullptr;
+    e->heads_wait = nullptr;
+    if (rc) return rc;
+    HP_CUDA_TRY(cudaEventRecord(sl.conv_done, e->stream));
+    HP_CUDA_TRY(cudaStreamWaitEvent(dec_stream, sl.conv_done, 0));
+    rc = hp_pifpaf_process_device(sl.decoder, e->d_conf, e->d_paf, sl.N, e->out_h, e->out_w, (void*)dec_stream);
+    if (rc) return rc;
+    rc = hp_pifpaf_copy_results_host_async(sl.decoder, sl.pin_humans, sl.pin_counts, sl.N, (void*)dec_stream);
+    if (rc) return rc;
+    HP_CUDA_TRY(cudaEventRecord(sl.done, dec_stream));
+    return HP_OK;
+}
+
+static int pose_submit_pifpaf(hp_engine* e, hp_pifpaf* dec, const uint8_t* frames, int N, int* ticket, bool device_src)
+{
+    if (!e || !dec || !frames || !ticket) { set_error("hp_pose_submit_pifpaf: null argument"); return HP_ERR_ARG; }
+    if (N <= 0 || N > e->max_batch) { set_error("Input batch size overflow: Yours@%d Max@%d", N, e->max_batch); return HP_ERR_BATCH; }
+    if (e->hdr.head_type != 1) { set_error("hp_pose_submit_pifpaf: the model pack has conf / PAF outputs (use hp_pose_submit_u8_host)"); return HP_ERR_UNSUPPORTED; }
+    HP_CUDA_TRY(cudaSetDevice(e->device));
+    const int idx = e->next_slot;
+    hp_engine::PoseSlot& sl = e->slots[idx];
+    if (sl.busy) { set_error("hp_pose_submit_pifpaf: two batches are already in flight -- collect ticket %d first", idx); return HP_ERR_ARG; }
+    int rc = pifpaf_slot_prepare(e, sl, dec, N);
+    if (rc) return rc;
+    // the decoder's growth kernel (one warp per frame) runs underneath the next batch's convolutions: leave it some SMs
+    {
+        static const char* rs = getenv("HPB_PIFPAF_RESERVE_SMS");
+        const int want = rs ? atoi(rs) : std::min(e->max_batch, 16);
+        e->reserve_sms = std::max(0, std::min(want, e->num_sms / 2));
+    }
+    const size_t bytes = (size_t)N * e->in_h * e->in_w * 3;
+    if (device_src) {
+        HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, frames, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    } else {
+        cudaPointerAttributes attr;
+        const bool pinned = (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+        if (!pinned) cudaGetLastError();
+        const uint8_t* src = frames;
+        if (!pinned) {
+            if (!sl.pin_frames) HP_CUDA_TRY(cudaMallocHost(&sl.pin_frames, (size_t)e->max_batch * e->in_h * e->in_w * 3));
+            memcpy(sl.pin_frames, frames, bytes);
+            src = sl.pin_frames;
+        }
+        HP_CUDA_TRY(cudaMemcpyAsync(sl.d_frames, src, bytes, cudaMemcpyHostToDevice, e->copy_stream));
+        HP_CUDA_TRY(cudaEventRecord(sl.h2d_done, e->copy_stream));
+        HP_CUDA_TRY(cudaStreamWaitEvent(e->stream, sl.h2d_done, 0));
+    }
+    rc = pifpaf_enqueue(e, sl);
+    if (rc) return rc;
+    sl.busy = true;
+    e->next_slot = idx ^ 1;
+    *ticket = idx;
+    return HP_OK;
+}
 
 static int pose_submit(hp_engine* e, hp_paf* parser, const uint8_t* frames, int N, int* ticket, bool device_src)
 {
@@ -1846,6 +1949,16 @@ int hp_pose_submit_u8_device(hp_engine* e, hp_paf* parser, const uint8_t* d_fram
     return pose_submit(e, parser, d_frames, N, ticket, true);
 }
 
+int hp_pose_submit_pifpaf_u8_host(hp_engine* e, hp_pifpaf* decoder, const uint8_t* frames, int N, int* ticket)
+{
+    return pose_submit_pifpaf(e, decoder, frames, N, ticket, false);
+}
+
+int hp_pose_submit_pifpaf_u8_device(hp_engine* e, hp_pifpaf* decoder, const uint8_t* d_frames, int N, int* ticket)
+{
+    return pose_submit_pifpaf(e, decoder, d_frames, N, ticket, true);
+}
+
 int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out)
 {
     if (!e || ticket < 0 || ticket > 1 || !out || !n_out || cap < 0) { set_error("hp_pose_collect: bad argument"); return HP_ERR_ARG; }
@@ -1855,7 +1968,24 @@ int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out
     HP_CUDA_TRY(cudaEventSynchronize(sl.done));
     sl.busy = false;
     const int N = sl.N;
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    for (int attempt = 0; sl.decoder && attempt < 5; ++attempt) {
+        int flags = 0;
+        for (int f = 0; f < N; ++f) flags |= sl.pin_counts[N + f];
+        if (!flags) break;
+        // the reference decoder is unbounded: grow what overflowed and run this slot again, alone (the other batch in flight is
+        // waited for first: its fields live in the same engine outputs)
+        if (hp_pifpaf_grow_capacity(sl.decoder, flags) != HP_OK) { set_error("hp_pose_collect: decoder capacity limit reached (flags=%d)", flags); return HP_ERR_CAPACITY; }
+        void* dst = nullptr;
+        hp_pifpaf_pipeline_info(sl.decoder, &dst, nullptr, nullptr);
+        HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        HP_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)dst));
+        int rc = pifpaf_slot_prepare(e, sl, sl.decoder, N);
+        if (rc) return rc;
+        rc = pifpaf_enqueue(e, sl);
+        if (rc) return rc;
+        HP_CUDA_TRY(cudaEventSynchronize(sl.done));
+    }
+    for (int attempt = 0; !sl.decoder && attempt < 8; ++attempt) {
         int flags = 0;
         for (int f = 0; f < N; ++f) flags |= sl.pin_counts[N + f];
         if (!flags) break;

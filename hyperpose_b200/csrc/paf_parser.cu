@@ -135,12 +135,13 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     __shared__ float sHl[HL_ROWS * UT_LD];   // horizontal lerp of the tile's source rows
     __shared__ int sXi[UT_W], sYi[UT_H];
     __shared__ float sXf[UT_W], sYf[UT_H];
+    __shared__ int2 sYo[UT_H];
     __shared__ float sMax[K1_THREADS / 32];
     __shared__ int sSkip;
 
     const int tid = threadIdx.x;
-    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-    const int part = blockIdx.y, frame = blockIdx.z;
+    const int tx = blockIdx.x, ty = blockIdx.y / HP_N_PARTS;        // grid (tiles_x, tiles_y * 18, N): no run-time division
+    const int part = blockIdx.y - ty * HP_N_PARTS, frame = blockIdx.z;
     const int x0 = tx * TW, y0 = ty * TH;
     const int H = p.H, W = p.W, UH = p.UH, UW = p.UW;
     const float* src = p.conf + ((size_t)frame * p.c_conf + part) * H * W;
@@ -173,12 +174,23 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
     const int sh = sr1 - sr0 + 1, sw = sc1 - sc0 + 1; // <= SRC_MAX_H x SRC_MAX_W because UH >= H, UW >= W
     float* sSrc = sA;
     float lmax = -INFINITY;
-    for (int i = tid; i < sh * sw; i += K1_THREADS) {
-        const int r = i / sw, c = i - r * sw;
-        const float v = __ldg(src + (size_t)(sr0 + r) * W + sc0 + c);
-        sSrc[i] = v;
-        lmax = fmaxf(lmax, v); // fmaxf ignores NaN: a NaN never enables the skip on its own
-        if (v != v) lmax = INFINITY;
+    if (sw <= 64) {   // thread = (row mod 3, column): no run-time division (the default resolutions: sw ~ 37)
+        const int c = tid & 63;
+        if (c < sw)
+            for (int r = tid >> 6; r < sh; r += K1_THREADS / 64) {
+                const float v = __ldg(src + (size_t)(sr0 + r) * W + sc0 + c);
+                sSrc[r * sw + c] = v;
+                lmax = fmaxf(lmax, v); // fmaxf ignores NaN: a NaN never enables the skip on its own
+                if (v != v) lmax = INFINITY;
+            }
+    } else {
+        for (int i = tid; i < sh * sw; i += K1_THREADS) {
+            const int r = i / sw, c = i - r * sw;
+            const float v = __ldg(src + (size_t)(sr0 + r) * W + sc0 + c);
+            sSrc[i] = v;
+            lmax = fmaxf(lmax, v);
+            if (v != v) lmax = INFINITY;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -192,8 +204,10 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
         } else {
             const int j = i - UT_W;
             const int ry = refl101(y0 - HALO + j, UH);
-            sYi[j] = __ldg(p.yi + ry);
+            const int sy0 = __ldg(p.yi + ry);
+            sYi[j] = sy0;
             sYf[j] = __ldg(p.yf + ry);
+            sYo[j] = make_int2((sy0 - sr0) * UT_LD, (min(sy0 + 1, H - 1) - sr0) * UT_LD);   // offsets into the cached horizontal lerp
         }
     }
     __syncthreads();
@@ -228,14 +242,14 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
             for (int rp = rp0; rp < rp0 + UT_H / 4; ++rp) {
                 float2 o;
                 {
-                    const int sy0 = sYi[2 * rp], sy1 = min(sy0 + 1, H - 1);
+                    const int2 so = sYo[2 * rp];
                     const float b1 = sYf[2 * rp], b0 = __fsub_rn(1.f, b1);
-                    o.x = __fadd_rn(__fmul_rn(col[(sy0 - sr0) * UT_LD], b0), __fmul_rn(col[(sy1 - sr0) * UT_LD], b1));
+                    o.x = __fadd_rn(__fmul_rn(col[so.x], b0), __fmul_rn(col[so.y], b1));
                 }
                 {
-                    const int sy0 = sYi[2 * rp + 1], sy1 = min(sy0 + 1, H - 1);
+                    const int2 so = sYo[2 * rp + 1];
                     const float b1 = sYf[2 * rp + 1], b0 = __fsub_rn(1.f, b1);
-                    o.y = __fadd_rn(__fmul_rn(col[(sy0 - sr0) * UT_LD], b0), __fmul_rn(col[(sy1 - sr0) * UT_LD], b1));
+                    o.y = __fadd_rn(__fmul_rn(col[so.x], b0), __fmul_rn(col[so.y], b1));
                 }
                 sU2[rp * UT_LD + vx] = o;
             }
@@ -311,30 +325,61 @@ __global__ void __launch_bounds__(K1_THREADS) paf_peaks_kernel(const PeakParams 
 #pragma unroll
         for (int k = 0; k < RUN + 16; ++k) w[k] = *reinterpret_cast<const float2*>(sTmp + (r0 + k) * RT_LD + c);
         const float2 g8 = make_float2(c_g17[8], c_g17[8]);
+        float2 res[RUN];
+        // the whole tile lies in one column class almost always (CTA-uniform tests): one chain, taps outermost so that a
+        // coefficient pair serves all RUN outputs
+        const int jlo = x0 - 1, jhi = x0 - 1 + RT_W - 1;
+        if (jhi < p.n8) {
 #pragma unroll
-        for (int o = 0; o < RUN; ++o) {
-            float2 sf = __fmul2_rn(g8, w[o + 8]), sn = sf;
+            for (int o = 0; o < RUN; ++o) res[o] = __fmul2_rn(g8, w[o + 8]);
 #pragma unroll
             for (int t = 1; t <= 8; ++t) {
-                const float2 a = __fadd2_rn(w[o + 8 + t], w[o + 8 - t]);
                 const float2 g = make_float2(c_g17[8 + t], c_g17[8 + t]);
-                if (fma0 || fma1) sf = __ffma2_rn(g, a, sf);
-                if (!fma0 || !fma1) sn = __fadd2_rn(sn, __fmul2_rn(g, a));
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) res[o] = __ffma2_rn(g, __fadd2_rn(w[o + 8 + t], w[o + 8 - t]), res[o]);
             }
-            const float v0 = fma0 ? sf.x : sn.x, v1 = fma1 ? sf.y : sn.y;
+        } else if (jlo >= p.n8) {
+#pragma unroll
+            for (int o = 0; o < RUN; ++o) res[o] = __fmul2_rn(g8, w[o + 8]);
+#pragma unroll
+            for (int t = 1; t <= 8; ++t) {
+                const float2 g = make_float2(c_g17[8 + t], c_g17[8 + t]);
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) res[o] = __fadd2_rn(res[o], __fmul2_rn(g, __fadd2_rn(w[o + 8 + t], w[o + 8 - t])));
+            }
+        } else {   // the class boundary runs through this tile: both chains, each lane keeps its own
+#pragma unroll
+            for (int o = 0; o < RUN; ++o) {
+                float2 sf = __fmul2_rn(g8, w[o + 8]), sn = sf;
+#pragma unroll
+                for (int t = 1; t <= 8; ++t) {
+                    const float2 a = __fadd2_rn(w[o + 8 + t], w[o + 8 - t]);
+                    const float2 g = make_float2(c_g17[8 + t], c_g17[8 + t]);
+                    sf = __ffma2_rn(g, a, sf);
+                    sn = __fadd2_rn(sn, __fmul2_rn(g, a));
+                }
+                res[o] = make_float2(fma0 ? sf.x : sn.x, fma1 ? sf.y : sn.y);
+            }
+        }
+        const bool col0 = j0 >= 0 && j0 < UW, col1 = j1 >= 0 && j1 < UW;
+#pragma unroll
+        for (int o = 0; o < RUN; ++o) {
             const int i = y0 - 1 + r0 + o;
             const bool row_ok = i >= 0 && i < UH;
-            sS[(r0 + o) * RT_LD + c] = (row_ok && j0 >= 0 && j0 < UW) ? v0 : -INFINITY; // out-of-image neighbours never win the max
-            sS[(r0 + o) * RT_LD + c + 1] = (row_ok && j1 >= 0 && j1 < UW) ? v1 : -INFINITY;
+            float2 v;   // out-of-image neighbours never win the max
+            v.x = (row_ok && col0) ? res[o].x : -INFINITY;
+            v.y = (row_ok && col1) ? res[o].y : -INFINITY;
+            *reinterpret_cast<float2*>(sS + (r0 + o) * RT_LD + c) = v;
         }
     }
     __syncthreads();
 
     // ---- threshold + 3x3 NMS (same_max_pool_3x3_2d skips out-of-range neighbours) + emission
-    for (int it = tid; it < TH * TW; it += K1_THREADS) {
-        const int r = it / TW, c = it - r * TW;
+    static_assert(TW <= 64 && K1_THREADS % 64 == 0, "NMS: thread = (row mod 3, column)");
+    const int c = tid & 63;
+    for (int r = tid >> 6; r < TH; r += K1_THREADS / 64) {
         const int i = y0 + r, j = x0 + c;
-        if (i >= UH || j >= UW) continue;
+        if (c >= TW || i >= UH || j >= UW) continue;
         const float* q = sS + (r + 1) * RT_LD + (c + 1);
         const float v = q[0];
         if (!(v > p.thresh)) continue;
@@ -439,12 +484,17 @@ __global__ void __launch_bounds__(256) resize_area_generic_kernel(const ResizePa
 // Round 1 ran (a), (b+c) and (d) as three launches with one warp per frame for (d): 6 + 39 + 141 us per 16 frames, most of
 // it the latency chain of global loads inside (d)'s sequential loop.
 // ---------------------------------------------------------------------------------------------
-constexpr int K3_THREADS = 128;
+constexpr int K3_THREADS = 256;
 constexpr int MAX_PCAP = 4096;   // bitmap size for the greedy pass
 constexpr int SM_CAND = 512;     // candidates per limb kept in shared memory (more: global scratch)
 constexpr int SM_KEYS = 512;     // raw peak keys per part staged for the rank sort
 constexpr int SM_CONN = 1024;    // connections per frame staged for the assembly
 constexpr int SM_PSC = 2048;     // peak scores per frame staged for the assembly
+constexpr int SM_TAB = 1024;     // up-sampling table entries (UW + UH) staged for the line integrals
+constexpr int ASM_WARPS = 2;     // component-parallel assembly: one LANE per connected component, 32 * ASM_WARPS components per frame
+constexpr int ASM_CMAX = 32 * ASM_WARPS;
+constexpr int ASM_SLOTS = 8;     // partial humans ever created inside one component (more: sequential fallback)
+constexpr int ASM_IFIELDS = 3;   // per slot: score, n_parts, creation index as 32-bit words; the 18 part ids as 16-bit values (ids < SM_PSC)
 
 struct LimbParams {
     const float* paf; // [N, c_paf, H, W]
@@ -467,6 +517,7 @@ struct LimbParams {
     int* human_cnt;                  // [N]
     int* flags;
     int stage_bytes; // dynamic smem available for staging the two PAF channels (0 = never stage)
+    int fast_asm;    // 1: the dynamic shared memory holds the component-parallel assembly state
     const float* up_paf; // resolutions that shrink an axis: resized PAF maps [N, c_paf, UH, UW] (resize_area_generic_kernel); else null
     unsigned long long* dbg_t; // optional phase timestamps (%globaltimer, ns): [N][19][4] per CTA (start, ordered, candidates, matched) + [N][2] assembly (start, end); null = off
 };
@@ -480,13 +531,14 @@ __device__ __forceinline__ unsigned long long gtimer()
 
 // up-sampled PAF value at up-map pixel (lx, ly), recomputed from the low-resolution field
 // exactly as orc_resize_area_up does (horizontal lerp on two source rows, then vertical).
+template <bool kTabSmem> // kTabSmem: the tables were staged in shared memory (plain loads); else global memory through the read-only path
 __device__ __forceinline__ float up_sample(const float* P, int W, int H, int lx, int ly,
                                            const int* xi, const float* xf, const int* yi, const float* yf)
 {
-    const int sx0 = __ldg(xi + lx), sx1 = min(sx0 + 1, W - 1);
-    const int sy0 = __ldg(yi + ly), sy1 = min(sy0 + 1, H - 1);
-    const float a1 = __ldg(xf + lx), a0 = __fsub_rn(1.f, a1);
-    const float b1 = __ldg(yf + ly), b0 = __fsub_rn(1.f, b1);
+    const int sx0 = kTabSmem ? xi[lx] : __ldg(xi + lx), sx1 = min(sx0 + 1, W - 1);
+    const int sy0 = kTabSmem ? yi[ly] : __ldg(yi + ly), sy1 = min(sy0 + 1, H - 1);
+    const float a1 = kTabSmem ? xf[lx] : __ldg(xf + lx), a0 = __fsub_rn(1.f, a1);
+    const float b1 = kTabSmem ? yf[ly] : __ldg(yf + ly), b0 = __fsub_rn(1.f, b1);
     const float h0 = __fadd_rn(__fmul_rn(P[sy0 * W + sx0], a0), __fmul_rn(P[sy0 * W + sx1], a1));
     const float h1 = __fadd_rn(__fmul_rn(P[sy1 * W + sx0], a0), __fmul_rn(P[sy1 * W + sx1], a1));
     return __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
@@ -610,259 +662,21 @@ __device__ __forceinline__ hp_connection ld_conn_cg(const hp_connection* c)
     return r;
 }
 
-__global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams p)
+// The strictly sequential get_humans (one warp): register path (partial humans two per lane) and, beyond 64 humans or an unstaged
+// connection list, the shared-memory path.  Runs for the frames the component-parallel path of paf_limbs_kernel hands back
+// (fabricated ids, > 64 components, > 4 partial humans in a component, > 1024 connections, > 2048 peaks) and when the dynamic
+// shared memory is too small for it.  Not inlined: its register appetite (two partial humans per lane) stays out of the kernel's budget.
+__device__ __noinline__ void assemble_sequential(const LimbParams& p, const int frame, const int lane, const bool conn_staged, const bool psc_in_smem,
+                                                 const int n_peaks, const int* sCnt, const hp_connection* sConn, const float2* sConnPs, const float* sPsc,
+                                                 int* rParts, float* rScore, int* rNparts, unsigned long long* dbg_a)
 {
-    extern __shared__ __align__(16) unsigned char sDyn[];   // phase (b): the two PAF channels; phase (d): the assembly state
-    __shared__ int sNcand, sLast;
-    __shared__ __align__(8) unsigned long long sBulkBar;
-    __shared__ int sBase[HP_N_PARTS + 1];
-    __shared__ unsigned sUsedA[MAX_PCAP / 32], sUsedB[MAX_PCAP / 32];
-    __shared__ unsigned long long sCand[SM_CAND], sSorted[SM_CAND];
-    __shared__ int sKeys[SM_KEYS];
-
-    const int limb = blockIdx.x, frame = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pa = c_pairs[limb][0], pb = c_pairs[limb][1];
-    const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
-    unsigned long long* dbg = p.dbg_t ? p.dbg_t + ((size_t)frame * HP_N_PAIRS + limb) * 4 : nullptr;
-    if (dbg && tid == 0) dbg[0] = gtimer();
-    if (tid == 0) {
-        int bsum = 0;
-        for (int q = 0; q < HP_N_PARTS; ++q) { sBase[q] = bsum; bsum += min(cnt[q], p.pcap); }
-        sBase[HP_N_PARTS] = bsum;
-        sNcand = 0;
-    }
-    __syncthreads();
-    if (limb == 0 && tid <= HP_N_PARTS) p.part_base[frame * (HP_N_PARTS + 1) + tid] = sBase[tid];
-    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
-    int* px = p.px + peak_off;
-    int* py = p.py + peak_off;
-    float* pscore = p.pscore + peak_off;
-
-    // ---- (a) order the peaks of this limb's two parts (post_process.hpp:175-192: ids follow the scan order)
-    for (int which = 0; which < 2; ++which) {
-        const int part = which ? pb : pa;
-        const int n = sBase[part + 1] - sBase[part];
-        const size_t raw = ((size_t)frame * HP_N_PARTS + part) * p.pcap;
-        const int* keys = p.raw_key + raw;
-        const bool staged = n <= SM_KEYS;
-        __syncthreads();   // sKeys of the previous part is dead
-        if (staged) {
-            for (int i = tid; i < n; i += K3_THREADS) sKeys[i] = keys[i];
-            __syncthreads();
-        }
-        const int out = sBase[part];
-        for (int i = tid; i < n; i += K3_THREADS) {
-            const int k = staged ? sKeys[i] : keys[i];
-            int rank = 0;
-            if (staged) { for (int q = 0; q < n; ++q) rank += (sKeys[q] < k); }   // keys are unique pixel positions
-            else        { for (int q = 0; q < n; ++q) rank += (keys[q] < k); }
-            px[out + rank] = k % p.UW;
-            py[out + rank] = k / p.UW;
-            pscore[out + rank] = p.raw_score[raw + i];
-        }
-    }
-    __syncthreads();   // this CTA's own global writes are visible to all of its threads from here on
-    if (dbg && tid == 0) dbg[1] = gtimer();
-
-    const int base_a = sBase[pa], na = sBase[pa + 1] - base_a;
-    const int base_b = sBase[pb], nb = sBase[pb + 1] - base_b;
-    int* conn_cnt = p.conn_cnt + frame * HP_N_PAIRS + limb;
-    const int H = p.H, W = p.W;
-    if (na == 0 || nb == 0) {
-        if (tid == 0) *conn_cnt = 0;
-    } else {
-        const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
-        const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
-        const int npairs = na * nb;
-        const float* U1 = nullptr; const float* U2 = nullptr;   // materialised up-maps of the two channels (shrinking resolutions)
-        if (p.up_paf) {
-            U1 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * p.UH * p.UW;
-            U2 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * p.UH * p.UW;
-        }
-        // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
-        if (!p.up_paf && npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
-            float* sPaf = reinterpret_cast<float*>(sDyn);
-            const unsigned plane_bytes = (unsigned)(H * W * sizeof(float));
-            if ((plane_bytes & 15u) == 0u && ((size_t)P1 & 15) == 0 && ((size_t)P2 & 15) == 0) {
-                // two bulk async copies (TMA, 1-D) issued by one thread instead of ~60 dependent load / store rounds per thread
-                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBulkBar);
-                if (tid == 0) {
-                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * plane_bytes) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf)), "l"(P1), "r"(plane_bytes), "r"(bar) : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf + H * W)), "l"(P2), "r"(plane_bytes), "r"(bar) : "memory");
-                }
-                __syncthreads();   // the barrier is initialised before anybody polls it
-                unsigned done;
-                do {
-                    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(bar) : "memory");
-                } while (!done);
-            } else {
-                for (int i = tid; i < H * W; i += K3_THREADS) {
-                    sPaf[i] = __ldg(P1 + i);
-                    sPaf[H * W + i] = __ldg(P2 + i);
-                }
-            }
-            P1 = sPaf;
-            P2 = sPaf + H * W;
-        }
-        __syncthreads();
-
-        unsigned long long* cand = p.cand + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
-        unsigned long long* sorted = p.cand_sorted + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
-
-        // ---- (b) get_connection_candidates: 3 peak pairs per warp pass, 10 lanes (= 10 samples) per pair
-        const int grp = lane / STEP_PAF, smp = lane - grp * STEP_PAF;
-        const unsigned gmask = (grp < 3) ? (0x3ffu << (grp * STEP_PAF)) : 0u;
-        constexpr int NW = K3_THREADS / 32;
-        for (int pb0 = warp * 3; pb0 < npairs; pb0 += NW * 3) { // warp-uniform trip count
-            const int pidx = pb0 + grp;
-            const bool active = (grp < 3) && (pidx < npairs);
-            int ia = 0, ib = 0;
-            float score = 0.f, norm = 1.f;
-            bool valid = false;
-            if (active) {
-                ia = pidx / nb;
-                ib = pidx - ia * nb;
-                const int ax = px[base_a + ia], ay = py[base_a + ia];
-                const int bx = px[base_b + ib], by = py[base_b + ib];
-                const int dx = bx - ax, dy = by - ay;
-                norm = (float)sqrt((double)(dx * dx + dy * dy)); // paf.cpp:104
-                valid = !((double)norm < 1e-12);                   // paf.cpp:105
-                if (valid) {
-                    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
-                    const float stepx = __fdiv_rn((float)dx, (float)STEP_PAF); // paf.cpp:77-78
-                    const float stepy = __fdiv_rn((float)dy, (float)STEP_PAF);
-                    const float fx = __fadd_rn((float)ax, __fmul_rn((float)smp, stepx));
-                    const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
-                    const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
-                    const int ly = (int)((double)fy + 0.5);
-                    const float vpx = U1 ? __ldg(U1 + (size_t)ly * p.UW + lx) : up_sample(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
-                    const float vpy = U2 ? __ldg(U2 + (size_t)ly * p.UW + lx) : up_sample(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
-                    score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
-                }
-            }
-            const unsigned ball = __ballot_sync(0xffffffffu, valid && score > p.paf_thresh);
-            const int criterion1 = __popc(ball & gmask);
-            float sum = 0.f; // sequential i = 0..9 accumulation order of paf.cpp:121-127
-#pragma unroll
-            for (int i = 0; i < STEP_PAF; ++i) {
-                const int srcl = min(grp * STEP_PAF + i, 31);
-                sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, score, srcl));
-            }
-            if (valid && smp == 0) {
-                double pen = 0.5 * (double)p.feat_height / (double)norm - 1.0; // paf.cpp:129
-                if (pen > 0.0) pen = 0.0;
-                const float criterion2 = (float)((double)__fdiv_rn(sum, (float)STEP_PAF) + pen);
-                if (criterion1 > THRESH_VECTOR_CNT1 && criterion2 > 0.f) {
-                    const int slot = atomicAdd(&sNcand, 1);
-                    const unsigned long long key = make_key(criterion2, ia, ib);
-                    if (slot < SM_CAND) sCand[slot] = key;
-                    else if (slot < p.ccap) cand[slot] = key;
-                }
-            }
-        }
-        __syncthreads();
-        if (dbg && tid == 0) dbg[2] = gtimer();
-        int ncand = sNcand;
-        if (ncand > p.ccap) {
-            if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
-            ncand = p.ccap;
-        }
-        // the common case keeps the whole list in shared memory; a longer one moves to the global scratch arrays
-        const bool in_smem = ncand <= SM_CAND;
-        if (!in_smem) {
-            for (int i = tid; i < SM_CAND; i += K3_THREADS) cand[i] = sCand[i];
-            __threadfence_block();
-            __syncthreads();
-        }
-        const unsigned long long* cin = in_smem ? sCand : cand;
-        unsigned long long* cout = in_smem ? sSorted : sorted;
-
-        // ---- (c) std::sort by score desc (paf.cpp:249-250): rank sort on unique keys
-        for (int i = tid; i < ncand; i += K3_THREADS) {
-            const unsigned long long k = cin[i];
-            int rank = 0;
-            for (int q = 0; q < ncand; ++q) rank += (cin[q] > k);
-            cout[rank] = k;
-        }
-        for (int i = tid; i < MAX_PCAP / 32; i += K3_THREADS) { sUsedA[i] = 0u; sUsedB[i] = 0u; }
-        __threadfence_block();
-        __syncthreads();
-
-        // greedy one-to-one selection in score order (paf.cpp:252-270)
-        if (tid == 0) {
-            hp_connection* conn = p.conn + ((size_t)frame * HP_N_PAIRS + limb) * p.pcap;
-            const int max_conn = min(na, nb);
-            int nconn = 0;
-            for (int i = 0; i < ncand && nconn < max_conn; ++i) {
-                const unsigned long long k = cout[i];
-                const unsigned inv = 0xffffffffu - (unsigned)(k & 0xffffffffu);
-                const int ia = (int)(inv >> 16), ib = (int)(inv & 0xffffu);
-                if ((sUsedA[ia >> 5] >> (ia & 31)) & 1u) continue;
-                if ((sUsedB[ib >> 5] >> (ib & 31)) & 1u) continue;
-                sUsedA[ia >> 5] |= 1u << (ia & 31);
-                sUsedB[ib >> 5] |= 1u << (ib & 31);
-                hp_connection c;
-                c.cid1 = base_a + ia; // peak ids == index in the ordered all_peaks list
-                c.cid2 = base_b + ib;
-                c.score = __uint_as_float((unsigned)(k >> 32));
-                conn[nconn++] = c;
-            }
-            *conn_cnt = nconn;
-        }
-    }
-
-    // ---- (d) the last CTA of the frame to arrive assembles the humans
-    if (dbg && tid == 0) dbg[3] = gtimer();
-    __threadfence();   // ordered peaks, connections and counts of this CTA: visible device-wide before the arrival is counted
-    __syncthreads();
-    if (tid == 0) sLast = (atomicAdd(p.frame_done + frame, 1) == HP_N_PAIRS - 1) ? 1 : 0;
-    __syncthreads();
-    if (!sLast) return;
-    __threadfence();
-    unsigned long long* dbg_a = p.dbg_t ? p.dbg_t + (size_t)gridDim.y * HP_N_PAIRS * 4 + (size_t)frame * 2 : nullptr;
-    if (dbg_a && tid == 0) dbg_a[0] = gtimer();
-
-    const int n_peaks = sBase[HP_N_PARTS];
     const int MAXR = p.max_refs;
-    int* rParts = reinterpret_cast<int*>(sDyn);                       // [18][MAXR] part-major: lane h reads parts[q][h] conflict-free
-    float* rScore = reinterpret_cast<float*>(rParts + HP_N_PARTS * MAXR);
-    int* rNparts = reinterpret_cast<int*>(rScore + MAXR);
-    hp_connection* sConn = reinterpret_cast<hp_connection*>(rNparts + MAXR);   // [SM_CONN]
-    float* sPsc = reinterpret_cast<float*>(sConn + SM_CONN);                   // [SM_PSC]
-    float2* sConnPs = reinterpret_cast<float2*>(sPsc + SM_PSC);                // [SM_CONN] peak scores of (cid1, cid2)
-    int* sCnt = reinterpret_cast<int*>(sUsedA);                                // [20] connection offsets (bitmaps are dead)
-    if (tid < 32) {   // connection counts of the 19 limbs (other CTAs wrote them: read past L1), exclusive prefix by shuffles
-        const int c = tid < HP_N_PAIRS ? __ldcg(p.conn_cnt + frame * HP_N_PAIRS + tid) : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += v;
-        }
-        if (tid <= HP_N_PAIRS) sCnt[tid] = incl - c;   // sCnt[19] = total (lane 19 holds c = 0)
-    }
-    __syncthreads();
-    const int n_conn = sCnt[HP_N_PAIRS];
-    const bool conn_staged = n_conn <= SM_CONN, psc_staged = n_peaks <= SM_PSC;
+    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
+    const int* px = p.px + peak_off;
+    const int* py = p.py + peak_off;
+    const float* pscore = p.pscore + peak_off;
     const hp_connection* gconn = p.conn + (size_t)frame * HP_N_PAIRS * p.pcap;
-    if (conn_staged)
-        for (int q = 0; q < HP_N_PAIRS; ++q)
-            for (int i = tid; i < sCnt[q + 1] - sCnt[q]; i += K3_THREADS) {
-                const hp_connection c = ld_conn_cg(gconn + (size_t)q * p.pcap + i);
-                sConn[sCnt[q] + i] = c;
-                sConnPs[sCnt[q] + i] = make_float2(__ldcg(pscore + c.cid1), __ldcg(pscore + c.cid2));
-            }
-    if (psc_staged)
-        for (int i = tid; i < n_peaks; i += K3_THREADS) sPsc[i] = __ldcg(pscore + i);   // other CTAs wrote these: read past L1
-    __syncthreads();
-    if (warp != 0) return;
-    const float* psc = psc_staged ? sPsc : pscore;   // (unstaged: > 2048 peaks in one frame; plain loads are fine for values no earlier read of this SM cached)
+    const float* psc = psc_in_smem ? sPsc : pscore;   // (unstaged: > 2048 peaks in one frame; plain loads are fine for values no earlier read of this SM cached)
 
     if (conn_staged) {   // fast path: partial humans in registers, two per lane
         RegHuman ha, hb;
@@ -897,7 +711,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
                             bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
                             if (id >= 0 && id < n_peaks) {   // ids fabricated by the `+=` merge quirk are reported absent (see below)
                                 bp.has_value = 1;
-                                bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
+                                bp.score = psc_in_smem ? psc[id] : __ldcg(pscore + id);
                                 bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
                                 bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
                             }
@@ -910,7 +724,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
                 no += __popc(bal);
             }
             if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
-            if (dbg_a && lane == 0) dbg_a[1] = gtimer();
+            if (dbg_a && lane == 0) dbg_a[1] = gtimer() & ~3ull;   // low bits 0: the register path ran
             return;
         }
     }
@@ -1001,7 +815,7 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
                     // reference; like the oracle, such parts are reported absent.
                     if (id != -1 && id >= 0 && id < n_peaks) {
                         bp.has_value = 1;
-                        bp.score = psc_staged ? psc[id] : __ldcg(pscore + id);
+                        bp.score = psc_in_smem ? psc[id] : __ldcg(pscore + id);
                         bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
                         bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
                     }
@@ -1014,14 +828,515 @@ __global__ void __launch_bounds__(K3_THREADS) paf_limbs_kernel(const LimbParams 
         no += __popc(bal);
     }
     if (lane == 0) p.human_cnt[frame] = min(no, p.hcap);
-    if (dbg_a && lane == 0) dbg_a[1] = gtimer() | 1ull;   // odd: the shared-memory path ran
+    if (dbg_a && lane == 0) dbg_a[1] = (gtimer() & ~3ull) | 1ull;   // low bits 1: the shared-memory path ran
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 3) paf_limbs_kernel(const LimbParams p)
+{
+    extern __shared__ __align__(16) unsigned char sDyn[];   // phase (b): the two PAF channels; phase (d): the assembly state
+    __shared__ int sNcand, sLast, sFast, sNComp, sNKeep;
+    __shared__ __align__(8) unsigned long long sBulkBar;
+    __shared__ int sBase[HP_N_PARTS + 1];
+    __shared__ unsigned sUsedA[MAX_PCAP / 32], sUsedB[MAX_PCAP / 32];
+    __shared__ unsigned long long sCand[SM_CAND], sSorted[SM_CAND];
+    __shared__ int sKeys[SM_KEYS];
+    // behind the staged PAF planes (phase b only; the assembly of phase d reuses the whole dynamic region):
+    int* sTabI = reinterpret_cast<int*>(sDyn + p.stage_bytes);     // [SM_TAB] xi[UW] then yi[UH]
+    float* sTabF = reinterpret_cast<float*>(sTabI + SM_TAB);       // [SM_TAB] xf[UW] then yf[UH]
+    int (*sPk)[SM_KEYS] = reinterpret_cast<int (*)[SM_KEYS]>(sTabF + SM_TAB);   // [2][SM_KEYS] ordered peaks of the limb's two parts, x | y << 16
+
+    const int limb = blockIdx.x, frame = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pa = c_pairs[limb][0], pb = c_pairs[limb][1];
+    const int* cnt = p.peak_cnt + frame * HP_N_PARTS;
+    unsigned long long* dbg = p.dbg_t ? p.dbg_t + ((size_t)frame * HP_N_PAIRS + limb) * 4 : nullptr;
+    if (dbg && tid == 0) dbg[0] = gtimer();
+    if (tid == 0) {
+        int bsum = 0;
+        for (int q = 0; q < HP_N_PARTS; ++q) { sBase[q] = bsum; bsum += min(cnt[q], p.pcap); }
+        sBase[HP_N_PARTS] = bsum;
+        sNcand = 0;
+    }
+    // the up-sampling tables of the line integrals: one coalesced pass instead of four dependent global loads per sample
+    const bool tab_staged = !p.up_paf && p.UW + p.UH <= SM_TAB;
+    if (tab_staged) {
+        for (int i = tid; i < p.UW + p.UH; i += K3_THREADS) {
+            const bool isx = i < p.UW;
+            sTabI[i] = isx ? __ldg(p.xi + i) : __ldg(p.yi + (i - p.UW));
+            sTabF[i] = isx ? __ldg(p.xf + i) : __ldg(p.yf + (i - p.UW));
+        }
+    }
+    __syncthreads();
+    if (limb == 0 && tid <= HP_N_PARTS) p.part_base[frame * (HP_N_PARTS + 1) + tid] = sBase[tid];
+    const size_t peak_off = (size_t)frame * HP_N_PARTS * p.pcap;
+    int* px = p.px + peak_off;
+    int* py = p.py + peak_off;
+    float* pscore = p.pscore + peak_off;
+
+    // ---- (a) order the peaks of this limb's two parts (post_process.hpp:175-192: ids follow the scan order)
+    const bool pk_staged = p.UW < 65536 && p.UH < 32768 && sBase[pa + 1] - sBase[pa] <= SM_KEYS && sBase[pb + 1] - sBase[pb] <= SM_KEYS;
+    for (int which = 0; which < 2; ++which) {
+        const int part = which ? pb : pa;
+        const int n = sBase[part + 1] - sBase[part];
+        const size_t raw = ((size_t)frame * HP_N_PARTS + part) * p.pcap;
+        const int* keys = p.raw_key + raw;
+        const bool staged = n <= SM_KEYS;
+        __syncthreads();   // sKeys of the previous part is dead
+        if (staged) {
+            for (int i = tid; i < n; i += K3_THREADS) sKeys[i] = keys[i];
+            __syncthreads();
+        }
+        const int out = sBase[part];
+        for (int i = tid; i < n; i += K3_THREADS) {
+            const int k = staged ? sKeys[i] : keys[i];
+            int rank = 0;
+            if (staged) { for (int q = 0; q < n; ++q) rank += (sKeys[q] < k); }   // keys are unique pixel positions
+            else        { for (int q = 0; q < n; ++q) rank += (keys[q] < k); }
+            const int x = k % p.UW, y = k / p.UW;
+            px[out + rank] = x;
+            py[out + rank] = y;
+            pscore[out + rank] = p.raw_score[raw + i];
+            if (pk_staged) sPk[which][rank] = x | (y << 16);
+        }
+    }
+    __syncthreads();   // this CTA's own global writes are visible to all of its threads from here on
+    if (dbg && tid == 0) dbg[1] = gtimer();
+
+    const int base_a = sBase[pa], na = sBase[pa + 1] - base_a;
+    const int base_b = sBase[pb], nb = sBase[pb + 1] - base_b;
+    int* conn_cnt = p.conn_cnt + frame * HP_N_PAIRS + limb;
+    const int H = p.H, W = p.W;
+    if (na == 0 || nb == 0) {
+        if (tid == 0) *conn_cnt = 0;
+    } else {
+        const float* P1 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * H * W;
+        const float* P2 = p.paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * H * W;
+        const int npairs = na * nb;
+        const float* U1 = nullptr; const float* U2 = nullptr;   // materialised up-maps of the two channels (shrinking resolutions)
+        if (p.up_paf) {
+            U1 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][0]) * p.UH * p.UW;
+            U2 = p.up_paf + ((size_t)frame * p.c_paf + c_pairs_net[limb][1]) * p.UH * p.UW;
+        }
+        // stage both channels when enough pairs will reuse them (one coalesced pass instead of scattered gathers)
+        if (!p.up_paf && npairs >= 6 && (int)(2 * H * W * sizeof(float)) <= p.stage_bytes) {
+            float* sPaf = reinterpret_cast<float*>(sDyn);
+            const unsigned plane_bytes = (unsigned)(H * W * sizeof(float));
+            if ((plane_bytes & 15u) == 0u && ((size_t)P1 & 15) == 0 && ((size_t)P2 & 15) == 0) {
+                // two bulk async copies (TMA, 1-D) issued by one thread instead of ~60 dependent load / store rounds per thread
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sBulkBar);
+                if (tid == 0) {
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * plane_bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf)), "l"(P1), "r"(plane_bytes), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((unsigned)__cvta_generic_to_shared(sPaf + H * W)), "l"(P2), "r"(plane_bytes), "r"(bar) : "memory");
+                }
+                __syncthreads();   // the barrier is initialised before anybody polls it
+                unsigned done;
+                do {
+                    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+                } while (!done);
+            } else {
+                for (int i = tid; i < H * W; i += K3_THREADS) {
+                    sPaf[i] = __ldg(P1 + i);
+                    sPaf[H * W + i] = __ldg(P2 + i);
+                }
+            }
+            P1 = sPaf;
+            P2 = sPaf + H * W;
+        }
+        __syncthreads();
+
+        unsigned long long* cand = p.cand + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+        unsigned long long* sorted = p.cand_sorted + ((size_t)frame * HP_N_PAIRS + limb) * p.ccap;
+
+        // ---- (b) get_connection_candidates: 3 peak pairs per warp pass, 10 lanes (= 10 samples) per pair
+        const int grp = lane / STEP_PAF, smp = lane - grp * STEP_PAF;
+        const unsigned gmask = (grp < 3) ? (0x3ffu << (grp * STEP_PAF)) : 0u;
+        constexpr int NW = K3_THREADS / 32;
+        for (int pb0 = warp * 3; pb0 < npairs; pb0 += NW * 3) { // warp-uniform trip count
+            const int pidx = pb0 + grp;
+            const bool active = (grp < 3) && (pidx < npairs);
+            int ia = 0, ib = 0;
+            float score = 0.f, norm = 1.f;
+            bool valid = false;
+            if (active) {
+                ia = pidx / nb;
+                ib = pidx - ia * nb;
+                int ax, ay, bx, by;
+                if (pk_staged) {
+                    const int ka = sPk[0][ia], kb = sPk[1][ib];
+                    ax = ka & 0xffff; ay = ka >> 16; bx = kb & 0xffff; by = kb >> 16;
+                } else {
+                    ax = px[base_a + ia]; ay = py[base_a + ia]; bx = px[base_b + ib]; by = py[base_b + ib];
+                }
+                const int dx = bx - ax, dy = by - ay;
+                norm = (float)sqrt((double)(dx * dx + dy * dy)); // paf.cpp:104
+                valid = !((double)norm < 1e-12);                   // paf.cpp:105
+                if (valid) {
+                    const float vx = __fdiv_rn((float)dx, norm), vy = __fdiv_rn((float)dy, norm);
+                    const float stepx = __fdiv_rn((float)dx, (float)STEP_PAF); // paf.cpp:77-78
+                    const float stepy = __fdiv_rn((float)dy, (float)STEP_PAF);
+                    const float fx = __fadd_rn((float)ax, __fmul_rn((float)smp, stepx));
+                    const float fy = __fadd_rn((float)ay, __fmul_rn((float)smp, stepy));
+                    const int lx = (int)((double)fx + 0.5); // roundpaf (paf.cpp:74): float + double literal
+                    const int ly = (int)((double)fy + 0.5);
+                    float vpx, vpy;
+                    if (U1) {
+                        vpx = __ldg(U1 + (size_t)ly * p.UW + lx);
+                        vpy = __ldg(U2 + (size_t)ly * p.UW + lx);
+                    } else if (tab_staged) {
+                        vpx = up_sample<true>(P1, W, H, lx, ly, sTabI, sTabF, sTabI + p.UW, sTabF + p.UW);
+                        vpy = up_sample<true>(P2, W, H, lx, ly, sTabI, sTabF, sTabI + p.UW, sTabF + p.UW);
+                    } else {
+                        vpx = up_sample<false>(P1, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                        vpy = up_sample<false>(P2, W, H, lx, ly, p.xi, p.xf, p.yi, p.yf);
+                    }
+                    score = __fadd_rn(__fmul_rn(vx, vpx), __fmul_rn(vy, vpy)); // paf.cpp:122
+                }
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, valid && score > p.paf_thresh);
+            const int criterion1 = __popc(ball & gmask);
+            float sum = 0.f; // sequential i = 0..9 accumulation order of paf.cpp:121-127
+#pragma unroll
+            for (int i = 0; i < STEP_PAF; ++i) {
+                const int srcl = min(grp * STEP_PAF + i, 31);
+                sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, score, srcl));
+            }
+            if (valid && smp == 0) {
+                double pen = 0.5 * (double)p.feat_height / (double)norm - 1.0; // paf.cpp:129
+                if (pen > 0.0) pen = 0.0;
+                const float criterion2 = (float)((double)__fdiv_rn(sum, (float)STEP_PAF) + pen);
+                if (criterion1 > THRESH_VECTOR_CNT1 && criterion2 > 0.f) {
+                    const int slot = atomicAdd(&sNcand, 1);
+                    const unsigned long long key = make_key(criterion2, ia, ib);
+                    if (slot < SM_CAND) sCand[slot] = key;
+                    else if (slot < p.ccap) cand[slot] = key;
+                }
+            }
+        }
+        __syncthreads();
+        if (dbg && tid == 0) dbg[2] = gtimer();
+        int ncand = sNcand;
+        if (ncand > p.ccap) {
+            if (tid == 0) atomicOr(p.flags + frame, FLAG_CAND_OVERFLOW);
+            ncand = p.ccap;
+        }
+        // the common case keeps the whole list in shared memory; a longer one moves to the global scratch arrays
+        const bool in_smem = ncand <= SM_CAND;
+        if (!in_smem) {
+            for (int i = tid; i < SM_CAND; i += K3_THREADS) cand[i] = sCand[i];
+            __threadfence_block();
+            __syncthreads();
+        }
+        const unsigned long long* cin = in_smem ? sCand : cand;
+        unsigned long long* cout = in_smem ? sSorted : sorted;
+
+        // ---- (c) std::sort by score desc (paf.cpp:249-250): rank sort on unique keys
+        for (int i = tid; i < ncand; i += K3_THREADS) {
+            const unsigned long long k = cin[i];
+            int rank = 0;
+            for (int q = 0; q < ncand; ++q) rank += (cin[q] > k);
+            cout[rank] = k;
+        }
+        for (int i = tid; i < MAX_PCAP / 32; i += K3_THREADS) { sUsedA[i] = 0u; sUsedB[i] = 0u; }
+        __threadfence_block();
+        __syncthreads();
+
+        // greedy one-to-one selection in score order (paf.cpp:252-270)
+        if (tid == 0) {
+            hp_connection* conn = p.conn + ((size_t)frame * HP_N_PAIRS + limb) * p.pcap;
+            const int max_conn = min(na, nb);
+            int nconn = 0;
+            for (int i = 0; i < ncand && nconn < max_conn; ++i) {
+                const unsigned long long k = cout[i];
+                const unsigned inv = 0xffffffffu - (unsigned)(k & 0xffffffffu);
+                const int ia = (int)(inv >> 16), ib = (int)(inv & 0xffffu);
+                if ((sUsedA[ia >> 5] >> (ia & 31)) & 1u) continue;
+                if ((sUsedB[ib >> 5] >> (ib & 31)) & 1u) continue;
+                sUsedA[ia >> 5] |= 1u << (ia & 31);
+                sUsedB[ib >> 5] |= 1u << (ib & 31);
+                hp_connection c;
+                c.cid1 = base_a + ia; // peak ids == index in the ordered all_peaks list
+                c.cid2 = base_b + ib;
+                c.score = __uint_as_float((unsigned)(k >> 32));
+                conn[nconn++] = c;
+            }
+            *conn_cnt = nconn;
+        }
+    }
+
+    // ---- (d) the last CTA of the frame to arrive assembles the humans
+    if (dbg && tid == 0) dbg[3] = gtimer();
+    __threadfence();   // ordered peaks, connections and counts of this CTA: visible device-wide before the arrival is counted
+    __syncthreads();
+    if (tid == 0) sLast = (atomicAdd(p.frame_done + frame, 1) == HP_N_PAIRS - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    unsigned long long* dbg_a = p.dbg_t ? p.dbg_t + (size_t)gridDim.y * HP_N_PAIRS * 4 + (size_t)frame * 6 : nullptr;
+    if (dbg_a && tid == 0) dbg_a[0] = gtimer();
+
+    const int n_peaks = sBase[HP_N_PARTS];
+    const int MAXR = p.max_refs;
+    // dynamic shared memory of the assembly: [connections | their peak scores | all peak scores | UNION { component-parallel state ;
+    // partial humans of the sequential shared-memory path }]
+    hp_connection* sConn = reinterpret_cast<hp_connection*>(sDyn);             // [SM_CONN]
+    float2* sConnPs = reinterpret_cast<float2*>(sConn + SM_CONN);              // [SM_CONN] peak scores of (cid1, cid2)
+    int* uni = reinterpret_cast<int*>(sConnPs + SM_CONN);
+    float* sPsc = reinterpret_cast<float*>(uni);                               // [SM_PSC] (sequential paths only)
+    int* rParts = uni + SM_PSC;                                       // [18][MAXR] part-major: lane h reads parts[q][h] conflict-free
+    float* rScore = reinterpret_cast<float*>(rParts + HP_N_PARTS * MAXR);
+    int* rNparts = reinterpret_cast<int*>(rScore + MAXR);
+    int* sLabel = uni;                                                         // [SM_PSC] component labels of the peaks
+    int* sCompCnt = sLabel + SM_PSC;                                           // [ASM_CMAX] fill pointers
+    int* sCompOff = sCompCnt + ASM_CMAX;                                       // [ASM_CMAX + 1]
+    int* sKeep = sCompOff + ASM_CMAX + 1;                                      // [ASM_CMAX * ASM_SLOTS] keys of the surviving humans
+    int* sSlotI = sKeep + ASM_CMAX * ASM_SLOTS;                                // [ASM_WARPS][ASM_SLOTS][ASM_IFIELDS][32]
+    short* sSlotP = reinterpret_cast<short*>(sSlotI + ASM_WARPS * ASM_SLOTS * ASM_IFIELDS * 32);   // [ASM_WARPS][ASM_SLOTS][18][32] part ids, -1 = absent
+    unsigned short* sList = reinterpret_cast<unsigned short*>(sSlotP + ASM_WARPS * ASM_SLOTS * HP_N_PARTS * 32);   // [SM_CONN] connections grouped by component
+    unsigned short* sConnPair = sList + SM_CONN;                               // [SM_CONN] part1 | part2 << 5 | pair << 10
+    unsigned char* sConnComp = reinterpret_cast<unsigned char*>(sConnPair + SM_CONN);   // [SM_CONN] component of the connection
+    int* sCnt = reinterpret_cast<int*>(sUsedA);                                // [20] connection offsets (bitmaps are dead)
+    if (tid < 32) {   // connection counts of the 19 limbs (other CTAs wrote them: read past L1), exclusive prefix by shuffles
+        const int c = tid < HP_N_PAIRS ? __ldcg(p.conn_cnt + frame * HP_N_PAIRS + tid) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += v;
+        }
+        if (tid <= HP_N_PAIRS) sCnt[tid] = incl - c;   // sCnt[19] = total (lane 19 holds c = 0)
+    }
+    __syncthreads();
+    const int n_conn = sCnt[HP_N_PAIRS];
+    const bool conn_staged = n_conn <= SM_CONN, psc_staged = n_peaks <= SM_PSC;
+    const hp_connection* gconn = p.conn + (size_t)frame * HP_N_PAIRS * p.pcap;
+    const bool fast_try = p.fast_asm && conn_staged && psc_staged;
+    if (conn_staged)   // one connection per thread and round: the loads of all limbs are in flight together (two dependent L2 latencies in total)
+        for (int i = tid; i < n_conn; i += K3_THREADS) {
+            int q = 0;
+            while (sCnt[q + 1] <= i) ++q;
+            const hp_connection c = ld_conn_cg(gconn + (size_t)q * p.pcap + (i - sCnt[q]));
+            sConn[i] = c;
+            sConnPs[i] = make_float2(__ldcg(pscore + c.cid1), __ldcg(pscore + c.cid2));
+            if (fast_try) sConnPair[i] = (unsigned short)(c_pairs[q][0] | (c_pairs[q][1] << 5) | (q << 10));
+        }
+    const bool psc_in_smem = psc_staged && !fast_try;   // (the component-parallel state lives where sPsc would)
+    if (psc_in_smem)
+        for (int i = tid; i < n_peaks; i += K3_THREADS) sPsc[i] = __ldcg(pscore + i);   // other CTAs wrote these: read past L1
+
+    // ---- component-parallel get_humans.  The reference walks the connections strictly in order, but a connection can only
+    // "touch" (paf.cpp:33-36) a partial human that already holds one of its two peaks, so partial humans of different CONNECTED
+    // COMPONENTS of the (peaks, connections) graph never interact: each component is replayed sequentially by ONE LANE, all
+    // components at once, and the survivors are put back into the reference's vector order afterwards -- a human's position in
+    // the vector follows its creation (erase keeps the relative order, a merge keeps the earlier human, paf.cpp:191-205), so the
+    // order is the ascending index of the creating connection.  The one cross-component effect of the reference is the id
+    // FABRICATED by `parts[i] += other.parts[i] + 1` when both humans hold a part and one of the ids is 0 (the `id > 0` quirk,
+    // paf.cpp:185): such a frame -- like one with more components / partial humans than fit -- is redone by the sequential paths below.
+    if (fast_try) {
+        if (tid == 0) { sFast = 1; sNComp = 0; sNKeep = 0; }
+        for (int i = tid; i < n_peaks; i += K3_THREADS) sLabel[i] = i | 0x40000000;   // not an end point of any connection
+        for (int i = tid; i < ASM_CMAX; i += K3_THREADS) sCompCnt[i] = 0;
+        for (int i = tid; i < ASM_WARPS * ASM_SLOTS * (ASM_IFIELDS + HP_N_PARTS / 2) * 32; i += K3_THREADS) sSlotI[i] = -1;   // every part of every slot absent, n_parts < 0 (the 16-bit part array follows the words)
+        __syncthreads();
+        if (dbg_a && tid == 0) dbg_a[2] = gtimer();
+        for (int i = tid; i < n_conn; i += K3_THREADS) { const hp_connection c = sConn[i]; sLabel[c.cid1] = c.cid1; sLabel[c.cid2] = c.cid2; }
+        __syncthreads();
+        while (true) {   // min-label propagation with one pointer jump per visit; labels are always end points of the same component
+            int changed = 0;
+            for (int i = tid; i < n_conn; i += K3_THREADS) {
+                const hp_connection c = sConn[i];
+                int a = sLabel[c.cid1], b = sLabel[c.cid2];
+                a = min(a, sLabel[a]); b = min(b, sLabel[b]);
+                const int m = min(a, b);
+                if (sLabel[c.cid1] > m) { atomicMin(&sLabel[c.cid1], m); changed = 1; }
+                if (sLabel[c.cid2] > m) { atomicMin(&sLabel[c.cid2], m); changed = 1; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        // fixed point: one label L per component with sLabel[L] == L; number the components (any order: the output order is restored below)
+        for (int i = tid; i < n_peaks; i += K3_THREADS)
+            if (sLabel[i] == i) sLabel[i] = -(atomicAdd(&sNComp, 1) + 1);
+        __syncthreads();
+        const int n_comp = sNComp;
+        if (dbg_a && tid == 0) dbg_a[3] = gtimer();
+        if (n_comp <= ASM_CMAX) {
+            for (int i = tid; i < n_conn; i += K3_THREADS) {
+                int l = sLabel[sConn[i].cid1];
+                if (l >= 0) l = sLabel[l];
+                const int cc = -l - 1;
+                sConnComp[i] = (unsigned char)cc;
+                atomicAdd(&sCompCnt[cc], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // exclusive scan of the component sizes (ASM_CMAX = 32 * ASM_WARPS values, ASM_WARPS per lane)
+                int v[ASM_WARPS], tot = 0;
+#pragma unroll
+                for (int k = 0; k < ASM_WARPS; ++k) { v[k] = sCompCnt[lane * ASM_WARPS + k]; tot += v[k]; }
+                int incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                int run = incl - tot;
+#pragma unroll
+                for (int k = 0; k < ASM_WARPS; ++k) { sCompOff[lane * ASM_WARPS + k] = run; sCompCnt[lane * ASM_WARPS + k] = run; run += v[k]; }
+                if (lane == 31) sCompOff[ASM_CMAX] = run;
+                __syncwarp();
+                // stable grouping: the connections of a component keep their global order
+                for (int base = 0; base < n_conn; base += 32) {
+                    const int i = base + lane;
+                    const unsigned cc = i < n_conn ? (unsigned)sConnComp[i] : 0xffffu;
+                    const unsigned peers = __match_any_sync(0xffffffffu, cc);
+                    const int rank = __popc(peers & ((1u << lane) - 1u));
+                    const int pos = cc != 0xffffu ? sCompCnt[cc] + rank : 0;
+                    __syncwarp();
+                    if (cc != 0xffffu && rank == 0) sCompCnt[cc] += __popc(peers);
+                    __syncwarp();
+                    if (cc != 0xffffu) sList[pos] = (unsigned short)i;
+                }
+            }
+            __syncthreads();
+            if (dbg_a && tid == 0) dbg_a[4] = gtimer();
+            if (warp < ASM_WARPS) {
+                const int ci = warp * 32 + lane;
+                int* S = sSlotI + warp * ASM_SLOTS * ASM_IFIELDS * 32 + lane;   // lane-private columns: the bank follows the lane, never a conflict
+                short* Q = sSlotP + warp * ASM_SLOTS * HP_N_PARTS * 32 + lane;
+#define HP_SI(slot, f) S[((slot) * ASM_IFIELDS + (f)) * 32]
+#define HP_SP(slot, f) Q[((slot) * HP_N_PARTS + (f)) * 32]
+                constexpr int F_SCORE = 0, F_NP = 1, F_MADE = 2;
+                bool ok = true;
+                int ns = 0;   // partial humans ever created in this component (slots are never reused: a merged-away human is marked dead)
+                if (ci < n_comp) {
+                    const int beg = sCompOff[ci], end = sCompOff[ci + 1];
+                    int gi_next = sList[beg];   // (a component has at least one connection)
+                    for (int k = beg; k < end; ++k) {
+                        const int gi = gi_next;
+                        if (k + 1 < end) gi_next = sList[k + 1];
+                        const hp_connection cn = sConn[gi];
+                        const float2 ps = sConnPs[gi];
+                        const int code = sConnPair[gi];
+                        const int P1 = code & 31, P2 = (code >> 5) & 31, pair_id = code >> 10;
+                        // one batch of independent loads for every slot created so far (one shared-memory latency, not one per slot)
+                        int vn[ASM_SLOTS], v1[ASM_SLOTS], v2[ASM_SLOTS];
+#pragma unroll
+                        for (int sl = 0; sl < ASM_SLOTS; ++sl) {
+                            vn[sl] = -1; v1[sl] = -2; v2[sl] = -2;
+                            if (sl < ns) { vn[sl] = HP_SI(sl, F_NP); v1[sl] = HP_SP(sl, P1); v2[sl] = HP_SP(sl, P2); }
+                        }
+                        int t0 = -1, t1 = -1, np0 = 0, p2_0 = -2;   // first two touching humans in vector order (paf.cpp:33-36,160-170)
+#pragma unroll
+                        for (int sl = ASM_SLOTS - 1; sl >= 0; --sl)
+                            if (vn[sl] >= 0 && (v1[sl] == cn.cid1 || v2[sl] == cn.cid2)) { t1 = t0; t0 = sl; np0 = vn[sl]; p2_0 = v2[sl]; }
+                        if (t0 < 0) {
+                            if (pair_id <= 16) {   // !is_virtual_pair (coco.hpp:6, paf.cpp:211-220)
+                                if (ns >= ASM_SLOTS) { ok = false; break; }
+                                HP_SP(ns, P1) = (short)cn.cid1; HP_SP(ns, P2) = (short)cn.cid2;   // (the other parts were preset to -1)
+                                HP_SI(ns, F_NP) = 2;
+                                HP_SI(ns, F_SCORE) = __float_as_int(__fadd_rn(__fadd_rn(ps.x, ps.y), cn.score));
+                                HP_SI(ns, F_MADE) = gi;
+                                ++ns;
+                            }
+                        } else if (t1 < 0) {   // paf.cpp:172-178
+                            if (p2_0 != cn.cid2) {
+                                HP_SP(t0, P2) = (short)cn.cid2;
+                                HP_SI(t0, F_NP) = np0 + 1;
+                                HP_SI(t0, F_SCORE) = __float_as_int(__fadd_rn(__int_as_float(HP_SI(t0, F_SCORE)), __fadd_rn(ps.y, cn.score)));
+                            }
+                        } else {               // paf.cpp:179-210
+                            bool shared_part = false, fabricates = false;
+                            int a[HP_N_PARTS], b[HP_N_PARTS];
+#pragma unroll
+                            for (int f = 0; f < HP_N_PARTS; ++f) { a[f] = HP_SP(t0, f); b[f] = HP_SP(t1, f); }
+#pragma unroll
+                            for (int f = 0; f < HP_N_PARTS; ++f) {
+                                shared_part |= (a[f] > 0 && b[f] > 0);   // `id > 0` quirk (paf.cpp:185)
+                                fabricates |= (a[f] >= 0 && b[f] >= 0);
+                            }
+                            if (!shared_part) {
+                                if (fabricates) { ok = false; break; }   // the merge would invent a peak id: sequential paths
+#pragma unroll
+                                for (int f = 0; f < HP_N_PARTS; ++f) HP_SP(t0, f) = (short)(a[f] + b[f] + 1);   // paf.cpp:193
+                                HP_SI(t0, F_NP) = np0 + HP_SI(t1, F_NP);
+                                HP_SI(t0, F_SCORE) = __float_as_int(__fadd_rn(__fadd_rn(__int_as_float(HP_SI(t0, F_SCORE)), __int_as_float(HP_SI(t1, F_SCORE))), cn.score));
+                                HP_SI(t1, F_NP) = -1;   // vector::erase (paf.cpp:201-205)
+                            } else {
+                                HP_SP(t0, P2) = (short)cn.cid2;
+                                HP_SI(t0, F_NP) = np0 + 1;
+                                HP_SI(t0, F_SCORE) = __float_as_int(__fadd_rn(__int_as_float(HP_SI(t0, F_SCORE)), __fadd_rn(ps.y, cn.score)));
+                            }
+                        }
+                    }
+                    if (ok) {   // filter (paf.cpp:226-230)
+                        for (int sl = 0; sl < ns; ++sl) {
+                            const int np = HP_SI(sl, F_NP);
+                            if (np < 0 || np < THRESH_PART_CNT || __fdiv_rn(__int_as_float(HP_SI(sl, F_SCORE)), (float)np) < 0.4f) continue;
+                            sKeep[atomicAdd(&sNKeep, 1)] = (HP_SI(sl, F_MADE) << 9) | (ci << 3) | sl;
+                        }
+                    }
+                }
+                if (!ok) sFast = 0;
+#undef HP_SI
+#undef HP_SP
+            }
+            __syncthreads();
+            if (dbg_a && tid == 0) dbg_a[5] = gtimer();
+            if (sFast) {
+                // conversion (paf.cpp:359-372) in vector order: one warp per surviving human, one lane per part
+                const int nk = sNKeep;
+                for (int h = warp; h < nk; h += K3_THREADS / 32) {
+                    const int key = sKeep[h];
+                    int rank = 0;
+                    for (int q = lane; q < nk; q += 32) rank += (sKeep[q] < key);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+                    if (rank >= p.hcap) { if (lane == 0) atomicOr(p.flags + frame, FLAG_HUMAN_OVERFLOW); continue; }
+                    const int ci = (key >> 3) & (ASM_CMAX - 1), sl = key & 7;
+                    const int* Sx = sSlotI + ((ci >> 5) * ASM_SLOTS + sl) * ASM_IFIELDS * 32 + (ci & 31);
+                    const short* Qx = sSlotP + ((ci >> 5) * ASM_SLOTS + sl) * HP_N_PARTS * 32 + (ci & 31);
+                    hp_human* o = p.humans + (size_t)frame * p.hcap + rank;
+                    if (lane < HP_N_PARTS) {
+                        const int id = Qx[lane * 32];
+                        hp_body_part bp;
+                        bp.has_value = 0; bp.x = 0.f; bp.y = 0.f; bp.score = 0.f;
+                        if (id >= 0 && id < n_peaks) {
+                            bp.has_value = 1;
+                            bp.score = __ldcg(pscore + id);
+                            bp.x = __fdiv_rn((float)__ldcg(px + id), (float)p.UW);
+                            bp.y = __fdiv_rn((float)__ldcg(py + id), (float)p.UH);
+                        }
+                        o->parts[lane] = bp;
+                    } else if (lane == HP_N_PARTS) {
+                        o->score = __int_as_float(Sx[0]);
+                    }
+                }
+                if (tid == 0) p.human_cnt[frame] = min(nk, p.hcap);
+                if (dbg_a && tid == 0) dbg_a[1] = (gtimer() & ~3ull) | 2ull;   // low bits 2: the component-parallel path ran
+                return;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    assemble_sequential(p, frame, lane, conn_staged, psc_in_smem, n_peaks, sCnt, sConn, sConnPs, sPsc, rParts, rScore, rNparts, dbg_a);
 }
 
 // bytes of dynamic shared memory the assembly phase of paf_limbs_kernel needs for `max_refs` partial humans
-constexpr size_t assemble_smem_bytes(int max_refs)
+constexpr size_t ASM_COMMON_BYTES = (size_t)SM_CONN * sizeof(hp_connection) + (size_t)SM_CONN * sizeof(float2);
+// the component-parallel state; it shares the union region with the peak scores + partial humans of the sequential paths
+constexpr size_t ASM_FAST_BYTES = ((size_t)SM_PSC + ASM_CMAX + ASM_CMAX + 1 + ASM_CMAX * ASM_SLOTS + ASM_WARPS * ASM_SLOTS * (ASM_IFIELDS + HP_N_PARTS / 2) * 32) * 4
+                                  + (size_t)SM_CONN * 2 * 2 + SM_CONN + 16;
+constexpr size_t assemble_smem_bytes(int max_refs, bool fast)
 {
-    return (size_t)max_refs * (HP_N_PARTS + 2) * 4 + (size_t)SM_CONN * sizeof(hp_connection) + (size_t)SM_PSC * 4 + (size_t)SM_CONN * sizeof(float2);
+    return ASM_COMMON_BYTES + std::max((size_t)SM_PSC * 4 + (size_t)max_refs * (HP_N_PARTS + 2) * 4, fast ? ASM_FAST_BYTES : (size_t)0);
 }
+// phase (b) keeps the up-sampling tables and the packed peaks of the limb behind the staged PAF planes
+constexpr size_t LIMB_PHASE_B_EXTRA = (size_t)SM_TAB * 8 + (size_t)2 * SM_KEYS * 4;
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -1292,7 +1607,7 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k1.peak_cnt = p->peak_cnt(); k1.raw_key = p->raw_key.p; k1.raw_score = p->raw_score.p; k1.flags = p->flags();
     k1.n8 = UW & ~7;
     k1.n4 = (UW - k1.n8 >= 4) ? k1.n8 + 4 : k1.n8;
-    dim3 g1(k1.tiles_x * k1.tiles_y, HP_N_PARTS, N);
+    dim3 g1(k1.tiles_x, k1.tiles_y * HP_N_PARTS, N);
     k1.up = nullptr;
     if (p->generic) {   // resolutions that shrink an axis: materialise cv::resize(INTER_AREA) of every channel, then run from the maps
         ResizeParams rz;
@@ -1324,12 +1639,13 @@ int launch_pipeline(hp_paf* p, const float* d_conf, const float* d_paf, int N, c
     k3.up_paf = p->generic ? p->up_paf.p : nullptr;
     k3.dbg_t = nullptr;
     if (getenv("HPB_PAF_TIMING")) {
-        HP_CUDA_TRY(p->dbg_t.ensure((size_t)p->cap_N * (HP_N_PAIRS * 4 + 2)));
+        HP_CUDA_TRY(p->dbg_t.ensure((size_t)p->cap_N * (HP_N_PAIRS * 4 + 6)));
         k3.dbg_t = p->dbg_t.p;
     }
     const int want = 2 * p->H * p->W * (int)sizeof(float);
-    k3.stage_bytes = (want <= p->limb_dyn_bytes) ? want : 0;
-    const size_t dyn = std::max((size_t)k3.stage_bytes, assemble_smem_bytes(p->max_refs));
+    k3.stage_bytes = (want + (int)LIMB_PHASE_B_EXTRA <= p->limb_dyn_bytes) ? want : 0;
+    k3.fast_asm = (ASM_COMMON_BYTES + ASM_FAST_BYTES <= (size_t)p->limb_dyn_bytes && !getenv("HPB_PAF_SEQ_ASSEMBLY")) ? 1 : 0;
+    const size_t dyn = std::max((size_t)k3.stage_bytes + LIMB_PHASE_B_EXTRA, assemble_smem_bytes(p->max_refs, k3.fast_asm != 0));
     paf_limbs_kernel<<<dim3(HP_N_PAIRS, N), K3_THREADS, dyn, st>>>(k3);
     HP_CUDA_TRY(cudaGetLastError());
     p->launches += 2;
@@ -1473,7 +1789,7 @@ int hp_paf_create(hp_paf** out, float conf_thresh, float paf_thresh, int res_w, 
         cudaGetLastError();
         p->limb_dyn_bytes = 48 * 1024 - (int)static_smem;
     }
-    p->assemble_max_refs = (int)((p->limb_dyn_bytes - (SM_CONN * sizeof(hp_connection) + SM_PSC * 4 + SM_CONN * sizeof(float2))) / ((HP_N_PARTS + 2) * 4));
+    p->assemble_max_refs = (int)((p->limb_dyn_bytes - (ASM_COMMON_BYTES + SM_PSC * 4)) / ((HP_N_PARTS + 2) * 4));
     if (p->max_refs > p->assemble_max_refs) p->max_refs = p->assemble_max_refs;
     *out = p;
     return HP_OK;
@@ -1648,7 +1964,7 @@ int hp_paf_debug_timing(hp_paf* p, unsigned long long* out, int N)
     if (!p || !out || N != p->last_N || !p->dbg_t.p) { hpb::set_error("hp_paf_debug_timing: no timing data (set HPB_PAF_TIMING=1)"); return HP_ERR_ARG; }
     HP_CUDA_TRY(cudaSetDevice(p->device));
     HP_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
-    HP_CUDA_TRY(cudaMemcpy(out, p->dbg_t.p, (size_t)N * (HP_N_PAIRS * 4 + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    HP_CUDA_TRY(cudaMemcpy(out, p->dbg_t.p, (size_t)N * (HP_N_PAIRS * 4 + 6) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return HP_OK;
 }
 

@@ -677,6 +677,7 @@ struct hp_pifpaf {
     std::vector<hp_human> host_h; std::vector<int> host_c;
     long long launches = 0;
     int last_N = 0;
+    cudaEvent_t inputs_free = nullptr;   // recorded behind the last kernel that reads the field tensors (the greedy growth reads the decoder's own lists)
 };
 
 extern "C" {
@@ -702,6 +703,7 @@ void hp_pifpaf_destroy(hp_pifpaf* p)
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    if (p->inputs_free) cudaEventDestroy(p->inputs_free);
     p->hr.release(); p->lists.release(); p->in_pif.release(); p->in_paf.release(); p->seeds_raw.release(); p->seeds.release();
     p->counters.release(); p->occ_grow.release(); p->occ_nms.release(); p->anns.release(); p->humans.release();
     delete p;
@@ -736,6 +738,8 @@ int hp_pifpaf_process_device(hp_pifpaf* p, const float* d_pif, const float* d_pa
     pif_seeds_kernel<<<N, 256, 0, st>>>(d_pif, p->hr.p, g, p->seeds_raw.p, seed_cnt, p->seed_cap, flags);
     pif_seed_sort_kernel<<<dim3((p->seed_cap + 255) / 256, N), 256, 0, st>>>(p->seeds_raw.p, p->seeds.p, seed_cnt, p->seed_cap);
     caf_filter_kernel<<<dim3(NBONE, N), 256, 0, st>>>(d_paf, p->hr.p, g, p->lists.p, list_cnt);
+    if (!p->inputs_free) HP_CUDA_TRY(cudaEventCreateWithFlags(&p->inputs_free, cudaEventDisableTiming));
+    HP_CUDA_TRY(cudaEventRecord(p->inputs_free, st));   // d_pif / d_paf may be overwritten from here on (pipelined callers wait for this, not for the growth)
     GrowParams gp;
     gp.g = g; gp.seeds = p->seeds.p; gp.seed_cnt = seed_cnt; gp.seed_cap = p->seed_cap; gp.lists = p->lists.p; gp.list_cnt = list_cnt;
     gp.occ_grow = p->occ_grow.p; gp.occ_nms = p->occ_nms.p; gp.nms_h = nms_h; gp.nms_w = nms_w; gp.anns = p->anns.p; gp.ann_cap = p->ann_cap;
@@ -841,6 +845,40 @@ int hp_pifpaf_process_host(hp_pifpaf* p, const float* pif, const float* paf, int
 }
 
 long long hp_pifpaf_launch_count(const hp_pifpaf* p) { return p ? p->launches : 0; }
+
+// ---- building blocks of the pipelined end-to-end call (engine.cu: hp_pose_submit_pifpaf_u8_host / hp_pose_collect) ----
+// the decoder's own stream, the event recorded once the field tensors of the last hp_pifpaf_process_device call have been consumed
+// (NULL before the first call), and the per-frame human capacity of the result buffer
+int hp_pifpaf_pipeline_info(hp_pifpaf* p, void** stream, void** inputs_free_event, int* hcap)
+{
+    if (!p) return HP_ERR_ARG;
+    if (stream) *stream = (void*)p->stream;
+    if (inputs_free_event) *inputs_free_event = (void*)p->inputs_free;
+    if (hcap) *hcap = p->hcap;
+    return HP_OK;
+}
+// Enqueues the D2H of the last batch's records on `stream`: humans[N * hcap] and counts_flags[2N] (counts, then overflow flags)
+// into caller-owned PINNED host memory; no synchronisation.
+int hp_pifpaf_copy_results_host_async(hp_pifpaf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream)
+{
+    if (!p || !pin_humans || !pin_counts_flags || N != p->last_N) { hpb::set_error("hp_pifpaf_copy_results_host_async: bad argument"); return HP_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : p->stream;
+    const int* human_cnt = p->counters.p + N + (size_t)N * NBONE * 2;   // [N counts | N flags] are adjacent
+    HP_CUDA_TRY(cudaMemcpyAsync(pin_counts_flags, human_cnt, sizeof(int) * 2 * N, cudaMemcpyDeviceToHost, st));
+    HP_CUDA_TRY(cudaMemcpyAsync(pin_humans, p->humans.p, sizeof(hp_human) * (size_t)N * p->hcap, cudaMemcpyDeviceToHost, st));
+    return HP_OK;
+}
+// After a batch whose flags (OR over its frames) report an overflow: grow those capacities like hp_pifpaf_process_host does.
+int hp_pifpaf_grow_capacity(hp_pifpaf* p, int flags)
+{
+    if (!p) return HP_ERR_ARG;
+    if (!(flags & (1 | 2 | 8))) return HP_ERR_CAPACITY;   // the fixed NMS map
+    if (flags & 1) p->seed_cap *= 4;
+    if (flags & 2) p->ann_cap *= 4;
+    if (flags & 8) p->hcap *= 4;
+    if (p->seed_cap > (1 << 20) || p->ann_cap > (1 << 18) || p->hcap > (1 << 16)) return HP_ERR_CAPACITY;
+    return HP_OK;
+}
 
 // test hook: the high-resolution core map of (frame, field) of the last call, HR x WR floats
 int hp_pifpaf_debug_hr(hp_pifpaf* p, int frame, int field, float* out)

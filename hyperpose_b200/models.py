@@ -232,37 +232,68 @@ def _r64(c: int) -> int:
     return (c + 63) // 64 * 64
 
 
-def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6) -> Graph:
+def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6, weights=None) -> Graph:
     """OpenPose on MobilenetThin (BASELINE.json config 2): hyperpose/Model/backbones.py:240-297 (3x3/2 stem + 11
     depthwise-separable blocks, three scales concatenated to 1152 channels at stride 8) and
     hyperpose/Model/openpose/model/mbv2_th_openpose.py:106-158 (init + 5 refinement stages of separable blocks).
-    Inference-time BatchNorm is folded (random statistics): depthwise conv + BN + ReLU -> one OP_DWCONV;
-    1x1 conv + BN (+ReLU) -> one OP_CONV.  The stem is Conv(act=relu) followed by BatchNorm(act=relu)
-    (mbv2_th_openpose.py:160-166), which cannot be folded through the inner ReLU: conv(+bias, ReLU) then a 1x1
-    depthwise affine + ReLU.  Both branches of a stage run together (grouped 1x1 convs, block-diagonal output conv)."""
+    Inference-time BatchNorm is folded: depthwise conv + BN (+ReLU) -> one OP_DWCONV; 1x1 conv + BN (+ReLU) -> one OP_CONV.
+    The stem is Conv(act=relu) followed by BatchNorm(act=relu) (mbv2_th_openpose.py:160-166), which cannot be folded through
+    the inner ReLU: conv(+bias, ReLU) then a 1x1 depthwise affine + ReLU.  The last separable block of a stage is built with
+    act=None (:121,:127,:144,:151): BOTH of its BatchNorms are linear.  Both branches of a stage run together (grouped 1x1
+    convs, block-diagonal output conv).
+    `weights`: a hyperpose_b200.weights.MobilenetThinWeights (trained TensorLayer model); default = seeded random values."""
     rng = np.random.default_rng(seed)
+    ws = weights
     g = Graph("mobilenet_thin_openpose", 19, 38, 3, mean=(0.0, 0.0, 0.0))
     relu = lambda n: np.zeros(n, np.float32)
     lin = lambda n: np.ones(n, np.float32)
 
-    def dw(in_buf, out_buf, C, K, stride=1, in_off=0, out_off=0, name="dw"):
-        w = (rng.standard_normal((C, K, K)) * np.sqrt(2.0 / (K * K))).astype(np.float32)
-        sc, sh = _bn_fold(rng, C)
-        g.add_dwconv(in_buf, out_buf, w * sc[:, None, None], sh, relu(C), stride=stride, in_ch_off=in_off, out_ch_off=out_off, name=name)
+    # every tensor comes from `ws` by name when a trained model is imported, else from the seeded generator (same draw order as ever)
+    def dw_w(name, C, K):
+        return ws.dwconv(name, C, K) if ws else (rng.standard_normal((C, K, K)) * np.sqrt(2.0 / (K * K))).astype(np.float32)
 
-    def pw(in_buf, out_buf, groups, cin_g, cout_g, act=True, out_off=0, cin_real=None, name="pw", **kw):
-        w = _he(rng, groups, cout_g, cin_g, 1, 1, 2.0 if act else 1.0)
-        if cin_real is not None:
-            w[:, :, cin_real:] = 0
-        sc, sh = _bn_fold(rng, groups * cout_g)
+    def bn(name, C):
+        return ws.bn(name, C) if ws else _bn_fold(rng, C)
+
+    def dw(in_buf, out_buf, C, K, stride=1, in_off=0, out_off=0, name="dw", act=True, wname=None):
+        """wname: one weight name, or a list of (name, channels) whose depthwise filters / BatchNorms are laid side by side"""
+        parts = wname if isinstance(wname, list) else [(wname or name, C)]
+        if ws:
+            w = np.concatenate([dw_w(n_ + ".dw", c_, K) for n_, c_ in parts])
+            sc, sh = (np.concatenate(x) for x in zip(*[bn(n_ + ".dwbn", c_) for n_, c_ in parts]))
+        else:
+            w = dw_w(name, C, K); sc, sh = bn(name, C)
+        g.add_dwconv(in_buf, out_buf, w * sc[:, None, None], sh, relu(C) if act else lin(C), stride=stride, in_ch_off=in_off, out_ch_off=out_off, name=name)
+
+    def pw(in_buf, out_buf, groups, cin_g, cout_g, act=True, out_off=0, cin_real=None, name="pw", wname=None, **kw):
+        """wname: None (random), one name (groups == 1) or one name per group"""
+        if ws:
+            names = wname if isinstance(wname, list) else [wname]
+            w = np.zeros((groups, cout_g, cin_g, 1, 1), np.float32)
+            scs, shs = [], []
+            for gi, n_ in enumerate(names):
+                ci = cin_real if cin_real is not None else cin_g
+                w[gi, :, :ci] = ws.conv(n_ + ".pw", cout_g, ci, 1)[0]
+                sc_, sh_ = bn(n_ + ".pwbn", cout_g); scs.append(sc_); shs.append(sh_)
+            sc, sh = np.concatenate(scs), np.concatenate(shs)
+        else:
+            w = _he(rng, groups, cout_g, cin_g, 1, 1, 2.0 if act else 1.0)
+            if cin_real is not None:
+                w[:, :, cin_real:] = 0
+            sc, sh = bn(name, groups * cout_g)
         w = w * sc.reshape(groups, cout_g, 1, 1, 1)
         g.add_conv(in_buf, out_buf, w, sh, relu(groups * cout_g) if act else lin(groups * cout_g), out_ch_off=out_off, name=name, **kw)
 
     # ---- stem: conv 3x3/2 3->32 (+bias, ReLU), BN, ReLU ----
     b_col = g.add_buffer(64, 1); g.add_im2col(b_col, stride=2)
     b0 = g.add_buffer(64, 1)
-    g.add_conv(b_col, b0, _he(rng, 1, 32, 3, 3, 3), (rng.standard_normal(32) * 0.05).astype(np.float32), relu(32), im2col_input=1, name="convblock_0")
-    sc, sh = _bn_fold(rng, 32)
+    if ws:
+        w0, bias0 = ws.conv("convblock_0.conv", 32, 3, 3)
+        w0 = w0[None]
+    else:
+        w0, bias0 = _he(rng, 1, 32, 3, 3, 3), (rng.standard_normal(32) * 0.05).astype(np.float32)
+    g.add_conv(b_col, b0, w0, bias0, relu(32), im2col_input=1, name="convblock_0")
+    sc, sh = bn("convblock_0.bn", 32)
     b0b = g.add_buffer(64, 1)
     g.add_dwconv(b0, b0b, sc.reshape(32, 1, 1), sh, relu(32), name="convblock_0_bn")
     cur, cur_off, cur_c, cur_d = b0b, 0, 32, 1
@@ -273,42 +304,52 @@ def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6) -> Graph:
     for i, (co, st) in enumerate(blocks, start=1):
         d_out = cur_d + (1 if st == 2 else 0)
         t = g.add_buffer(_r64(cur_c), d_out)
-        dw(cur, t, cur_c, 3, stride=st, in_off=cur_off, name=f"convblock_{i}_dw")
+        dw(cur, t, cur_c, 3, stride=st, in_off=cur_off, name=f"convblock_{i}_dw", wname=f"convblock_{i}")
         if i in (7, 11):     # concat_list[1] / [2] (backbones.py:288,293): written straight into the concat buffer
             off = 128 if i == 7 else 640
-            pw(t, cat, 1, _r64(cur_c), co, out_off=off, cin_real=cur_c, name=f"convblock_{i}_pw")
+            pw(t, cat, 1, _r64(cur_c), co, out_off=off, cin_real=cur_c, name=f"convblock_{i}_pw", wname=f"convblock_{i}")
             cur, cur_off = cat, off
         else:
             nxt = g.add_buffer(_r64(co), d_out)
-            pw(t, nxt, 1, _r64(cur_c), co, cin_real=cur_c, name=f"convblock_{i}_pw")
+            pw(t, nxt, 1, _r64(cur_c), co, cin_real=cur_c, name=f"convblock_{i}_pw", wname=f"convblock_{i}")
             cur, cur_off = nxt, 0
         if i == 3:           # concat_list[0] = maxpool(x) (backbones.py:283)
             g.add_maxpool(cur, cat, 128, "maxpool")
         cur_c, cur_d = co, d_out
-    _dw_orig = dw
 
     def stage(cin_real, mid, last, name):
         """two branches of 5 separable blocks (mbv2_th_openpose.py:111-158) executed together"""
         C = cat_c
+        br_names = [f"{name}.conf", f"{name}.paf"]
         wide = g.add_buffer(2 * C, 3)
         for br in range(2):
-            wd = (rng.standard_normal((C, 3, 3)) * np.sqrt(2.0 / 9)).astype(np.float32)
-            wd[cin_real:] = 0
-            sc, sh = _bn_fold(rng, C)
-            sh[cin_real:] = 0
+            if ws:
+                wd = np.zeros((C, 3, 3), np.float32); wd[:cin_real] = dw_w(f"{br_names[br]}.1.dw", cin_real, 3)
+                sc = np.ones(C, np.float32); sh = np.zeros(C, np.float32)
+                sc[:cin_real], sh[:cin_real] = bn(f"{br_names[br]}.1.dwbn", cin_real)
+            else:
+                wd = dw_w("", C, 3)
+                wd[cin_real:] = 0
+                sc, sh = bn("", C)
+                sh[cin_real:] = 0
             g.add_dwconv(cat, wide, wd * sc[:, None, None], sh, relu(C), out_ch_off=br * C, name=f"{name}_1_dw{br}")
         a = g.add_buffer(256, 3); b = g.add_buffer(256, 3)
-        pw(wide, a, 2, C, 128, cin_real=cin_real, name=f"{name}_1_pw")
+        pw(wide, a, 2, C, 128, cin_real=cin_real, name=f"{name}_1_pw", wname=[f"{n_}.1" for n_ in br_names])
         for k in (2, 3):
-            _dw_orig(a, b, 256, 3, name=f"{name}_{k}_dw")
-            pw(b, a, 2, 128, 128, name=f"{name}_{k}_pw")
-        _dw_orig(a, b, 256, 1, name=f"{name}_4_dw")
+            dw(a, b, 256, 3, name=f"{name}_{k}_dw", wname=[(f"{n_}.{k}", 128) for n_ in br_names])
+            pw(b, a, 2, 128, 128, name=f"{name}_{k}_pw", wname=[f"{n_}.{k}" for n_ in br_names])
+        dw(a, b, 256, 1, name=f"{name}_4_dw", wname=[(f"{n_}.4", 128) for n_ in br_names])
         m = g.add_buffer(2 * mid, 3)
-        pw(b, m, 2, 128, mid, name=f"{name}_4_pw")
+        pw(b, m, 2, 128, mid, name=f"{name}_4_pw", wname=[f"{n_}.4" for n_ in br_names])
         m2 = g.add_buffer(2 * mid, 3)
-        _dw_orig(m, m2, 2 * mid, 1, name=f"{name}_5_dw")
-        w = _block_diag(_he(rng, 1, 19, mid, 1, 1, 1.0), _he(rng, 1, 38, mid, 1, 1, 1.0))
-        sc, sh = _bn_fold(rng, 57)
+        # block 5 is separable_block(act=None): its depthwise BatchNorm is linear too
+        dw(m, m2, 2 * mid, 1, name=f"{name}_5_dw", act=False, wname=[(f"{n_}.5", mid) for n_ in br_names])
+        if ws:
+            w = _block_diag(ws.conv(f"{name}.conf.5.pw", 19, mid, 1)[0][None], ws.conv(f"{name}.paf.5.pw", 38, mid, 1)[0][None])
+            sc, sh = (np.concatenate(x) for x in zip(bn(f"{name}.conf.5.pwbn", 19), bn(f"{name}.paf.5.pwbn", 38)))
+        else:
+            w = _block_diag(_he(rng, 1, 19, mid, 1, 1, 1.0), _he(rng, 1, 38, mid, 1, 1, 1.0))
+            sc, sh = bn("", 57)
         w = w * sc.reshape(1, 57, 1, 1, 1)
         if last:
             g.add_conv(m2, 0, w, sh, lin(57), out_mode=OUT_F32_NCHW_SPLIT, split=19, name=f"{name}_out")
@@ -321,38 +362,28 @@ def mobilenet_thin_openpose(seed: int = 0, n_stages: int = 6) -> Graph:
     return g
 
 
-def resnet50_lw_openpose(seed: int = 0) -> Graph:
-    """Lightweight-OpenPose head on ResNet-50 at stride 8 (BASELINE.json config 4):
-    hyperpose/Model/backbones.py:587-698 (7x7/2 stem, 3x3/2 max-pool, 16 bottleneck blocks; block_3_1 / block_4_1 keep
-    stride 1 when scale_size == 8, :598-601) + hyperpose/Model/openpose/model/lw_openpose.py:106-191 (CPM, init stage,
-    one refinement stage with residual blocks).  BatchNorm folded; residual adds run in the conv epilogue
-    (ResNet: relu(conv + res); LW blocks: relu(bn(conv)) + res).  The two stride-2 convs of block_2_1 are computed at
-    stride 1 and sub-sampled by a one-hot depthwise 3x3/2 (centre tap of the TF-SAME window) / 1x1/2 op -- exact."""
-    rng = np.random.default_rng(seed)
-    g = Graph("resnet50_lw_openpose", 19, 38, 3, mean=(0.0, 0.0, 0.0))
+def _resnet50_body(g, rng, ws, cur, cur_c, cur_d, layout):
+    """the 16 bottleneck blocks of Resnet50_backbone (backbones.py:598-698).  BatchNorm folded; the residual add runs in the conv
+    epilogue (relu(conv3 + res)).  A stride-2 block computes its 3x3 (and its 1x1 projection) at stride 1 and sub-samples with a
+    one-hot depthwise 3x3/2 (centre tap of the TF-SAME window) / 1x1/2 op -- exact.  Returns (buffer, channels, down_shift)."""
     relu = lambda n: np.zeros(n, np.float32)
     lin = lambda n: np.ones(n, np.float32)
-    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
 
-    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", gain=None, **kw):
-        w = _he(rng, 1, co, ci, k, k, gain if gain is not None else (2.0 if act else 1.0))
-        sc, sh = _bn_fold(rng, co)
+    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", gain=None, wname=None, **kw):
+        if ws:
+            w = ws.conv(wname[0], co, ci, k)[0][None]
+            sc, sh = ws.bn(wname[1], co)
+        else:
+            w = _he(rng, 1, co, ci, k, k, gain if gain is not None else (2.0 if act else 1.0))
+            sc, sh = _bn_fold(rng, co)
         g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh, relu(co) if act else lin(co), name=name, **kw)
 
     def subsample(in_buf, out_buf, C, centre3: bool, name):
-        """x[2i(+1)] picker: one-hot depthwise op with stride 2 (see docstring)"""
         w = np.zeros((C, 3, 3), np.float32) if centre3 else np.ones((C, 1, 1), np.float32)
         if centre3:
             w[:, 1, 1] = 1.0
         g.add_dwconv(in_buf, out_buf, w, np.zeros(C, np.float32), lin(C), stride=2, name=name)
 
-    col = g.add_buffer(192, 1); g.add_im2col(col, stride=2, ksize=7)
-    c1 = g.add_buffer(64, 1)
-    w = _he(rng, 1, 64, 3, 7, 7); sc, sh = _bn_fold(rng, 64)
-    g.add_conv(col, c1, w * sc.reshape(1, 64, 1, 1, 1), sh, relu(64), im2col_input=1, name="conv1+bn1")
-    x = g.add_buffer(64, 2); g.add_maxpool(c1, x, 64, "maxpool_1", ksize=3)
-    cur, cur_c, cur_d = x, 64, 2
-    layout = [(64, 3, 1), (128, 4, 2), (256, 6, 1), (512, 3, 1)]     # (n_filter, blocks, stride of the first block) at scale_size 8
     for bi, (nf, nblk, st0) in enumerate(layout, start=1):
         for k in range(1, nblk + 1):
             st = st0 if k == 1 else 1
@@ -364,108 +395,139 @@ def resnet50_lw_openpose(seed: int = 0) -> Graph:
                 if st == 2:
                     src = g.add_buffer(_r64(cur_c), d_out); subsample(cur, src, cur_c, False, f"{name}_ds_sub")
                 res = g.add_buffer(4 * nf, d_out)
-                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds", gain=0.5)
+                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds", gain=0.5, wname=(f"{name}.ds_conv1", f"{name}.ds_bn1"))
             else:
                 res = cur
-            a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1")
-            b = g.add_buffer(_r64(nf), cur_d); conv_bn(a, b, nf, nf, 3, name=f"{name}_conv2")
+            a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1", wname=(f"{name}.conv1", f"{name}.bn1"))
+            b = g.add_buffer(_r64(nf), cur_d); conv_bn(a, b, nf, nf, 3, name=f"{name}_conv2", wname=(f"{name}.conv2", f"{name}.bn2"))
             if st == 2:
                 b2 = g.add_buffer(_r64(nf), d_out); subsample(b, b2, nf, True, f"{name}_conv2_sub"); b = b2
             out = g.add_buffer(4 * nf, d_out)
-            # (small gain on the residual branch, like a trained net's near-zero last gamma: keeps the random-init
+            # (random init: small gain on the residual branch, like a trained net's near-zero last gamma: keeps the
             #  activations of 16 stacked blocks inside the fp16 range)
-            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", gain=0.1, res_buf=res, res_mode=1)   # relu(x + res)
+            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", gain=0.1, res_buf=res, res_mode=1,
+                    wname=(f"{name}.conv3", f"{name}.bn3"))   # relu(x + res)
             cur, cur_c, cur_d = out, 4 * nf, d_out
+    return cur, cur_c, cur_d
 
-    def lw_conv(in_buf, out_buf, ci, co, k, act=True, name="c", **kw):      # Conv2d(+bias, relu)
-        g.add_conv(in_buf, out_buf, _he(rng, 1, co, ci, k, k, 2.0 if act else 1.0), b_(co), relu(co) if act else lin(co), name=name, **kw)
 
-    def lw_block(in_buf, out_buf, ci, co, k, name, **kw):                   # conv_block: Conv2d(+bias) + BN + relu (lw_openpose.py:193-199)
-        w = _he(rng, 1, co, ci, k, k); sc, sh = _bn_fold(rng, co)
-        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh + b_(co) * sc, relu(co), name=name, **kw)
+def resnet50_lw_openpose(seed: int = 0, weights=None) -> Graph:
+    """Lightweight-OpenPose head on ResNet-50 at stride 8 (BASELINE.json config 4):
+    hyperpose/Model/backbones.py:587-698 (7x7/2 stem, 3x3/2 max-pool, 16 bottleneck blocks; block_3_1 / block_4_1 keep
+    stride 1 when scale_size == 8, :598-601) + hyperpose/Model/openpose/model/lw_openpose.py:106-191 (CPM, init stage,
+    one refinement stage with residual blocks).  BatchNorm folded; residual adds run in the conv epilogue
+    (ResNet: relu(conv + res); LW blocks: relu(bn(conv)) + res).
+    `weights`: a hyperpose_b200.weights.Resnet50LwWeights (trained TensorLayer model); default = seeded random values."""
+    rng = np.random.default_rng(seed)
+    ws = weights
+    g = Graph("resnet50_lw_openpose", 19, 38, 3, mean=(0.0, 0.0, 0.0))
+    relu = lambda n: np.zeros(n, np.float32)
+    lin = lambda n: np.ones(n, np.float32)
+    b_ = lambda n: (rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    col = g.add_buffer(192, 1); g.add_im2col(col, stride=2, ksize=7)
+    c1 = g.add_buffer(64, 1)
+    if ws:
+        w = ws.conv("conv1", 64, 3, 7)[0][None]; sc, sh = ws.bn("bn1", 64)
+    else:
+        w = _he(rng, 1, 64, 3, 7, 7); sc, sh = _bn_fold(rng, 64)
+    g.add_conv(col, c1, w * sc.reshape(1, 64, 1, 1, 1), sh, relu(64), im2col_input=1, name="conv1+bn1")
+    x = g.add_buffer(64, 2); g.add_maxpool(c1, x, 64, "maxpool_1", ksize=3)
+    # (n_filter, blocks, stride of the first block) at scale_size 8
+    cur, cur_c, cur_d = _resnet50_body(g, rng, ws, x, 64, 2, [(64, 3, 1), (128, 4, 2), (256, 6, 1), (512, 3, 1)])
+
+    def lw_conv(in_buf, out_buf, ci, co, k, act=True, name="c", wname=None, **kw):      # Conv2d(+bias, relu)
+        if ws:
+            w, b = ws.conv(wname, co, ci, k); w = w[None]
+        else:
+            w, b = _he(rng, 1, co, ci, k, k, 2.0 if act else 1.0), b_(co)
+        g.add_conv(in_buf, out_buf, w, b, relu(co) if act else lin(co), name=name, **kw)
+
+    def lw_block(in_buf, out_buf, ci, co, k, name, wname=None, **kw):                   # conv_block: Conv2d(+bias) + BN + relu (lw_openpose.py:193-199)
+        if ws:
+            w, b = ws.conv(wname, co, ci, k); w = w[None]; sc, sh = ws.bn(wname + ".bn", co)
+        else:
+            w = _he(rng, 1, co, ci, k, k); sc, sh = _bn_fold(rng, co); b = b_(co)
+        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh + b * sc, relu(co), name=name, **kw)
+
+    def head_pair(in_buf, wide_buf, out_spec, prefix, name_mid, name_out):
+        """conf_block / paf_block (lw_openpose.py:131-143,166-177): 1x1x512 (relu) + 1x1x{19,38} each; the two 512-channel convs
+        share their input (one conv, cout 1024), the two output convs form one block-diagonal conv"""
+        if ws:
+            (wc1, bc1), (wp1, bp1) = ws.conv(f"{prefix}.conf.1", 512, 128, 1), ws.conv(f"{prefix}.paf.1", 512, 128, 1)
+            w1, b1 = np.concatenate([wc1, wp1], axis=0)[None], np.concatenate([bc1, bp1])
+            (wc2, bc2), (wp2, bp2) = ws.conv(f"{prefix}.conf.2", 19, 512, 1), ws.conv(f"{prefix}.paf.2", 38, 512, 1)
+            w2, b2 = _block_diag(wc2[None], wp2[None]), np.concatenate([bc2, bp2])
+        else:
+            w1, b1 = np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024)
+        g.add_conv(in_buf, wide_buf, w1, b1, relu(1024), name=name_mid)
+        if not ws:
+            w2, b2 = _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57)
+        g.add_conv(wide_buf, out_spec[0], w2, b2, lin(57), name=name_out, **out_spec[1])
 
     # ---- CPM (lw_openpose.py:106-121) ----
-    t0 = g.add_buffer(128, 3); lw_conv(cur, t0, 2048, 128, 1, name="cpm_init")
-    t1 = g.add_buffer(128, 3); lw_block(t0, t1, 128, 128, 3, "cpm_b1")
-    t2 = g.add_buffer(128, 3); lw_block(t1, t2, 128, 128, 3, "cpm_b2")
-    t3 = g.add_buffer(128, 3); lw_block(t2, t3, 128, 128, 3, "cpm_b3", res_buf=t0, res_mode=2)          # x + main_block(x)
+    t0 = g.add_buffer(128, 3); lw_conv(cur, t0, 2048, 128, 1, name="cpm_init", wname="cpm.init")
+    t1 = g.add_buffer(128, 3); lw_block(t0, t1, 128, 128, 3, "cpm_b1", wname="cpm.b1")
+    t2 = g.add_buffer(128, 3); lw_block(t1, t2, 128, 128, 3, "cpm_b2", wname="cpm.b2")
+    t3 = g.add_buffer(128, 3); lw_block(t2, t3, 128, 128, 3, "cpm_b3", wname="cpm.b3", res_buf=t0, res_mode=2)          # x + main_block(x)
     cat = g.add_buffer(192, 3)                                                                            # [cpm 128 | conf 19 | paf 38 | 7]
-    lw_conv(t3, cat, 128, 128, 3, name="cpm_end")
+    lw_conv(t3, cat, 128, 128, 3, name="cpm_end", wname="cpm.end")
     # ---- init stage (:123-149) ----
-    i1 = g.add_buffer(128, 3); lw_conv(cat, i1, 128, 128, 3, name="init_1")
-    i2 = g.add_buffer(128, 3); lw_conv(i1, i2, 128, 128, 3, name="init_2")
-    i3 = g.add_buffer(128, 3); lw_conv(i2, i3, 128, 128, 3, name="init_3")
+    i1 = g.add_buffer(128, 3); lw_conv(cat, i1, 128, 128, 3, name="init_1", wname="init.1")
+    i2 = g.add_buffer(128, 3); lw_conv(i1, i2, 128, 128, 3, name="init_2", wname="init.2")
+    i3 = g.add_buffer(128, 3); lw_conv(i2, i3, 128, 128, 3, name="init_3", wname="init.3")
     wide = g.add_buffer(1024, 3)
-    g.add_conv(i3, wide, np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024), relu(1024), name="init_4")
-    g.add_conv(wide, cat, _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57), lin(57), out_ch_off=128, name="init_out")
+    head_pair(i3, wide, (cat, dict(out_ch_off=128)), "init", "init_4", "init_out")
     # ---- refinement stage (:151-191): 5 residual blocks, then 1x1x512 + 1x1x{19,38} ----
     src, ci = cat, 185
     for k in range(1, 6):
         r0 = g.add_buffer(128, 3)
-        w = _he(rng, 1, 128, ci, 1, 1)
-        g.add_conv(src, r0, w, b_(128), relu(128), name=f"ref_b{k}_init")
-        r1 = g.add_buffer(128, 3); lw_block(r0, r1, 128, 128, 3, f"ref_b{k}_c1")
-        r2 = g.add_buffer(128, 3); lw_block(r1, r2, 128, 128, 3, f"ref_b{k}_c2", res_buf=r0, res_mode=2)
+        if ws:
+            w, b = ws.conv(f"ref.b{k}.init", 128, ci, 1)
+            w = w[None]
+        else:
+            w, b = _he(rng, 1, 128, ci, 1, 1), b_(128)
+        g.add_conv(src, r0, w, b, relu(128), name=f"ref_b{k}_init")
+        r1 = g.add_buffer(128, 3); lw_block(r0, r1, 128, 128, 3, f"ref_b{k}_c1", wname=f"ref.b{k}.c1")
+        r2 = g.add_buffer(128, 3); lw_block(r1, r2, 128, 128, 3, f"ref_b{k}_c2", wname=f"ref.b{k}.c2", res_buf=r0, res_mode=2)
         src, ci = r2, 128
     wide2 = g.add_buffer(1024, 3)
-    g.add_conv(src, wide2, np.concatenate([_he(rng, 1, 512, 128, 1, 1), _he(rng, 1, 512, 128, 1, 1)], axis=1), b_(1024), relu(1024), name="ref_4")
-    g.add_conv(wide2, 0, _block_diag(_he(rng, 1, 19, 512, 1, 1, 1.0), _he(rng, 1, 38, 512, 1, 1, 1.0)), b_(57), lin(57),
-               out_mode=OUT_F32_NCHW_SPLIT, split=19, name="ref_out")
+    head_pair(src, wide2, (0, dict(out_mode=OUT_F32_NCHW_SPLIT, split=19)), "ref", "ref_4", "ref_out")
     return g
 
 
-def resnet50_pifpaf(seed: int = 0) -> Graph:
+def resnet50_pifpaf(seed: int = 0, weights=None) -> Graph:
     """OpenPifPaf on ResNet-50 (BASELINE.json config 5): hyperpose/Model/pifpaf/model.py:41-51 (Resnet50_backbone(use_pool=False,
     scale_size=32): 7x7/2 stem, NO max-pool, stride-2 first blocks in stages 2-4 => stride 16), :215-281 (two 1x1 heads to
     17*5*4 and 19*9*4 channels, pixel-shuffle x2, sigmoid / softplus) -> fields at stride 8, cropped to 2*h16 - 1 (49 for 385).
     Input normalisation (x - mean) / std (model.py:38-39,58): the mean is subtracted in the patch gather, 1/std is folded
-    into the stem weights."""
+    into the stem weights.  `weights`: a hyperpose_b200.weights.Resnet50PifPafWeights; default = seeded random values."""
     rng = np.random.default_rng(seed)
+    ws = weights
     mean = (0.485, 0.456, 0.406); std = np.array([0.229, 0.224, 0.225], np.float32)
     g = Graph("resnet50_pifpaf", 85, 171, 4, mean=mean, head_type=1)
     relu = lambda n: np.zeros(n, np.float32)
     lin = lambda n: np.ones(n, np.float32)
 
-    def conv_bn(in_buf, out_buf, ci, co, k, act=True, name="c", gain=None, **kw):
-        w = _he(rng, 1, co, ci, k, k, gain if gain is not None else (2.0 if act else 1.0))
-        sc, sh = _bn_fold(rng, co)
-        g.add_conv(in_buf, out_buf, w * sc.reshape(1, co, 1, 1, 1), sh, relu(co) if act else lin(co), name=name, **kw)
-
-    def subsample(in_buf, out_buf, C, centre3, name):
-        w = np.zeros((C, 3, 3), np.float32) if centre3 else np.ones((C, 1, 1), np.float32)
-        if centre3:
-            w[:, 1, 1] = 1.0
-        g.add_dwconv(in_buf, out_buf, w, np.zeros(C, np.float32), lin(C), stride=2, name=name)
-
     col = g.add_buffer(192, 1); g.add_im2col(col, stride=2, ksize=7)
     c1 = g.add_buffer(64, 1)
-    w = _he(rng, 1, 64, 3, 7, 7) / std.reshape(1, 1, 3, 1, 1); sc, sh = _bn_fold(rng, 64)
+    if ws:
+        w = ws.conv("conv1", 64, 3, 7)[0][None] / std.reshape(1, 1, 3, 1, 1); sc, sh = ws.bn("bn1", 64)
+    else:
+        w = _he(rng, 1, 64, 3, 7, 7) / std.reshape(1, 1, 3, 1, 1); sc, sh = _bn_fold(rng, 64)
     g.add_conv(col, c1, w * sc.reshape(1, 64, 1, 1, 1), sh, relu(64), im2col_input=1, name="conv1+bn1")
-    cur, cur_c, cur_d = c1, 64, 1
-    for bi, (nf, nblk, st0) in enumerate([(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)], start=1):
-        for k in range(1, nblk + 1):
-            st = st0 if k == 1 else 1
-            name = f"block_{bi}_{k}"
-            d_out = cur_d + (1 if st == 2 else 0)
-            if st != 1 or cur_c != 4 * nf:
-                src = cur
-                if st == 2:
-                    src = g.add_buffer(_r64(cur_c), d_out); subsample(cur, src, cur_c, False, f"{name}_ds_sub")
-                res = g.add_buffer(4 * nf, d_out)
-                conv_bn(src, res, cur_c, 4 * nf, 1, act=False, name=f"{name}_ds", gain=0.5)
-            else:
-                res = cur
-            a = g.add_buffer(_r64(nf), cur_d); conv_bn(cur, a, cur_c, nf, 1, name=f"{name}_conv1")
-            b = g.add_buffer(_r64(nf), cur_d); conv_bn(a, b, nf, nf, 3, name=f"{name}_conv2")
-            if st == 2:
-                b2 = g.add_buffer(_r64(nf), d_out); subsample(b, b2, nf, True, f"{name}_conv2_sub"); b = b2
-            out = g.add_buffer(4 * nf, d_out)
-            conv_bn(b, out, nf, 4 * nf, 1, act=True, name=f"{name}_conv3", gain=0.1, res_buf=res, res_mode=1)
-            cur, cur_c, cur_d = out, 4 * nf, d_out
+    cur, cur_c, cur_d = _resnet50_body(g, rng, ws, c1, 64, 1, [(64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)])
     # heads (model.py:229,262): 1x1 conv + bias, no activation
     pif_raw = g.add_buffer(512, 4); paf_raw = g.add_buffer(768, 4)
-    g.add_conv(cur, pif_raw, _he(rng, 1, 340, 2048, 1, 1, 0.5), (rng.standard_normal(340) * 0.1).astype(np.float32), lin(340), name="pif_head")
-    g.add_conv(cur, paf_raw, _he(rng, 1, 684, 2048, 1, 1, 0.5), (rng.standard_normal(684) * 0.1).astype(np.float32), lin(684), name="paf_head")
+    if ws:
+        (wpif, bpif), (wpaf, bpaf) = ws.conv("pif_head", 340, 2048, 1), ws.conv("paf_head", 684, 2048, 1)
+        wpif, wpaf = wpif[None], wpaf[None]
+    else:
+        wpif, bpif = _he(rng, 1, 340, 2048, 1, 1, 0.5), (rng.standard_normal(340) * 0.1).astype(np.float32)
+    g.add_conv(cur, pif_raw, wpif, bpif, lin(340), name="pif_head")
+    if not ws:
+        wpaf, bpaf = _he(rng, 1, 684, 2048, 1, 1, 0.5), (rng.standard_normal(684) * 0.1).astype(np.float32)
+    g.add_conv(cur, paf_raw, wpaf, bpaf, lin(684), name="paf_head")
     g.ops.append(Op(OP_PIFPAF_HEAD, in_buf=pif_raw, res_buf=paf_raw, name="pifpaf_heads"))
     return g
 

@@ -100,7 +100,7 @@ int hp_paf_debug_peaks(hp_paf* p, int frame, hp_peak* out, int cap, int* n_out);
 int hp_paf_debug_connections(hp_paf* p, int frame, int pair_id, hp_connection* out, int cap, int* n_out);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long hp_paf_launch_count(const hp_paf* p);
-/* diagnostics: with HPB_PAF_TIMING=1 in the environment the limb kernel stamps its phases (%globaltimer, ns); N * (19 * 4 + 2) values */
+/* diagnostics: with HPB_PAF_TIMING=1 in the environment the limb kernel stamps its phases (%globaltimer, ns); N * (19 * 4 + 6) values */
 int hp_paf_debug_timing(hp_paf* p, unsigned long long* out, int N);
 /* multi-GPU gather leg: copies the last batch's records (padded to `cap` >= the parser's human capacity per
  * frame) and counts into caller-owned DEVICE buffers, asynchronously on `stream` (NULL = the batch's stream),
@@ -240,6 +240,17 @@ int hp_pose_submit_u8_host(hp_engine* e, hp_paf* parser, const uint8_t* frames, 
 int hp_pose_submit_u8_device(hp_engine* e, hp_paf* parser, const uint8_t* d_frames, int N, int* ticket);   /* frames already in HBM */
 int hp_pose_collect(hp_engine* e, int ticket, hp_human* out, int cap, int* n_out);
 int hp_pose_stats(const hp_engine* e, long long* graph_captures, long long* graph_launches);
+/* The pipelined call for OpenPifPaf packs: engine.inference(batch) + pifpaf.process(packet[0], packet[1]) per image
+ * (examples/operator_api_batched_images_pifpaf.example.cpp:48-64), two batches in flight.  The decoder's greedy growth is a
+ * latency chain on one warp per frame (2 ms per batch of 16 while 16 of 148 SMs do anything at all), so it runs on the DECODER's
+ * stream underneath the convolutions of the next batch: the engine's persistent kernels leave `reserve` SMs to it (default
+ * min(max_batch, 16); env HPB_PIFPAF_RESERVE_SMS), and the next batch's head kernels wait only until the field tensors have
+ * been consumed (decoder kernels P1-P3), not for the growth.  Tickets / hp_pose_collect as above. */
+int hp_pose_submit_pifpaf_u8_host(hp_engine* e, hp_pifpaf* decoder, const uint8_t* frames, int N, int* ticket);
+int hp_pose_submit_pifpaf_u8_device(hp_engine* e, hp_pifpaf* decoder, const uint8_t* d_frames, int N, int* ticket);
+int hp_pifpaf_pipeline_info(hp_pifpaf* p, void** stream, void** inputs_free_event, int* hcap);
+int hp_pifpaf_copy_results_host_async(hp_pifpaf* p, hp_human* pin_humans, int* pin_counts_flags, int N, void* stream);
+int hp_pifpaf_grow_capacity(hp_pifpaf* p, int flags);
 /* building blocks of the above (also usable on their own): pre-allocate for a geometry / read the state a captured launch
  * sequence bakes in / enqueue the record D2H into PINNED caller memory / grow after an overflow */
 int hp_paf_prepare(hp_paf* p, int N, int c_conf, int c_paf, int H, int W);

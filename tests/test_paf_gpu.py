@@ -97,6 +97,51 @@ def test_noise_field_many_peaks_capacity_growth():
     parser.close()
 
 
+def _assembly_paths(parser, N):
+    """which get_humans path assembled each frame of the last batch (needs HPB_PAF_TIMING=1): 2 component-parallel, 0 register, 1 shared memory"""
+    _, asm = parser.debug_timing(N)
+    return [int(v) & 3 for v in asm[:, 1]]
+
+
+def test_component_parallel_assembly_is_the_path_taken_and_the_sequential_paths_agree(monkeypatch):
+    """crowd frames: the component-parallel get_humans (one lane per connected component of the peak / connection graph) is what runs,
+    and it equals the oracle; with HPB_PAF_SEQ_ASSEMBLY=1 the same frames go through the sequential register path -- same bytes"""
+    monkeypatch.setenv("HPB_PAF_TIMING", "1")
+    N, hf, wf = 6, 46, 82
+    conf, paf = syn.make_batch_tensors(1000, N, (10, 20), hf, wf)
+    want = [oracle.oracle_process(conf[i], paf[i]) for i in range(N)]
+    parser = capi.PafParser()
+    parser.set_capacity(128, 2048, 64)
+    got = parser.process_batch(conf, paf)
+    assert _assembly_paths(parser, N) == [2] * N
+    for i in range(N):
+        _cmp_frame(got[i], want[i], f"fast frame{i}")
+    monkeypatch.setenv("HPB_PAF_SEQ_ASSEMBLY", "1")
+    got2 = parser.process_batch(conf, paf)
+    assert all(v in (0, 1) for v in _assembly_paths(parser, N))
+    for i in range(N):
+        assert got2[i].tobytes() == got[i].tobytes()
+    parser.close()
+
+
+@pytest.mark.parametrize("seed", range(300, 312))
+def test_noisy_crowds_vs_oracle(seed, monkeypatch):
+    """skeletons + noise strong enough to add spurious peaks, connections, merges of partial humans and (some seeds) the
+    reference's fabricated part ids: whichever assembly path a frame ends on, the humans equal the oracle's"""
+    monkeypatch.setenv("HPB_PAF_TIMING", "1")
+    rng = np.random.default_rng(seed)
+    hf, wf = 30, 40
+    conf, paf = syn.make_frame_tensors(seed, int(rng.integers(3, 9)), hf, wf)
+    amp = float(rng.uniform(0.05, 0.25))
+    conf = (conf + rng.random(conf.shape, dtype=np.float32) * amp).astype(np.float32)
+    paf = (paf + (rng.random(paf.shape, dtype=np.float32) - 0.5) * 2 * amp).astype(np.float32)
+    orc = oracle.oracle_process(conf, paf, peak_cap=1 << 18, conn_cap=1 << 14)
+    parser = capi.PafParser()
+    got = parser.process(conf, paf)
+    _cmp_frame(got, orc, f"seed {seed} amp {amp:.2f} path {_assembly_paths(parser, 1)}")
+    parser.close()
+
+
 def test_thresholds_and_setters():
     conf, paf = syn.make_frame_tensors(3, (10, 20), 46, 54)
     parser = capi.PafParser(0.05, 0.05)
