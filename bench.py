@@ -425,7 +425,9 @@ def measure(args, key, dist_ctx, headline=True):
     # value: frames already resident in HBM, results left on the device (rank 0 after the gather).  The launch sequence of a
     # batch is replayed from the CUDA graph hp_pose_submit_u8_device captured (two batches in flight: the host collects batch
     # i-1 while batch i runs); --no-graph (and the OpenPifPaf workload) launches every kernel on the stream instead.
-    use_graph = not PIFPAF and not args.no_graph
+    # (OpenPifPaf: the same two-deep submit / collect, without a CUDA graph -- the decoder runs on its own stream underneath the next
+    #  batch's convolutions: hp_pose_submit_pifpaf_u8_device)
+    use_graph = not args.no_graph
     dpend = {"t": None}
     pstate = {"events": None}     # pass B: CUDA events around the parser launches of every step
 
@@ -462,11 +464,6 @@ def measure(args, key, dist_ctx, headline=True):
     pend = {"t": None}
 
     def step_host(i):
-        if PIFPAF:   # engine.inference(batch) + pifpaf.process per image: host frames in, humans out (fields stay on the device)
-            engine.infer_u8(frames_np[i % N_INPUT_SETS])
-            _, _, es = engine.device_outputs()
-            parser.process_device(out_conf_ptr, out_paf_ptr, BATCH, HF, WF, es)
-            return parser.fetch(BATCH, cap=HCAP)
         t = engine.submit_pose(parser, frames_np[i % N_INPUT_SETS])
         humans = engine.collect_pose(pend["t"], cap=HCAP) if pend["t"] is not None else None
         pend["t"] = t
@@ -527,7 +524,7 @@ def measure(args, key, dist_ctx, headline=True):
     if ref_h is None:
         ref_h = parser.fetch(BATCH, cap=HCAP)
     step_host(0)
-    host_h = drain_host() if not PIFPAF else step_host(0)
+    host_h = drain_host()
     assert all(a.tobytes() == b.tobytes() for a, b in zip(ref_h, host_h)), "device and host paths disagree"
     n_humans = sum(len(h) for h in host_h)
 
@@ -571,12 +568,13 @@ def measure(args, key, dist_ctx, headline=True):
     # the synchronous form of the same public call (one batch in flight), for the record
     sync_steps = max(3, steps // 2)
     if PIFPAF:
-        ms_sync = None
+        def step_sync(i):       # one batch in flight: submit + collect
+            return engine.collect_pose(engine.submit_pose(parser, frames_np[i % N_INPUT_SETS]), cap=HCAP)
     else:
         def step_sync(i):
             return engine.run_pose(parser, frames_np[i % N_INPUT_SETS], cap=HCAP)
-        ms_sync, _ = timed(step_sync, sync_steps, 3)
-        ms_sync = max(ms_sync, 1e-6)
+    ms_sync, _ = timed(step_sync, sync_steps, 3)
+    ms_sync = max(ms_sync, 1e-6)
 
     frames_total = world * BATCH * steps
     value = frames_total / (ms_total / 1e3)
@@ -641,9 +639,9 @@ def measure(args, key, dist_ctx, headline=True):
                       else "f16 operands, f32 accumulate (conv); f32/f64 (parse)"), "data": "synthetic",
             "config": cfg,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": ("hp_engine_infer_u8_host + hp_pifpaf_process_device + hp_pifpaf_fetch (synchronous per batch)" if PIFPAF else
+                    "api": ("hp_pose_submit_pifpaf_u8_host / hp_pose_collect (pinned host frames in, human_t records out, two batches in flight: the decoder runs on its own stream under the next batch's convs)" if PIFPAF else
                             "hp_pose_submit_u8_host / hp_pose_collect (pinned host frames in, human_t records out, two batches in flight, CUDA-graph replay)"),
-                    "synchronous_call": (None if ms_sync is None else {"value": world * BATCH * sync_steps / (ms_sync / 1e3), "api": "hp_pose_run_u8_host (one batch in flight)"}),
+                    "synchronous_call": {"value": world * BATCH * sync_steps / (ms_sync / 1e3), "api": "submit + collect, one batch in flight" if PIFPAF else "hp_pose_run_u8_host (one batch in flight)"},
                     "graphs": engine.pose_stats()},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,

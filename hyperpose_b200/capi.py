@@ -408,7 +408,11 @@ class Engine:
         `frames` must stay alive until collect_pose when it is page-locked memory (DMA reads it directly)."""
         assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
         t = C.c_int(-1)
-        check(lib().hp_pose_submit_u8_host(self._h, parser._h, frames.ctypes.data, frames.shape[0], C.byref(t)))
+        if isinstance(parser, PifPafParser):   # OpenPifPaf pack: decoder on its own stream underneath the next batch's convs
+            lib().hp_pose_submit_pifpaf_u8_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+            check(lib().hp_pose_submit_pifpaf_u8_host(self._h, parser._h, frames.ctypes.data, frames.shape[0], C.byref(t)))
+        else:
+            check(lib().hp_pose_submit_u8_host(self._h, parser._h, frames.ctypes.data, frames.shape[0], C.byref(t)))
         self._ticket_n = getattr(self, "_ticket_n", {})
         self._ticket_n[t.value] = frames.shape[0]
         return t.value
@@ -416,7 +420,11 @@ class Engine:
     def submit_pose_device(self, parser: "PafParser", d_frames_ptr: int, n: int) -> int:
         """hp_pose_submit_u8_device: the frames are already in device memory"""
         t = C.c_int(-1)
-        check(lib().hp_pose_submit_u8_device(self._h, parser._h, d_frames_ptr, n, C.byref(t)))
+        if isinstance(parser, PifPafParser):
+            lib().hp_pose_submit_pifpaf_u8_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+            check(lib().hp_pose_submit_pifpaf_u8_device(self._h, parser._h, d_frames_ptr, n, C.byref(t)))
+        else:
+            check(lib().hp_pose_submit_u8_device(self._h, parser._h, d_frames_ptr, n, C.byref(t)))
         self._ticket_n = getattr(self, "_ticket_n", {})
         self._ticket_n[t.value] = n
         return t.value
@@ -489,7 +497,9 @@ class Pool:
 # OpenPifPaf decoder
 # ---------------------------------------------------------------------------------------------
 EXPORTS += ["hp_pifpaf_create", "hp_pifpaf_destroy", "hp_pifpaf_process_host", "hp_pifpaf_process_device", "hp_pifpaf_fetch",
-            "hp_pifpaf_launch_count", "hp_pifpaf_debug_counts", "hp_pifpaf_debug_hr"]
+            "hp_pifpaf_launch_count", "hp_pifpaf_debug_counts", "hp_pifpaf_debug_hr",
+            "hp_pifpaf_pipeline_info", "hp_pifpaf_copy_results_host_async", "hp_pifpaf_grow_capacity",
+            "hp_pose_submit_pifpaf_u8_host", "hp_pose_submit_pifpaf_u8_device"]
 
 
 class PifPafParser:

@@ -1467,6 +1467,228 @@ conv_stem3_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 7x7 / stride-2 stem (ResNet-50 first layer), built like conv_stem3_kernel: table-driven u8 -> fp16 normalisation, the 21 bytes
+// of a filter row (7 pixels x BGR, contiguous in the frame) as six aligned 32-bit loads + funnel shifts, patches only ever in
+// shared memory.  conv_stem_kernel<7> (the first version: ~2600 instructions per pixel, 168 registers, one CTA per SM) ran at
+// 36 TFLOP/s = 0.68 ms per 32-frame batch at cfg4, 10 % of the step, for 0.2 % of the FLOPs.
+// K layout (chosen here, the weights are packed to match at load time): filter row r owns 24 slots, slot r * 24 + s * 3 + c
+// (3 pad slots per row), i.e. 48 bytes = three 16-byte pieces that never straddle a 64-slot chunk; 7 rows = 168 slots in three
+// chunks; the pieces never written (slots 168..191) are zeroed once and stay zero.  One A stage (48 KiB) per CTA and two CTAs per
+// SM: the second CTA's gather overlaps this CTA's MMA / epilogue.  11 MMA slices per tile (4 + 4 + 3).
+// Warp roles as in conv_stem3_kernel: 0-3 gather (one thread per pixel), 4-7 epilogue, 8 weights + MMA issue + TMEM.
+// ---------------------------------------------------------------------------------------------
+constexpr int STEM7_ROW_SLOTS = 24, STEM7_CHUNKS = 3;
+constexpr int STEM7_A_BYTES = STEM7_CHUNKS * CONV_A_BYTES;   // 48 KiB
+
+template <bool FLIP>
+__global__ void __launch_bounds__(STEM_THREADS, 2)
+conv_stem7_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o, const StemParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                                          // [3 chunks][128 rows x 128 B]
+    uint8_t* sB = sA + STEM7_A_BYTES;                            // [3 chunks][BN x 128 B] weights, resident
+    uint8_t* sOut = sB + (size_t)STEM7_CHUNKS * p.BN * 128;      // 2 x 16 KiB staging
+    __half* lut = (__half*)(sOut + 2 * CONV_A_BYTES);            // [3][256] + one zero entry (padded to 1552 B)
+    uint64_t* full_bar = (uint64_t*)((uint8_t*)lut + 1552);      // gather -> MMA (128 arrivals)
+    uint64_t* empty_bar = full_bar + 1;                          // MMA -> gather
+    uint64_t* tfull_bar = empty_bar + 1;                         // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                        // [2]
+    uint64_t* w_bar = tempty_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(w_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_px = p.Nb * p.OH * p.OW;
+    const int total_tiles = (total_px + CONV_BLOCK_M - 1) / CONV_BLOCK_M;
+    const int tmem_cols = p.BN <= 64 ? 128 : 256;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_b);
+        ptx::prefetch_tmap(&tmap_o);
+        ptx::mbar_init(ptx::smem_u32(full_bar), 128);
+        ptx::mbar_init(ptx::smem_u32(empty_bar), 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4);
+        }
+        ptx::mbar_init(ptx::smem_u32(w_bar), 1);
+        ptx::fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 3 * 256 + 8; i += STEM_THREADS) {
+        float v = 0.f;
+        if (i < 768) {
+            const int c = i >> 8, u = i & 255;
+            v = (float)((double)u * p.factor) - (c == 0 ? p.m0 : c == 1 ? p.m1 : p.m2);
+        }
+        lut[i] = __float2half_rn(v);
+    }
+    // slots 168..191 (pieces 5..7 of chunk 2) are never written by the gather: zero the tile once
+    for (int i = threadIdx.x; i < STEM7_A_BYTES / 16; i += STEM_THREADS) ((uint4*)sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async();
+    if (warp == 8) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)tmem_cols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== gather: one thread per pixel of the tile =====================
+        const int row = threadIdx.x; // 0..127
+        const uint32_t lut_s = ptx::smem_u32(lut);
+        const uint32_t swz = (uint32_t)(row & 7);
+        const long long total_bytes = (long long)p.Nb * p.H * p.W * 3;
+        const uint8_t* frames = p.frames;
+        const uint32_t arow = ptx::smem_u32(sA) + (uint32_t)row * 128u;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int px = tile * CONV_BLOCK_M + row;
+            const bool valid = px < total_px;
+            int n = 0, oh = 0, ow = 0;
+            if (valid) { n = px / (p.OH * p.OW); const int rem = px - n * p.OH * p.OW; oh = rem / p.OW; ow = rem - oh * p.OW; }
+            const int h0 = oh * p.stride - p.pad_h, w0 = ow * p.stride - p.pad_w;
+            unsigned cmask = 0u;   // bit s: column w0 + s lies inside the frame
+#pragma unroll
+            for (int s2 = 0; s2 < 7; ++s2) cmask |= ((w0 + s2) >= 0 && (w0 + s2) < p.W) ? (1u << s2) : 0u;
+            ptx::mbar_wait(ptx::smem_u32(empty_bar), phase ^ 1);   // the previous tile's MMAs have read the stage
+#pragma unroll 1
+            for (int r = 0; r < 7; ++r) {
+                const int hh = h0 + r;
+                const bool rok = valid && hh >= 0 && hh < p.H;
+                const long long off = (((long long)n * p.H + (rok ? hh : 0)) * p.W + w0) * 3;
+                const long long a0 = off & ~3ll;
+                const uint32_t sh = (uint32_t)(off & 3) * 8u;
+                uint32_t wd[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const long long a = a0 + 4 * i;
+                    wd[i] = (rok && a >= 0 && a < total_bytes) ? __ldg((const uint32_t*)(frames + a)) : 0u;
+                }
+                uint32_t seg[6];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) seg[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
+                seg[5] = wd[5] >> sh;
+                uint32_t hv[STEM7_ROW_SLOTS];
+#pragma unroll
+                for (int s2 = 0; s2 < 7; ++s2) {
+                    const bool ok = rok && ((cmask >> s2) & 1u);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const int j = s2 * 3 + b;                 // byte of the row segment (memory order B, G, R)
+                        const int c = FLIP ? 2 - b : b;           // model channel fed by this byte
+                        const uint32_t byte = __byte_perm(seg[j >> 2], 0u, 0x4440u | (uint32_t)(j & 3));
+                        const uint32_t idx = ok ? (byte * 2u + (uint32_t)(c * 512)) : 1536u; // entry 768 is zero
+                        uint32_t v;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(lut_s + idx));
+                        hv[s2 * 3 + c] = v;
+                    }
+                }
+                hv[21] = 0u; hv[22] = 0u; hv[23] = 0u;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int piece = r * 3 + i;                  // 16-byte piece of the 384-byte patch row
+                    const uint32_t a = arow + (uint32_t)(piece >> 3) * (uint32_t)CONV_A_BYTES + (((uint32_t)(piece & 7)) ^ swz) * 16u;
+                    ptx::st_shared_v4(a, make_uint4(hv[8 * i] | (hv[8 * i + 1] << 16), hv[8 * i + 2] | (hv[8 * i + 3] << 16),
+                                                    hv[8 * i + 4] | (hv[8 * i + 5] << 16), hv[8 * i + 6] | (hv[8 * i + 7] << 16)));
+                }
+            }
+            ptx::fence_proxy_async(); // generic-proxy writes -> visible to the tensor core (async proxy)
+            ptx::mbar_arrive(ptx::smem_u32(full_bar));
+            phase ^= 1;
+        }
+    } else if (warp == 8) {
+        // ===================== weights (once) + MMA issuer =====================
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(ptx::smem_u32(w_bar), (uint32_t)(STEM7_CHUNKS * p.BN * 128));
+            for (int c = 0; c < STEM7_CHUNKS; ++c)
+                ptx::tma_load_2d(ptx::smem_u32(sB + (size_t)c * p.BN * 128), &tmap_b, ptx::smem_u32(w_bar), c * CONV_BLOCK_K, 0);
+            ptx::mbar_wait(ptx::smem_u32(w_bar), 0);
+            const uint32_t idesc = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN);
+            uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
+                ptx::mbar_wait(ptx::smem_u32(full_bar), phase);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+#pragma unroll
+                for (int c = 0; c < STEM7_CHUNKS; ++c) {
+                    const uint64_t da = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sA + (size_t)c * CONV_A_BYTES));
+                    const uint64_t db = ptx::make_sw128_kmajor_desc(ptx::smem_u32(sB + (size_t)c * p.BN * 128));
+#pragma unroll
+                    for (int k = 0; k < (c == 2 ? 3 : 4); ++k)     // chunk 2: slots 128..175 (168..175 are zeros)
+                        ptx::umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
+                }
+                ptx::umma_commit(ptx::smem_u32(empty_bar));
+                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
+                phase ^= 1;
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (warps 4..7): bias + PReLU -> fp16 -> swizzled staging -> TMA store =====================
+        const int ew = warp - 4, row = ew * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        int acc = 0; uint32_t acc_phase = 0, stage_ctr = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int p0 = tile * CONV_BLOCK_M;
+            ptx::mbar_wait(ptx::smem_u32(tfull_bar + acc), acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                uint8_t* sbuf = sOut + (stage_ctr & 1) * CONV_A_BYTES;
+                if (leader) ptx::bulk_wait_group_read<1>();
+                ptx::named_bar_sync(1, 128);
+                const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = sub * 64 + q * 16;
+                    uint32_t v[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                    ptx::tmem_ld_wait();
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 bv = __ldg((const float4*)(p.bias + c0) + j4);
+                        const float4 av = __ldg((const float4*)(p.alpha + c0) + j4);
+                        float a0 = __uint_as_float(v[4 * j4]) + bv.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bv.y;
+                        float a2 = __uint_as_float(v[4 * j4 + 2]) + bv.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bv.w;
+                        a0 = a0 > 0.f ? a0 : a0 * av.x; a1 = a1 > 0.f ? a1 : a1 * av.y;
+                        a2 = a2 > 0.f ? a2 : a2 * av.z; a3 = a3 > 0.f ? a3 : a3 * av.w;
+                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                        pk[2 * j4] = *(const uint32_t*)&h01;
+                        pk[2 * j4 + 1] = *(const uint32_t*)&h23;
+                    }
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                    ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+                }
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(1, 128);
+                if (leader) {
+                    ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + sub * 64, p0);
+                    ptx::bulk_commit_group();
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tempty_bar + acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (leader) ptx::bulk_wait_group_read<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+}
+
+inline size_t conv_stem7_smem_bytes(int BN)
+{
+    return 1024 + (size_t)STEM7_A_BYTES + (size_t)STEM7_CHUNKS * BN * 128 + 2 * CONV_A_BYTES + 1552 + 7 * 8 + 16;
+}
+
 inline size_t conv_stem3_smem_bytes(int BN)
 {
     return 1024 + (size_t)STEM3_STAGES * CONV_A_BYTES + (size_t)BN * 128 + 2 * CONV_A_BYTES + 1552 + (2 * STEM3_STAGES + 5) * 8 + 16;

@@ -501,6 +501,9 @@ struct ConvPlan {
     bool stem = false;
     int stem_R = 3;
     bool stem3_v2 = false;      // 3x3 stem: conv_stem3_kernel (table-driven gather, two CTAs per SM)
+    bool stem7_v2 = false;      // 7x7 stem: conv_stem7_kernel (same design; weights re-packed with 24 K slots per filter row)
+    __half* d_w7 = nullptr;
+    CUtensorMap tmap_b7;
     // halo-box kernel (conv_halo_kernel): one TMA box per 16 x 8-pixel tile and channel chunk serves every filter tap
     bool halo = false;
     HaloParams hp;
@@ -885,7 +888,21 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
             sp.BN = BN; sp.cout = cout_g; sp.bias = pl.d_bias; sp.alpha = pl.d_alpha; sp.out_ch_off = (int)po.out_ch_off;
             pl.stem = true; pl.stem_R = R;
             pl.stem3_v2 = (R == 3 && !getenv("HPB_STEM3_V1"));
-            pl.stem_smem = pl.stem3_v2 ? conv_stem3_smem_bytes(BN) : conv_stem_smem_bytes(R, BN);
+            pl.stem7_v2 = (R == 7 && cin_g == 3 && !getenv("HPB_STEM7_V1"));
+            pl.stem_smem = pl.stem3_v2 ? conv_stem3_smem_bytes(BN) : pl.stem7_v2 ? conv_stem7_smem_bytes(BN) : conv_stem_smem_bytes(R, BN);
+            if (pl.stem7_v2) {
+                // K layout of conv_stem7_kernel: filter row r owns 24 slots, slot r * 24 + s * 3 + c; 192 slots per output channel
+                std::vector<__half> w7((size_t)cout_pad * 192, __float2half(0.f));
+                for (int o = 0; o < cout_g; ++o)
+                    for (int c = 0; c < 3; ++c)
+                        for (int r = 0; r < 7; ++r)
+                            for (int s2 = 0; s2 < 7; ++s2)
+                                w7[(size_t)o * 192 + r * STEM7_ROW_SLOTS + s2 * 3 + c] = __float2half_rn(W[(((size_t)o * 3 + c) * 7 + r) * 7 + s2]);
+                HP_CUDA_TRY(cudaMalloc(&pl.d_w7, w7.size() * sizeof(__half)));
+                HP_CUDA_TRY(cudaMemcpy(pl.d_w7, w7.data(), w7.size() * sizeof(__half), cudaMemcpyHostToDevice));
+                rc = make_tmap_wgt(&pl.tmap_b7, pl.d_w7, cout_pad, 192, BN);
+                if (rc) return rc;
+            }
             o2.fused_into_stem = true;
             break;
         }
@@ -917,6 +934,9 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         if (pl.stem3_v2) {
             if (sp.flip) conv_stem3_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
             else conv_stem3_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+        } else if (pl.stem7_v2) {
+            if (sp.flip) conv_stem7_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b7, pl.tmap_o, sp);
+            else conv_stem7_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b7, pl.tmap_o, sp);
         } else if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         else conv_stem_kernel<7><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         e->launches++;
@@ -1132,6 +1152,7 @@ void free_engine(hp_engine* e)
     for (auto& b : e->bufs) if (b.d) cudaFree(b.d);
     for (auto& o : e->ops) {
         if (o.plan.d_w) cudaFree(o.plan.d_w);
+        if (o.plan.d_w7) cudaFree(o.plan.d_w7);
         if (o.plan.d_w32) cudaFree(o.plan.d_w32);
         if (o.plan.d_bias) cudaFree(o.plan.d_bias);
         if (o.plan.d_alpha) cudaFree(o.plan.d_alpha);
@@ -1331,10 +1352,16 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (halo)", halo_smem);
         return fail(HP_ERR_CUDA);
     }
-    size_t stem_smem = 0, stem3_smem = 0;
+    size_t stem_smem = 0, stem3_smem = 0, stem7_smem = 0;
     for (auto& o : e->ops) {
         if (o.plan.stem && o.plan.stem3_v2) stem3_smem = std::max(stem3_smem, o.plan.stem_smem);
+        else if (o.plan.stem && o.plan.stem7_v2) stem7_smem = std::max(stem7_smem, o.plan.stem_smem);
         else if (o.plan.stem) stem_smem = std::max(stem_smem, o.plan.stem_smem);
+    }
+    if (stem7_smem && (cudaFuncSetAttribute(conv_stem7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem7_smem) != cudaSuccess ||
+                       cudaFuncSetAttribute(conv_stem7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem7_smem) != cudaSuccess)) {
+        set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (7x7 stem)", stem7_smem);
+        return fail(HP_ERR_CUDA);
     }
     if (stem3_smem && (cudaFuncSetAttribute(conv_stem3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem3_smem) != cudaSuccess ||
                        cudaFuncSetAttribute(conv_stem3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem3_smem) != cudaSuccess)) {

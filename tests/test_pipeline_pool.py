@@ -175,3 +175,39 @@ def test_default_device_selector(monkeypatch):
     assert L.hp_default_device() == n - 1
     monkeypatch.setenv("HPB_DEVICE", "99")
     assert L.hp_default_device() == 0
+
+
+def test_pipelined_pifpaf_call_equals_the_plain_sequence():
+    """hp_pose_submit_pifpaf_u8_host / hp_pose_collect (decoder on its own stream underneath the next batch's convolutions, SMs
+    reserved for it) against engine.inference + decoder.process of the same fields; synthetic PIF / PAF fields are copied over the
+    random-weight network's outputs (hp_engine_set_output_override) so that there are people to find."""
+    import torch
+    N, HW = 2, 129
+    eng = capi.Engine(models.resnet50_pifpaf(0).to_pack(), (HW, HW), max_batch_size=N)
+    hf = wf = (HW - 1) // 8 + 1
+    fields = [syn.make_pifpaf_fields(70 + i, (1, 3), hf, wf) for i in range(N)]
+    pif = np.stack([f[0] for f in fields]).astype(np.float32); paf = np.stack([f[1] for f in fields]).astype(np.float32)
+    d_pif, d_paf = torch.from_numpy(pif).cuda(), torch.from_numpy(paf).cuda()
+    eng.set_output_override(d_pif.data_ptr(), d_paf.data_ptr())
+    dec = capi.PifPafParser(HW, HW, 0.1)
+    want = [h.tobytes() for h in dec.process_batch(pif, paf)]
+    assert sum(len(w) for w in want) > 0
+    batches = [syn.make_frames_u8(90 + k, N, HW, HW) for k in range(4)]
+    got = []
+    t_prev = eng.submit_pose(dec, batches[0])
+    for k in range(1, len(batches)):
+        t = eng.submit_pose(dec, batches[k])
+        assert t != t_prev
+        got.append(eng.collect_pose(t_prev, cap=128))
+        t_prev = t
+    got.append(eng.collect_pose(t_prev, cap=128))
+    for g in got:
+        assert [h.tobytes() for h in g] == want
+    # device-resident frames, one batch in flight
+    d_frames = torch.from_numpy(batches[0]).cuda()
+    g = eng.collect_pose(eng.submit_pose_device(dec, d_frames.data_ptr(), N), cap=128)
+    assert [h.tobytes() for h in g] == want
+    # a PAF-parser handle is refused on an OpenPifPaf pack and vice versa
+    with pytest.raises(capi.HyperposeError):
+        eng.submit_pose(capi.PafParser(), batches[0])
+    eng.close(); dec.close()
