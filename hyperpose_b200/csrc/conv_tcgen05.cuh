@@ -31,6 +31,7 @@ constexpr int CONV_BLOCK_K = 64;    // fp16 channels per k-step == one 128-byte 
 constexpr int CONV_UMMA_K = 16;     // K of one tcgen05.mma.kind::f16
 constexpr int CONV_MAX_STAGES = 8;
 constexpr int CONV_THREADS = 256;
+constexpr int CONV_IM2COL_THREADS = 384;   // conv_tcgen05_kernel: warps 0-3 roles, 4-7 epilogue, 8-11 second epilogue set
 constexpr int CONV_A_BYTES = CONV_BLOCK_M * CONV_BLOCK_K * 2; // 16 KiB
 constexpr size_t CONV_SMEM_LIMIT = 227 * 1024;
 
@@ -61,6 +62,8 @@ struct ConvParams {
     const __half* res;         // residual input [pixels, res_ld] (+ res_ch_off), or nullptr
     int res_ld, res_ch_off;
     int res_mode;              // 1: y = act(v + res)   2: y = act(v) + res
+    int relu_only;             // 1: every slope of the layer is 0 (plain ReLU): the epilogue skips the slope loads
+    int epi_warps;             // conv_tcgen05_kernel: 8 = two epilogue warps per TMEM lane quarter (each takes half of the channels), 4 = one
 };
 
 namespace ptx {
@@ -286,8 +289,36 @@ __device__ __forceinline__ PixelPos unflatten(const ConvParams& p, int px)
     return q;
 }
 
+
+// Epilogue arithmetic of one pixel for 16 consecutive output channels: bias (+ residual) + PReLU -> fp16 pairs.
+// relu_only layers compute max(a, 0) with the sign of a negative input kept on the zero, which is what a * 0.f gives
+// (bit-identical with the general form, one FMNMX + LOP3 instead of FSETP + FMUL + FSEL, and no slope loads).
+template <bool kRes>
+__device__ __forceinline__ void conv_epilogue16(const uint32_t (&v)[16], const float (&bv)[16], const float (&av)[16], const bool relu_only,
+                                                const int res_mode, const __half2 (&rs)[8], uint32_t (&pk)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
+        float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
+        float r0 = 0.f, r1 = 0.f;
+        if (kRes && res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
+        if (kRes && res_mode == 1) { a0 += r0; a1 += r1; }
+        if (relu_only) {
+            a0 = __uint_as_float(__float_as_uint(fmaxf(a0, 0.f)) | (__float_as_uint(a0) & 0x80000000u));
+            a1 = __uint_as_float(__float_as_uint(fmaxf(a1, 0.f)) | (__float_as_uint(a1) & 0x80000000u));
+        } else {
+            a0 = a0 > 0.f ? a0 : a0 * av[2 * j];
+            a1 = a1 > 0.f ? a1 : a1 * av[2 * j + 1];
+        }
+        if (kRes && res_mode == 2) { a0 += r0; a1 += r1; }
+        const __half2 h2 = __floats2half2_rn(a0, a1);
+        pk[j] = *(const uint32_t*)&h2;
+    }
+}
+
 template <bool kRes> // kRes: residual epilogue compiled in (ResNet / LW-OpenPose blocks); false keeps the plain epilogue lean
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_IM2COL_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p)
 {
@@ -326,7 +357,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
-            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4); // one arrive per epilogue warp
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), (uint32_t)p.epi_warps); // one arrive per epilogue warp
             ptx::mbar_init(ptx::smem_u32(res_bar + i), 1);
         }
         ptx::fence_barrier_init();
@@ -393,9 +424,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + p.epi_warps) {
         // ===================== epilogue: TMEM -> registers -> global =====================
-        const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may access
+        // A lone epilogue warp per scheduler cannot hide its own latencies (tcgen05.ld -> wait -> loads -> stores: ~0.16 IPC measured on
+        // the residual 1x1 layers), so with epi_warps == 8 every TMEM lane quarter has TWO warps, each taking half of the channels.
+        const int ew = (warp - 4) & 3;            // == warp % 4: the TMEM lane quarter this warp may access
+        const int eh = (warp - 4) >> 2;           // which half of every 64-channel sub-tile (always 0 with 4 epilogue warps)
+        const int q_step = p.epi_warps == 8 ? 2 : 4, epi_threads = 32 * p.epi_warps;
         const int row = ew * 32 + lane;           // accumulator row == pixel index inside the tile
         const int total_px = p.Nb * p.H * p.W;
         int acc = 0;
@@ -437,17 +472,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
                     uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
                     if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
-                    ptx::named_bar_sync(1, 128);
+                    ptx::named_bar_sync(1, epi_threads);
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
                     const uint8_t* rrow = res_stage + (res_used & 1) * CONV_A_BYTES + row * 128;
                     if (kRes && res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & 1)), (res_used >> 1) & 1);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int qq = 0; qq < 4; ++qq) {   // 16 channels per TMEM load; the other loads of the step are issued before the wait
+                        if (qq >= q_step) break;
+                        const int q = eh * q_step + qq;
                         const int c0 = sub * 64 + q * 16;
                         uint32_t v[16];
                         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-                        ptx::tmem_ld_wait();
-                        uint32_t pk[8];
                         __half2 rs[8];
                         if (kRes && res_tma) { // the residual tile sits in smem in the same 128B-swizzled layout as the output tile
                             *(uint4*)&rs[0] = *(const uint4*)(rrow + (((q * 2) ^ (row & 7)) * 16));
@@ -462,32 +497,23 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 for (int j = 0; j < 8; ++j) rs[j] = __floats2half2_rn(0.f, 0.f);
                             }
                         }
-                        // bias / PReLU slope of these 16 channels: four 16-byte loads each (the tile origin is a multiple of 64 channels)
+                        // bias / PReLU slope of these 16 channels (the tile origin is a multiple of 64 channels)
                         float bv[16], av[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            *(float4*)&bv[4 * j] = __ldg((const float4*)(bias + c0) + j);
-                            *(float4*)&av[4 * j] = __ldg((const float4*)(alpha + c0) + j);
-                        }
+                        for (int j = 0; j < 4; ++j) *(float4*)&bv[4 * j] = __ldg((const float4*)(bias + c0) + j);
+                        if (!p.relu_only) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
-                            float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
-                            float r0 = 0.f, r1 = 0.f;
-                            if (kRes && p.res_mode) { const float2 rf = __half22float2(rs[j]); r0 = rf.x; r1 = rf.y; }
-                            if (kRes && p.res_mode == 1) { a0 += r0; a1 += r1; }
-                            a0 = a0 > 0.f ? a0 : a0 * av[2 * j];
-                            a1 = a1 > 0.f ? a1 : a1 * av[2 * j + 1];
-                            if (kRes && p.res_mode == 2) { a0 += r0; a1 += r1; }
-                            const __half2 h2 = __floats2half2_rn(a0, a1);
-                            pk[j] = *(const uint32_t*)&h2;
+                            for (int j = 0; j < 4; ++j) *(float4*)&av[4 * j] = __ldg((const float4*)(alpha + c0) + j);
                         }
+                        ptx::tmem_ld_wait();
+                        uint32_t pk[8];
+                        conv_epilogue16<kRes>(v, bv, av, p.relu_only != 0, p.res_mode, rs, pk);
                         const int ch0 = q * 2; // 16-byte chunk index inside the 128-byte row
                         ptx::st_shared_v4(srow + (uint32_t)(((ch0) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
                         ptx::st_shared_v4(srow + (uint32_t)(((ch0 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                     }
                     ptx::fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
-                    ptx::named_bar_sync(1, 128);
+                    ptx::named_bar_sync(1, epi_threads);
                     if (leader) {
                         ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
                         ptx::bulk_commit_group();
@@ -496,7 +522,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ++res_used;
                 }
             } else
-            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            for (int c0 = eh * 16; c0 < p.BN; c0 += (p.epi_warps == 8 ? 32 : 16)) {
                 if (c0 >= n_valid) break; // warp-uniform: the remaining columns are padding
                 uint32_t v[16];
                 ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v); // warp-collective: executed by all lanes
@@ -794,6 +820,7 @@ struct HaloParams {
     int b_resident;             // 1: the layer's whole weight matrix (one group, one n-tile) stays in shared memory
     int tmem_cols;
     const float* bias; const float* alpha;
+    int relu_only;              // 1: every slope of the layer is 0 (plain ReLU)
 };
 
 template <int KR> // KR > 0: R == S == KR, tap loops unrolled (descriptor offsets become immediates); 0: run-time R, S
@@ -991,20 +1018,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const int c0 = sub * 64 + q * 16;
                     uint32_t v[16];
                     ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                    float bv[16], av[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *(float4*)&bv[4 * j] = __ldg((const float4*)(bias + c0) + j);
+                    if (!p.relu_only) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *(float4*)&av[4 * j] = __ldg((const float4*)(alpha + c0) + j);
+                    }
                     ptx::tmem_ld_wait();
                     uint32_t pk[8];
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 bv = __ldg((const float4*)(bias + c0) + j4);
-                        const float4 av = __ldg((const float4*)(alpha + c0) + j4);
-                        float a0 = __uint_as_float(v[4 * j4]) + bv.x, a1 = __uint_as_float(v[4 * j4 + 1]) + bv.y;
-                        float a2 = __uint_as_float(v[4 * j4 + 2]) + bv.z, a3 = __uint_as_float(v[4 * j4 + 3]) + bv.w;
-                        a0 = a0 > 0.f ? a0 : a0 * av.x; a1 = a1 > 0.f ? a1 : a1 * av.y;
-                        a2 = a2 > 0.f ? a2 : a2 * av.z; a3 = a3 > 0.f ? a3 : a3 * av.w;
-                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-                        pk[2 * j4] = *(const uint32_t*)&h01;
-                        pk[2 * j4 + 1] = *(const uint32_t*)&h23;
-                    }
+                    __half2 rs[8];
+                    conv_epilogue16<false>(v, bv, av, p.relu_only != 0, 0, rs, pk);
                     ptx::st_shared_v4(srow + (uint32_t)(((q * 2) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
                     ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                 }

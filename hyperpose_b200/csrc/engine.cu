@@ -669,6 +669,8 @@ int build_conv_plan_tf32(hp_engine* e, EngOp& op, const float* blob)
     while (tc < 2 * BN) tc *= 2;
     p.tmem_cols = tc;
     p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.relu_only = 1;
+    for (float a : alpha) if (a != 0.f) { p.relu_only = 0; break; }
     p.out_mode = (int)po.out_mode;
     if (po.out_mode == OUT_F32_NCHW_SPLIT) {
         p.out = e->d_conf; p.out2 = e->d_paf; p.split = (int)po.split;
@@ -771,6 +773,8 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     while (tc < 2 * BN) tc *= 2;
     p.tmem_cols = tc;
     p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.relu_only = 1;
+    for (float a : alpha) if (a != 0.f) { p.relu_only = 0; break; }
     p.out_mode = (int)po.out_mode;
     if (po.out_mode == OUT_F32_NCHW_SPLIT) {
         p.out = e->d_conf; p.out2 = e->d_paf; p.split = (int)po.split;
@@ -856,7 +860,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
                 for (int nb = 3; nb >= 2; --nb)
                     if (conv_halo_smem_bytes(eR, eS, BN, nb, w_tiles) <= CONV_SMEM_LIMIT) { h.num_boxes = nb; h.num_b_stages = w_tiles; h.b_resident = 1; break; }
             }
-            h.tmem_cols = p.tmem_cols; h.bias = pl.d_bias; h.alpha = pl.d_alpha;
+            h.tmem_cols = p.tmem_cols; h.bias = pl.d_bias; h.alpha = pl.d_alpha; h.relu_only = p.relu_only;
             if (h.num_b_stages >= 3) {
                 rc = make_tmap_act_box(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, HALO_TW + eS - 1, HALO_TH + eR - 1);
                 if (rc) return rc;
@@ -978,8 +982,10 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms - e->reserve_sms, n_tiles);
-    if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
-    else conv_tcgen05_kernel<false><<<grid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    static const bool epi4 = getenv("HPB_EPI4") != nullptr;   // diagnostic: one epilogue warp per TMEM lane quarter
+    p.epi_warps = epi4 ? 4 : 8;
+    if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    else conv_tcgen05_kernel<false><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
     return HP_OK;
 }
