@@ -821,10 +821,11 @@ struct HaloParams {
     int tmem_cols;
     const float* bias; const float* alpha;
     int relu_only;              // 1: every slope of the layer is 0 (plain ReLU)
+    int epi_warps;              // 8: two epilogue warps per TMEM lane quarter (each takes half of the channels), 4: one
 };
 
 template <int KR> // KR > 0: R == S == KR, tap loops unrolled (descriptor offsets become immediates); 0: run-time R, S
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_IM2COL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const HaloParams p)
 {
@@ -870,7 +871,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
-            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), 4);
+            ptx::mbar_init(ptx::smem_u32(tempty_bar + i), (uint32_t)p.epi_warps);
         }
         ptx::mbar_init(ptx::smem_u32(w_bar), 1);
         ptx::fence_barrier_init();
@@ -995,9 +996,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + p.epi_warps) {
         // ===================== epilogue: TMEM lane j = pixel (j >> 3, j & 7) of the tile =====================
-        const int ew = warp - 4, row = ew * 32 + lane;
+        // (epi_warps == 8: two warps per lane quarter, each converting half of the channels -- a 9-k-step tile is paced by its epilogue)
+        const int ew = (warp - 4) & 3, eh = (warp - 4) >> 2, row = ew * 32 + lane;
+        const int q_step = p.epi_warps == 8 ? 2 : 4, epi_threads = 32 * p.epi_warps;
         const bool leader = (warp == 4 && lane == 0);
         int acc = 0; uint32_t acc_phase = 0, stage_ctr = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -1011,10 +1014,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
                 uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
                 if (leader) ptx::bulk_wait_group_read<1>();
-                ptx::named_bar_sync(1, 128);
+                ptx::named_bar_sync(1, epi_threads);
                 const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (qq >= q_step) break;
+                    const int q = eh * q_step + qq;
                     const int c0 = sub * 64 + q * 16;
                     uint32_t v[16];
                     ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
@@ -1033,7 +1038,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                 }
                 ptx::fence_proxy_async();
-                ptx::named_bar_sync(1, 128);
+                ptx::named_bar_sync(1, epi_threads);
                 if (leader) {
                     // box {64 ch, 8, 16, 1}: staging row y * 8 + x == TMEM lane; pixels outside the image are clipped by the TMA unit
                     ptx::tma_store_4d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + g * p.cout_g + n0 + sub * 64, x0, y0, n);

@@ -951,8 +951,14 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         h.Nb = N;
         const long items = (long)N * h.tiles_x * h.tiles_y * h.groups * (h.cout_g_pad / h.BN);
         const int hgrid = (int)std::min<long>(e->num_sms - e->reserve_sms, items);
-        if (h.R == 3 && h.S == 3) conv_halo_kernel<3><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
-        else conv_halo_kernel<0><<<hgrid, CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        {
+            static const char* epi_env = getenv("HPB_EPI");
+            const int ksteps = h.R * h.S * (h.cin_g / CONV_BLOCK_K);
+            (void)ksteps;   // measured: the 9-k-step halo layers are paced by the MMA issue loop as much as by the epilogue -- a second warp set gains nothing
+            h.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : 4;
+        }
+        if (h.R == 3 && h.S == 3) conv_halo_kernel<3><<<hgrid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        else conv_halo_kernel<0><<<hgrid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
         e->launches++;
         return HP_OK;
     }
@@ -982,8 +988,11 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms - e->reserve_sms, n_tiles);
-    static const bool epi4 = getenv("HPB_EPI4") != nullptr;   // diagnostic: one epilogue warp per TMEM lane quarter
-    p.epi_warps = epi4 ? 4 : 8;
+    // two epilogue warps per TMEM lane quarter where the epilogue paces the tile (short k-loops: the 1x1 layers, ResNet conv3 with its
+    // residual); long k-loops hide a single set and run ~1.5 % faster without the extra warps (measured, profiles/r02_bench_*_epi{4,8}.json)
+    static const char* epi_env = getenv("HPB_EPI");   // diagnostic: HPB_EPI=4|8 forces one choice for every layer
+    const int ksteps = p.R * p.S * (p.cin_g / CONV_BLOCK_K);
+    p.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : ((ksteps <= 16 || (p.res_mode && ksteps <= 24)) ? 8 : 4);
     if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     else conv_tcgen05_kernel<false><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
