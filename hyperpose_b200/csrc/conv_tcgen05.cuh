@@ -64,6 +64,9 @@ struct ConvParams {
     int res_mode;              // 1: y = act(v + res)   2: y = act(v) + res
     int relu_only;             // 1: every slope of the layer is 0 (plain ReLU): the epilogue skips the slope loads
     int epi_warps;             // conv_tcgen05_kernel: 8 = two epilogue warps per TMEM lane quarter (each takes half of the channels), 4 = one
+    // a 1x1 "depthwise" op that follows the conv (per-channel scale + bias + PReLU: the filter_size (1,1) separable blocks of
+    // MobilenetThin-OpenPose) applied in the epilogue, with the fp16 rounding of the tensor in between kept: bit-identical with the two launches
+    const float* post_w; const float* post_b; const float* post_a;   // [groups * cout_g] each, or nullptr
 };
 
 namespace ptx {
@@ -196,6 +199,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
 {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem desc] * B[smem desc];  accumulate = 0 overwrites D
@@ -316,6 +322,27 @@ __device__ __forceinline__ void conv_epilogue16(const uint32_t (&v)[16], const f
         pk[j] = *(const uint32_t*)&h2;
     }
 }
+// the fused 1x1 depthwise stage on 16 packed channels: x = the fp16 value the conv would have stored; y = fp16(act(x * w + b))
+// with dwconv_kernel<1, 1>'s arithmetic (fmaf(x, w, 0) + b, slope, round)
+__device__ __forceinline__ void conv_post16(uint32_t (&pk)[8], const float* __restrict__ pw, const float* __restrict__ pb, const float* __restrict__ pa)
+{
+    float w[16], b[16], a[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        *(float4*)&w[4 * j] = __ldg((const float4*)pw + j);
+        *(float4*)&b[4 * j] = __ldg((const float4*)pb + j);
+        *(float4*)&a[4 * j] = __ldg((const float4*)pa + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float2 x = __half22float2(*(const __half2*)&pk[j]);
+        float y0 = fmaf(x.x, w[2 * j], 0.f) + b[2 * j], y1 = fmaf(x.y, w[2 * j + 1], 0.f) + b[2 * j + 1];
+        y0 = y0 > 0.f ? y0 : y0 * a[2 * j];
+        y1 = y1 > 0.f ? y1 : y1 * a[2 * j + 1];
+        const __half2 h2 = __floats2half2_rn(y0, y1);
+        pk[j] = *(const uint32_t*)&h2;
+    }
+}
 
 template <bool kRes> // kRes: residual epilogue compiled in (ResNet / LW-OpenPose blocks); false keeps the plain epilogue lean
 __global__ void __launch_bounds__(CONV_IM2COL_THREADS, 1)
@@ -323,6 +350,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     // 1024-byte alignment: required by the 128B swizzle atoms shared by TMA and UMMA
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * CONV_BLOCK_K * 2;
@@ -367,6 +395,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -508,6 +537,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tmem_ld_wait();
                         uint32_t pk[8];
                         conv_epilogue16<kRes>(v, bv, av, p.relu_only != 0, p.res_mode, rs, pk);
+                        if (p.post_w) {
+                            const int pc = t.g * p.cout_g + t.n0 + c0;
+                            conv_post16(pk, p.post_w + pc, p.post_b + pc, p.post_a + pc);
+                        }
                         const int ch0 = q * 2; // 16-byte chunk index inside the 128-byte row
                         ptx::st_shared_v4(srow + (uint32_t)(((ch0) ^ (row & 7)) * 16), make_uint4(pk[0], pk[1], pk[2], pk[3]));
                         ptx::st_shared_v4(srow + (uint32_t)(((ch0 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
@@ -613,6 +646,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          const __grid_constant__ CUtensorMap tmap_bh, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int W_BYTES = 128 * CONV_BLOCK_K * 2;          // 16 KiB weight tile (128 channels x 64 k)
     const int npx = p.npx;
@@ -668,6 +702,7 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (kMC) ptx::cluster_sync();   // the peer's barriers exist before anything is multicast into them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp == 0) {
         if (ptx::elect_one()) {
@@ -824,12 +859,20 @@ struct HaloParams {
     int epi_warps;              // 8: two epilogue warps per TMEM lane quarter (each takes half of the channels), 4: one
 };
 
-template <int KR> // KR > 0: R == S == KR, tap loops unrolled (descriptor offsets become immediates); 0: run-time R, S
+// kPool: the 2x2 / stride-2 max-pool that follows the layer is taken in the epilogue (VGG conv1_2 -> maxpool_1: the un-pooled
+// 494 MB activation is never written and the pool kernel disappears).  A tile is 16 x 8 pixels with TMEM lane j = pixel (j >> 3, j & 7),
+// so a 2x2 window is the lanes j, j^1, j^8, j^9 of ONE warp.  The maximum is taken on the raw fp32 accumulators BEFORE bias /
+// activation / rounding -- all three are monotone (slopes >= 0 are required), so fp16(act(max(v) + b)) == max(fp16(act(v + b))) bit for
+// bit -- by a transposing butterfly: in the x step a lane keeps 8 of its 16 channels and trades the other 8 with its partner, in the y
+// step 4 of 8, so afterwards EVERY lane holds 4 channels of one pooled pixel and none is idle.  The pooled tile (8 x 4 pixels x 64
+// channels) goes out as one TMA box {64, 4, 8, 1} of the pooled tensor.
+template <int KR, bool kPool = false> // KR > 0: R == S == KR, tap loops unrolled (descriptor offsets become immediates); 0: run-time R, S
 __global__ void __launch_bounds__(CONV_IM2COL_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_o, const HaloParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * CONV_BLOCK_K * 2;
     uint8_t* s_box = smem;                                              // [num_boxes][box_bytes]
@@ -881,6 +924,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     // item -> (spatial tile, n-tile); n-tiles vary fastest so that neighbouring CTAs share a halo box in L2
     auto decode = [&](int item, int& n, int& y0, int& x0, int& g, int& n0) {
@@ -1011,6 +1055,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
             const float* bias = p.bias + g * p.cout_g_pad + n0;
             const float* alpha = p.alpha + g * p.cout_g_pad + n0;
+            if (kPool) {
+                const int lx = lane & 7, ly = lane >> 3;                       // pixel of this lane inside the warp's 4 x 8 strip
+                const bool xo = (lx & 1) != 0, yo = (ly & 1) != 0;
+                const int cbase = (xo ? 8 : 0) + (yo ? 4 : 0);                  // the 4 channels (of every 16) this lane ends up with
+                const int row_p = ((ew * 4 + ly) >> 1) * 4 + (lx >> 1);         // pooled pixel inside the 8 x 4 pooled tile
+                for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                    uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
+                    if (leader) ptx::bulk_wait_group_read<1>();
+                    ptx::named_bar_sync(1, epi_threads);
+                    const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row_p * 128u;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        if (qq >= q_step) break;
+                        const int q = eh * q_step + qq;
+                        const int c0 = sub * 64 + q * 16;
+                        uint32_t v[16];
+                        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+                        const float4 bv = __ldg((const float4*)(bias + c0 + cbase));
+                        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!p.relu_only) av = __ldg((const float4*)(alpha + c0 + cbase));
+                        ptx::tmem_ld_wait();
+                        float m1[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {   // x step: even columns keep channels 0..7, odd columns 8..15
+                            const float send = xo ? __uint_as_float(v[i]) : __uint_as_float(v[8 + i]);
+                            const float keep = xo ? __uint_as_float(v[8 + i]) : __uint_as_float(v[i]);
+                            m1[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                        }
+                        float m2[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {   // y step: even rows keep the first 4 of those, odd rows the last 4
+                            const float send = yo ? m1[i] : m1[4 + i];
+                            const float keep = yo ? m1[4 + i] : m1[i];
+                            m2[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                        }
+                        float a0 = m2[0] + bv.x, a1 = m2[1] + bv.y, a2 = m2[2] + bv.z, a3 = m2[3] + bv.w;
+                        if (p.relu_only) {
+                            a0 = __uint_as_float(__float_as_uint(fmaxf(a0, 0.f)) | (__float_as_uint(a0) & 0x80000000u));
+                            a1 = __uint_as_float(__float_as_uint(fmaxf(a1, 0.f)) | (__float_as_uint(a1) & 0x80000000u));
+                            a2 = __uint_as_float(__float_as_uint(fmaxf(a2, 0.f)) | (__float_as_uint(a2) & 0x80000000u));
+                            a3 = __uint_as_float(__float_as_uint(fmaxf(a3, 0.f)) | (__float_as_uint(a3) & 0x80000000u));
+                        } else {
+                            a0 = a0 > 0.f ? a0 : a0 * av.x; a1 = a1 > 0.f ? a1 : a1 * av.y;
+                            a2 = a2 > 0.f ? a2 : a2 * av.z; a3 = a3 > 0.f ? a3 : a3 * av.w;
+                        }
+                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                        const uint32_t chunk = (uint32_t)(q * 2 + (cbase >> 3));
+                        const uint32_t addr = srow + ((chunk ^ (uint32_t)(row_p & 7)) * 16u) + (uint32_t)((cbase & 4) * 2);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*(const uint32_t*)&h01), "r"(*(const uint32_t*)&h23) : "memory");
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(1, epi_threads);
+                    if (leader) {
+                        // box {64 ch, 4, 8, 1} of the pooled tensor; pooled pixels outside it are clipped by the TMA unit
+                        ptx::tma_store_4d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + g * p.cout_g + n0 + sub * 64, x0 >> 1, y0 >> 1, n);
+                        ptx::bulk_commit_group();
+                    }
+                }
+            } else
             for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
                 uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
                 if (leader) ptx::bulk_wait_group_read<1>();
@@ -1107,6 +1210,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     constexpr int KCH = (KTOT + 63) / 64;           // 64-wide k chunks (1 for 3x3, 3 for 7x7)
     constexpr int A_BYTES = KCH * CONV_A_BYTES;     // one stage of patches: KCH tiles of 128 rows x 128 B
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                         // [STEM_STAGES][KCH][128 x 128 B]
     uint8_t* sB = sA + (size_t)STEM_STAGES * A_BYTES;           // [KCH][BN x 128 B] weights, resident
@@ -1145,6 +1249,7 @@ conv_stem_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp < 4) {
         // ===================== producers: one thread per pixel of the tile =====================
@@ -1300,6 +1405,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 2)
 conv_stem3_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o, const StemParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                          // [STAGES][128 rows x 128 B]
     uint8_t* sB = sA + (size_t)STEM3_STAGES * CONV_A_BYTES;      // [BN x 128 B] weights, resident
@@ -1346,6 +1452,7 @@ conv_stem3_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp < 4) {
         // ===================== gather: one thread per pixel of the tile =====================
@@ -1515,6 +1622,7 @@ __global__ void __launch_bounds__(STEM_THREADS, 2)
 conv_stem7_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o, const StemParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                          // [3 chunks][128 rows x 128 B]
     uint8_t* sB = sA + STEM7_A_BYTES;                            // [3 chunks][BN x 128 B] weights, resident
@@ -1560,6 +1668,7 @@ conv_stem7_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_const
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
     if (warp < 4) {
         // ===================== gather: one thread per pixel of the tile =====================

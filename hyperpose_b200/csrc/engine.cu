@@ -298,6 +298,83 @@ __global__ void __launch_bounds__(256, 3) dwconv3_col_kernel(const __half* __res
 #undef HP_FMA4
 }
 
+// Two depthwise 3x3 / stride-1 convolutions of the SAME input with different filters (the first separable block of the conf and
+// the paf branch of a MobilenetThin-OpenPose stage, mbv2_th_openpose.py:111-128: both read the 1216-channel concat tensor) in one
+// pass: a thread owns one column x, 2 channels and a run of rows, loads each input pixel ONCE (3 x 4-byte loads per row) and feeds
+// both filter sets; outputs go to out0 / out1.  Same column-marching scheme and the same accumulation order per output as
+// dwconv3_col_kernel (bit-identical); the second read of the 48 MB input and six of the twelve launches per network disappear.
+__global__ void __launch_bounds__(256, 3) dwconv3_col_dual_kernel(const __half* __restrict__ in, int in_ld, __half* __restrict__ out0, __half* __restrict__ out1, int out_ld,
+                                                               const float* __restrict__ w0 /*[9][C] | bias[C] | alpha[C]*/, const float* __restrict__ w1,
+                                                               int N, int H, int W, int C, int rows_per_chunk, int chunks)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cv = C / 2;
+    const size_t total = (size_t)N * chunks * W * cv;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % cv) * 2;
+    size_t t = idx / cv;
+    const int x = (int)(t % W); t /= W;
+    const int chunk = (int)(t % chunks);
+    const int n = (int)(t / chunks);
+    const int oh0 = chunk * rows_per_chunk, oh1 = min(oh0 + rows_per_chunk, H);
+    if (oh0 >= oh1) return;
+    float2 wa[9], wb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wa[k] = __ldg((const float2*)(w0 + (size_t)k * C + c0)); wb[k] = __ldg((const float2*)(w1 + (size_t)k * C + c0)); }
+    const float2 bsa = __ldg((const float2*)(w0 + (size_t)9 * C + c0)), ala = __ldg((const float2*)(w0 + (size_t)10 * C + c0));
+    const float2 bsb = __ldg((const float2*)(w1 + (size_t)9 * C + c0)), alb = __ldg((const float2*)(w1 + (size_t)10 * C + c0));
+    const bool has_l = x > 0, has_r = x + 1 < W;
+    const size_t row_in = (size_t)W * in_ld, row_out = (size_t)W * out_ld;
+    const __half* rp = in + ((size_t)n * H * W + x) * in_ld + c0;
+    __half* opa = out0 + ((size_t)n * H * W + x) * out_ld + c0 + (size_t)oh0 * row_out;
+    __half* opb = out1 + ((size_t)n * H * W + x) * out_ld + c0 + (size_t)oh0 * row_out;
+    float2 a0 = { 0.f, 0.f }, a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;   // output rows ih-1, ih, ih+1 of branch a / b
+#define HP_FMA2(acc, wv, xv) { acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y); }
+#define HP_DWD_EMIT(A, B)                                                                                                          \
+    {                                                                                                                               \
+        float y0 = A.x + bsa.x, y1 = A.y + bsa.y, z0 = B.x + bsb.x, z1 = B.y + bsb.y;                                                 \
+        y0 = y0 > 0.f ? y0 : y0 * ala.x; y1 = y1 > 0.f ? y1 : y1 * ala.y;                                                             \
+        z0 = z0 > 0.f ? z0 : z0 * alb.x; z1 = z1 > 0.f ? z1 : z1 * alb.y;                                                             \
+        *(__half2*)opa = __floats2half2_rn(y0, y1);                                                                                   \
+        *(__half2*)opb = __floats2half2_rn(z0, z1);                                                                                   \
+        opa += row_out; opb += row_out;                                                                                               \
+    }
+#define HP_DWD_STEP(A0, A1, A2, B0, B1, B2, IH)                                                                                    \
+    {                                                                                                                               \
+        uint32_t ul = 0u, ur = 0u;                                                                                                   \
+        const uint32_t uc = *(const uint32_t*)rp;                                                                                    \
+        if (has_l) ul = *(const uint32_t*)(rp - in_ld);                                                                              \
+        if (has_r) ur = *(const uint32_t*)(rp + in_ld);                                                                              \
+        rp += row_in;                                                                                                                \
+        const float2 vl = __half22float2(*(const __half2*)&ul), vm = __half22float2(*(const __half2*)&uc), vr = __half22float2(*(const __half2*)&ur); \
+        HP_FMA2(A0, wa[6], vl); HP_FMA2(A0, wa[7], vm); HP_FMA2(A0, wa[8], vr);                                                      \
+        HP_FMA2(A1, wa[3], vl); HP_FMA2(A1, wa[4], vm); HP_FMA2(A1, wa[5], vr);                                                      \
+        A2 = make_float2(0.f, 0.f);                                                                                                  \
+        HP_FMA2(A2, wa[0], vl); HP_FMA2(A2, wa[1], vm); HP_FMA2(A2, wa[2], vr);                                                      \
+        HP_FMA2(B0, wb[6], vl); HP_FMA2(B0, wb[7], vm); HP_FMA2(B0, wb[8], vr);                                                      \
+        HP_FMA2(B1, wb[3], vl); HP_FMA2(B1, wb[4], vm); HP_FMA2(B1, wb[5], vr);                                                      \
+        B2 = make_float2(0.f, 0.f);                                                                                                  \
+        HP_FMA2(B2, wb[0], vl); HP_FMA2(B2, wb[1], vm); HP_FMA2(B2, wb[2], vr);                                                      \
+        if ((IH) - 1 >= oh0) HP_DWD_EMIT(A0, B0);                                                                                    \
+    }
+    const int ih_first = max(oh0 - 1, 0), ih_last = min(oh1, H - 1);
+    rp += (size_t)ih_first * row_in;
+    int ih = ih_first;
+    for (; ih + 2 <= ih_last; ih += 3) {
+        HP_DWD_STEP(a0, a1, a2, b0, b1, b2, ih);
+        HP_DWD_STEP(a1, a2, a0, b1, b2, b0, ih + 1);
+        HP_DWD_STEP(a2, a0, a1, b2, b0, b1, ih + 2);
+    }
+    for (; ih <= ih_last; ++ih) {
+        HP_DWD_STEP(a0, a1, a2, b0, b1, b2, ih);
+        a0 = a1; a1 = a2; b0 = b1; b1 = b2;
+    }
+    if (oh1 - 1 >= ih_last) HP_DWD_EMIT(a0, b0);
+#undef HP_DWD_STEP
+#undef HP_DWD_EMIT
+#undef HP_FMA2
+}
+
 // OpenPifPaf heads (hyperpose/Model/pifpaf/model.py:215-281): raw 1x1-conv outputs [N,hc,wc,C] fp16 ->
 //   pixel_shuffle(scale 2) (pifpaf/utils.py:371-379: in-channel ((nc*2+dy)*2+dx) -> out[nc, 2h+dy, 2w+dx]), crop to 2*hc-1,
 //   reshape [fields, comps, ho, wo]; sigmoid on the confidences, softplus on the scales (inference branch, model.py:238-241,270-274);
@@ -506,6 +583,8 @@ struct ConvPlan {
     CUtensorMap tmap_b7;
     // halo-box kernel (conv_halo_kernel): one TMA box per 16 x 8-pixel tile and channel chunk serves every filter tap
     bool halo = false;
+    bool pool_fused = false;    // the 2x2 max-pool that follows is taken in the halo kernel's epilogue (tmap_o describes the POOLED buffer)
+    bool monotone_act = false;  // every PReLU slope of the layer is >= 0
     HaloParams hp;
     StemParams sp;
     size_t stem_smem = 0;
@@ -515,6 +594,8 @@ struct ConvPlan {
 
 struct EngOp {
     bool fused_into_stem = false; // OP_IM2COL3 whose consumer runs conv_stem_kernel: skipped for u8 input
+    bool fused_into_prev = false; // OP_MAXPOOL2 taken in the epilogue of the halo conv before it / second OP_DWCONV of a dual launch: never launched
+    bool dual_with_next = false;  // OP_DWCONV: the next op is a depthwise conv of the same input -- one dwconv3_col_dual_kernel serves both
     PackOp po;
     ConvPlan plan;              // OP_CONV only
     float* d_dw = nullptr;      // OP_DWCONV: [K*K][C] weights | bias[C] | alpha[C]
@@ -529,6 +610,7 @@ inline int same_pad_before(int in, int k, int stride)
 }
 
 struct EngBuffer {
+    bool fused_away = false;   // never written: its only consumer (a 2x2 max-pool) runs inside the producing conv's epilogue
     int channels = 0, down = 0, H = 0, W = 0;
     __half* d = nullptr;
 };
@@ -775,6 +857,8 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     p.bias = pl.d_bias; p.alpha = pl.d_alpha;
     p.relu_only = 1;
     for (float a : alpha) if (a != 0.f) { p.relu_only = 0; break; }
+    pl.monotone_act = true;
+    for (float a : alpha) if (!(a >= 0.f)) { pl.monotone_act = false; break; }
     p.out_mode = (int)po.out_mode;
     if (po.out_mode == OUT_F32_NCHW_SPLIT) {
         p.out = e->d_conf; p.out2 = e->d_paf; p.split = (int)po.split;
@@ -914,6 +998,25 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     return HP_OK;
 }
 
+// Launch with programmatic dependent launch allowed: the kernel may begin (prologue: barrier init, TMEM allocation, tensor-map
+// prefetch) on every SM the previous kernel of the stream has already left, and orders itself behind that kernel's completion with
+// griddepcontrol.wait before it touches memory.  The persistent conv kernels trigger their dependents at their own start.
+// MEASURED NEGATIVE (profiles/r02_bench_cfg{3,4}_{pdl,nopdl}.json, same box, graph replay): cfg3 2168 vs 2219 frames/s, cfg4 5072 vs 5158 --
+// inside a CUDA graph the plain kernel -> kernel edge is already cheaper than the programmatic one, so this is opt-in (HPB_PDL=1).
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    static const bool no_pdl = getenv("HPB_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
 {
     ConvPlan& pl = op.plan;
@@ -936,11 +1039,11 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
         const int per_sm = pl.stem_smem <= 110 * 1024 ? 2 : 1; // two resident CTAs hide the gather latency of the 3x3 stem
         const int grid = std::min((e->num_sms - e->reserve_sms) * per_sm, tiles);
         if (pl.stem3_v2) {
-            if (sp.flip) conv_stem3_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
-            else conv_stem3_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
+            if (sp.flip) launch_pdl(conv_stem3_kernel<true>, grid, STEM_THREADS, pl.stem_smem, st, pl.tmap_b, pl.tmap_o, sp);
+            else launch_pdl(conv_stem3_kernel<false>, grid, STEM_THREADS, pl.stem_smem, st, pl.tmap_b, pl.tmap_o, sp);
         } else if (pl.stem7_v2) {
-            if (sp.flip) conv_stem7_kernel<true><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b7, pl.tmap_o, sp);
-            else conv_stem7_kernel<false><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b7, pl.tmap_o, sp);
+            if (sp.flip) launch_pdl(conv_stem7_kernel<true>, grid, STEM_THREADS, pl.stem_smem, st, pl.tmap_b7, pl.tmap_o, sp);
+            else launch_pdl(conv_stem7_kernel<false>, grid, STEM_THREADS, pl.stem_smem, st, pl.tmap_b7, pl.tmap_o, sp);
         } else if (pl.stem_R == 3) conv_stem_kernel<3><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         else conv_stem_kernel<7><<<grid, STEM_THREADS, pl.stem_smem, st>>>(pl.tmap_b, pl.tmap_o, sp);
         e->launches++;
@@ -957,8 +1060,11 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
             (void)ksteps;   // measured: the 9-k-step halo layers are paced by the MMA issue loop as much as by the epilogue -- a second warp set gains nothing
             h.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : 4;
         }
-        if (h.R == 3 && h.S == 3) conv_halo_kernel<3><<<hgrid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
-        else conv_halo_kernel<0><<<hgrid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        if (pl.pool_fused) {
+            if (h.R == 3 && h.S == 3) launch_pdl(conv_halo_kernel<3, true>, hgrid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+            else launch_pdl(conv_halo_kernel<0, true>, hgrid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        } else if (h.R == 3 && h.S == 3) launch_pdl(conv_halo_kernel<3>, hgrid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
+        else launch_pdl(conv_halo_kernel<0>, hgrid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
         e->launches++;
         return HP_OK;
     }
@@ -981,7 +1087,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
             cfg.attrs = at; cfg.numAttrs = 1;
             HP_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tcgen05_swap_kernel<true>, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p));
         } else {
-            conv_tcgen05_swap_kernel<false><<<std::min(e->num_sms - e->reserve_sms, units * gc), CONV_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p);
+            launch_pdl(conv_tcgen05_swap_kernel<false>, std::min(e->num_sms - e->reserve_sms, units * gc), CONV_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_o2, pl.tmap_bh, p);
         }
         e->launches++;
         return HP_OK;
@@ -993,8 +1099,8 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     static const char* epi_env = getenv("HPB_EPI");   // diagnostic: HPB_EPI=4|8 forces one choice for every layer
     const int ksteps = p.R * p.S * (p.cin_g / CONV_BLOCK_K);
     p.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : ((ksteps <= 16 || (p.res_mode && ksteps <= 24)) ? 8 : 4);
-    if (p.res_mode) conv_tcgen05_kernel<true><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
-    else conv_tcgen05_kernel<false><<<grid, CONV_IM2COL_THREADS, pl.smem, st>>>(pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    if (p.res_mode) launch_pdl(conv_tcgen05_kernel<true>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    else launch_pdl(conv_tcgen05_kernel<false>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
     e->launches++;
     return HP_OK;
 }
@@ -1105,6 +1211,22 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             pifpaf_head_kernel<__half><<<(int)((t1 + 255) / 256), 256, 0, st>>>(a.d, a.channels, e->d_conf, N, a.H, a.W, 17, 5, e->out_h, e->out_w, 0);
             pifpaf_head_kernel<__half><<<(int)((t2 + 255) / 256), 256, 0, st>>>(b.d, b.channels, e->d_paf, N, b.H, b.W, 19, 9, e->out_h, e->out_w, 1);
             e->launches += 2;
+        } else if (po.type == OP_DWCONV && op.fused_into_prev) {
+            // served by the dual launch of the depthwise op before it
+        } else if (po.type == OP_DWCONV && op.dual_with_next) {
+            EngBuffer& ib = e->bufs[po.in_buf];
+            EngBuffer& ob = e->bufs[po.out_buf];
+            const EngOp& nx = e->ops[oi + 1];
+            const int C = (int)po.cout_g;
+            const size_t base = ((size_t)N * ib.W * (C / 2) + 255) / 256;
+            int chunks = (int)((4 * (size_t)e->num_sms + base - 1) / base);
+            chunks = std::max(1, std::min(chunks, std::max(1, ib.H / 4)));
+            const int rows = (ib.H + chunks - 1) / chunks;
+            chunks = (ib.H + rows - 1) / rows;
+            const size_t tot = (size_t)N * chunks * ib.W * (C / 2);
+            dwconv3_col_dual_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.d + nx.po.out_ch_off, ob.channels,
+                op.d_dw, nx.d_dw, N, ib.H, ib.W, C, rows, chunks);
+            e->launches++;
         } else if (po.type == OP_DWCONV) {
             EngBuffer& ib = e->bufs[po.in_buf];
             EngBuffer& ob = e->bufs[po.out_buf];
@@ -1128,6 +1250,8 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             else        { if (stride == 2) HP_DW(1, 2); else HP_DW(1, 1); }
 #undef HP_DW
             e->launches++;
+        } else if (po.type == OP_MAXPOOL2 && op.fused_into_prev) {
+            // taken in the epilogue of the conv before it
         } else if (po.type == OP_MAXPOOL2) {
             EngBuffer& ib = e->bufs[po.in_buf];
             EngBuffer& ob = e->bufs[po.out_buf];
@@ -1346,6 +1470,82 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
             return fail(HP_ERR_UNSUPPORTED);
         }
     }
+    // conv (halo kernel) -> 2x2 max-pool: the pool moves into the conv's epilogue when nobody else reads the un-pooled tensor
+    // (VGG conv1_2 -> maxpool_1: 0.10 ms and a 494 MB write per cfg3 step).  HPB_NO_POOL_FUSE=1 keeps the two launches.
+    if (dtype == HP_DTYPE_F16 && !getenv("HPB_NO_POOL_FUSE")) {
+        for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
+            EngOp& c = e->ops[i]; EngOp& m = e->ops[i + 1];
+            if (c.po.type != OP_CONV || !c.plan.halo || !c.plan.monotone_act || m.po.type != OP_MAXPOOL2 || (m.po.R != 0 && m.po.R != 2)) continue;
+            const EngBuffer& cb = e->bufs[c.po.out_buf];
+            const EngBuffer& pb = e->bufs[m.po.out_buf];
+            const int C = (int)c.po.groups * (int)c.po.cout_g;
+            if (m.po.in_buf != c.po.out_buf || m.po.in_ch_off != c.po.out_ch_off || (int)m.po.cout_g != C || c.plan.hp.cout_g_pad != c.plan.hp.cout_g ||
+                (cb.H & 1) || (cb.W & 1) || pb.H != cb.H / 2 || pb.W != cb.W / 2 || (int)m.po.out_ch_off + C > pb.channels) continue;
+            bool other_reader = false;
+            for (size_t k = 0; k < e->ops.size(); ++k) {
+                if (k == i + 1) continue;
+                const PackOp& q = e->ops[k].po;
+                if (q.type == OP_IM2COL3) continue;
+                if (q.in_buf == c.po.out_buf || ((q.type == OP_CONV && q.res_mode) || q.type == OP_PIFPAF_HEAD) && q.res_buf == c.po.out_buf) other_reader = true;
+            }
+            if (other_reader) continue;
+            if (make_tmap_act_box(&c.plan.tmap_o, pb.d, e->max_batch, pb.H, pb.W, pb.channels, HALO_TW / 2, HALO_TH / 2) != HP_OK) return fail(HP_ERR_CUDA);
+            c.plan.hp.out_ch_off = (int)m.po.out_ch_off;
+            c.plan.pool_fused = true;
+            m.fused_into_prev = true;
+            e->bufs[c.po.out_buf].fused_away = true;
+        }
+    }
+    // conv -> 1x1 "depthwise" (per-channel affine + PReLU; the filter_size (1,1) separable blocks, mbv2_th_openpose.py:121,127,144,151):
+    // applied in the conv's epilogue when the tensor in between has no other reader before it is overwritten.  HPB_NO_DW1_FUSE=1 keeps both launches.
+    if (dtype == HP_DTYPE_F16 && !getenv("HPB_NO_DW1_FUSE")) {
+        for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
+            EngOp& c = e->ops[i]; EngOp& d = e->ops[i + 1];
+            if (c.po.type != OP_CONV || d.po.type != OP_DWCONV || d.po.R != 1 || (d.po.stride ? d.po.stride : 1) != 1) continue;
+            const ConvParams& cp = c.plan.prm;
+            const int Ctot = (int)c.po.groups * (int)c.po.cout_g;
+            if (c.plan.halo || c.plan.stem || cp.swap_ab || !cp.tma_store || c.po.out_mode != OUT_F16_NHWC || cp.cout_g_pad != cp.cout_g || cp.cout_g % 16 ||
+                d.po.in_buf != c.po.out_buf || d.po.in_ch_off != c.po.out_ch_off || (int)d.po.cout_g != Ctot || d.po.out_buf == c.po.out_buf) continue;
+            if (d.po.out_buf == c.po.in_buf) {
+                // the fused conv would write the tensor it reads.  That is safe only when every tile reads exactly the (pixels, channels) it
+                // writes and has consumed them before its epilogue: a 1x1 conv whose group g maps channels [off + g*c, off + (g+1)*c) onto
+                // themselves with ONE n-tile per group (MobilenetThin's grouped 128 -> 128 pointwise convs on the ping-pong buffers)
+                if (cp.R != 1 || cp.S != 1 || cp.cin_g != cp.cout_g || cp.BN != cp.cout_g || (int)d.po.out_ch_off != cp.in_ch_off) continue;
+            }
+            if (c.po.res_mode && d.po.out_buf == c.po.res_buf) continue;
+            // the tensor between the two must be dead afterwards: no reader before the next writer of the same channels
+            bool safe = true, rewritten = false;
+            for (size_t k = i + 2; k < e->ops.size() && safe && !rewritten; ++k) {
+                const PackOp& q = e->ops[k].po;
+                if (q.type == OP_IM2COL3) continue;
+                if (q.in_buf == c.po.out_buf || (((q.type == OP_CONV && q.res_mode) || q.type == OP_PIFPAF_HEAD) && q.res_buf == c.po.out_buf)) safe = false;
+                else if (q.type != OP_PIFPAF_HEAD && q.out_mode != OUT_F32_NCHW_SPLIT && q.out_buf == c.po.out_buf) {
+                    const int qc = q.type == OP_CONV ? (int)q.groups * (int)q.cout_g : (int)q.cout_g;
+                    if (q.out_ch_off <= c.po.out_ch_off && (int)q.out_ch_off + qc >= (int)c.po.out_ch_off + Ctot) rewritten = true; else safe = false;
+                }
+            }
+            if (!safe) continue;
+            const EngBuffer& ob = e->bufs[d.po.out_buf];
+            if ((int)d.po.out_ch_off + Ctot > ob.channels) continue;
+            if (make_tmap_out(&c.plan.tmap_o, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels) != HP_OK) return fail(HP_ERR_CUDA);
+            c.plan.prm.out_ch_off = (int)d.po.out_ch_off;
+            c.plan.prm.post_w = d.d_dw; c.plan.prm.post_b = d.d_dw + Ctot; c.plan.prm.post_a = d.d_dw + 2 * (size_t)Ctot;
+            d.fused_into_prev = true;
+            if (!rewritten) e->bufs[c.po.out_buf].fused_away = true;   // its final content would have been this conv's output
+        }
+    }
+    // two depthwise 3x3 / stride-1 convs of the same input (conf / paf branch of a MobilenetThin stage): one dual launch
+    if (dtype == HP_DTYPE_F16 && !getenv("HPB_NO_DW_DUAL") && !getenv("HPB_DW_STRIP")) {
+        for (size_t i = 0; i + 1 < e->ops.size(); ++i) {
+            EngOp& a = e->ops[i]; EngOp& b = e->ops[i + 1];
+            if (a.po.type != OP_DWCONV || b.po.type != OP_DWCONV || a.fused_into_prev) continue;
+            const int st_a = a.po.stride ? (int)a.po.stride : 1, st_b = b.po.stride ? (int)b.po.stride : 1;
+            if (a.po.R != 3 || b.po.R != 3 || st_a != 1 || st_b != 1 || a.po.in_buf != b.po.in_buf || a.po.in_ch_off != b.po.in_ch_off ||
+                a.po.cout_g != b.po.cout_g || a.po.out_buf != b.po.out_buf || a.po.out_buf == a.po.in_buf) continue;
+            a.dual_with_next = true;
+            b.fused_into_prev = true;
+        }
+    }
     if (max_smem > 0 && dtype == HP_DTYPE_TF32) {
         if (cudaFuncSetAttribute(conv_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
             cudaFuncSetAttribute(conv_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) {
@@ -1363,7 +1563,9 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
     size_t halo_smem = 0;
     for (auto& o : e->ops) if (o.plan.halo) halo_smem = std::max(halo_smem, o.plan.smem);
     if (halo_smem && (cudaFuncSetAttribute(conv_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess ||
-                      cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess)) {
+                      cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess ||
+                      cudaFuncSetAttribute(conv_halo_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess ||
+                      cudaFuncSetAttribute(conv_halo_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)halo_smem) != cudaSuccess)) {
         set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (halo)", halo_smem);
         return fail(HP_ERR_CUDA);
     }
@@ -1666,6 +1868,7 @@ int hp_engine_debug_read_buffer(hp_engine* e, int buf, void* out_f16, int N, int
     if (H) *H = b.H;
     if (W) *W = b.W;
     if (C) *C = b.channels;
+    if (b.fused_away && out_f16) { set_error("hp_engine_debug_read_buffer: buffer %d is not materialised (its max-pool runs in the producing conv's epilogue; HPB_NO_POOL_FUSE=1 keeps it)", buf); return HP_ERR_UNSUPPORTED; }
     HP_CUDA_TRY(cudaStreamSynchronize(e->stream));
     const size_t es = e->dtype == HP_DTYPE_TF32 ? sizeof(float) : sizeof(__half);   // element type follows the engine's dtype
     if (out_f16) HP_CUDA_TRY(cudaMemcpy(out_f16, b.d, (size_t)N * b.H * b.W * b.channels * es, cudaMemcpyDeviceToHost));
@@ -1837,6 +2040,7 @@ int pose_launch(hp_engine* e, hp_engine::PoseSlot& sl)
             for (auto& op : e->ops) {
                 const uint32_t t = op.po.type;
                 if (t == OP_IM2COL3 && op.fused_into_stem) continue;
+                if ((t == OP_MAXPOOL2 || t == OP_DWCONV) && op.fused_into_prev) continue;
                 n_k += (t == OP_PIFPAF_HEAD) ? 2 : 1;
             }
             e->launches += n_k;

@@ -39,7 +39,13 @@ def _every_buffer(g, eng, frames, N, rel, abs_, skip=()):
     for bi in range(len(g.buffers)):
         if bi in skip:
             continue
-        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        try:
+            got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        except capi.HyperposeError as ex:
+            # the un-pooled output of a conv whose 2x2 max-pool runs in its epilogue is never written; the pooled buffer that
+            # follows is compared like every other one, which checks conv + pool together
+            assert ex.status == capi.HP_ERR_UNSUPPORTED, ex
+            continue
         ref = rbufs[bi].cpu().numpy()
         c = ref.shape[1]
         d, m = _cmp(got[:, :c], ref, rel, abs_, f"{g.name} buffer {bi} {tuple(ref.shape)}")

@@ -39,7 +39,13 @@ def test_tiny_net_every_layer(hw, N):
     conf, paf = eng.read_outputs(N)
     rconf, rpaf, rbufs = torch_ref.run_graph(g, frames, emulate_fp16=True)
     for bi in range(len(g.buffers)):
-        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        try:
+            got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        except capi.HyperposeError as ex:
+            # the un-pooled output of a conv whose 2x2 max-pool runs in its epilogue is never written; the pooled buffer that
+            # follows is compared like every other one, which checks conv + pool together
+            assert ex.status == capi.HP_ERR_UNSUPPORTED, ex
+            continue
         ref = rbufs[bi].cpu().numpy()
         if bi == 0:   # im2col buffer: compare its centre tap (k = 4*3 + c) with the normalised image
             if not os.environ.get("HPB_NO_STEM3"):
@@ -90,7 +96,13 @@ def test_mobilenet_thin_openpose(hw, N):
     conf, paf = eng.read_outputs(N)
     rconf, rpaf, rbufs = torch_ref.run_graph(g, frames, emulate_fp16=True)
     for bi in range(1, len(g.buffers)):
-        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        try:
+            got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        except capi.HyperposeError as ex:
+            # the un-pooled output of a conv whose 2x2 max-pool runs in its epilogue is never written; the pooled buffer that
+            # follows is compared like every other one, which checks conv + pool together
+            assert ex.status == capi.HP_ERR_UNSUPPORTED, ex
+            continue
         _check(got, rbufs[bi].cpu().numpy(), 4e-3, 4e-3, f"buffer {bi}")
     _check(conf, rconf.cpu().numpy(), 4e-3, 4e-3, "conf")
     _check(paf, rpaf.cpu().numpy(), 4e-3, 4e-3, "paf")
@@ -113,7 +125,13 @@ def test_resnet50_lw_openpose(hw, N):
     conf, paf = eng.read_outputs(N)
     rconf, rpaf, rbufs = torch_ref.run_graph(g, frames, emulate_fp16=True)
     for bi in range(1, len(g.buffers)):
-        got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        try:
+            got = eng.debug_read_buffer(bi, N).astype(np.float32).transpose(0, 3, 1, 2)
+        except capi.HyperposeError as ex:
+            # the un-pooled output of a conv whose 2x2 max-pool runs in its epilogue is never written; the pooled buffer that
+            # follows is compared like every other one, which checks conv + pool together
+            assert ex.status == capi.HP_ERR_UNSUPPORTED, ex
+            continue
         _check(got, rbufs[bi].cpu().numpy(), 6e-3, 6e-3, f"buffer {bi}")
     _check(conf, rconf.cpu().numpy(), 6e-3, 6e-3, "conf")
     _check(paf, rpaf.cpu().numpy(), 6e-3, 6e-3, "paf")
@@ -353,3 +371,58 @@ def test_weight_multicast_swap_kernel_is_bit_identical():
             outs.append(np.load(f.name))
     assert np.isfinite(outs[0]).all() and np.abs(outs[0]).max() > 0
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_max_pool_fused_into_the_halo_epilogue_is_bit_identical(monkeypatch):
+    """conv (halo kernel) -> 2x2 max-pool with the pool taken in the conv's epilogue (on the raw accumulators, before bias / ReLU /
+    rounding -- all monotone) against the two separate launches (HPB_NO_POOL_FUSE=1): every materialised buffer and both outputs
+    must be the same BYTES; the un-pooled buffer is the one that is no longer written."""
+    g = models.openpose_vgg19(0, n_stages=2)
+    H, W, N = 112, 136, 3                  # 112 = 7 x 16, 136 = 17 x 8: interior, edge and corner tiles; even sizes
+    frames = syn.make_frames_u8(17, N, H, W)
+
+    def run():
+        eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+        eng.infer_u8(frames)
+        outs = eng.read_outputs(N)
+        bufs = {}
+        for bi in range(1, len(g.buffers)):
+            try:
+                bufs[bi] = eng.debug_read_buffer(bi, N).tobytes()
+            except capi.HyperposeError as ex:
+                assert ex.status == capi.HP_ERR_UNSUPPORTED
+        eng.close()
+        return outs, bufs
+
+    fused_outs, fused = run()
+    monkeypatch.setenv("HPB_NO_POOL_FUSE", "1")
+    plain_outs, plain = run()
+    assert len(plain) == len(g.buffers) - 1 and len(fused) == len(plain) - 1, "exactly one buffer (conv1_2's un-pooled output) is fused away"
+    for bi, b in fused.items():
+        assert b == plain[bi], f"buffer {bi} differs between the fused and the two-launch form"
+    assert fused_outs[0].tobytes() == plain_outs[0].tobytes() and fused_outs[1].tobytes() == plain_outs[1].tobytes()
+
+
+def test_fused_depthwise_forms_are_bit_identical(monkeypatch):
+    """MobilenetThin-OpenPose: (a) the 1x1 "depthwise" ops (per-channel affine + ReLU) applied in the preceding conv's epilogue, with the
+    fp16 rounding of the tensor in between kept, and (b) the two depthwise 3x3 convs of a stage's first block served by one dual
+    launch -- against the plain one-launch-per-op form (HPB_NO_DW1_FUSE / HPB_NO_DW_DUAL): identical bytes in both outputs."""
+    g = models.mobilenet_thin_openpose(0, n_stages=3)
+    H, W, N = 96, 128, 2
+    frames = syn.make_frames_u8(19, N, H, W)
+
+    def run():
+        eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+        launches0 = eng.launch_count
+        eng.infer_u8(frames)
+        outs = eng.read_outputs(N)
+        n = eng.launch_count - launches0
+        eng.close()
+        return outs, n
+
+    fused, n_fused = run()
+    monkeypatch.setenv("HPB_NO_DW1_FUSE", "1")
+    monkeypatch.setenv("HPB_NO_DW_DUAL", "1")
+    plain, n_plain = run()
+    assert n_fused < n_plain, (n_fused, n_plain)
+    assert fused[0].tobytes() == plain[0].tobytes() and fused[1].tobytes() == plain[1].tobytes()
