@@ -908,6 +908,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         const long total_px = (long)e->max_batch * ib.H * ib.W;
         p.npx = getenv("HPB_NPX") ? atoi(getenv("HPB_NPX")) : conv_swap_pick_npx(total_px, G * (cout_pad / 128), e->num_sms);
         p.num_stages = conv_swap_pick_stages(p.npx);
+        if (getenv("HPB_SWAP_STAGES")) p.num_stages = std::max(2, std::min(p.num_stages, atoi(getenv("HPB_SWAP_STAGES"))));   // experiment: pipeline depth
         rc = make_tmap_act_im2col(&pl.tmap_a, ib.d, e->max_batch, ib.H, ib.W, ib.channels, eR, eS, p.npx);
         if (rc) return rc;
         rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, 128);
@@ -927,7 +928,9 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         const int ty = (ib.H + HALO_TH - 1) / HALO_TH, tx = (ib.W + HALO_TW - 1) / HALO_TW;
         const double waste = (double)ty * HALO_TH * tx * HALO_TW / ((double)ib.H * ib.W) - 1.0;
         const bool shape_ok = !im2col && eR == eS && (eR == 3 || eR == 5 || eR == 7) && !po.res_mode && p.tma_store && cout_pad % BN == 0;
-        const bool want = hv ? (strcmp(hv, "all") == 0) : (eR == 3 && waste <= 0.06 && !p.swap_ab);
+        // (3x3 layers that also qualify for the swapped-operand kernel come here too: measured on VGG conv2_2, 128 -> 128 at 184x328,
+        //  0.250 -> 0.218 ms, and its 2x2 max-pool then runs in the epilogue -- profiles/r02_bench_cfg3_halopool.json)
+        const bool want = hv ? (strcmp(hv, "all") == 0) : (eR == 3 && waste <= 0.06);
         if (shape_ok && want && !(hv && strcmp(hv, "0") == 0)) {
             const EngBuffer& ob = e->bufs[po.out_buf];
             HaloParams& h = pl.hp;
@@ -1419,8 +1422,8 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
     }
     e->ops.resize(hdr.n_ops);
     size_t max_smem = 0;
+    for (uint32_t i = 0; i < hdr.n_ops; ++i) e->ops[i].po = pops[i];   // (plan building looks at neighbouring ops)
     for (uint32_t i = 0; i < hdr.n_ops; ++i) {
-        e->ops[i].po = pops[i];
         const PackOp& po = pops[i];
         if ((po.type != OP_IM2COL3 && po.in_buf >= hdr.n_buffers) || (po.out_mode != OUT_F32_NCHW_SPLIT && po.type != OP_PIFPAF_HEAD && po.out_buf >= hdr.n_buffers)) {
             set_error("engine: op %u references a missing buffer", i);
