@@ -431,23 +431,29 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const uint64_t da_first = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem)), stage_step = (uint64_t)(stage_bytes >> 4);
+            const uint32_t full_first = ptx::smem_u32(full_bar), empty_first = ptx::smem_u32(empty_bar);
+            uint64_t da_cur = da_first;
+            uint32_t full_cur = full_first, empty_cur = empty_first;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1); // epilogue drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
+                    // descriptors and barrier addresses of the stage are ready before the wait (advanced incrementally: the stage buffers are
+                    // 1024-byte multiples); only the MMAs sit between the arrival of the data and their issue
+                    const uint64_t da = da_cur, db = da_cur + (uint64_t)(CONV_A_BYTES >> 4);
+                    const uint32_t fb = full_cur, eb = empty_cur;
+                    ptx::mbar_wait(fb, phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
-                    const uint64_t db = ptx::make_sw128_kmajor_desc(sa + CONV_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k) {
                         // advancing K by 16 fp16 = 32 bytes inside the 128-byte swizzled row: +2 in the (>>4) address field
                         ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit(ptx::smem_u32(empty_bar + stage)); // frees the smem slot when these MMAs retire
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                    ptx::umma_commit(eb); // frees the smem slot when these MMAs retire
+                    da_cur += stage_step; full_cur += 8u; empty_cur += 8u;
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; da_cur = da_first; full_cur = full_first; empty_cur = empty_first; }
                 }
                 ptx::umma_commit(ptx::smem_u32(tfull_bar + acc)); // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -739,22 +745,30 @@ conv_tcgen05_swap_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            // stage 0's weight-tile descriptor / barrier addresses and the per-stage increments (the stage buffers are 1024-byte multiples,
+            // so the descriptor's address field just advances by stage_bytes >> 4; the pixel tile follows the weight tile by W_BYTES)
+            const uint64_t dw_first = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem)), stage_step = (uint64_t)(stage_bytes >> 4);
+            const uint32_t full_first = ptx::smem_u32(full_bar), empty_first = ptx::smem_u32(empty_bar);
+            uint64_t dw_cur = dw_first;
+            uint32_t full_cur = full_first, empty_cur = empty_first;
             for (int item = my_first; item < total_items; item += my_step) {
                 ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    ptx::mbar_wait(ptx::smem_u32(full_bar + stage), phase);
+                    // the descriptors of this stage are ready BEFORE the wait: nothing but the four MMAs sits between the arrival of the
+                    // data and their issue (they were computed after the wait: ~30 dependent uniform-datapath instructions per k-step)
+                    const uint64_t dw = dw_cur, dx = dw_cur + (uint64_t)(W_BYTES >> 4);
+                    const uint32_t fb = full_cur, eb = empty_cur;
+                    ptx::mbar_wait(fb, phase);
                     ptx::tc_fence_after();
-                    const uint32_t sw = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t dw = ptx::make_sw128_kmajor_desc(sw);           // "A" operand: weights, M = 128 channels
-                    const uint64_t dx = ptx::make_sw128_kmajor_desc(sw + W_BYTES); // "B" operand: NPX pixel rows
 #pragma unroll
                     for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
                         ptx::umma_f16(d_tmem, dw + (uint64_t)(k * 2), dx + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
-                    if (kMC) ptx::umma_commit_mc(ptx::smem_u32(empty_bar + stage), (uint16_t)3);   // frees the slot in BOTH CTAs' view
-                    else ptx::umma_commit(ptx::smem_u32(empty_bar + stage));
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                    if (kMC) ptx::umma_commit_mc(eb, (uint16_t)3);   // frees the slot in BOTH CTAs' view
+                    else ptx::umma_commit(eb);
+                    dw_cur += stage_step; full_cur += 8u; empty_cur += 8u;
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; dw_cur = dw_first; full_cur = full_first; empty_cur = empty_first; }
                 }
                 ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
