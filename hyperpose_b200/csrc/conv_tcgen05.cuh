@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace hpb {
 
 constexpr int CONV_BLOCK_M = 128;   // pixels per tile == TMEM lanes == UMMA M
@@ -67,6 +69,7 @@ struct ConvParams {
     // a 1x1 "depthwise" op that follows the conv (per-channel scale + bias + PReLU: the filter_size (1,1) separable blocks of
     // MobilenetThin-OpenPose) applied in the epilogue, with the fp16 rounding of the tensor in between kept: bit-identical with the two launches
     const float* post_w; const float* post_b; const float* post_a;   // [groups * cout_g] each, or nullptr
+    int split_from, total_items;   // conv_tcgen05_kernel work list: items >= split_from are N-halves (see decode_tile); total_items = tiles + (tiles - split_from)
 };
 
 namespace ptx {
@@ -267,16 +270,23 @@ __host__ __device__ inline uint32_t make_idesc_f16(int M, int N)
 
 struct ConvTile {
     int p0, g, n0; // first output pixel (flattened n,h,w), group, first output channel of the tile
+    int bn;        // channels of the tile: BN, or BN / 2 for the N-halves of the ragged last round (split_from)
 };
 
-__device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int tile, int n_tiles_g)
+// Work item -> tile.  Items [0, split_from) are the full 128 x BN tiles of the rounds that fill the persistent grid; the tiles of
+// a ragged last round (fewer than half a wave) are cut into two N-halves each, items split_from + 2 j + {0, 1}: the tail of the
+// kernel runs twice as many CTAs for ~0.6 of a tile time (472 tiles on 148 SMs: 3 rounds + 28 tiles -> 3 rounds + 56 half tiles).
+__device__ __forceinline__ ConvTile decode_tile(const ConvParams& p, int item, int n_tiles_g)
 {
     ConvTile t;
+    int tile = item, half = 0;
+    t.bn = p.BN;
+    if (item >= p.split_from) { const int j = item - p.split_from; tile = p.split_from + (j >> 1); half = j & 1; t.bn = p.BN >> 1; }
     const int n_tiles_total = p.groups * n_tiles_g;
     const int nt = tile % n_tiles_total;
     const int mt = tile / n_tiles_total;
     t.g = nt / n_tiles_g;
-    t.n0 = (nt - t.g * n_tiles_g) * p.BN;
+    t.n0 = (nt - t.g * n_tiles_g) * p.BN + half * (p.BN >> 1);
     t.p0 = mt * CONV_BLOCK_M;
     return t;
 }
@@ -347,7 +357,8 @@ __device__ __forceinline__ void conv_post16(uint32_t (&pk)[8], const float* __re
 template <bool kRes> // kRes: residual epilogue compiled in (ResNet / LW-OpenPose blocks); false keeps the plain epilogue lean
 __global__ void __launch_bounds__(CONV_IM2COL_THREADS, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p)
+                    const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
+                    const __grid_constant__ CUtensorMap tmap_bh /* weight box of BN / 2 rows (N-halves) */, const ConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     ptx::pdl_launch_dependents();   // the next kernel may start its prologue on every SM this grid has left
@@ -369,7 +380,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_g = p.cout_g_pad / p.BN;
-    const int total_tiles = p.m_tiles * p.groups * n_tiles_g;
+    const int total_tiles = p.total_items;   // work items: full tiles, then the N-halves of a ragged last round
     const int chunks = p.cin_g / CONV_BLOCK_K;
     const int ksteps = p.R * p.S * chunks;
 
@@ -415,10 +426,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             ptx::mbar_wait(ptx::smem_u32(empty_bar + stage), phase ^ 1);
                             const uint32_t fb = ptx::smem_u32(full_bar + stage);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                            ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                            ptx::mbar_expect_tx(fb, (uint32_t)(CONV_A_BYTES + t.bn * CONV_BLOCK_K * 2));
                             ptx::tma_load_im2col_4d(ptx::smem_u32(sa), &tmap_a, fb, a_ch0 + c * CONV_BLOCK_K,
                                                     q0.w - pad_w, q0.h - pad_h, q0.n, s, r);
-                            ptx::tma_load_2d(ptx::smem_u32(sa + CONV_A_BYTES), &tmap_b, fb, kcol, b_row);
+                            ptx::tma_load_2d(ptx::smem_u32(sa + CONV_A_BYTES), t.bn == p.BN ? &tmap_b : &tmap_bh, fb, kcol, b_row);
                             if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         }
             }
@@ -426,7 +437,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN);
+            const uint32_t idesc_full = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN), idesc_half = ptx::make_idesc_f16(CONV_BLOCK_M, p.BN >> 1);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -439,6 +450,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1); // epilogue drained this accumulator
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                const uint32_t idesc = tile < p.split_from ? idesc_full : idesc_half;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     // descriptors and barrier addresses of the stage are ready before the wait (advanced incrementally: the stage buffers are
                     // 1024-byte multiples); only the MMAs sit between the arrival of the data and their issue
@@ -473,7 +485,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t stage_ctr = 0;
         // residual tiles: sub-tile k of this CTA's (tile, sub) sequence lands in res_stage[k & 1]; the leader keeps two in flight
         const bool res_tma = kRes && p.res_mode != 0 && p.tma_store != 0;
-        const int subs = p.BN / 64;
         uint32_t res_issued = 0, res_used = 0;
         int ri_tile = blockIdx.x, ri_sub = 0;
         auto issue_residual = [&]() { // leader only
@@ -484,7 +495,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             ptx::tma_load_2d(ptx::smem_u32(res_stage + (res_issued & 1) * CONV_A_BYTES), &tmap_r, rb,
                              p.res_ch_off + rt.g * p.cout_g + rt.n0 + ri_sub * 64, rt.p0);
             ++res_issued;
-            if (++ri_sub == subs) { ri_sub = 0; ri_tile += gridDim.x; }
+            if (++ri_sub == rt.bn / 64) { ri_sub = 0; ri_tile += gridDim.x; }
         };
         if (kRes && res_tma && warp == 4 && lane == 0) { issue_residual(); issue_residual(); }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -497,14 +508,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.BN);
             const float* bias = p.bias + t.g * p.cout_g_pad + t.n0;
             const float* alpha = p.alpha + t.g * p.cout_g_pad + t.n0;
-            const int n_valid = min(p.BN, p.cout_g - t.n0); // real (unpadded) channels of this tile
+            const int n_valid = min(t.bn, p.cout_g - t.n0); // real (unpadded) channels of this tile
             const size_t pix = (size_t)(t.p0 + row);
             if (p.tma_store) {
                 // 64 channels at a time: registers -> swizzled smem tile -> one TMA tensor store (coalesced, clipped
                 // at the image border by the TMA unit); double-buffered so the store of sub-tile k overlaps the
                 // TMEM reads of sub-tile k+1.
                 const bool leader = (warp == 4 && lane == 0);
-                for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
+                for (int sub = 0; sub < t.bn / 64; ++sub, ++stage_ctr) {
                     uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
                     if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
                     ptx::named_bar_sync(1, epi_threads);
@@ -561,7 +572,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ++res_used;
                 }
             } else
-            for (int c0 = eh * 16; c0 < p.BN; c0 += (p.epi_warps == 8 ? 32 : 16)) {
+            for (int c0 = eh * 16; c0 < t.bn; c0 += (p.epi_warps == 8 ? 32 : 16)) {
                 if (c0 >= n_valid) break; // warp-uniform: the remaining columns are padding
                 uint32_t v[16];
                 ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v); // warp-collective: executed by all lanes
@@ -1006,53 +1017,59 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint64_t db0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(s_b));
             const uint64_t b_step = (uint64_t)(b_bytes >> 4);               // one weight tile, in descriptor address units
             const uint64_t tap_step = b_step * (uint64_t)chunks;            // resident layout: tile (t, c) at (t * chunks + c)
-            int box = 0; uint32_t box_phase = 0;
-            int st = 0; uint32_t st_phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            if (p.b_resident) ptx::mbar_wait(ptx::smem_u32(w_bar), 0);
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int c = 0; c < chunks; ++c) {
-                    ptx::mbar_wait(ptx::smem_u32(a_full + box), box_phase);
+            // resident / streamed weights are two instantiations of the loop (the per-tap test of a run-time flag kept the streamed path's
+            // barrier wait and commit in the resident stream: ~45 instructions per tap on a 9-tap tile that is paced by exactly this thread)
+            auto issue = [&](auto resident_tag) {
+                constexpr bool kResident = decltype(resident_tag)::value;
+                int box = 0; uint32_t box_phase = 0;
+                int st = 0; uint32_t st_phase = 0;
+                int acc = 0; uint32_t acc_phase = 0;
+                if (kResident) ptx::mbar_wait(ptx::smem_u32(w_bar), 0);
+                for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                    ptx::mbar_wait(ptx::smem_u32(tempty_bar + acc), acc_phase ^ 1);
                     ptx::tc_fence_after();
-                    const uint32_t box_addr = ptx::smem_u32(s_box + (size_t)box * p.box_bytes);
-                    // A: rows = the 16 x 8 pixels at box offset (r, s2); K-major, 128B swizzle, row groups one box row apart
-                    const uint64_t da0 = (uint64_t)((box_addr & 0x3ffffu) >> 4) | a_hi;
-                    uint64_t db_res = db0 + b_step * (uint64_t)c;
-                    auto tap = [&](int r, int s2, bool first) {
-                        uint64_t db;
-                        if (p.b_resident) { db = db_res; db_res += tap_step; }
-                        else {
-                            ptx::mbar_wait(ptx::smem_u32(b_full + st), st_phase);
-                            ptx::tc_fence_after();
-                            db = db0 + b_step * (uint64_t)st;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+                    for (int c = 0; c < chunks; ++c) {
+                        const uint32_t box_addr = ptx::smem_u32(s_box + (size_t)box * p.box_bytes);
+                        // A: rows = the 16 x 8 pixels at box offset (r, s2); K-major, 128B swizzle, row groups one box row apart
+                        const uint64_t da0 = (uint64_t)((box_addr & 0x3ffffu) >> 4) | a_hi;
+                        uint64_t db_res = db0 + b_step * (uint64_t)c;
+                        ptx::mbar_wait(ptx::smem_u32(a_full + box), box_phase);
+                        ptx::tc_fence_after();
+                        auto tap = [&](int r, int s2, bool first) {
+                            uint64_t db;
+                            if (kResident) { db = db_res; db_res += tap_step; }
+                            else {
+                                ptx::mbar_wait(ptx::smem_u32(b_full + st), st_phase);
+                                ptx::tc_fence_after();
+                                db = db0 + b_step * (uint64_t)st;
+                            }
+                            const uint64_t da = da0 + (uint64_t)((r * BW + s2) * 8);
+#pragma unroll
+                            for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
+                                ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                            if (!kResident) {
+                                ptx::umma_commit(ptx::smem_u32(b_empty + st));
+                                if (++st == p.num_b_stages) { st = 0; st_phase ^= 1; }
+                            }
+                        };
+                        if (KR > 0) {
+#pragma unroll
+                            for (int r = 0; r < (KR > 0 ? KR : 1); ++r)
+#pragma unroll
+                                for (int s2 = 0; s2 < (KR > 0 ? KR : 1); ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
+                        } else {
+                            for (int r = 0; r < p.R; ++r)
+                                for (int s2 = 0; s2 < p.S; ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
                         }
-                        const uint64_t da = da0 + (uint64_t)((r * BW + s2) * 8);
-#pragma unroll
-                        for (int k = 0; k < CONV_BLOCK_K / CONV_UMMA_K; ++k)
-                            ptx::umma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
-                        if (!p.b_resident) {
-                            ptx::umma_commit(ptx::smem_u32(b_empty + st));
-                            if (++st == p.num_b_stages) { st = 0; st_phase ^= 1; }
-                        }
-                    };
-                    if (KR > 0) {
-#pragma unroll
-                        for (int r = 0; r < (KR > 0 ? KR : 1); ++r)
-#pragma unroll
-                            for (int s2 = 0; s2 < (KR > 0 ? KR : 1); ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
-                    } else {
-                        for (int r = 0; r < p.R; ++r)
-                            for (int s2 = 0; s2 < p.S; ++s2) tap(r, s2, c == 0 && r == 0 && s2 == 0);
+                        ptx::umma_commit(ptx::smem_u32(a_empty + box)); // every tap of this chunk has read the box
+                        if (++box == p.num_boxes) { box = 0; box_phase ^= 1; }
                     }
-                    ptx::umma_commit(ptx::smem_u32(a_empty + box)); // every tap of this chunk has read the box
-                    if (++box == p.num_boxes) { box = 0; box_phase ^= 1; }
+                    ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                ptx::umma_commit(ptx::smem_u32(tfull_bar + acc));
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            }
+            };
+            if (p.b_resident) issue(std::true_type{}); else issue(std::false_type{});
         }
     } else if (warp >= 4 && warp < 4 + p.epi_warps) {
         // ===================== epilogue: TMEM lane j = pixel (j >> 3, j & 7) of the tile =====================

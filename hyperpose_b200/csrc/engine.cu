@@ -375,6 +375,132 @@ __global__ void __launch_bounds__(256, 3) dwconv3_col_dual_kernel(const __half* 
 #undef HP_FMA2
 }
 
+// Depthwise 3x3 / stride 1 with the input staged by TMA (channel counts that are multiples of 64; NB = 1: one filter set, NB = 2: the two
+// filter sets of a MobilenetThin stage's conf / paf branch on the same input).  The per-lane loads of dwconv3_col_kernel keep too few
+// bytes in flight (ncu: 58 % of the stall cycles are L1TEX scoreboard waits at 15 % DRAM throughput), so here a persistent CTA pulls
+// whole tiles -- {64 channels, wbo + 2 columns, hb + 2 rows} of one frame, the 1-pixel halo included, out-of-image elements zero-filled
+// by the TMA unit = the SAME padding -- through a ring of `stages` shared-memory buffers, one bulk tensor copy per tile, issued
+// `stages - 1` tiles ahead.  Compute is the column march of dwconv3_col_kernel from shared memory: a lane owns a channel pair (the 32
+// lanes of a warp read one pixel's 128 bytes: conflict-free), a warp a column of the tile; the accumulation order per output is the
+// same (tap-row major, tap-column ascending, absent taps as zeros), on the packed fp32 pipe (FFMA2 = two IEEE fmas): bit-identical.
+struct DwTmaParams {
+    __half* out0; __half* out1; int out_ld;
+    const float* w0; const float* w1;   // [9][C] | bias[C] | alpha[C]
+    int N, H, W, C, ctiles, tiles_x, tiles_y, wbo, hb, n_items, stages;
+};
+constexpr int DWT_THREADS = 576;   // 18 warps: the 54 columns of a 46x54 map = 3 full rounds
+constexpr int DWT_STAGE_MAX = 65536;   // bytes of one tile buffer at most (3 of them + barriers fit 227 KB)
+
+template <int NB>
+__global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const DwTmaParams p)
+{
+    extern __shared__ uint8_t dwt_smem_raw[];
+    const uint32_t base = (ptx::smem_u32(dwt_smem_raw) + 127u) & ~127u;
+    const int bw = p.wbo + 2;
+    const uint32_t stage_bytes = (uint32_t)(p.hb + 2) * (uint32_t)bw * 128u;
+    const uint32_t bars = base + (uint32_t)p.stages * stage_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ptx::pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tmap(&tmap_in);
+        for (int s = 0; s < p.stages; ++s) ptx::mbar_init(bars + 8u * s, 1);
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+    // k-th tile of this CTA -> its buffer (thread 0 only)
+    auto issue = [&](int k) {
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        if (item >= p.n_items) return;
+        int t = item;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int n = t % p.N; const int ct = t / p.N;
+        const int s = k % p.stages;
+        ptx::mbar_expect_tx(bars + 8u * s, stage_bytes);
+        ptx::tma_load_4d(base + (uint32_t)s * stage_bytes, &tmap_in, bars + 8u * s, ct * 64, tx * p.wbo - 1, ty * p.hb - 1, n);
+    };
+    ptx::pdl_wait();   // (HPB_PDL) the prologue above may run under the previous kernel's tail; its results are visible from here on
+    if (threadIdx.x == 0)
+        for (int k = 0; k < p.stages - 1; ++k) issue(k);
+    const size_t row_out = (size_t)p.W * p.out_ld;
+    float2 wa[9], wb[9], bsa, ala, bsb, alb;
+    int ct_loaded = -1;
+    for (int k = 0;; ++k) {
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        if (item >= p.n_items) break;
+        __syncthreads();   // every warp is done with tile k-1: its buffer takes tile k + stages - 1
+        if (threadIdx.x == 0) issue(k + p.stages - 1);
+        int t = item;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int n = t % p.N; const int ct = t / p.N;   // the channel tile varies slowest: a CTA's consecutive tiles mostly share their filters
+        const int c0 = ct * 64 + lane * 2;
+        if (ct != ct_loaded) {
+            ct_loaded = ct;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                wa[q] = __ldg((const float2*)(p.w0 + (size_t)q * p.C + c0));
+                if (NB == 2) wb[q] = __ldg((const float2*)(p.w1 + (size_t)q * p.C + c0));
+            }
+            bsa = __ldg((const float2*)(p.w0 + (size_t)9 * p.C + c0)); ala = __ldg((const float2*)(p.w0 + (size_t)10 * p.C + c0));
+            if (NB == 2) { bsb = __ldg((const float2*)(p.w1 + (size_t)9 * p.C + c0)); alb = __ldg((const float2*)(p.w1 + (size_t)10 * p.C + c0)); }
+        }
+        const int x_lo = tx * p.wbo, y_lo = ty * p.hb;
+        const int ncols = min(p.wbo, p.W - x_lo), nrows = min(p.hb, p.H - y_lo);
+        const int s = k % p.stages;
+        ptx::mbar_wait(bars + 8u * s, (uint32_t)(k / p.stages) & 1u);
+        const uint32_t* tile = (const uint32_t*)(dwt_smem_raw + (base - ptx::smem_u32(dwt_smem_raw)) + (size_t)s * stage_bytes) + lane;
+        const int row_words = bw * 32;
+        for (int col = warp; col < ncols; col += DWT_THREADS / 32) {
+            const uint32_t* sp = tile + col * 32;   // box row 0 (image row y_lo - 1), box columns col, col+1, col+2 = image x-1, x, x+1
+            const size_t o = (((size_t)n * p.H + y_lo) * p.W + x_lo + col) * p.out_ld + c0;
+            __half* opa = p.out0 + o;
+            __half* opb = NB == 2 ? p.out1 + o : nullptr;
+            float2 a0 = { 0.f, 0.f }, a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+#define HP_DWT_EMIT(A, B)                                                                                                          \
+            {                                                                                                                       \
+                float y0 = A.x + bsa.x, y1 = A.y + bsa.y;                                                                            \
+                y0 = y0 > 0.f ? y0 : y0 * ala.x; y1 = y1 > 0.f ? y1 : y1 * ala.y;                                                    \
+                *(__half2*)opa = __floats2half2_rn(y0, y1); opa += row_out;                                                          \
+                if (NB == 2) {                                                                                                      \
+                    float z0 = B.x + bsb.x, z1 = B.y + bsb.y;                                                                        \
+                    z0 = z0 > 0.f ? z0 : z0 * alb.x; z1 = z1 > 0.f ? z1 : z1 * alb.y;                                                \
+                    *(__half2*)opb = __floats2half2_rn(z0, z1); opb += row_out;                                                      \
+                }                                                                                                                   \
+            }
+            // box row I: tap row 2 of output row I-2 (A0/B0, complete -> stored), tap row 1 of I-1 (A1/B1), tap row 0 of I (A2/B2, from zero)
+#define HP_DWT_STEP(A0, A1, A2, B0, B1, B2, I)                                                                                     \
+            {                                                                                                                       \
+                const uint32_t ul = sp[0], uc = sp[32], ur = sp[64];                                                                 \
+                sp += row_words;                                                                                                     \
+                const float2 vl = __half22float2(*(const __half2*)&ul), vm = __half22float2(*(const __half2*)&uc), vr = __half22float2(*(const __half2*)&ur); \
+                A0 = __ffma2_rn(vl, wa[6], A0); A0 = __ffma2_rn(vm, wa[7], A0); A0 = __ffma2_rn(vr, wa[8], A0);                      \
+                A1 = __ffma2_rn(vl, wa[3], A1); A1 = __ffma2_rn(vm, wa[4], A1); A1 = __ffma2_rn(vr, wa[5], A1);                      \
+                A2 = __ffma2_rn(vl, wa[0], make_float2(0.f, 0.f)); A2 = __ffma2_rn(vm, wa[1], A2); A2 = __ffma2_rn(vr, wa[2], A2);   \
+                if (NB == 2) {                                                                                                      \
+                    B0 = __ffma2_rn(vl, wb[6], B0); B0 = __ffma2_rn(vm, wb[7], B0); B0 = __ffma2_rn(vr, wb[8], B0);                  \
+                    B1 = __ffma2_rn(vl, wb[3], B1); B1 = __ffma2_rn(vm, wb[4], B1); B1 = __ffma2_rn(vr, wb[5], B1);                  \
+                    B2 = __ffma2_rn(vl, wb[0], make_float2(0.f, 0.f)); B2 = __ffma2_rn(vm, wb[1], B2); B2 = __ffma2_rn(vr, wb[2], B2); \
+                }                                                                                                                   \
+                if ((I) >= 2) HP_DWT_EMIT(A0, B0);                                                                                   \
+            }
+            const int R = nrows + 2;
+            int i = 0;
+            for (; i + 2 < R; i += 3) {   // three rows per trip: the accumulators rotate by renaming
+                HP_DWT_STEP(a0, a1, a2, b0, b1, b2, i);
+                HP_DWT_STEP(a1, a2, a0, b1, b2, b0, i + 1);
+                HP_DWT_STEP(a2, a0, a1, b2, b0, b1, i + 2);
+            }
+            for (; i < R; ++i) {
+                HP_DWT_STEP(a0, a1, a2, b0, b1, b2, i);
+                a0 = a1; a1 = a2; b0 = b1; b1 = b2;
+            }
+#undef HP_DWT_STEP
+#undef HP_DWT_EMIT
+        }
+    }
+}
+
 // OpenPifPaf heads (hyperpose/Model/pifpaf/model.py:215-281): raw 1x1-conv outputs [N,hc,wc,C] fp16 ->
 //   pixel_shuffle(scale 2) (pifpaf/utils.py:371-379: in-channel ((nc*2+dy)*2+dx) -> out[nc, 2h+dy, 2w+dx]), crop to 2*hc-1,
 //   reshape [fields, comps, ho, wo]; sigmoid on the confidences, softplus on the scales (inference branch, model.py:238-241,270-274);
@@ -549,6 +675,22 @@ int make_tmap_act_box(CUtensorMap* m, const __half* base, int N, int H, int W, i
     return HP_OK;
 }
 
+// a C-channel view (channel stride ld) of activations [N,H,W,ld] fp16 as a 4-D tiled tensor (C, W, H, N), box {64 ch, box_w, box_h, 1}, no
+// swizzle (a pixel's 64 channels = 128 contiguous bytes of shared memory): the halo'd tiles of dwconv3_tma_kernel
+int make_tmap_act_box_plain(CUtensorMap* m, const __half* base, int N, int H, int W, int C, int ld, int box_w, int box_h)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return HP_ERR_CUDA; }
+    cuuint64_t dims[4] = { (cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N };
+    cuuint64_t strides[3] = { (cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2 };
+    cuuint32_t box[4] = { 64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1 };
+    cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(plain box) failed: %d (N=%d H=%d W=%d C=%d ld=%d box %dx%d)", (int)r, N, H, W, C, ld, box_w, box_h); return HP_ERR_CUDA; }
+    return HP_OK;
+}
+
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 int pick_bn(int cout_g)
@@ -596,6 +738,10 @@ struct EngOp {
     bool fused_into_stem = false; // OP_IM2COL3 whose consumer runs conv_stem_kernel: skipped for u8 input
     bool fused_into_prev = false; // OP_MAXPOOL2 taken in the epilogue of the halo conv before it / second OP_DWCONV of a dual launch: never launched
     bool dual_with_next = false;  // OP_DWCONV: the next op is a depthwise conv of the same input -- one dwconv3_col_dual_kernel serves both
+    bool dw_tma = false;          // OP_DWCONV 3x3 / stride 1, C % 64 == 0: dwconv3_tma_kernel (input tiles staged by TMA)
+    CUtensorMap tmap_dw;
+    int dwt_wbo = 0, dwt_hb = 0, dwt_tiles_x = 0, dwt_tiles_y = 0, dwt_stages = 0;
+    size_t dwt_smem = 0;
     PackOp po;
     ConvPlan plan;              // OP_CONV only
     float* d_dw = nullptr;      // OP_DWCONV: [K*K][C] weights | bias[C] | alpha[C]
@@ -751,6 +897,7 @@ int build_conv_plan_tf32(hp_engine* e, EngOp& op, const float* blob)
     while (tc < 2 * BN) tc *= 2;
     p.tmem_cols = tc;
     p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.split_from = 0x7fffffff; p.total_items = 0;   // (decode_tile: no N-halves unless launch_conv sets them up)
     p.relu_only = 1;
     for (float a : alpha) if (a != 0.f) { p.relu_only = 0; break; }
     p.out_mode = (int)po.out_mode;
@@ -855,6 +1002,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     while (tc < 2 * BN) tc *= 2;
     p.tmem_cols = tc;
     p.bias = pl.d_bias; p.alpha = pl.d_alpha;
+    p.split_from = 0x7fffffff; p.total_items = 0;   // (decode_tile: no N-halves unless launch_conv sets them up)
     p.relu_only = 1;
     for (float a : alpha) if (a != 0.f) { p.relu_only = 0; break; }
     pl.monotone_act = true;
@@ -881,6 +1029,8 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     if (rc) return rc;
     rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
     if (rc) return rc;
+    memset(&pl.tmap_bh, 0, sizeof(pl.tmap_bh));
+    if (BN == 256) { rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, BN / 2); if (rc) return rc; }   // N-halves of a ragged last round
     memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
     if (p.tma_store) {
         const EngBuffer& ob = e->bufs[po.out_buf];
@@ -899,7 +1049,6 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     }
     // swapped-operand kernel: output channels in blocks of 128, enough k-steps to amortise the transposing epilogue
     memset(&pl.tmap_o2, 0, sizeof(pl.tmap_o2));
-    memset(&pl.tmap_bh, 0, sizeof(pl.tmap_bh));
     // (restricted to one 128-channel block per group: with several blocks every block would re-fetch the same pixels
     //  through L2, which the 2x larger L2->SM traffic does not pay for on the merged 256-channel layers)
     p.swap_ab = (p.tma_store && !po.res_mode && cout_pad == 128 && cout_g == cout_pad && eR * eS * (ecin / 64) >= 18 && !getenv("HPB_NO_SWAP")) ? 1 : 0;
@@ -1020,6 +1169,25 @@ static inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
     cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// depthwise 3x3 / stride 1 through dwconv3_tma_kernel; `pair` = the second depthwise op of a conf / paf branch pair (same input) or nullptr
+void launch_dw_tma(hp_engine* e, const EngOp& op, const EngOp* pair, int N, cudaStream_t st)
+{
+    const PackOp& po = op.po;
+    const EngBuffer& ib = e->bufs[po.in_buf];
+    const EngBuffer& ob = e->bufs[po.out_buf];
+    DwTmaParams p;
+    p.out0 = ob.d + po.out_ch_off;
+    p.out1 = pair ? e->bufs[pair->po.out_buf].d + pair->po.out_ch_off : nullptr;
+    p.out_ld = ob.channels;
+    p.w0 = op.d_dw; p.w1 = pair ? pair->d_dw : nullptr;
+    p.N = N; p.H = ib.H; p.W = ib.W; p.C = (int)po.cout_g; p.ctiles = p.C / 64;
+    p.tiles_x = op.dwt_tiles_x; p.tiles_y = op.dwt_tiles_y; p.wbo = op.dwt_wbo; p.hb = op.dwt_hb; p.stages = op.dwt_stages;
+    p.n_items = N * p.tiles_y * p.tiles_x * p.ctiles;
+    const int grid = std::min(p.n_items, std::max(1, e->num_sms - e->reserve_sms));
+    if (pair) launch_pdl(dwconv3_tma_kernel<2>, grid, DWT_THREADS, op.dwt_smem, st, op.tmap_dw, p);
+    else      launch_pdl(dwconv3_tma_kernel<1>, grid, DWT_THREADS, op.dwt_smem, st, op.tmap_dw, p);
+}
+
 int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
 {
     ConvPlan& pl = op.plan;
@@ -1097,13 +1265,21 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     }
     const int n_tiles = p.m_tiles * p.groups * (p.cout_g_pad / p.BN);
     const int grid = std::min(e->num_sms - e->reserve_sms, n_tiles);
+    // a ragged last round (fewer tiles than half the grid) runs as N-halves on twice as many CTAs (decode_tile); HPB_NO_SPLIT=1 disables
+    {
+        const bool no_split = getenv("HPB_NO_SPLIT") != nullptr;   // same-box A/B: profiles/r02_bench_cfg{3,4,5}_split.json
+        const int rem = n_tiles % grid;
+        const bool split = !no_split && p.BN == 256 && p.tma_store && rem > 0 && 2 * rem <= grid && n_tiles > grid;
+        p.split_from = split ? n_tiles - rem : n_tiles;
+        p.total_items = n_tiles + (n_tiles - p.split_from);
+    }
     // two epilogue warps per TMEM lane quarter where the epilogue paces the tile (short k-loops: the 1x1 layers, ResNet conv3 with its
     // residual); long k-loops hide a single set and run ~1.5 % faster without the extra warps (measured, profiles/r02_bench_*_epi{4,8}.json)
     static const char* epi_env = getenv("HPB_EPI");   // diagnostic: HPB_EPI=4|8 forces one choice for every layer
     const int ksteps = p.R * p.S * (p.cin_g / CONV_BLOCK_K);
     p.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : ((ksteps <= 16 || (p.res_mode && ksteps <= 24)) ? 8 : 4);
-    if (p.res_mode) launch_pdl(conv_tcgen05_kernel<true>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
-    else launch_pdl(conv_tcgen05_kernel<false>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, p);
+    if (p.res_mode) launch_pdl(conv_tcgen05_kernel<true>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, pl.tmap_bh, p);
+    else launch_pdl(conv_tcgen05_kernel<false>, grid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, pl.tmap_r, pl.tmap_bh, p);
     e->launches++;
     return HP_OK;
 }
@@ -1221,14 +1397,18 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             EngBuffer& ob = e->bufs[po.out_buf];
             const EngOp& nx = e->ops[oi + 1];
             const int C = (int)po.cout_g;
-            const size_t base = ((size_t)N * ib.W * (C / 2) + 255) / 256;
-            int chunks = (int)((4 * (size_t)e->num_sms + base - 1) / base);
-            chunks = std::max(1, std::min(chunks, std::max(1, ib.H / 4)));
-            const int rows = (ib.H + chunks - 1) / chunks;
-            chunks = (ib.H + rows - 1) / rows;
-            const size_t tot = (size_t)N * chunks * ib.W * (C / 2);
-            dwconv3_col_dual_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.d + nx.po.out_ch_off, ob.channels,
-                op.d_dw, nx.d_dw, N, ib.H, ib.W, C, rows, chunks);
+            if (op.dw_tma) {
+                launch_dw_tma(e, op, &nx, N, st);
+            } else {
+                const size_t base = ((size_t)N * ib.W * (C / 2) + 255) / 256;
+                int chunks = (int)((4 * (size_t)e->num_sms + base - 1) / base);
+                chunks = std::max(1, std::min(chunks, std::max(1, ib.H / 4)));
+                const int rows = (ib.H + chunks - 1) / chunks;
+                chunks = (ib.H + rows - 1) / rows;
+                const size_t tot = (size_t)N * chunks * ib.W * (C / 2);
+                dwconv3_col_dual_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.d + nx.po.out_ch_off, ob.channels,
+                    op.d_dw, nx.d_dw, N, ib.H, ib.W, C, rows, chunks);
+            }
             e->launches++;
         } else if (po.type == OP_DWCONV) {
             EngBuffer& ib = e->bufs[po.in_buf];
@@ -1239,7 +1419,9 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
             const float* dw = op.d_dw;
 #define HP_DW(KK, SS) dwconv_kernel<KK, SS><<<blocks, 256, 0, st>>>(ib.d + po.in_ch_off, ib.channels, ob.d + po.out_ch_off, ob.channels, dw, \
                 dw + (size_t)KK * KK * C, dw + (size_t)KK * KK * C + C, N, ib.H, ib.W, C, ob.H, ob.W, same_pad_before(ib.H, KK, SS), same_pad_before(ib.W, KK, SS))
-            if (K == 3 && stride == 1 && !getenv("HPB_DW_STRIP")) {
+            if (op.dw_tma) {
+                launch_dw_tma(e, op, nullptr, N, st);
+            } else if (K == 3 && stride == 1 && !getenv("HPB_DW_STRIP")) {
                 // column-marching kernel: enough row chunks to give every SM a few blocks
                 const size_t base = ((size_t)N * ib.W * (C / 4) + 255) / 256;
                 int chunks = (int)((4 * (size_t)e->num_sms + base - 1) / base);
@@ -1547,6 +1729,41 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
                 a.po.cout_g != b.po.cout_g || a.po.out_buf != b.po.out_buf || a.po.out_buf == a.po.in_buf) continue;
             a.dual_with_next = true;
             b.fused_into_prev = true;
+        }
+    }
+    // depthwise 3x3 / stride 1 on a multiple of 64 channels: input tiles through TMA (dwconv3_tma_kernel)
+    if (dtype == HP_DTYPE_F16 && !getenv("HPB_NO_DW_TMA") && !getenv("HPB_DW_STRIP")) {
+        size_t dwt_max = 0;
+        for (size_t i = 0; i < e->ops.size(); ++i) {
+            EngOp& a = e->ops[i];
+            const PackOp& po = a.po;
+            if (po.type != OP_DWCONV || a.fused_into_prev || po.R != 3 || (po.stride ? (int)po.stride : 1) != 1 || po.cout_g % 64 || po.in_buf == po.out_buf) continue;
+            const EngBuffer& ib = e->bufs[po.in_buf];
+            if (ib.channels % 8 || po.in_ch_off % 8) continue;
+            const int C = (int)po.cout_g;
+            const int nx = (ib.W + 61) / 62, wbo = (ib.W + nx - 1) / nx, bw = wbo + 2;
+            // tile height: the tallest of 6 / 4 / 3 / 2 rows that fits a buffer and still gives every SM two tiles at the full batch
+            int hb = 2;
+            for (int cand : { 6, 4, 3, 2 }) {
+                if (cand > std::max(2, ib.H) || (size_t)(cand + 2) * bw * 128 > (size_t)DWT_STAGE_MAX) continue;
+                const size_t items = (size_t)e->max_batch * ((ib.H + cand - 1) / cand) * nx * (C / 64);
+                hb = cand;
+                if (items >= 2 * (size_t)e->num_sms) break;
+            }
+            const size_t stage = (size_t)(hb + 2) * bw * 128;
+            if (stage > (size_t)DWT_STAGE_MAX) continue;
+            a.dwt_stages = (int)std::min<size_t>(4, (200 * 1024) / stage);
+            if (a.dwt_stages < 2) continue;
+            a.dwt_wbo = wbo; a.dwt_hb = hb; a.dwt_tiles_x = nx; a.dwt_tiles_y = (ib.H + hb - 1) / hb;
+            a.dwt_smem = a.dwt_stages * stage + 128 + 64;
+            if (make_tmap_act_box_plain(&a.tmap_dw, ib.d + po.in_ch_off, e->max_batch, ib.H, ib.W, C, ib.channels, bw, hb + 2) != HP_OK) return fail(HP_ERR_CUDA);
+            a.dw_tma = true;
+            dwt_max = std::max(dwt_max, a.dwt_smem);
+        }
+        if (dwt_max > 0 && (cudaFuncSetAttribute(dwconv3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dwt_max) != cudaSuccess ||
+                            cudaFuncSetAttribute(dwconv3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dwt_max) != cudaSuccess)) {
+            set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (depthwise)", dwt_max);
+            return fail(HP_ERR_CUDA);
         }
     }
     if (max_smem > 0 && dtype == HP_DTYPE_TF32) {

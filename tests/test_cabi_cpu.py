@@ -62,7 +62,7 @@ def test_conv_traffic_json_is_the_fold_of_the_committed_launch_list():
     import json
     import subprocess
     import sys
-    csv_path = os.path.join(ROOT, "profiles", "r02_launches_step.csv")
+    csv_path = os.path.join(ROOT, "profiles", "r02_final_launches_step.csv")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "summarize_launches.py"), csv_path, "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     fold = json.loads(r.stdout[r.stdout.index("{"):])

@@ -426,3 +426,59 @@ def test_fused_depthwise_forms_are_bit_identical(monkeypatch):
     plain, n_plain = run()
     assert n_fused < n_plain, (n_fused, n_plain)
     assert fused[0].tobytes() == plain[0].tobytes() and fused[1].tobytes() == plain[1].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw,N", [((96, 128), 2), ((368, 432), 3), ((200, 1040), 1)])
+def test_tma_tiled_depthwise_kernel_is_bit_identical(monkeypatch, hw, N):
+    """MobilenetThin-OpenPose with the 3x3 / stride-1 depthwise layers of >= 64 channels on dwconv3_tma_kernel (input tiles with their
+    halo staged by TMA, single and dual filter sets) against the per-lane-load kernels (HPB_NO_DW_TMA): every activation buffer and both
+    outputs must be the same BYTES.  368x432 has ragged bottom tiles (46 rows); 200x1040 is wider than one 62-column tile at every
+    resolution (520 / 260 / 130 columns: several x tiles with ragged right edges)."""
+    g = models.mobilenet_thin_openpose(0, n_stages=2)
+    H, W = hw
+    frames = syn.make_frames_u8(23, N, H, W)
+
+    def run():
+        eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+        eng.infer_u8(frames)
+        outs = eng.read_outputs(N)
+        bufs = {}
+        for bi in range(1, len(g.buffers)):
+            try:
+                bufs[bi] = eng.debug_read_buffer(bi, N).tobytes()
+            except capi.HyperposeError as ex:
+                assert ex.status == capi.HP_ERR_UNSUPPORTED
+        eng.close()
+        return outs, bufs
+
+    tiled_outs, tiled = run()
+    monkeypatch.setenv("HPB_NO_DW_TMA", "1")
+    plain_outs, plain = run()
+    assert tiled.keys() == plain.keys()
+    for bi, b in tiled.items():
+        assert b == plain[bi], f"buffer {bi} ({g.buffers[bi]}) differs between the TMA-tiled and the per-lane-load depthwise kernels"
+    assert tiled_outs[0].tobytes() == plain_outs[0].tobytes() and tiled_outs[1].tobytes() == plain_outs[1].tobytes()
+
+
+@pytest.mark.gpu
+def test_n_half_tiles_of_a_ragged_last_round_are_bit_identical(monkeypatch):
+    """conv_tcgen05_kernel's work list: when the last round of 128-pixel x 256-channel tiles would occupy at most half of the CTAs, those
+    tiles run as N-halves (128 x 128) on twice as many CTAs.  Same MMAs per output element, same k order: the bytes must not change
+    (HPB_NO_SPLIT=1 = the plain tile list).  ResNet50 at 368x432 / batch 5 has such layers (46x54 maps: 98 pixel tiles; 512 output
+    channels -> 196 tiles, 48 in the ragged round; 2048 channels -> 784 tiles, 44 in the ragged round)."""
+    g = models.resnet50_lw_openpose(0)
+    H, W, N = 368, 432, 5
+    frames = syn.make_frames_u8(29, N, H, W)
+
+    def run():
+        eng = capi.Engine(g.to_pack(), (W, H), max_batch_size=N)
+        eng.infer_u8(frames)
+        outs = eng.read_outputs(N)
+        eng.close()
+        return outs
+
+    split = run()
+    monkeypatch.setenv("HPB_NO_SPLIT", "1")
+    plain = run()
+    assert split[0].tobytes() == plain[0].tobytes() and split[1].tobytes() == plain[1].tobytes()
