@@ -69,6 +69,7 @@ struct ConvParams {
     // a 1x1 "depthwise" op that follows the conv (per-channel scale + bias + PReLU: the filter_size (1,1) separable blocks of
     // MobilenetThin-OpenPose) applied in the epilogue, with the fp16 rounding of the tensor in between kept: bit-identical with the two launches
     const float* post_w; const float* post_b; const float* post_a;   // [groups * cout_g] each, or nullptr
+    int res_stages;                // depth of the residual-tile ring of conv_tcgen05_kernel's TMA-store epilogue (2 or 4)
     int split_from, total_items;   // conv_tcgen05_kernel work list: items >= split_from are N-halves (see decode_tile); total_items = tiles + (tiles - split_from)
 };
 
@@ -188,6 +189,12 @@ template <int N> __device__ __forceinline__ void bulk_wait_group_read()
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v)
 {
@@ -371,11 +378,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* empty_bar = full_bar + CONV_MAX_STAGES;          // [stages]  MMA -> TMA
     uint64_t* tfull_bar = empty_bar + CONV_MAX_STAGES;         // [2]       MMA -> epilogue
     uint64_t* tempty_bar = tfull_bar + 2;                      // [2]       epilogue -> MMA
-    uint64_t* res_bar = tempty_bar + 2;                        // [2]       residual TMA loads -> epilogue
-    uint32_t* tmem_slot = (uint32_t*)(res_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;                        // [4]       residual TMA loads -> epilogue
+    uint32_t* tmem_slot = (uint32_t*)(res_bar + 4);
     // two 16 KiB staging tiles (128 pixels x 64 channels fp16, 128B-swizzled) for the TMA-store epilogue
     uint8_t* out_stage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
-    // residual epilogue (res_tma): two more 16 KiB tiles, filled by TMA loads the epilogue leader issues ahead of use
+    // residual epilogue (res_tma): res_stages (2 or 4) more 16 KiB tiles, filled by TMA loads the epilogue leader issues ahead of use
     uint8_t* res_stage = out_stage + 2 * CONV_A_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -397,8 +404,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(tfull_bar + i), 1);
             ptx::mbar_init(ptx::smem_u32(tempty_bar + i), (uint32_t)p.epi_warps); // one arrive per epilogue warp
-            ptx::mbar_init(ptx::smem_u32(res_bar + i), 1);
         }
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(ptx::smem_u32(res_bar + i), 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -486,18 +493,23 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // residual tiles: sub-tile k of this CTA's (tile, sub) sequence lands in res_stage[k & 1]; the leader keeps two in flight
         const bool res_tma = kRes && p.res_mode != 0 && p.tma_store != 0;
         uint32_t res_issued = 0, res_used = 0;
+        const uint32_t res_mask = p.res_stages == 4 ? 3u : 1u, res_shift = p.res_stages == 4 ? 2u : 1u;
         int ri_tile = blockIdx.x, ri_sub = 0;
-        auto issue_residual = [&]() { // leader only
+        ConvTile rt = decode_tile(p, min(ri_tile, total_tiles - 1), n_tiles_g);   // tile of the next residual load (decoded once per tile: the
+        auto issue_residual = [&]() { // leader only                                  // leader issues between two barriers the other warps wait at)
             if (ri_tile >= total_tiles) return;
-            const ConvTile rt = decode_tile(p, ri_tile, n_tiles_g);
-            const uint32_t rb = ptx::smem_u32(res_bar + (res_issued & 1));
+            const uint32_t rb = ptx::smem_u32(res_bar + (res_issued & res_mask));
             ptx::mbar_expect_tx(rb, (uint32_t)CONV_A_BYTES);
-            ptx::tma_load_2d(ptx::smem_u32(res_stage + (res_issued & 1) * CONV_A_BYTES), &tmap_r, rb,
+            ptx::tma_load_2d(ptx::smem_u32(res_stage + (res_issued & res_mask) * CONV_A_BYTES), &tmap_r, rb,
                              p.res_ch_off + rt.g * p.cout_g + rt.n0 + ri_sub * 64, rt.p0);
             ++res_issued;
-            if (++ri_sub == rt.bn / 64) { ri_sub = 0; ri_tile += gridDim.x; }
+            if (++ri_sub == rt.bn / 64) {
+                ri_sub = 0; ri_tile += gridDim.x;
+                if (ri_tile < total_tiles) rt = decode_tile(p, ri_tile, n_tiles_g);
+            }
         };
-        if (kRes && res_tma && warp == 4 && lane == 0) { issue_residual(); issue_residual(); }
+        if (kRes && res_tma && warp == 4 && lane == 0)
+            for (int i = 0; i <= (int)res_mask; ++i) issue_residual();
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const ConvTile t = decode_tile(p, tile, n_tiles_g);
             const bool in_img = (t.p0 + row) < total_px;
@@ -520,8 +532,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
                     ptx::named_bar_sync(1, epi_threads);
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
-                    const uint8_t* rrow = res_stage + (res_used & 1) * CONV_A_BYTES + row * 128;
-                    if (kRes && res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & 1)), (res_used >> 1) & 1);
+                    const uint32_t rrow = ptx::smem_u32(res_stage) + (res_used & res_mask) * (uint32_t)CONV_A_BYTES + (uint32_t)row * 128u;
+                    if (kRes && res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & res_mask)), (res_used >> res_shift) & 1);
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {   // 16 channels per TMEM load; the other loads of the step are issued before the wait
                         if (qq >= q_step) break;
@@ -531,8 +543,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
                         __half2 rs[8];
                         if (kRes && res_tma) { // the residual tile sits in smem in the same 128B-swizzled layout as the output tile
-                            *(uint4*)&rs[0] = *(const uint4*)(rrow + (((q * 2) ^ (row & 7)) * 16));
-                            *(uint4*)&rs[4] = *(const uint4*)(rrow + (((q * 2 + 1) ^ (row & 7)) * 16));
+                            *(uint4*)&rs[0] = ptx::ld_shared_v4(rrow + (uint32_t)(((q * 2) ^ (row & 7)) * 16));
+                            *(uint4*)&rs[4] = ptx::ld_shared_v4(rrow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16));
                         } else if (kRes && p.res_mode) { // 16 residual channels of this pixel: two 16-byte loads
                             if (in_img) {
                                 const uint4* rp = (const uint4*)(p.res + pix * p.res_ld + p.res_ch_off + t.g * p.cout_g + t.n0 + c0);
@@ -567,7 +579,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (leader) {
                         ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
                         ptx::bulk_commit_group();
-                        if (kRes && res_tma) issue_residual(); // everybody is past the barrier: res_stage[res_used & 1] is free again
+                        if (kRes && res_tma) issue_residual(); // everybody is past the barrier: this sub-tile's residual buffer is free again
                     }
                     ++res_used;
                 }
@@ -1869,10 +1881,10 @@ inline size_t conv_stem_smem_bytes(int R, int BN)
     return 1024 + (size_t)STEM_STAGES * kch * CONV_A_BYTES + (size_t)kch * BN * 128 + 2 * CONV_A_BYTES + (2 * STEM_STAGES + 5) * 8 + 16;
 }
 
-constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 6) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
-inline size_t conv_smem_bytes(int BN, int stages, bool tma_store, bool res_tma = false)
+constexpr size_t CONV_SMEM_FIXED = 1024 /*base alignment*/ + (2 * CONV_MAX_STAGES + 8) * 8 + 16 /*tmem slot*/ + 1024 /*staging alignment*/;
+inline size_t conv_smem_bytes(int BN, int stages, bool tma_store, bool res_tma = false, int res_stages = 2)
 {
-    return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0) + (res_tma ? 2 * CONV_A_BYTES : 0);
+    return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + BN * CONV_BLOCK_K * 2) + (tma_store ? 2 * CONV_A_BYTES : 0) + (res_tma ? res_stages * CONV_A_BYTES : 0);
 }
 inline size_t conv_swap_smem_bytes(int npx, int stages) { return CONV_SMEM_FIXED + (size_t)stages * (CONV_A_BYTES + npx * 128) + 2 * CONV_A_BYTES; }
 inline int conv_swap_pick_stages(int npx)
@@ -1894,9 +1906,9 @@ inline int conv_swap_pick_npx(long total_px, int gc, int num_sms)
     }
     return best;
 }
-inline int conv_pick_stages(int BN, bool tma_store, bool res_tma = false)
+inline int conv_pick_stages(int BN, bool tma_store, bool res_tma = false, int res_stages = 2)
 {
-    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - (tma_store ? 2 * CONV_A_BYTES : 0) - (res_tma ? 2 * CONV_A_BYTES : 0);
+    const size_t avail = CONV_SMEM_LIMIT - CONV_SMEM_FIXED - (tma_store ? 2 * CONV_A_BYTES : 0) - (res_tma ? res_stages * CONV_A_BYTES : 0);
     const int st = (int)(avail / (size_t)(CONV_A_BYTES + BN * CONV_BLOCK_K * 2));
     return st > CONV_MAX_STAGES ? CONV_MAX_STAGES : st;
 }

@@ -386,10 +386,10 @@ __global__ void __launch_bounds__(256, 3) dwconv3_col_dual_kernel(const __half* 
 struct DwTmaParams {
     __half* out0; __half* out1; int out_ld;
     const float* w0; const float* w1;   // [9][C] | bias[C] | alpha[C]
-    int N, H, W, C, ctiles, tiles_x, tiles_y, wbo, hb, n_items, stages;
+    int N, H, W, C, ctiles, tiles_x, tiles_y, wbo, hb, n_items, stages, ct_fastest;
 };
-constexpr int DWT_THREADS = 576;   // 18 warps: the 54 columns of a 46x54 map = 3 full rounds
-constexpr int DWT_STAGE_MAX = 65536;   // bytes of one tile buffer at most (3 of them + barriers fit 227 KB)
+constexpr int DWT_THREADS = 384;   // 12 warps (sweep on cfg2, profiles/r02_dwtma_sweep.txt: 384 > 480 > 576 threads, 8-row tiles > 6 > 4)
+constexpr int DWT_STAGE_MAX = 73728;   // bytes of one tile buffer at most (3 of them + barriers fit 227 KB)
 
 template <int NB>
 __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const DwTmaParams p)
@@ -411,10 +411,12 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __gri
     auto issue = [&](int k) {
         const int item = (int)blockIdx.x + k * (int)gridDim.x;
         if (item >= p.n_items) return;
-        int t = item;
+        int t = item, ct = 0;
+        if (p.ct_fastest) { ct = t % p.ctiles; t /= p.ctiles; }
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int n = t % p.N; const int ct = t / p.N;
+        const int n = t % p.N;
+        if (!p.ct_fastest) ct = t / p.N;
         const int s = k % p.stages;
         ptx::mbar_expect_tx(bars + 8u * s, stage_bytes);
         ptx::tma_load_4d(base + (uint32_t)s * stage_bytes, &tmap_in, bars + 8u * s, ct * 64, tx * p.wbo - 1, ty * p.hb - 1, n);
@@ -430,10 +432,12 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __gri
         if (item >= p.n_items) break;
         __syncthreads();   // every warp is done with tile k-1: its buffer takes tile k + stages - 1
         if (threadIdx.x == 0) issue(k + p.stages - 1);
-        int t = item;
+        int t = item, ct = 0;
+        if (p.ct_fastest) { ct = t % p.ctiles; t /= p.ctiles; }
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int n = t % p.N; const int ct = t / p.N;   // the channel tile varies slowest: a CTA's consecutive tiles mostly share their filters
+        const int n = t % p.N;
+        if (!p.ct_fastest) ct = t / p.N;
         const int c0 = ct * 64 + lane * 2;
         if (ct != ct_loaded) {
             ct_loaded = ct;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __gri
         ptx::mbar_wait(bars + 8u * s, (uint32_t)(k / p.stages) & 1u);
         const uint32_t* tile = (const uint32_t*)(dwt_smem_raw + (base - ptx::smem_u32(dwt_smem_raw)) + (size_t)s * stage_bytes) + lane;
         const int row_words = bw * 32;
-        for (int col = warp; col < ncols; col += DWT_THREADS / 32) {
+        for (int col = warp; col < ncols; col += (int)(blockDim.x >> 5)) {
             const uint32_t* sp = tile + col * 32;   // box row 0 (image row y_lo - 1), box columns col, col+1, col+2 = image x-1, x, x+1
             const size_t o = (((size_t)n * p.H + y_lo) * p.W + x_lo + col) * p.out_ld + c0;
             __half* opa = p.out0 + o;
@@ -459,13 +463,11 @@ __global__ void __launch_bounds__(DWT_THREADS, 1) dwconv3_tma_kernel(const __gri
             float2 a0 = { 0.f, 0.f }, a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
 #define HP_DWT_EMIT(A, B)                                                                                                          \
             {                                                                                                                       \
-                float y0 = A.x + bsa.x, y1 = A.y + bsa.y;                                                                            \
-                y0 = y0 > 0.f ? y0 : y0 * ala.x; y1 = y1 > 0.f ? y1 : y1 * ala.y;                                                    \
-                *(__half2*)opa = __floats2half2_rn(y0, y1); opa += row_out;                                                          \
+                const float2 y = __fadd2_rn(A, bsa), ys = __fmul2_rn(y, ala);                                                        \
+                *(__half2*)opa = __floats2half2_rn(y.x > 0.f ? y.x : ys.x, y.y > 0.f ? y.y : ys.y); opa += row_out;                  \
                 if (NB == 2) {                                                                                                      \
-                    float z0 = B.x + bsb.x, z1 = B.y + bsb.y;                                                                        \
-                    z0 = z0 > 0.f ? z0 : z0 * alb.x; z1 = z1 > 0.f ? z1 : z1 * alb.y;                                                \
-                    *(__half2*)opb = __floats2half2_rn(z0, z1); opb += row_out;                                                      \
+                    const float2 z = __fadd2_rn(B, bsb), zs = __fmul2_rn(z, alb);                                                    \
+                    *(__half2*)opb = __floats2half2_rn(z.x > 0.f ? z.x : zs.x, z.y > 0.f ? z.y : zs.y); opb += row_out;              \
                 }                                                                                                                   \
             }
             // box row I: tap row 2 of output row I-2 (A0/B0, complete -> stored), tap row 1 of I-1 (A1/B1), tap row 0 of I (A2/B2, from zero)
@@ -824,6 +826,7 @@ struct hp_engine {
         const void* key_ovr[2] = { nullptr, nullptr };
     } slots[2];
     int next_slot = 0;
+    bool use_pdl = false;                  // programmatic dependent launch for the conv / depthwise kernels (launch-bound networks)
     int reserve_sms = 0;                   // SMs the persistent conv kernels leave to a decoder running underneath them (pipelined pifpaf call)
     cudaEvent_t heads_wait = nullptr;      // run_graph: the head op waits for this event (the previous batch's fields have been consumed)
     cudaStream_t copy_stream = nullptr;
@@ -1032,6 +1035,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     memset(&pl.tmap_bh, 0, sizeof(pl.tmap_bh));
     if (BN == 256) { rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, BN / 2); if (rc) return rc; }   // N-halves of a ragged last round
     memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
+    p.res_stages = 2;
     if (p.tma_store) {
         const EngBuffer& ob = e->bufs[po.out_buf];
         if ((int)po.out_ch_off + (G - 1) * cout_g + cout_pad > ob.channels) p.tma_store = 0; // padded sub-tile would leave the buffer
@@ -1039,7 +1043,12 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
             rc = make_tmap_out(&pl.tmap_o, ob.d, (size_t)e->max_batch * ob.H * ob.W, ob.channels);
             if (rc) return rc;
         }
-        p.num_stages = conv_pick_stages(BN, p.tma_store != 0, p.tma_store && po.res_mode);
+        // experiment switch (HPB_RES_STAGES=4): four 16 KiB residual tiles in flight instead of two for the short-k residual layers (ResNet conv3),
+        // paid with A/B ring stages.  Measured neutral to slightly negative (profiles/r02_bench_cfg{4,5}_res{2,4}.json): those layers are paced by
+        // the epilogue's own latency chain (ncu: barrier and TMEM-load waits of 8 epilogue warps), not by the residual stream, so 2 stays.
+        if (p.tma_store && po.res_mode && getenv("HPB_RES_STAGES") && atoi(getenv("HPB_RES_STAGES")) == 4 &&
+            eR * eS * (cin_g / CONV_BLOCK_K) <= (getenv("HPB_RES4_KMAX") ? atoi(getenv("HPB_RES4_KMAX")) : 4) && conv_pick_stages(BN, true, true, 4) >= 2) p.res_stages = 4;
+        p.num_stages = conv_pick_stages(BN, p.tma_store != 0, p.tma_store && po.res_mode, p.res_stages);
     }
     memset(&pl.tmap_r, 0, sizeof(pl.tmap_r));
     if (p.tma_store && po.res_mode) { // residual tiles are TMA-loaded into smem ahead of the epilogue
@@ -1068,7 +1077,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
         if (rc) return rc;
         pl.smem = conv_swap_smem_bytes(p.npx, p.num_stages);
     } else {
-        pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode);
+        pl.smem = conv_smem_bytes(BN, p.num_stages, p.tma_store != 0, p.tma_store && po.res_mode, p.res_stages);
     }
     // Halo-box kernel for RxS layers whose 16 x 8 tile grid wastes little of the image (the early VGG layers): the A operand comes
     // from L2 once per chunk instead of once per tap.  HPB_HALO=0 disables it, HPB_HALO=all takes every eligible layer.
@@ -1153,12 +1162,15 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
 // Launch with programmatic dependent launch allowed: the kernel may begin (prologue: barrier init, TMEM allocation, tensor-map
 // prefetch) on every SM the previous kernel of the stream has already left, and orders itself behind that kernel's completion with
 // griddepcontrol.wait before it touches memory.  The persistent conv kernels trigger their dependents at their own start.
-// MEASURED NEGATIVE (profiles/r02_bench_cfg{3,4}_{pdl,nopdl}.json, same box, graph replay): cfg3 2168 vs 2219 frames/s, cfg4 5072 vs 5158 --
-// inside a CUDA graph the plain kernel -> kernel edge is already cheaper than the programmatic one, so this is opt-in (HPB_PDL=1).
+// Measured (same box, graph replay): NEGATIVE where the kernels are long -- cfg3 2168 vs 2219 frames/s, cfg4 5072 vs 5158
+// (profiles/r02_bench_cfg{3,4}_{pdl,nopdl}.json) -- and POSITIVE where the step is a chain of short kernels -- cfg2 (73 launches of
+// ~15 us): 5530 -> 5773 frames/s (profiles/r02_bench_cfg2_{nopdl,pdl}.json).  So the engine turns it on by itself when the mean work
+// per launch is small (hp_engine::use_pdl, decided at creation); HPB_PDL=0|1 overrides.
+thread_local bool tl_use_pdl = false;   // set by the op loop from hp_engine::use_pdl for the launches it issues on this thread
 template <typename... KArgs, typename... Args>
 static inline void launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args)
 {
-    static const bool no_pdl = getenv("HPB_PDL") == nullptr;
+    const bool no_pdl = !tl_use_pdl;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -1184,8 +1196,11 @@ void launch_dw_tma(hp_engine* e, const EngOp& op, const EngOp* pair, int N, cuda
     p.tiles_x = op.dwt_tiles_x; p.tiles_y = op.dwt_tiles_y; p.wbo = op.dwt_wbo; p.hb = op.dwt_hb; p.stages = op.dwt_stages;
     p.n_items = N * p.tiles_y * p.tiles_x * p.ctiles;
     const int grid = std::min(p.n_items, std::max(1, e->num_sms - e->reserve_sms));
-    if (pair) launch_pdl(dwconv3_tma_kernel<2>, grid, DWT_THREADS, op.dwt_smem, st, op.tmap_dw, p);
-    else      launch_pdl(dwconv3_tma_kernel<1>, grid, DWT_THREADS, op.dwt_smem, st, op.tmap_dw, p);
+    static const int threads = getenv("HPB_DWT_THREADS") ? std::max(32, std::min(DWT_THREADS, atoi(getenv("HPB_DWT_THREADS")) / 32 * 32)) : DWT_THREADS;
+    static const int order = getenv("HPB_DWT_ORDER") ? atoi(getenv("HPB_DWT_ORDER")) : 1;   // channel tile fastest: concurrent CTAs read whole pixels
+    p.ct_fastest = order;
+    if (pair) launch_pdl(dwconv3_tma_kernel<2>, grid, threads, op.dwt_smem, st, op.tmap_dw, p);
+    else      launch_pdl(dwconv3_tma_kernel<1>, grid, threads, op.dwt_smem, st, op.tmap_dw, p);
 }
 
 int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
@@ -1360,6 +1375,7 @@ int run_graph(hp_engine* e, int N, bool u8_input, cudaStream_t st, int first = 0
         evset = e->ev.data() + (size_t)(e->ev_head % hp_engine::EV_DEPTH) * (e->ops.size() + 1);
         cudaEventRecord(evset[0], st);
     }
+    tl_use_pdl = e->use_pdl;
     for (int oi = first; oi <= last; ++oi) {
         EngOp& op = e->ops[oi];
         const PackOp& po = op.po;
@@ -1742,9 +1758,11 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
             if (ib.channels % 8 || po.in_ch_off % 8) continue;
             const int C = (int)po.cout_g;
             const int nx = (ib.W + 61) / 62, wbo = (ib.W + nx - 1) / nx, bw = wbo + 2;
-            // tile height: the tallest of 6 / 4 / 3 / 2 rows that fits a buffer and still gives every SM two tiles at the full batch
+            // tile height: the tallest of 8 / 6 / 4 / 3 / 2 rows that fits a buffer and still gives every SM two tiles at the full batch
             int hb = 2;
-            for (int cand : { 6, 4, 3, 2 }) {
+            const int hb_max = getenv("HPB_DWT_HB") ? atoi(getenv("HPB_DWT_HB")) : 8;
+            for (int cand : { 8, 6, 4, 3, 2 }) {
+                if (cand > hb_max) continue;
                 if (cand > std::max(2, ib.H) || (size_t)(cand + 2) * bw * 128 > (size_t)DWT_STAGE_MAX) continue;
                 const size_t items = (size_t)e->max_batch * ((ib.H + cand - 1) / cand) * nx * (C / 64);
                 hb = cand;
@@ -1765,6 +1783,16 @@ int hp_engine_create_ex(hp_engine** out, const void* pack, size_t pack_bytes, in
             set_error("engine: cannot opt in to %zu bytes of dynamic shared memory (depthwise)", dwt_max);
             return fail(HP_ERR_CUDA);
         }
+    }
+    // programmatic dependent launch pays where the step is a chain of short kernels (MobilenetThin: 73 launches of ~2 GFLOP at batch 8)
+    // and costs where they are long (VGG19: 140 GFLOP per launch); see launch_pdl
+    {
+        int launches = 0;
+        for (const EngOp& o : e->ops)
+            if ((o.po.type == OP_CONV || o.po.type == OP_DWCONV || o.po.type == OP_MAXPOOL2) && !o.fused_into_prev) ++launches;
+        const double per_launch = launches ? e->flops_per_frame * e->max_batch / launches : 0.0;
+        e->use_pdl = dtype == HP_DTYPE_F16 && launches > 0 && per_launch < 10e9;
+        if (const char* v = getenv("HPB_PDL")) e->use_pdl = atoi(v) != 0;
     }
     if (max_smem > 0 && dtype == HP_DTYPE_TF32) {
         if (cudaFuncSetAttribute(conv_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
