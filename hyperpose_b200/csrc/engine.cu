@@ -1033,7 +1033,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     rc = make_tmap_wgt(&pl.tmap_b, pl.d_w, G * cout_pad, K, BN);
     if (rc) return rc;
     memset(&pl.tmap_bh, 0, sizeof(pl.tmap_bh));
-    if (BN == 256) { rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, BN / 2); if (rc) return rc; }   // N-halves of a ragged last round
+    if (BN == 256 || BN == 128) { rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, BN / 2); if (rc) return rc; }   // N-halves of a ragged last round
     memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
     p.res_stages = 2;
     if (p.tma_store) {
@@ -1284,7 +1284,7 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
     {
         const bool no_split = getenv("HPB_NO_SPLIT") != nullptr;   // same-box A/B: profiles/r02_bench_cfg{3,4,5}_split.json
         const int rem = n_tiles % grid;
-        const bool split = !no_split && p.BN == 256 && p.tma_store && rem > 0 && 2 * rem <= grid && n_tiles > grid;
+        const bool split = !no_split && (p.BN == 256 || p.BN == 128) && p.tma_store && rem > 0 && 2 * rem <= grid && n_tiles > grid;
         p.split_from = split ? n_tiles - rem : n_tiles;
         p.total_items = n_tiles + (n_tiles - p.split_from);
     }

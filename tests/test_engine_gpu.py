@@ -464,11 +464,12 @@ def test_tma_tiled_depthwise_kernel_is_bit_identical(monkeypatch, hw, N):
 @pytest.mark.gpu
 def test_n_half_tiles_of_a_ragged_last_round_are_bit_identical(monkeypatch):
     """conv_tcgen05_kernel's work list: when the last round of 128-pixel x 256-channel tiles would occupy at most half of the CTAs, those
-    tiles run as N-halves (128 x 128) on twice as many CTAs.  Same MMAs per output element, same k order: the bytes must not change
-    (HPB_NO_SPLIT=1 = the plain tile list).  ResNet50 at 368x432 / batch 5 has such layers (46x54 maps: 98 pixel tiles; 512 output
-    channels -> 196 tiles, 48 in the ragged round; 2048 channels -> 784 tiles, 44 in the ragged round)."""
+    tiles run as N-halves (128 x 128; 128 x 64 for 128-channel tiles) on twice as many CTAs.  Same MMAs per output element, same k order:
+    the bytes must not change (HPB_NO_SPLIT=1 = the plain tile list).  ResNet50 + LW-OpenPose at 368x432 / batch 8 has such layers of
+    every kind (46x54 maps = 156 pixel tiles: 128 channels -> 8 tiles in the ragged round, 512 -> 16, 1024 -> 32, 2048 -> 64;
+    92x108 maps = 621 pixel tiles: 256 channels -> 29)."""
     g = models.resnet50_lw_openpose(0)
-    H, W, N = 368, 432, 5
+    H, W, N = 368, 432, 8
     frames = syn.make_frames_u8(29, N, H, W)
 
     def run():
