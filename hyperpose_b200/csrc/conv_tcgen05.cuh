@@ -69,6 +69,7 @@ struct ConvParams {
     // a 1x1 "depthwise" op that follows the conv (per-channel scale + bias + PReLU: the filter_size (1,1) separable blocks of
     // MobilenetThin-OpenPose) applied in the epilogue, with the fp16 rounding of the tensor in between kept: bit-identical with the two launches
     const float* post_w; const float* post_b; const float* post_a;   // [groups * cout_g] each, or nullptr
+    int epi_one_bar;               // conv_tcgen05_kernel TMA-store epilogue: one named barrier per 64-channel sub-tile instead of two (see there)
     int res_stages;                // depth of the residual-tile ring of conv_tcgen05_kernel's TMA-store epilogue (2 or 4)
     int split_from, total_items;   // conv_tcgen05_kernel work list: items >= split_from are N-halves (see decode_tile); total_items = tiles + (tiles - split_from)
 };
@@ -529,8 +530,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const bool leader = (warp == 4 && lane == 0);
                 for (int sub = 0; sub < t.bn / 64; ++sub, ++stage_ctr) {
                     uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
-                    if (leader) ptx::bulk_wait_group_read<1>(); // the store that last used this buffer has drained it
-                    ptx::named_bar_sync(1, epi_threads);
+                    // Two-barrier form: the leader waits until the store that last used this buffer has drained it, everybody syncs, fills
+                    // the buffer, syncs again, the leader stores.  One-barrier form (epi_one_bar): the leader drains ALL earlier stores just
+                    // before the second barrier of the PREVIOUS sub-tile (they were issued a whole sub-tile ago, so this rarely waits); past that
+                    // barrier every warp knows the other buffer is free, and the leader's serial work after it (store, commit, next residual
+                    // load) overlaps the other warps' next sub-tile instead of holding them at a barrier.
+                    if (!p.epi_one_bar) {
+                        if (leader) ptx::bulk_wait_group_read<1>();
+                        ptx::named_bar_sync(1, epi_threads);
+                    }
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
                     const uint32_t rrow = ptx::smem_u32(res_stage) + (res_used & res_mask) * (uint32_t)CONV_A_BYTES + (uint32_t)row * 128u;
                     if (kRes && res_tma) ptx::mbar_wait(ptx::smem_u32(res_bar + (res_used & res_mask)), (res_used >> res_shift) & 1);
@@ -575,6 +583,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         ptx::st_shared_v4(srow + (uint32_t)(((ch0 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                     }
                     ptx::fence_proxy_async(); // generic-proxy smem writes -> visible to the TMA (async proxy)
+                    if (p.epi_one_bar && leader) ptx::bulk_wait_group_read<0>(); // the other staging buffer is free for the next sub-tile
                     ptx::named_bar_sync(1, epi_threads);
                     if (leader) {
                         ptx::tma_store_2d(&tmap_o, ptx::smem_u32(sbuf), p.out_ch_off + t.g * p.cout_g + t.n0 + sub * 64, t.p0);
