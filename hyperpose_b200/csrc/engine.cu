@@ -1036,7 +1036,7 @@ int build_conv_plan(hp_engine* e, EngOp& op, const float* blob)
     if (BN == 256 || BN == 128) { rc = make_tmap_wgt(&pl.tmap_bh, pl.d_w, G * cout_pad, K, BN / 2); if (rc) return rc; }   // N-halves of a ragged last round
     memset(&pl.tmap_o, 0, sizeof(pl.tmap_o));
     p.res_stages = 2;
-    p.epi_one_bar = getenv("HPB_EPI_1BAR") ? atoi(getenv("HPB_EPI_1BAR")) : 0;
+    p.epi_one_bar = getenv("HPB_EPI_1BAR") ? atoi(getenv("HPB_EPI_1BAR")) : 1;   // same-box A/B: profiles/r02_bench_cfg{2,3,4,5}_epi{1,2}bar.json
     if (p.tma_store) {
         const EngBuffer& ob = e->bufs[po.out_buf];
         if ((int)po.out_ch_off + (G - 1) * cout_g + cout_pad > ob.channels) p.tma_store = 0; // padded sub-tile would leave the buffer
