@@ -903,7 +903,6 @@ struct HaloParams {
     const float* bias; const float* alpha;
     int relu_only;              // 1: every slope of the layer is 0 (plain ReLU)
     int epi_warps;              // 8: two epilogue warps per TMEM lane quarter (each takes half of the channels), 4: one
-    int epi_one_bar;            // one named barrier per sub-tile in the TMA-store epilogue (see conv_tcgen05_kernel)
 };
 
 // kPool: the 2x2 / stride-2 max-pool that follows the layer is taken in the epilogue (VGG conv1_2 -> maxpool_1: the un-pooled
@@ -1115,10 +1114,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int row_p = ((ew * 4 + ly) >> 1) * 4 + (lx >> 1);         // pooled pixel inside the 8 x 4 pooled tile
                 for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
                     uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
-                    if (!p.epi_one_bar) {
-                        if (leader) ptx::bulk_wait_group_read<1>();
-                        ptx::named_bar_sync(1, epi_threads);
-                    }
+                    if (leader) ptx::bulk_wait_group_read<1>();
+                    ptx::named_bar_sync(1, epi_threads);
                     const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row_p * 128u;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
@@ -1161,7 +1158,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*(const uint32_t*)&h01), "r"(*(const uint32_t*)&h23) : "memory");
                     }
                     ptx::fence_proxy_async();
-                    if (p.epi_one_bar && leader) ptx::bulk_wait_group_read<0>();
                     ptx::named_bar_sync(1, epi_threads);
                     if (leader) {
                         // box {64 ch, 4, 8, 1} of the pooled tensor; pooled pixels outside it are clipped by the TMA unit
@@ -1172,10 +1168,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             } else
             for (int sub = 0; sub < p.BN / 64; ++sub, ++stage_ctr) {
                 uint8_t* sbuf = out_stage + (stage_ctr & 1) * CONV_A_BYTES;
-                if (!p.epi_one_bar) {
-                    if (leader) ptx::bulk_wait_group_read<1>();
-                    ptx::named_bar_sync(1, epi_threads);
-                }
+                if (leader) ptx::bulk_wait_group_read<1>();
+                ptx::named_bar_sync(1, epi_threads);
                 const uint32_t srow = ptx::smem_u32(sbuf) + (uint32_t)row * 128u;
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
@@ -1199,7 +1193,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     ptx::st_shared_v4(srow + (uint32_t)(((q * 2 + 1) ^ (row & 7)) * 16), make_uint4(pk[4], pk[5], pk[6], pk[7]));
                 }
                 ptx::fence_proxy_async();
-                if (p.epi_one_bar && leader) ptx::bulk_wait_group_read<0>();
                 ptx::named_bar_sync(1, epi_threads);
                 if (leader) {
                     // box {64 ch, 8, 16, 1}: staging row y * 8 + x == TMEM lane; pixels outside the image are clipped by the TMA unit

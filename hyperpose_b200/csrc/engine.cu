@@ -1246,7 +1246,6 @@ int launch_conv(hp_engine* e, EngOp& op, int N, cudaStream_t st, bool u8_input)
             const int ksteps = h.R * h.S * (h.cin_g / CONV_BLOCK_K);
             (void)ksteps;   // measured: the 9-k-step halo layers are paced by the MMA issue loop as much as by the epilogue -- a second warp set gains nothing
             h.epi_warps = epi_env ? (atoi(epi_env) == 4 ? 4 : 8) : 4;
-            h.epi_one_bar = getenv("HPB_HALO_1BAR") ? atoi(getenv("HPB_HALO_1BAR")) : 0;   // (opt-in until measured)
         }
         if (pl.pool_fused) {
             if (h.R == 3 && h.S == 3) launch_pdl(conv_halo_kernel<3, true>, hgrid, CONV_IM2COL_THREADS, pl.smem, st, pl.tmap_a, pl.tmap_b, pl.tmap_o, h);
