@@ -36,7 +36,9 @@ print(f"# cuobjdump -sass {os.path.basename(lib)}: instruction counts per kernel
 tot = collections.Counter()
 for k, c in per.items():
     name = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip()
-    name = re.sub(r"\(.*", "", name)[-90:]
+    name = name.replace("(anonymous namespace)::", "").replace("hpb::", "")
+    name = re.sub(r"^void ", "", name)
+    name = re.sub(r"\((?!anonymous).*", "", name)[-90:]   # drop the parameter list, keep template arguments
     cols = " ".join(f"{w}={c[w]}" for w in WATCH if c[w])
     print(f"{name:<92} total={c['__total']:<6} {cols}")
     tot.update(c)
