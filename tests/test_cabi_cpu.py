@@ -70,3 +70,12 @@ def test_conv_traffic_json_is_the_fold_of_the_committed_launch_list():
     assert fold["conv_launches"] == committed["conv_launches"] == 52
     assert abs(fold["dram_bytes_per_step"] - committed["dram_bytes_per_step"]) < 1.0
     assert 0.85 < fold["conv_share_of_step_device_time"] < 0.99
+
+
+def test_docs_have_no_unfilled_number_placeholders():
+    """DESIGN.md / README.md take their headline numbers from the final bench line through tools/fill_doc_numbers.py; a placeholder
+    left in the text means the docs were not refreshed after the last measurement."""
+    import re
+    for name in ("DESIGN.md", "README.md", "INTEGRATION.md"):
+        text = open(os.path.join(ROOT, name)).read()
+        assert not re.findall(r"\{[A-Z][A-Z0-9]{2,}\}", text), name
